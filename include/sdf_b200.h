@@ -1,0 +1,121 @@
+/*
+ * sdf_b200.h — C ABI of libsdf_b200.so: the sm_100a kernels behind
+ * stable-dreamfusion's operator surface (raymarching.*, grid_encode, sh_encode,
+ * freq_encode, sd_utils.StableDiffusion.train_step).
+ *
+ * Conventions:
+ *   - every pointer is a raw DEVICE pointer unless its name starts with host_;
+ *     all arrays are contiguous, row-major;
+ *   - the caller allocates every output; nothing is allocated or retained
+ *     natively except small per-device scratch (documented per function);
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream);
+ *     no entry point synchronises the host unless stated;
+ *   - return value: 0 = ok, <0 = error (SDF_ERR_*), message via sdf_last_error();
+ *     launch errors are checked with cudaPeekAtLastError after each launch.
+ * Each declaration cites the reference interface it replaces
+ * (paths relative to the reference repository root).
+ */
+#ifndef SDF_B200_H
+#define SDF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SDF_OK 0
+#define SDF_ERR_ARG (-1)
+#define SDF_ERR_CUDA (-2)
+#define SDF_ERR_UNSUPPORTED (-3)
+
+const char* sdf_last_error(void);
+int sdf_abi_version(void);
+
+/* ------------------------------------------------------------------ raymarching
+ * replaces raymarching/src/raymarching.h:6-18 (pybind: raymarching/src/bindings.cpp:5-19) */
+
+/* near_far_from_aabb (raymarching.h:6; kernel raymarching.cu:92) */
+int sdf_near_far_from_aabb(const float* rays_o, const float* rays_d, const float* aabb, uint32_t N, float min_near,
+                           float* nears, float* fars, void* stream);
+/* sph_from_ray (raymarching.h:7; raymarching.cu:163) */
+int sdf_sph_from_ray(const float* rays_o, const float* rays_d, float radius, uint32_t N, float* coords, void* stream);
+/* morton3D / morton3D_invert (raymarching.h:8-9; raymarching.cu:214,237) */
+int sdf_morton3D(const int* coords, uint32_t N, int* indices, void* stream);
+int sdf_morton3D_invert(const int* indices, uint32_t N, int* coords, void* stream);
+/* packbits (raymarching.h:10; raymarching.cu:268).  N = number of output bytes; grid 16-byte aligned. */
+int sdf_packbits(const float* grid, uint32_t N, float thresh, uint8_t* bitfield, void* stream);
+/* flatten_rays (raymarching.h:11; raymarching.cu:303) */
+int sdf_flatten_rays(const int* rays, uint32_t N, uint32_t M, int* res, void* stream);
+
+/* march_rays_train (raymarching.h:13; raymarching.cu:338,477).  The reference's
+ * two kernel passes around a host sync become:
+ *   _count: rays[N,2] <- (exclusive offset in ray order, count); counter[0] <- M on the device;
+ *           host_M (optional, pinned host int32) receives M via a device store.
+ *   _write: emits xyzs[M,3] dirs[M,3] ts[M,2] at the offsets in rays; rows beyond `capacity` are never written. */
+int sdf_march_rays_train_count(const float* rays_o, const float* rays_d, const uint8_t* grid, float bound, int contract,
+                               float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H,
+                               const float* nears, const float* fars, const float* noises /* may be NULL */,
+                               int* rays, int* counter, int* host_M, void* stream);
+int sdf_march_rays_train_write(const float* rays_o, const float* rays_d, const uint8_t* grid, float bound, int contract,
+                               float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H,
+                               const float* nears, const float* fars, const float* noises,
+                               float* xyzs, float* dirs, float* ts, const int* rays, uint32_t capacity, void* stream);
+
+/* composite_rays_train_forward / _backward (raymarching.h:14-15; raymarching.cu:501,606).
+ * forward writes weights for every sample of every valid ray (0 after early termination). */
+int sdf_composite_rays_train_forward(const float* sigmas, const float* rgbs, const float* ts, const int* rays,
+                                     uint32_t M, uint32_t N, float T_thresh, int binarize,
+                                     float* weights, float* weights_sum, float* depth, float* image, void* stream);
+int sdf_composite_rays_train_backward(const float* grad_weights /* may be NULL */, const float* grad_weights_sum /* may be NULL */,
+                                      const float* grad_depth /* may be NULL */, const float* grad_image,
+                                      const float* sigmas, const float* rgbs, const float* ts, const int* rays,
+                                      const float* weights_sum, const float* depth, const float* image,
+                                      uint32_t M, uint32_t N, float T_thresh, int binarize,
+                                      float* grad_sigmas, float* grad_rgbs, void* stream);
+
+/* march_rays / composite_rays, inference (raymarching.h:17-18; raymarching.cu:714,843) */
+int sdf_march_rays(uint32_t n_alive, uint32_t n_step, const int* rays_alive, const float* rays_t, const float* rays_o,
+                   const float* rays_d, float bound, int contract, float dt_gamma, uint32_t max_steps, uint32_t C, uint32_t H,
+                   const uint8_t* grid, const float* nears, const float* fars, float* xyzs, float* dirs, float* ts,
+                   const float* noises /* may be NULL */, void* stream);
+int sdf_composite_rays(uint32_t n_alive, uint32_t n_step, float T_thresh, int binarize, int* rays_alive, float* rays_t,
+                       const float* sigmas, const float* rgbs, const float* ts, float* weights_sum, float* depth, float* image,
+                       void* stream);
+
+/* ------------------------------------------------------------------ gridencoder
+ * replaces gridencoder/src/gridencoder.h:12-16 (pybind: gridencoder/src/bindings.cpp:5-10).
+ * dtype: 0 = fp32 table/outputs/grads, 1 = fp16.  inputs are fp32 in [0,1].
+ * Layout change vs the reference: outputs and grad are [B, L*C] (point-major, what
+ * grid.py:64 / :82 produce by permuting), dy_dx is [B, L, D, C] as in the reference. */
+int sdf_grid_encode_forward(const float* inputs, const void* embeddings, const int* offsets, void* outputs,
+                            uint32_t B, uint32_t D, uint32_t C, uint32_t L, uint32_t max_level, float S, uint32_t H,
+                            void* dy_dx /* may be NULL */, uint32_t gridtype, int align_corners, uint32_t interp, int dtype, void* stream);
+int sdf_grid_encode_backward(const void* grad, const float* inputs, const int* offsets, void* grad_embeddings /* accumulated into */,
+                             uint32_t B, uint32_t D, uint32_t C, uint32_t L, uint32_t max_level, float S, uint32_t H,
+                             const void* dy_dx /* may be NULL */, void* grad_inputs /* may be NULL */,
+                             uint32_t gridtype, int align_corners, uint32_t interp, int dtype /* of grad, dy_dx, grad_inputs */,
+                             int acc_dtype /* of grad_embeddings: (dtype,acc) in (0,0),(1,1),(1,0) */, void* stream);
+/* grad_total_variation / grad_weight_decay (gridencoder.h:15-16; gridencoder.cu:526,671), fp32 */
+int sdf_grid_grad_total_variation(const float* inputs, const float* embeddings, float* grad, const int* offsets, float weight,
+                                  uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S, uint32_t H, uint32_t gridtype,
+                                  int align_corners, void* stream);
+int sdf_grid_grad_weight_decay(const float* embeddings, float* grad, const int* offsets, float weight,
+                               uint32_t n_entries, uint32_t C, uint32_t L, void* stream);
+/* device-evaluated ceil(exp2f(level*S)*H) per level (gridencoder.cu:133), copied to host_out[L]; synchronises `stream`. */
+int sdf_grid_level_resolutions(const int* offsets, uint32_t L, float S, uint32_t H, uint32_t* host_out, void* stream);
+
+/* ------------------------------------------------------------------ freqencoder / shencoder
+ * replace freqencoder/src/freqencoder.h:6-9 and shencoder/src/shencoder.h:9-10 */
+int sdf_freq_encode_forward(const float* inputs, uint32_t B, uint32_t D, uint32_t deg, uint32_t C, float* outputs, void* stream);
+int sdf_freq_encode_backward(const float* grad, const float* outputs, uint32_t B, uint32_t D, uint32_t deg, uint32_t C,
+                             float* grad_inputs, void* stream);
+int sdf_sh_encode_forward(const float* inputs, float* outputs, uint32_t B, uint32_t D, uint32_t degree,
+                          float* dy_dx /* may be NULL; [B, 3, degree^2] */, void* stream);
+int sdf_sh_encode_backward(const float* grad, const float* inputs, uint32_t B, uint32_t D, uint32_t degree, const float* dy_dx,
+                           float* grad_inputs /* accumulated into */, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SDF_B200_H */

@@ -1,0 +1,43 @@
+// common.cuh — shared helpers for the sm_100a kernels behind the C-ABI (include/sdf_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#define SDF_API extern "C" __attribute__((visibility("default")))
+
+// error codes returned by every sdf_* entry point
+enum { SDF_OK = 0, SDF_ERR_ARG = -1, SDF_ERR_CUDA = -2, SDF_ERR_UNSUPPORTED = -3 };
+
+void sdf_set_error(const char* fmt, ...);
+
+#define SDF_CHECK_ARG(cond, ...)                                   \
+    do { if (!(cond)) { sdf_set_error(__VA_ARGS__); return SDF_ERR_ARG; } } while (0)
+
+#define SDF_CHECK_LAUNCH(name)                                                      \
+    do { cudaError_t e_ = cudaPeekAtLastError();                                    \
+         if (e_ != cudaSuccess) { sdf_set_error("%s: %s", name, cudaGetErrorString(e_)); \
+                                  (void)cudaGetLastError(); return SDF_ERR_CUDA; } } while (0)
+
+#define SDF_CHECK_CUDA(expr)                                                        \
+    do { cudaError_t e_ = (expr);                                                   \
+         if (e_ != cudaSuccess) { sdf_set_error("%s: %s", #expr, cudaGetErrorString(e_)); \
+                                  return SDF_ERR_CUDA; } } while (0)
+
+static inline uint32_t cdiv(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
+static inline uint64_t cdiv64(uint64_t a, uint64_t b) { return (a + b - 1) / b; }
+
+constexpr int kNumSMs = 148;   // B200
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}

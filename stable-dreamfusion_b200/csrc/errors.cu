@@ -1,0 +1,16 @@
+// errors.cu — last-error string of the C-ABI (include/sdf_b200.h: sdf_last_error).
+#include "common.cuh"
+#include <stdarg.h>
+
+static thread_local char g_err[512] = "";
+
+void sdf_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+}
+
+SDF_API const char* sdf_last_error(void) { return g_err; }
+
+SDF_API int sdf_abi_version(void) { return 1; }
