@@ -115,6 +115,30 @@ int sdf_sh_encode_forward(const float* inputs, float* outputs, uint32_t B, uint3
 int sdf_sh_encode_backward(const float* grad, const float* inputs, uint32_t B, uint32_t D, uint32_t degree, const float* dy_dx,
                            float* grad_inputs /* accumulated into */, void* stream);
 
+/* ------------------------------------------------------------------ fused radiance field
+ * replaces NeRFNetwork.forward / .density / .common_forward / .normal of the -O backbone
+ * (nerf/network_grid.py:68-142): hashgrid(L16, C2, smoothstep) -> MLP 32-64-64-4 -> trunc_exp(+density_blob) / sigmoid
+ * -> finite-difference normal (6 extra evaluations at x +- 1e-2) -> safe_normalize -> shading, in one kernel.
+ * xyzs [M,3] fp32 in [-bound,bound]; table_fp16 [n_entries,2] half; w*,b*: fp32 nn.Linear parameters of sigma_net;
+ * shading 0 albedo / 1 lambertian / 2 textureless / 3 normal; light_d [3] or [M,3] (light_per_sample);
+ * m_dev: optional device int32 with the live sample count (<= M).  aux [M,10] fp32: stash for the backward. */
+int sdf_field_forward(const float* xyzs, uint32_t M, const int* m_dev, const void* table_fp16, const int* offsets,
+                      uint32_t n_levels, uint32_t n_levels_active, float per_level_scale_log2, uint32_t base_resolution,
+                      int interp_smoothstep, const float* w1, const float* b1, const float* w2, const float* b2,
+                      const float* w3, const float* b3, float bound, float blob_density, float blob_radius,
+                      int shading, const float* light_d, int light_per_sample, float ambient_ratio,
+                      float* sigmas, float* colors /* may be NULL */, float* normals /* may be NULL */, float* aux /* may be NULL */,
+                      void* stream);
+/* backward: gradients are ACCUMULATED into grad_table [n_entries,2] fp32 and gw1 [64,32] gb1 [64] gw2 [64,64] gb2 [64] gw3 [4,64] gb3 [4]
+ * (replaces 7 x {MLP autograd, gridencoder.cu:253 kernel_grid_backward} of the reference). */
+int sdf_field_backward(const float* xyzs, uint32_t M, const int* m_dev, const void* table_fp16, const int* offsets,
+                       uint32_t n_levels, uint32_t n_levels_active, float per_level_scale_log2, uint32_t base_resolution,
+                       int interp_smoothstep, const float* w1, const float* b1, const float* w2, const float* b2,
+                       const float* w3, const float* b3, float bound, float blob_density, float blob_radius,
+                       int shading, const float* light_d, int light_per_sample, float ambient_ratio, const float* aux,
+                       const float* g_sigmas /* may be NULL */, const float* g_colors /* may be NULL */, const float* g_normals /* may be NULL */,
+                       float* grad_table, float* gw1, float* gb1, float* gw2, float* gb2, float* gw3, float* gb3, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,231 @@
+// field_common.cuh — device building blocks of the fused radiance-field kernels (fused_field.cu):
+// hash-grid lookup emitted directly in mma.sync A-fragment order, the 32-64-64-4 MLP on tensor
+// cores with register-chained activations, and the weight tiles in shared memory.
+#pragma once
+#include "grid_common.cuh"
+#include <mma.h>
+
+namespace field {
+
+constexpr int kLevels = 16;          // instant-NGP config of the -O backbone (nerf/network_grid.py:49, encoding.py:57)
+constexpr int kEncDim = 32;          // kLevels * 2 features
+constexpr int kHidden = 64;
+constexpr int kOut = 4;              // sigma logit + 3 albedo logits
+constexpr int kW1Stride = kEncDim + 8;   // halfs; +8 keeps B-fragment LDS conflict-free
+constexpr int kW2Stride = kHidden + 8;
+
+struct LevelSmem {
+    uint32_t offset, size, res, flags;   // flags bit0: hashed, bit1: size is a power of two
+};
+
+// Shared-memory weight block (fp16 weights, fp32 biases) — forward orientation W[out][in].
+struct WeightsSmem {
+    __half w1[kHidden][kW1Stride];
+    __half w2[kHidden][kW2Stride];
+    __half w3[8][kW2Stride];             // rows 4..7 are zero
+    float b1[kHidden], b2[kHidden], b3[8];
+    LevelSmem lv[kLevels];
+};
+
+struct FieldParams {
+    const __half2* table;                // fp16 hash table, [n_entries] half2 (2 features)
+    const float *w1, *b1, *w2, *b2, *w3, *b3;   // fp32 master weights of sigma_net (nn.Linear layout [out,in])
+    const LevelParams* lp;
+    float bound;
+    uint32_t n_levels_active;            // levels >= this produce zeros (progressive max_level)
+    float blob_density, blob_radius;     // density_blob (nerf/renderer.py:339-349), exp activation
+    int interp_smoothstep;
+};
+
+__device__ __forceinline__ void load_weights(WeightsSmem& s, const FieldParams& p) {
+    for (int i = threadIdx.x; i < kHidden * kEncDim; i += blockDim.x) s.w1[i / kEncDim][i % kEncDim] = __float2half_rn(p.w1[i]);
+    for (int i = threadIdx.x; i < kHidden * kHidden; i += blockDim.x) s.w2[i / kHidden][i % kHidden] = __float2half_rn(p.w2[i]);
+    for (int i = threadIdx.x; i < 8 * kHidden; i += blockDim.x)
+        s.w3[i / kHidden][i % kHidden] = (i / kHidden) < kOut ? __float2half_rn(p.w3[i]) : __float2half_rn(0.f);
+    for (int i = threadIdx.x; i < kHidden; i += blockDim.x) {
+        // biases pass through fp16 like the autocast nn.Linear of the reference
+        s.b1[i] = __half2float(__float2half_rn(p.b1[i]));
+        s.b2[i] = __half2float(__float2half_rn(p.b2[i]));
+    }
+    if (threadIdx.x < 8) s.b3[threadIdx.x] = threadIdx.x < kOut ? __half2float(__float2half_rn(p.b3[threadIdx.x])) : 0.f;
+    if (threadIdx.x < kLevels) {
+        const uint32_t l = threadIdx.x;
+        LevelSmem v;
+        v.offset = p.lp->offset[l]; v.size = p.lp->size[l]; v.res = p.lp->res[l];
+        // index rule of the reference (gridencoder.cu:62-79): dense while stride <= size, hash otherwise
+        uint32_t stride = 1;
+        for (int d = 0; d < 3; d++) if (stride <= v.size) stride *= v.res;
+        v.flags = (stride > v.size ? 1u : 0u) | (((v.size & (v.size - 1)) == 0) ? 2u : 0u);
+        s.lv[l] = v;
+    }
+}
+
+__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
+    const __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+__device__ __forceinline__ float2 unpack_half2(uint32_t u) {
+    return __half22float2(*reinterpret_cast<const __half2*>(&u));
+}
+
+__device__ __forceinline__ void mma16816(float c[4], const uint32_t a[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// Corner geometry of one (point, level): base cell, interpolation fractions (after smoothstep) and
+// whether the point is inside the unit cube.
+struct Cell {
+    uint32_t pg[3];
+    float f[3];
+    float df[3];      // d(smoothstep)/d(pos) * res  (only filled when WITH_DERIV)
+};
+
+template <bool WITH_DERIV>
+__device__ __forceinline__ void locate_cell(Cell& c, float x, float y, float z, uint32_t res, bool smooth) {
+    const float in[3] = {x, y, z};
+    const float rf = (float)res;
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+        float pos = fminf(fmaxf(fmaf(in[d], rf, -0.5f), 0.0f), rf - 1.0f);
+        const float fl = floorf(pos);
+        c.pg[d] = (uint32_t)fl;
+        pos -= fl;
+        if (smooth) {
+            if (WITH_DERIV) c.df[d] = 6.f * pos * (1.f - pos) * rf;
+            pos = pos * pos * (3.f - 2.f * pos);
+        } else if (WITH_DERIV) {
+            c.df[d] = rf;
+        }
+        c.f[d] = pos;
+    }
+}
+
+__device__ __forceinline__ uint32_t corner_index(const LevelSmem& lv, uint32_t x, uint32_t y, uint32_t z) {
+    if (lv.flags & 1u) {
+        const uint32_t h = x ^ (y * 2654435761u) ^ (z * 805459861u);
+        return (lv.flags & 2u) ? (h & (lv.size - 1)) : (h % lv.size);
+    }
+    // dense levels: the reference adds p_d * stride_d while stride_d <= size
+    uint32_t idx = x, stride = lv.res;
+    if (stride <= lv.size) { idx += y * stride; stride *= lv.res; }
+    if (stride <= lv.size) { idx += z * stride; }
+    return idx % lv.size;
+}
+
+// Trilinear (smoothstepped) lookup of one level for a point in [0,1]^3; returns the 2 features in fp32.
+__device__ __forceinline__ float2 encode_level(const __half2* __restrict__ table, const LevelSmem& lv,
+                                               float x, float y, float z, bool smooth) {
+    Cell c;
+    locate_cell<false>(c, x, y, z, lv.res, smooth);
+    const __half2* t = table + lv.offset;
+    const uint32_t x0 = c.pg[0], y0 = c.pg[1], z0 = c.pg[2];
+    const uint32_t x1 = min(x0 + 1, lv.res - 1), y1 = min(y0 + 1, lv.res - 1), z1 = min(z0 + 1, lv.res - 1);
+    const float fx = c.f[0], fy = c.f[1], fz = c.f[2];
+    float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const uint32_t xi = (k & 1) ? x1 : x0, yi = (k & 2) ? y1 : y0, zi = (k & 4) ? z1 : z0;
+        const float w = ((k & 1) ? fx : 1.f - fx) * ((k & 2) ? fy : 1.f - fy) * ((k & 4) ? fz : 1.f - fz);
+        const __half2 hv = __ldg(t + corner_index(lv, xi, yi, zi));
+        const float2 v = __half22float2(hv);
+        acc.x = fmaf(w, v.x, acc.x);
+        acc.y = fmaf(w, v.y, acc.y);
+    }
+    return acc;
+}
+
+// The encoder of one stencil point for the two rows a lane owns, in A-fragment order:
+//   a[kt][0] = (row g,   level 8kt + t)      a[kt][1] = (row g+8, level 8kt + t)
+//   a[kt][2] = (row g,   level 8kt + t + 4)  a[kt][3] = (row g+8, level 8kt + t + 4)
+// with g = lane>>2, t = lane&3 (two fp16 features per level = one 32-bit register).
+__device__ __forceinline__ void encode_rows(uint32_t a[2][4], const WeightsSmem& s, const FieldParams& p, int lane,
+                                            const float pa[3], bool va, const float pb[3], bool vb) {
+    const int t = lane & 3;
+    const bool smooth = p.interp_smoothstep != 0;
+#pragma unroll
+    for (int kt = 0; kt < 2; kt++) {
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const uint32_t level = kt * 8 + t + h * 4;
+            float2 ea = make_float2(0.f, 0.f), eb = make_float2(0.f, 0.f);
+            if (level < p.n_levels_active) {
+                const LevelSmem lv = s.lv[level];
+                if (va) ea = encode_level(p.table, lv, pa[0], pa[1], pa[2], smooth);
+                if (vb) eb = encode_level(p.table, lv, pb[0], pb[1], pb[2], smooth);
+            }
+            a[kt][h * 2 + 0] = pack_half2(ea.x, ea.y);
+            a[kt][h * 2 + 1] = pack_half2(eb.x, eb.y);
+        }
+    }
+}
+
+// 32 -> 64 -> 64 -> 4 MLP for a 16-row tile held as A fragments.  Returns the layer-3 accumulator tile
+// (cols 0..7; lane holds (row g, cols 2t,2t+1) in c[0],c[1] and (row g+8, ...) in c[2],c[3]).
+// When KEEP is set the post-ReLU activations of both hidden layers are returned as A fragments.
+template <bool KEEP>
+__device__ __forceinline__ void mlp_forward(float out[4], const uint32_t a0[2][4], const WeightsSmem& s, int lane,
+                                            uint32_t act1[4][4], uint32_t act2[4][4]) {
+    const int g = lane >> 2, t = lane & 3;
+    uint32_t a1[4][4];
+    // layer 1
+#pragma unroll
+    for (int nt = 0; nt < 8; nt++) {
+        const int n = nt * 8 + g;
+        float c[4];
+        c[0] = c[2] = s.b1[nt * 8 + 2 * t];
+        c[1] = c[3] = s.b1[nt * 8 + 2 * t + 1];
+#pragma unroll
+        for (int kt = 0; kt < 2; kt++) {
+            const uint32_t b0 = *reinterpret_cast<const uint32_t*>(&s.w1[n][kt * 16 + 2 * t]);
+            const uint32_t b1 = *reinterpret_cast<const uint32_t*>(&s.w1[n][kt * 16 + 2 * t + 8]);
+            mma16816(c, a0[kt], b0, b1);
+        }
+        // fp16 output of the linear layer, ReLU, straight into the next layer's A fragment
+        const int kt2 = nt >> 1, hi = (nt & 1) * 2;
+        a1[kt2][hi + 0] = pack_half2(fmaxf(c[0], 0.f), fmaxf(c[1], 0.f));
+        a1[kt2][hi + 1] = pack_half2(fmaxf(c[2], 0.f), fmaxf(c[3], 0.f));
+    }
+    uint32_t a2[4][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; nt++) {
+        const int n = nt * 8 + g;
+        float c[4];
+        c[0] = c[2] = s.b2[nt * 8 + 2 * t];
+        c[1] = c[3] = s.b2[nt * 8 + 2 * t + 1];
+#pragma unroll
+        for (int kt = 0; kt < 4; kt++) {
+            const uint32_t b0 = *reinterpret_cast<const uint32_t*>(&s.w2[n][kt * 16 + 2 * t]);
+            const uint32_t b1 = *reinterpret_cast<const uint32_t*>(&s.w2[n][kt * 16 + 2 * t + 8]);
+            mma16816(c, a1[kt], b0, b1);
+        }
+        const int kt2 = nt >> 1, hi = (nt & 1) * 2;
+        a2[kt2][hi + 0] = pack_half2(fmaxf(c[0], 0.f), fmaxf(c[1], 0.f));
+        a2[kt2][hi + 1] = pack_half2(fmaxf(c[2], 0.f), fmaxf(c[3], 0.f));
+    }
+    out[0] = out[2] = s.b3[2 * t];
+    out[1] = out[3] = s.b3[2 * t + 1];
+#pragma unroll
+    for (int kt = 0; kt < 4; kt++) {
+        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(&s.w3[g][kt * 16 + 2 * t]);
+        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(&s.w3[g][kt * 16 + 2 * t + 8]);
+        mma16816(out, a2[kt], b0, b1);
+    }
+    if (KEEP) {
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) { act1[i][j] = a1[i][j]; act2[i][j] = a2[i][j]; }
+    }
+}
+
+__device__ __forceinline__ float round_h(float v) { return __half2float(__float2half_rn(v)); }
+
+// density_blob with the exp activation (renderer.py:339-349): blob_density * exp(-|x|^2 / (2 r^2))
+__device__ __forceinline__ float blob(const FieldParams& p, const float x[3]) {
+    const float d = x[0] * x[0] + x[1] * x[1] + x[2] * x[2];
+    return p.blob_density * __expf(-d / (2.f * p.blob_radius * p.blob_radius));
+}
+
+}  // namespace field

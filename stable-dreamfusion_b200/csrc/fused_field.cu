@@ -1,0 +1,178 @@
+// fused_field.cu — fused radiance-field evaluation for the -O backbone, sm_100a.
+//
+// One kernel replaces, per point, the reference chain (nerf/network_grid.py:68-130):
+//   GridEncoder (16 level-kernels + fp16 table cast + permute) -> 3 cuBLAS GEMMs + 2 ReLU
+//   -> trunc_exp / sigmoid / density_blob -> 6 more of the same at x +- eps (finite-difference
+//   normal, network_grid.py:81-102) -> safe_normalize / nan_to_num -> Lambertian shading.
+// A warp owns 16 samples at a time.  Each lane gathers the hash-grid corners of (2 rows x 4
+// levels) so that the interpolated features land directly in mma.sync A-fragment registers;
+// the 32-64-64-4 MLP runs on tensor cores (m16n8k16, fp16 in / fp32 accumulate) with the
+// activations chained through registers; the 7 stencil densities of a sample end up in the
+// same lane, which finishes normal + shading.  Nothing but xyz in and (sigma, rgb, normal)
+// out touches HBM; the 24 MB fp16 table is served from L2.
+//
+// Algorithmic bytes: forward 540 B per point-eval (12 B xyz + 128 half2
+// corner reads + 16 B out).  Roofline: HBM.
+#include "field_common.cuh"
+
+using namespace field;
+
+namespace {
+
+constexpr float kFdEps = 1e-2f;     // finite_difference_normal epsilon (network_grid.py:81)
+
+constexpr int kAuxStride = 10;      // per-sample forward stash: sigma at the 7 stencil points + albedo
+
+enum Shading { kAlbedo = 0, kLambertian = 1, kTextureless = 2, kNormal = 3 };
+
+__device__ __forceinline__ float nan_to_num(float v) {
+    if (isnan(v)) return 0.f;
+    if (isinf(v)) return v > 0 ? 3.4028234663852886e38f : -3.4028234663852886e38f;
+    return v;
+}
+
+// stencil point p of a sample at x (clamped to the scene box, network_grid.py:83-88)
+__device__ __forceinline__ void stencil_point(float out[3], const float x[3], int p, float bound) {
+    out[0] = x[0]; out[1] = x[1]; out[2] = x[2];
+    if (p > 0) {
+        const int axis = (p - 1) >> 1;
+        const float e = ((p - 1) & 1) ? -kFdEps : kFdEps;
+        out[axis] = fminf(fmaxf(x[axis] + e, -bound), bound);
+    }
+}
+
+__device__ __forceinline__ bool to_unit(float u[3], const float x[3], float bound) {
+    const float inv = 1.f / (2.f * bound);
+    bool ok = true;
+#pragma unroll
+    for (int d = 0; d < 3; d++) { u[d] = (x[d] + bound) * inv; ok &= (u[d] >= 0.f && u[d] <= 1.f); }
+    return ok;
+}
+
+template <int SHADING>
+__global__ void __launch_bounds__(256, 2)
+k_field_forward(FieldParams p, const float* __restrict__ xyzs, const float* __restrict__ light_d, int light_per_sample,
+                float ratio, uint32_t M_cap, const int* __restrict__ m_dev,
+                float* __restrict__ sigmas, float* __restrict__ colors, float* __restrict__ normals, float* __restrict__ aux) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    WeightsSmem& s = *reinterpret_cast<WeightsSmem*>(smem_raw);
+    load_weights(s, p);
+    __syncthreads();
+
+    const uint32_t M = m_dev ? min((uint32_t)max(*m_dev, 0), M_cap) : M_cap;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    constexpr int NP = (SHADING == kAlbedo) ? 1 : 7;
+    const uint32_t n_groups = (M + 15) / 16;
+
+    for (uint32_t grp = blockIdx.x * (blockDim.x >> 5) + warp; grp < n_groups; grp += gridDim.x * (blockDim.x >> 5)) {
+        const uint32_t sa = grp * 16 + g, sb = sa + 8;
+        const bool ina = sa < M, inb = sb < M;
+        float xa[3] = {0.f, 0.f, 0.f}, xb[3] = {0.f, 0.f, 0.f};
+        if (ina) { xa[0] = xyzs[(size_t)sa * 3]; xa[1] = xyzs[(size_t)sa * 3 + 1]; xa[2] = xyzs[(size_t)sa * 3 + 2]; }
+        if (inb) { xb[0] = xyzs[(size_t)sb * 3]; xb[1] = xyzs[(size_t)sb * 3 + 1]; xb[2] = xyzs[(size_t)sb * 3 + 2]; }
+
+        float sig_a[NP], sig_b[NP];
+        float alb_a[3] = {0.f, 0.f, 0.f}, alb_b[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+        for (int sp = 0; sp < NP; sp++) {
+            float pa[3], pb[3], ua[3], ub[3];
+            stencil_point(pa, xa, sp, p.bound);
+            stencil_point(pb, xb, sp, p.bound);
+            const bool va = to_unit(ua, pa, p.bound) && ina, vb = to_unit(ub, pb, p.bound) && inb;
+            uint32_t a0[2][4];
+            encode_rows(a0, s, p, lane, ua, va, ub, vb);
+            float h[4];
+            mlp_forward<false>(h, a0, s, lane, nullptr, nullptr);
+            // lanes t==0: h[0],h[1] = logits 0,1 of row g ; h[2],h[3] = of row g+8.  lanes t==1: logits 2,3.
+            sig_a[sp] = __expf(round_h(h[0]) + blob(p, pa));
+            sig_b[sp] = __expf(round_h(h[2]) + blob(p, pb));
+            if (sp == 0) {
+                const float h2a = __shfl_down_sync(0xffffffffu, h[0], 1), h3a = __shfl_down_sync(0xffffffffu, h[1], 1);
+                const float h2b = __shfl_down_sync(0xffffffffu, h[2], 1), h3b = __shfl_down_sync(0xffffffffu, h[3], 1);
+                alb_a[0] = round_h(1.f / (1.f + __expf(-round_h(h[1])))); alb_a[1] = round_h(1.f / (1.f + __expf(-round_h(h2a)))); alb_a[2] = round_h(1.f / (1.f + __expf(-round_h(h3a))));
+                alb_b[0] = round_h(1.f / (1.f + __expf(-round_h(h[3])))); alb_b[1] = round_h(1.f / (1.f + __expf(-round_h(h2b)))); alb_b[2] = round_h(1.f / (1.f + __expf(-round_h(h3b))));
+            }
+        }
+        if (t != 0) continue;
+        // --- epilogue on the 8 lanes that hold the logits: two samples each
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+            const uint32_t si = r ? sb : sa;
+            if (!(r ? inb : ina)) continue;
+            const float* sg = r ? sig_b : sig_a;
+            const float* al = r ? alb_b : alb_a;
+            sigmas[si] = sg[0];
+            if (aux) {      // saved for the backward pass: the stencil densities and the albedo
+                float* ax = aux + (size_t)si * kAuxStride;
+#pragma unroll
+                for (int q = 0; q < 7; q++) ax[q] = q < NP ? sg[q] : 0.f;
+                ax[7] = al[0]; ax[8] = al[1]; ax[9] = al[2];
+            }
+            float col[3] = {al[0], al[1], al[2]};
+            if (SHADING != kAlbedo) {
+                float n[3];
+                n[0] = -(0.5f * (sg[1] - sg[2]) / kFdEps);
+                n[1] = -(0.5f * (sg[3] - sg[4]) / kFdEps);
+                n[2] = -(0.5f * (sg[5] - sg[6]) / kFdEps);
+                const float inv = 1.f / sqrtf(fmaxf(n[0] * n[0] + n[1] * n[1] + n[2] * n[2], 1e-20f));   // safe_normalize (nerf/utils.py:110)
+                n[0] = nan_to_num(n[0] * inv); n[1] = nan_to_num(n[1] * inv); n[2] = nan_to_num(n[2] * inv);
+                const float* l = light_d + (light_per_sample ? (size_t)si * 3 : 0);
+                const float lam = ratio + (1.f - ratio) * fmaxf(n[0] * l[0] + n[1] * l[1] + n[2] * l[2], 0.f);
+                if (SHADING == kTextureless) { col[0] = col[1] = col[2] = lam; }
+                else if (SHADING == kNormal) { col[0] = (n[0] + 1.f) * 0.5f; col[1] = (n[1] + 1.f) * 0.5f; col[2] = (n[2] + 1.f) * 0.5f; }
+                else { col[0] *= lam; col[1] *= lam; col[2] *= lam; }
+                if (normals) { normals[(size_t)si * 3] = n[0]; normals[(size_t)si * 3 + 1] = n[1]; normals[(size_t)si * 3 + 2] = n[2]; }
+            }
+            if (colors) { colors[(size_t)si * 3] = col[0]; colors[(size_t)si * 3 + 1] = col[1]; colors[(size_t)si * 3 + 2] = col[2]; }
+        }
+    }
+}
+
+}  // namespace
+
+// Fused NeRFNetwork.forward / .density (nerf/network_grid.py:104-142) for the hashgrid(L16,C2,smoothstep) + MLP(32-64-64-4)
+// backbone.  xyzs [M,3] fp32 in [-bound,bound]; table: fp16 [n_entries,2]; w*/b*: fp32 nn.Linear parameters of sigma_net.
+// shading: 0 albedo, 1 lambertian, 2 textureless, 3 normal.  light_d: [3] (light_per_sample=0) or [M,3].
+// m_dev (optional): device int32 holding the live sample count (<= M); lets a caller that never learned M on the host
+// launch with M = capacity.  colors / normals may be NULL (density-only query).  aux (optional, [M,10] fp32) receives the
+// per-sample stash sdf_field_backward needs.
+SDF_API int sdf_field_forward(const float* xyzs, uint32_t M, const int* m_dev, const void* table_fp16, const int* offsets,
+                              uint32_t n_levels, uint32_t n_levels_active, float per_level_scale_log2, uint32_t base_resolution,
+                              int interp_smoothstep, const float* w1, const float* b1, const float* w2, const float* b2,
+                              const float* w3, const float* b3, float bound, float blob_density, float blob_radius,
+                              int shading, const float* light_d, int light_per_sample, float ambient_ratio,
+                              float* sigmas, float* colors, float* normals, float* aux, void* stream) {
+    if (M == 0) return SDF_OK;
+    SDF_CHECK_ARG(xyzs && table_fp16 && offsets && w1 && b1 && w2 && b2 && w3 && b3 && sigmas, "field_forward: null pointer");
+    SDF_CHECK_ARG(n_levels == (uint32_t)kLevels, "field_forward: this build fuses the 16-level / 2-feature grid of the -O backbone");
+    SDF_CHECK_ARG(n_levels_active >= 1 && n_levels_active <= n_levels, "field_forward: bad active level count");
+    SDF_CHECK_ARG(shading >= 0 && shading <= 3, "field_forward: shading must be 0..3");
+    SDF_CHECK_ARG(shading == 0 || light_d, "field_forward: light_d required for shaded modes");
+    cudaStream_t st = (cudaStream_t)stream;
+    LevelParams* lp;
+    int rc = sdf_get_level_params(offsets, n_levels, per_level_scale_log2, base_resolution, st, &lp);
+    if (rc) return rc;
+    FieldParams p;
+    p.table = reinterpret_cast<const __half2*>(table_fp16);
+    p.w1 = w1; p.b1 = b1; p.w2 = w2; p.b2 = b2; p.w3 = w3; p.b3 = b3;
+    p.lp = lp; p.bound = bound; p.n_levels_active = n_levels_active;
+    p.blob_density = blob_density; p.blob_radius = blob_radius; p.interp_smoothstep = interp_smoothstep;
+    const size_t smem = sizeof(WeightsSmem);
+    static_assert(sizeof(WeightsSmem) <= 48 * 1024, "forward weights must fit the default dynamic smem window");
+    const uint32_t groups = (M + 15) / 16;
+    const uint32_t blocks = min((uint32_t)(kNumSMs * 2), (groups + 7) / 8);
+#define LAUNCH(SH)                                                                                                   \
+    do {                                                                                                             \
+        k_field_forward<SH><<<blocks, 256, smem, st>>>(p, xyzs, light_d, light_per_sample, ambient_ratio, M, m_dev, sigmas, colors, normals, aux); \
+    } while (0)
+    switch (shading) {
+        case 0: LAUNCH(kAlbedo); break;
+        case 1: LAUNCH(kLambertian); break;
+        case 2: LAUNCH(kTextureless); break;
+        default: LAUNCH(kNormal); break;
+    }
+#undef LAUNCH
+    SDF_CHECK_LAUNCH("field_forward");
+    return SDF_OK;
+}

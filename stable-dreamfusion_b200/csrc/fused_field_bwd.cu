@@ -1,0 +1,426 @@
+// fused_field_bwd.cu — backward of the fused radiance field (fused_field.cu), sm_100a.
+//
+// Replaces, per training step, the reference's autograd walk through 7 x (3 cuBLAS dgrad + 3 wgrad
+// GEMMs + ReLU/exp/sigmoid backward kernels + kernel_grid_backward with fp16 atomics + a 12.2 M-entry
+// zero-fill and cast-back), nerf/network_grid.py:68-130 and gridencoder/grid.py:72-96.
+//
+// One CTA (16 warps) owns 256 point-evals per round: each warp re-gathers the hash-grid features of its
+// 16 rows (recompute instead of saving 3 M x 160 activations), re-runs the MLP keeping the two hidden
+// activations in registers, back-propagates through the MLP on tensor cores (weights transposed in
+// shared memory), scatters d(enc) into the fp32 table gradient with vector float2 reductions, and
+// stages activations / deltas transposed in shared memory so the CTA can form the weight gradients
+// as [features x 256 rows] x [256 rows x features] tensor-core products whose accumulators live in
+// registers for the whole kernel (flushed once with atomics).  Bias gradients ride along as an extra
+// all-ones activation row.
+//
+// Algorithmic bytes: 1 052 B per point-eval (12 B xyz + 16 B upstream + 128 float2/half2
+// RMWs counted 8 B each).  Roofline: HBM (L2 atomics in practice).
+#include "field_common.cuh"
+
+using namespace field;
+
+namespace {
+
+constexpr float kFdEps = 1e-2f;
+constexpr int kAuxStride = 10;
+constexpr int kWarps = 16;
+constexpr int kRows = kWarps * 16;          // rows per CTA round
+constexpr int kTStride = kRows + 8;         // halfs; row stride of the transposed staging buffers
+constexpr int kWtStride = kHidden + 8;
+
+enum Shading { kAlbedo = 0, kLambertian = 1, kTextureless = 2, kNormal = 3 };
+
+struct BwdSmem {
+    WeightsSmem w;
+    __half w3t[kHidden][8];                 // W3^T [in][out(4, zero padded to 8)]
+    __half w2t[kHidden][kWtStride];         // W2^T [in][out]
+    __half w1t[kEncDim][kWtStride];         // W1^T [in][out]
+    // staging for the weight gradients, all [feature][row]
+    __half enct[kEncDim + 8][kTStride];     // + ones row (bias) + zero rows up to a full n-tile
+    __half a1t[kHidden + 8][kTStride];
+    __half a2t[kHidden + 8][kTStride];
+    __half dh1t[kHidden][kTStride];
+    __half dh2t[kHidden][kTStride];
+    __half dh3t[16][kTStride];              // 4 logits, zero padded to one m-tile
+};
+
+__device__ __forceinline__ void stencil_point(float out[3], const float x[3], int p, float bound) {
+    out[0] = x[0]; out[1] = x[1]; out[2] = x[2];
+    if (p > 0) {
+        const int axis = (p - 1) >> 1;
+        const float e = ((p - 1) & 1) ? -kFdEps : kFdEps;
+        out[axis] = fminf(fmaxf(x[axis] + e, -bound), bound);
+    }
+}
+__device__ __forceinline__ bool to_unit(float u[3], const float x[3], float bound) {
+    const float inv = 1.f / (2.f * bound);
+    bool ok = true;
+#pragma unroll
+    for (int d = 0; d < 3; d++) { u[d] = (x[d] + bound) * inv; ok &= (u[d] >= 0.f && u[d] <= 1.f); }
+    return ok;
+}
+
+// Per-sample upstream -> gradients wrt the 7 stencil densities and the 3 albedo logits.
+template <int SHADING>
+__device__ __forceinline__ void sample_grads(float gsig[7], float glogit[3], const float* __restrict__ ax,
+                                             float g_sigma, const float gcol[3], const float gnrm[3],
+                                             const float* __restrict__ l, float ratio) {
+    constexpr int NP = (SHADING == kAlbedo) ? 1 : 7;
+    const float alb[3] = {ax[7], ax[8], ax[9]};
+    float galb[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int q = 0; q < 7; q++) gsig[q] = 0.f;
+    gsig[0] = g_sigma;
+    if (SHADING == kAlbedo) {
+        galb[0] = gcol[0]; galb[1] = gcol[1]; galb[2] = gcol[2];
+    } else {
+        float nr[3];
+        nr[0] = -(0.5f * (ax[1] - ax[2]) / kFdEps);
+        nr[1] = -(0.5f * (ax[3] - ax[4]) / kFdEps);
+        nr[2] = -(0.5f * (ax[5] - ax[6]) / kFdEps);
+        const float q2 = nr[0] * nr[0] + nr[1] * nr[1] + nr[2] * nr[2];
+        const float inv = 1.f / sqrtf(fmaxf(q2, 1e-20f));
+        const float n[3] = {nr[0] * inv, nr[1] * inv, nr[2] * inv};
+        const float ndl = n[0] * l[0] + n[1] * l[1] + n[2] * l[2];
+        const float lam = ratio + (1.f - ratio) * fmaxf(ndl, 0.f);
+        float gn[3] = {gnrm[0], gnrm[1], gnrm[2]};
+        float glam = 0.f;
+        if (SHADING == kLambertian) {
+            glam = gcol[0] * alb[0] + gcol[1] * alb[1] + gcol[2] * alb[2];
+            galb[0] = gcol[0] * lam; galb[1] = gcol[1] * lam; galb[2] = gcol[2] * lam;
+        } else if (SHADING == kTextureless) {
+            glam = gcol[0] + gcol[1] + gcol[2];
+        } else {
+            gn[0] += 0.5f * gcol[0]; gn[1] += 0.5f * gcol[1]; gn[2] += 0.5f * gcol[2];
+        }
+        if (ndl > 0.f) {
+            const float k = glam * (1.f - ratio);
+            gn[0] += k * l[0]; gn[1] += k * l[1]; gn[2] += k * l[2];
+        }
+        float gnr[3];
+        if (q2 > 1e-20f) {
+            const float d = n[0] * gn[0] + n[1] * gn[1] + n[2] * gn[2];
+            gnr[0] = (gn[0] - n[0] * d) * inv; gnr[1] = (gn[1] - n[1] * d) * inv; gnr[2] = (gn[2] - n[2] * d) * inv;
+        } else {
+            gnr[0] = gn[0] * inv; gnr[1] = gn[1] * inv; gnr[2] = gn[2] * inv;
+        }
+        const float k = 0.5f / kFdEps;
+        gsig[1] = -k * gnr[0]; gsig[2] = k * gnr[0];
+        gsig[3] = -k * gnr[1]; gsig[4] = k * gnr[1];
+        gsig[5] = -k * gnr[2]; gsig[6] = k * gnr[2];
+    }
+    // trunc_exp backward (activation.py:14-18): g * exp(min(z, 15)); sigma_p = exp(z_p) is in the stash
+#pragma unroll
+    for (int q = 0; q < NP; q++) gsig[q] *= fminf(ax[q], 3269017.3724721107f);
+#pragma unroll
+    for (int c = 0; c < 3; c++) glogit[c] = galb[c] * alb[c] * (1.f - alb[c]);
+}
+
+// Scatter d(enc) of one (row, level) into the fp32 table gradient (same geometry as encode_level).
+__device__ __forceinline__ void scatter_level(float* __restrict__ grad_table, const LevelSmem& lv, float x, float y, float z,
+                                              bool smooth, float g0, float g1) {
+    Cell c;
+    locate_cell<false>(c, x, y, z, lv.res, smooth);
+    float* t = grad_table + (size_t)lv.offset * 2;
+    const uint32_t x0 = c.pg[0], y0 = c.pg[1], z0 = c.pg[2];
+    const uint32_t x1 = min(x0 + 1, lv.res - 1), y1 = min(y0 + 1, lv.res - 1), z1 = min(z0 + 1, lv.res - 1);
+    const float fx = c.f[0], fy = c.f[1], fz = c.f[2];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const uint32_t xi = (k & 1) ? x1 : x0, yi = (k & 2) ? y1 : y0, zi = (k & 4) ? z1 : z0;
+        const float w = ((k & 1) ? fx : 1.f - fx) * ((k & 2) ? fy : 1.f - fy) * ((k & 4) ? fz : 1.f - fz);
+        atomicAdd(reinterpret_cast<float2*>(t + (size_t)corner_index(lv, xi, yi, zi) * 2), make_float2(w * g0, w * g1));
+    }
+}
+
+__device__ __forceinline__ void st_half(__half* base, int stride, int feat, int row, float v) {
+    base[feat * stride + row] = __float2half_rn(v);
+}
+__device__ __forceinline__ void st_half2regs(__half* base, int stride, int feat, int row, uint32_t packed) {
+    const __half2 h = *reinterpret_cast<const __half2*>(&packed);
+    base[feat * stride + row] = __low2half(h);
+    base[(feat + 1) * stride + row] = __high2half(h);
+}
+
+template <int SHADING>
+__global__ void __launch_bounds__(kWarps * 32, 1)
+k_field_backward(FieldParams p, const float* __restrict__ xyzs, const float* __restrict__ light_d, int light_per_sample,
+                 float ratio, uint32_t M_cap, const int* __restrict__ m_dev, const float* __restrict__ aux,
+                 const float* __restrict__ g_sigmas, const float* __restrict__ g_colors, const float* __restrict__ g_normals,
+                 float* __restrict__ grad_table, float* __restrict__ gw1, float* __restrict__ gb1, float* __restrict__ gw2,
+                 float* __restrict__ gb2, float* __restrict__ gw3, float* __restrict__ gb3) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    BwdSmem& s = *reinterpret_cast<BwdSmem*>(smem_raw);
+    load_weights(s.w, p);
+    // transposed copies for the data-gradient products, constant rows of the staging buffers
+    for (int i = threadIdx.x; i < kHidden * 8; i += blockDim.x) {
+        const int in = i / 8, out = i % 8;
+        s.w3t[in][out] = out < kOut ? __float2half_rn(p.w3[out * kHidden + in]) : __float2half_rn(0.f);
+    }
+    for (int i = threadIdx.x; i < kHidden * kHidden; i += blockDim.x) s.w2t[i % kHidden][i / kHidden] = __float2half_rn(p.w2[i]);
+    for (int i = threadIdx.x; i < kHidden * kEncDim; i += blockDim.x) s.w1t[i % kEncDim][i / kEncDim] = __float2half_rn(p.w1[i]);
+    for (int i = threadIdx.x; i < 8 * kTStride; i += blockDim.x) {
+        const __half v = __float2half_rn((i / kTStride) == 0 ? 1.f : 0.f);
+        (&s.enct[kEncDim][0])[i] = v;
+        (&s.a1t[kHidden][0])[i] = v;
+        (&s.a2t[kHidden][0])[i] = v;
+    }
+    for (int i = threadIdx.x; i < 16 * kTStride; i += blockDim.x) (&s.dh3t[0][0])[i] = __float2half_rn(0.f);
+    __syncthreads();
+
+    const uint32_t M = m_dev ? min((uint32_t)max(*m_dev, 0), M_cap) : M_cap;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    constexpr int NP = (SHADING == kAlbedo) ? 1 : 7;
+    const bool smooth = p.interp_smoothstep != 0;
+    const uint32_t n_groups = (M + 15) / 16;
+    const uint32_t n_super = (n_groups + kWarps - 1) / kWarps;     // CTA rounds of 16 groups
+
+    // ---- weight-gradient tile assignment: 65 (m-tile, n-tile) pairs over 16 warps
+    //   q in [0,36): layer 2  (4 m-tiles x 9 n-tiles; n-tile 8 = ones row -> bias)
+    //   q in [36,56): layer 1 (4 x 5)           q in [56,65): layer 3 (1 x 9)
+    constexpr int kPairs = 65, kMaxPerWarp = 5;
+    float wacc[kMaxPerWarp][4];
+#pragma unroll
+    for (int j = 0; j < kMaxPerWarp; j++) wacc[j][0] = wacc[j][1] = wacc[j][2] = wacc[j][3] = 0.f;
+
+    for (uint32_t sup = blockIdx.x; sup < n_super; sup += gridDim.x) {
+        const uint32_t grp = sup * kWarps + warp;
+        const uint32_t sa = grp * 16 + g, sb = sa + 8;
+        const bool ina = sa < M, inb = sb < M;
+        float xa[3] = {0.f, 0.f, 0.f}, xb[3] = {0.f, 0.f, 0.f};
+        if (ina) { xa[0] = xyzs[(size_t)sa * 3]; xa[1] = xyzs[(size_t)sa * 3 + 1]; xa[2] = xyzs[(size_t)sa * 3 + 2]; }
+        if (inb) { xb[0] = xyzs[(size_t)sb * 3]; xb[1] = xyzs[(size_t)sb * 3 + 1]; xb[2] = xyzs[(size_t)sb * 3 + 2]; }
+
+        // per-sample gradient wrt the stencil densities / albedo logits (only the t==0 lanes need them)
+        float gsa[7], gsb[7], gla[3], glb[3];
+#pragma unroll
+        for (int q = 0; q < 7; q++) gsa[q] = gsb[q] = 0.f;
+        gla[0] = gla[1] = gla[2] = glb[0] = glb[1] = glb[2] = 0.f;
+        if (t == 0) {
+            const float zero3[3] = {0.f, 0.f, 0.f};
+            if (ina) {
+                const float gc[3] = {g_colors ? g_colors[(size_t)sa * 3] : 0.f, g_colors ? g_colors[(size_t)sa * 3 + 1] : 0.f, g_colors ? g_colors[(size_t)sa * 3 + 2] : 0.f};
+                const float gn[3] = {g_normals ? g_normals[(size_t)sa * 3] : 0.f, g_normals ? g_normals[(size_t)sa * 3 + 1] : 0.f, g_normals ? g_normals[(size_t)sa * 3 + 2] : 0.f};
+                sample_grads<SHADING>(gsa, gla, aux + (size_t)sa * kAuxStride, g_sigmas ? g_sigmas[sa] : 0.f, gc, gn,
+                                      light_d ? light_d + (light_per_sample ? (size_t)sa * 3 : 0) : zero3, ratio);
+            }
+            if (inb) {
+                const float gc[3] = {g_colors ? g_colors[(size_t)sb * 3] : 0.f, g_colors ? g_colors[(size_t)sb * 3 + 1] : 0.f, g_colors ? g_colors[(size_t)sb * 3 + 2] : 0.f};
+                const float gn[3] = {g_normals ? g_normals[(size_t)sb * 3] : 0.f, g_normals ? g_normals[(size_t)sb * 3 + 1] : 0.f, g_normals ? g_normals[(size_t)sb * 3 + 2] : 0.f};
+                sample_grads<SHADING>(gsb, glb, aux + (size_t)sb * kAuxStride, g_sigmas ? g_sigmas[sb] : 0.f, gc, gn,
+                                      light_d ? light_d + (light_per_sample ? (size_t)sb * 3 : 0) : zero3, ratio);
+            }
+        }
+
+#pragma unroll 1
+        for (int sp = 0; sp < NP; sp++) {
+            // ---- delta at the logits as an A fragment: k = logit index (0..3), zero beyond
+            float d0a = 0.f, d1a = 0.f, d0b = 0.f, d1b = 0.f;     // (k=2t, 2t+1) for rows g and g+8
+            {
+                float za = 0.f, zb = 0.f;
+#pragma unroll
+                for (int q = 0; q < NP; q++) if (q == sp) { za = gsa[q]; zb = gsb[q]; }
+                const float l1a = sp == 0 ? gla[0] : 0.f, l2a = sp == 0 ? gla[1] : 0.f, l3a = sp == 0 ? gla[2] : 0.f;
+                const float l1b = sp == 0 ? glb[0] : 0.f, l2b = sp == 0 ? glb[1] : 0.f, l3b = sp == 0 ? glb[2] : 0.f;
+                // lanes t==0 own the values; lane t==1 needs logits 2,3
+                const float r2a = __shfl_up_sync(0xffffffffu, l2a, 1), r3a = __shfl_up_sync(0xffffffffu, l3a, 1);
+                const float r2b = __shfl_up_sync(0xffffffffu, l2b, 1), r3b = __shfl_up_sync(0xffffffffu, l3b, 1);
+                if (t == 0) { d0a = za; d1a = l1a; d0b = zb; d1b = l1b; }
+                else if (t == 1) { d0a = r2a; d1a = r3a; d0b = r2b; d1b = r3b; }
+            }
+            // ---- forward recompute
+            float pa[3], pb[3], ua[3], ub[3];
+            stencil_point(pa, xa, sp, p.bound);
+            stencil_point(pb, xb, sp, p.bound);
+            const bool va = to_unit(ua, pa, p.bound) && ina, vb = to_unit(ub, pb, p.bound) && inb;
+            uint32_t a0[2][4], a1[4][4], a2[4][4];
+            encode_rows(a0, s.w, p, lane, ua, va, ub, vb);
+            float hdummy[4];
+            mlp_forward<true>(hdummy, a0, s.w, lane, a1, a2);
+
+            const int row_a = warp * 16 + g, row_b = row_a + 8;
+            // stage dh3^T (logit deltas) and the layer-3 input a2^T
+            if (t < 2) {
+                st_half(&s.dh3t[0][0], kTStride, 2 * t, row_a, d0a); st_half(&s.dh3t[0][0], kTStride, 2 * t + 1, row_a, d1a);
+                st_half(&s.dh3t[0][0], kTStride, 2 * t, row_b, d0b); st_half(&s.dh3t[0][0], kTStride, 2 * t + 1, row_b, d1b);
+            }
+#pragma unroll
+            for (int kt = 0; kt < 4; kt++) {
+                st_half2regs(&s.a2t[0][0], kTStride, kt * 16 + 2 * t, row_a, a2[kt][0]);
+                st_half2regs(&s.a2t[0][0], kTStride, kt * 16 + 2 * t, row_b, a2[kt][1]);
+                st_half2regs(&s.a2t[0][0], kTStride, kt * 16 + 2 * t + 8, row_a, a2[kt][2]);
+                st_half2regs(&s.a2t[0][0], kTStride, kt * 16 + 2 * t + 8, row_b, a2[kt][3]);
+                st_half2regs(&s.a1t[0][0], kTStride, kt * 16 + 2 * t, row_a, a1[kt][0]);
+                st_half2regs(&s.a1t[0][0], kTStride, kt * 16 + 2 * t, row_b, a1[kt][1]);
+                st_half2regs(&s.a1t[0][0], kTStride, kt * 16 + 2 * t + 8, row_a, a1[kt][2]);
+                st_half2regs(&s.a1t[0][0], kTStride, kt * 16 + 2 * t + 8, row_b, a1[kt][3]);
+            }
+#pragma unroll
+            for (int kt = 0; kt < 2; kt++) {
+                st_half2regs(&s.enct[0][0], kTStride, kt * 16 + 2 * t, row_a, a0[kt][0]);
+                st_half2regs(&s.enct[0][0], kTStride, kt * 16 + 2 * t, row_b, a0[kt][1]);
+                st_half2regs(&s.enct[0][0], kTStride, kt * 16 + 2 * t + 8, row_a, a0[kt][2]);
+                st_half2regs(&s.enct[0][0], kTStride, kt * 16 + 2 * t + 8, row_b, a0[kt][3]);
+            }
+
+            // ---- dh2 = (dh3 . W3) * relu'(a2)    A = dh3 [16 x 16(k: 4 valid)], B[k][n] = W3[k][n] = w3t[n][k]
+            uint32_t d3frag[4] = {pack_half2(d0a, d1a), pack_half2(d0b, d1b), 0u, 0u};
+            uint32_t dh2[4][4];
+#pragma unroll
+            for (int nt = 0; nt < 8; nt++) {
+                float c[4] = {0.f, 0.f, 0.f, 0.f};
+                const uint32_t b0 = *reinterpret_cast<const uint32_t*>(&s.w3t[nt * 8 + g][2 * t]);
+                mma16816(c, d3frag, b0, 0u);
+                const int kt2 = nt >> 1, hi = (nt & 1) * 2;
+                const float2 ma = unpack_half2(a2[kt2][hi + 0]), mb = unpack_half2(a2[kt2][hi + 1]);
+                c[0] = ma.x > 0.f ? c[0] : 0.f; c[1] = ma.y > 0.f ? c[1] : 0.f;
+                c[2] = mb.x > 0.f ? c[2] : 0.f; c[3] = mb.y > 0.f ? c[3] : 0.f;
+                dh2[kt2][hi + 0] = pack_half2(c[0], c[1]);
+                dh2[kt2][hi + 1] = pack_half2(c[2], c[3]);
+                st_half(&s.dh2t[0][0], kTStride, nt * 8 + 2 * t, row_a, c[0]); st_half(&s.dh2t[0][0], kTStride, nt * 8 + 2 * t + 1, row_a, c[1]);
+                st_half(&s.dh2t[0][0], kTStride, nt * 8 + 2 * t, row_b, c[2]); st_half(&s.dh2t[0][0], kTStride, nt * 8 + 2 * t + 1, row_b, c[3]);
+            }
+            // ---- dh1 = (dh2 . W2) * relu'(a1)    B[k][n] = W2[k][n] = w2t[n][k]
+            uint32_t dh1[4][4];
+#pragma unroll
+            for (int nt = 0; nt < 8; nt++) {
+                float c[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int kt = 0; kt < 4; kt++) {
+                    const uint32_t b0 = *reinterpret_cast<const uint32_t*>(&s.w2t[nt * 8 + g][kt * 16 + 2 * t]);
+                    const uint32_t b1 = *reinterpret_cast<const uint32_t*>(&s.w2t[nt * 8 + g][kt * 16 + 2 * t + 8]);
+                    mma16816(c, dh2[kt], b0, b1);
+                }
+                const int kt2 = nt >> 1, hi = (nt & 1) * 2;
+                const float2 ma = unpack_half2(a1[kt2][hi + 0]), mb = unpack_half2(a1[kt2][hi + 1]);
+                c[0] = ma.x > 0.f ? c[0] : 0.f; c[1] = ma.y > 0.f ? c[1] : 0.f;
+                c[2] = mb.x > 0.f ? c[2] : 0.f; c[3] = mb.y > 0.f ? c[3] : 0.f;
+                dh1[kt2][hi + 0] = pack_half2(c[0], c[1]);
+                dh1[kt2][hi + 1] = pack_half2(c[2], c[3]);
+                st_half(&s.dh1t[0][0], kTStride, nt * 8 + 2 * t, row_a, c[0]); st_half(&s.dh1t[0][0], kTStride, nt * 8 + 2 * t + 1, row_a, c[1]);
+                st_half(&s.dh1t[0][0], kTStride, nt * 8 + 2 * t, row_b, c[2]); st_half(&s.dh1t[0][0], kTStride, nt * 8 + 2 * t + 1, row_b, c[3]);
+            }
+            // ---- d(enc) = dh1 . W1 ; n-tile nt covers levels 4nt..4nt+3: lane gets (row g / g+8, level 4nt + t)
+#pragma unroll
+            for (int nt = 0; nt < 4; nt++) {
+                float c[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int kt = 0; kt < 4; kt++) {
+                    const uint32_t b0 = *reinterpret_cast<const uint32_t*>(&s.w1t[nt * 8 + g][kt * 16 + 2 * t]);
+                    const uint32_t b1 = *reinterpret_cast<const uint32_t*>(&s.w1t[nt * 8 + g][kt * 16 + 2 * t + 8]);
+                    mma16816(c, dh1[kt], b0, b1);
+                }
+                const uint32_t level = nt * 4 + t;
+                if (level < p.n_levels_active) {
+                    const LevelSmem lv = s.w.lv[level];
+                    if (va && (c[0] != 0.f || c[1] != 0.f)) scatter_level(grad_table, lv, ua[0], ua[1], ua[2], smooth, c[0], c[1]);
+                    if (vb && (c[2] != 0.f || c[3] != 0.f)) scatter_level(grad_table, lv, ub[0], ub[1], ub[2], smooth, c[2], c[3]);
+                }
+            }
+            __syncthreads();
+
+            // ---- weight gradients over the 256 staged rows
+#pragma unroll
+            for (int j = 0; j < kMaxPerWarp; j++) {
+                const int q = warp + j * kWarps;
+                if (q < kPairs) {
+                    const __half* A; const __half* B;
+                    int mt, nt;
+                    if (q < 36) { mt = q / 9; nt = q % 9; A = &s.dh2t[0][0]; B = &s.a1t[0][0]; }
+                    else if (q < 56) { mt = (q - 36) / 5; nt = (q - 36) % 5; A = &s.dh1t[0][0]; B = &s.enct[0][0]; }
+                    else { mt = 0; nt = q - 56; A = &s.dh3t[0][0]; B = &s.a2t[0][0]; }
+                    const __half* Ar0 = A + (mt * 16 + g) * kTStride;
+                    const __half* Ar1 = Ar0 + 8 * kTStride;
+                    const __half* Br = B + (nt * 8 + g) * kTStride;
+#pragma unroll 4
+                    for (int kt = 0; kt < kRows / 16; kt++) {
+                        uint32_t af[4];
+                        af[0] = *reinterpret_cast<const uint32_t*>(Ar0 + kt * 16 + 2 * t);
+                        af[1] = *reinterpret_cast<const uint32_t*>(Ar1 + kt * 16 + 2 * t);
+                        af[2] = *reinterpret_cast<const uint32_t*>(Ar0 + kt * 16 + 2 * t + 8);
+                        af[3] = *reinterpret_cast<const uint32_t*>(Ar1 + kt * 16 + 2 * t + 8);
+                        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(Br + kt * 16 + 2 * t);
+                        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(Br + kt * 16 + 2 * t + 8);
+                        mma16816(wacc[j], af, b0, b1);
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+
+    // ---- flush the weight-gradient accumulators: wacc[j] = (out = 16mt + g (+8), in = 8nt + 2t (+1))
+#pragma unroll
+    for (int j = 0; j < kMaxPerWarp; j++) {
+        const int q = warp + j * kWarps;
+        if (q >= kPairs) continue;
+        float* gw; float* gb; int mt, nt, in_dim, out_dim;
+        if (q < 36) { mt = q / 9; nt = q % 9; gw = gw2; gb = gb2; in_dim = kHidden; out_dim = kHidden; }
+        else if (q < 56) { mt = (q - 36) / 5; nt = (q - 36) % 5; gw = gw1; gb = gb1; in_dim = kEncDim; out_dim = kHidden; }
+        else { mt = 0; nt = q - 56; gw = gw3; gb = gb3; in_dim = kHidden; out_dim = kOut; }
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            const int out = mt * 16 + g + ((e & 2) ? 8 : 0);
+            const int in = nt * 8 + 2 * t + (e & 1);
+            const float v = wacc[j][e];
+            if (out < out_dim && v != 0.f) {
+                if (in < in_dim) atomicAdd(gw + out * in_dim + in, v);
+                else if (in == in_dim) atomicAdd(gb + out, v);
+            }
+        }
+    }
+}
+
+}  // namespace
+
+// Backward of sdf_field_forward.  Upstream gradients: g_sigmas [M] (may be NULL), g_colors [M,3] (may be NULL),
+// g_normals [M,3] (may be NULL).  aux: the [M,10] stash written by the forward.  All outputs are ACCUMULATED into
+// (caller zero-fills): grad_table fp32 [n_entries,2]; gw1 [64,32], gb1 [64], gw2 [64,64], gb2 [64], gw3 [4,64], gb3 [4].
+SDF_API int sdf_field_backward(const float* xyzs, uint32_t M, const int* m_dev, const void* table_fp16, const int* offsets,
+                               uint32_t n_levels, uint32_t n_levels_active, float per_level_scale_log2, uint32_t base_resolution,
+                               int interp_smoothstep, const float* w1, const float* b1, const float* w2, const float* b2,
+                               const float* w3, const float* b3, float bound, float blob_density, float blob_radius,
+                               int shading, const float* light_d, int light_per_sample, float ambient_ratio, const float* aux,
+                               const float* g_sigmas, const float* g_colors, const float* g_normals,
+                               float* grad_table, float* gw1, float* gb1, float* gw2, float* gb2, float* gw3, float* gb3,
+                               void* stream) {
+    if (M == 0) return SDF_OK;
+    SDF_CHECK_ARG(xyzs && table_fp16 && offsets && w1 && b1 && w2 && b2 && w3 && b3 && aux, "field_backward: null pointer");
+    SDF_CHECK_ARG(grad_table && gw1 && gb1 && gw2 && gb2 && gw3 && gb3, "field_backward: null gradient output");
+    SDF_CHECK_ARG(n_levels == (uint32_t)kLevels && n_levels_active >= 1 && n_levels_active <= n_levels, "field_backward: bad level count");
+    SDF_CHECK_ARG(shading >= 0 && shading <= 3, "field_backward: shading must be 0..3");
+    SDF_CHECK_ARG(shading == 0 || light_d, "field_backward: light_d required for shaded modes");
+    cudaStream_t st = (cudaStream_t)stream;
+    LevelParams* lp;
+    int rc = sdf_get_level_params(offsets, n_levels, per_level_scale_log2, base_resolution, st, &lp);
+    if (rc) return rc;
+    FieldParams p;
+    p.table = reinterpret_cast<const __half2*>(table_fp16);
+    p.w1 = w1; p.b1 = b1; p.w2 = w2; p.b2 = b2; p.w3 = w3; p.b3 = b3;
+    p.lp = lp; p.bound = bound; p.n_levels_active = n_levels_active;
+    p.blob_density = blob_density; p.blob_radius = blob_radius; p.interp_smoothstep = interp_smoothstep;
+    const int smem = (int)sizeof(BwdSmem);
+    const uint32_t n_super = ((M + 15) / 16 + kWarps - 1) / kWarps;
+    const uint32_t blocks = min((uint32_t)kNumSMs, n_super);
+#define LAUNCH(SH)                                                                                                        \
+    do {                                                                                                                  \
+        static bool attr_set[64] = {false};                                                                               \
+        int dev = 0; cudaGetDevice(&dev);                                                                                 \
+        if (dev < 64 && !attr_set[dev]) {                                                                                 \
+            SDF_CHECK_CUDA(cudaFuncSetAttribute(k_field_backward<SH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+            attr_set[dev] = true;                                                                                         \
+        }                                                                                                                 \
+        k_field_backward<SH><<<blocks, kWarps * 32, smem, st>>>(p, xyzs, light_d, light_per_sample, ambient_ratio, M, m_dev, aux, \
+                                                               g_sigmas, g_colors, g_normals, grad_table, gw1, gb1, gw2, gb2, gw3, gb3); \
+    } while (0)
+    switch (shading) {
+        case 0: LAUNCH(kAlbedo); break;
+        case 1: LAUNCH(kLambertian); break;
+        case 2: LAUNCH(kTextureless); break;
+        default: LAUNCH(kNormal); break;
+    }
+#undef LAUNCH
+    SDF_CHECK_LAUNCH("field_backward");
+    return SDF_OK;
+}

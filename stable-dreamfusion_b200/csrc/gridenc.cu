@@ -16,17 +16,9 @@
 //     accumulation so outputs are bit-identical to the reference extension.
 // The training hot path does not use these kernels (see fused_field.cu); they
 // back grid_encode / GridEncoder for drop-in and parity.
-#include "common.cuh"
+#include "grid_common.cuh"
 
 namespace {
-
-constexpr uint32_t kMaxLevels = 32;
-
-struct LevelParams {
-    uint32_t offset[kMaxLevels];      // first entry of the level
-    uint32_t size[kMaxLevels];        // entries in the level (hashmap_size)
-    uint32_t res[kMaxLevels];         // ceil(exp2f(level*S)*H)                  gridencoder.cu:133
-};
 
 // Level resolutions must come from the device's exp2f (the reference evaluates
 // it per thread on the GPU); one tiny kernel fills the table.
@@ -315,19 +307,6 @@ __global__ void k_grad_wd(const float* __restrict__ grid, float* __restrict__ gr
     grad[i] += 2 * weight * grid[i] / lp->size[level];
 }
 
-LevelParams* g_lp[64] = {nullptr};   // one scratch block per device
-
-int get_level_params(const int* offsets, uint32_t L, float S, uint32_t H, cudaStream_t st, LevelParams** out) {
-    int dev = 0;
-    SDF_CHECK_CUDA(cudaGetDevice(&dev));
-    SDF_CHECK_ARG(dev < 64, "too many devices");
-    if (!g_lp[dev]) SDF_CHECK_CUDA(cudaMalloc(&g_lp[dev], sizeof(LevelParams)));
-    k_level_params<<<1, kMaxLevels, 0, st>>>(offsets, L, S, H, g_lp[dev]);
-    SDF_CHECK_LAUNCH("grid level params");
-    *out = g_lp[dev];
-    return SDF_OK;
-}
-
 template <typename T, uint32_t D>
 int launch_fwd(uint32_t C, dim3 grid_dim, cudaStream_t st, const float* inputs, const T* grid, const LevelParams* lp, T* outputs,
                uint32_t B, uint32_t L, T* dy_dx, uint32_t gridtype, bool ac, uint32_t interp) {
@@ -357,7 +336,7 @@ template <typename T>
 int grid_forward_t(const float* inputs, const T* embeddings, const int* offsets, T* outputs, uint32_t B, uint32_t D, uint32_t C,
                    uint32_t L, uint32_t max_level, float S, uint32_t H, T* dy_dx, uint32_t gridtype, int ac, uint32_t interp, cudaStream_t st) {
     LevelParams* lp;
-    int rc = get_level_params(offsets, L, S, H, st, &lp);
+    int rc = sdf_get_level_params(offsets, L, S, H, st, &lp);
     if (rc) return rc;
     const dim3 g(cdiv(B, 256), max_level, 1);
     switch (D) {
@@ -376,7 +355,7 @@ int grid_backward_t(const T* grad, const float* inputs, const int* offsets, TA* 
                     uint32_t L, uint32_t max_level, float S, uint32_t H, const T* dy_dx, T* grad_inputs, uint32_t gridtype, int ac,
                     uint32_t interp, cudaStream_t st) {
     LevelParams* lp;
-    int rc = get_level_params(offsets, L, S, H, st, &lp);
+    int rc = sdf_get_level_params(offsets, L, S, H, st, &lp);
     if (rc) return rc;
     const dim3 g(cdiv(B, 256), max_level, 1);
     switch (D) {
@@ -395,6 +374,20 @@ int grid_backward_t(const T* grad, const float* inputs, const int* offsets, TA* 
 }
 
 }  // namespace
+
+static LevelParams* g_lp[64] = {nullptr};   // one scratch block per device
+
+int sdf_get_level_params(const int* offsets, uint32_t L, float S, uint32_t H, cudaStream_t st, LevelParams** out) {
+    int dev = 0;
+    SDF_CHECK_CUDA(cudaGetDevice(&dev));
+    SDF_CHECK_ARG(dev < 64, "too many devices");
+    if (!g_lp[dev]) SDF_CHECK_CUDA(cudaMalloc(&g_lp[dev], sizeof(LevelParams)));
+    k_level_params<<<1, kMaxLevels, 0, st>>>(offsets, L, S, H, g_lp[dev]);
+    SDF_CHECK_LAUNCH("grid level params");
+    *out = g_lp[dev];
+    return SDF_OK;
+}
+
 
 // dtype: 0 = fp32 table/outputs, 1 = fp16 table/outputs.  inputs always fp32 in [0,1].
 // outputs [B, L*C]; levels >= max_level are NOT written (caller zero-fills when max_level < L, grid.py:53).
@@ -435,7 +428,7 @@ SDF_API int sdf_grid_grad_total_variation(const float* inputs, const float* embe
     SDF_CHECK_ARG(L >= 1 && L <= kMaxLevels, "grad_total_variation: bad L");
     cudaStream_t st = (cudaStream_t)stream;
     LevelParams* lp;
-    int rc = get_level_params(offsets, L, S, H, st, &lp);
+    int rc = sdf_get_level_params(offsets, L, S, H, st, &lp);
     if (rc) return rc;
     const dim3 g(cdiv(B, 256), L, 1);
     const bool ac = align_corners != 0;
@@ -461,7 +454,7 @@ SDF_API int sdf_grid_grad_weight_decay(const float* embeddings, float* grad, con
     SDF_CHECK_ARG(L >= 1 && L <= kMaxLevels, "grad_weight_decay: bad L");
     cudaStream_t st = (cudaStream_t)stream;
     LevelParams* lp;
-    int rc = get_level_params(offsets, L, 0.f, 1, st, &lp);
+    int rc = sdf_get_level_params(offsets, L, 0.f, 1, st, &lp);
     if (rc) return rc;
     k_grad_wd<<<cdiv(n_entries * C, 256), 256, 0, st>>>(embeddings, grad, lp, weight, n_entries, C, L);
     SDF_CHECK_LAUNCH("grad_weight_decay");
@@ -473,7 +466,7 @@ SDF_API int sdf_grid_level_resolutions(const int* offsets, uint32_t L, float S, 
     SDF_CHECK_ARG(offsets && host_out && L >= 1 && L <= kMaxLevels, "grid_level_resolutions: bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
     LevelParams* lp;
-    int rc = get_level_params(offsets, L, S, H, st, &lp);
+    int rc = sdf_get_level_params(offsets, L, S, H, st, &lp);
     if (rc) return rc;
     LevelParams h;
     SDF_CHECK_CUDA(cudaMemcpyAsync(&h, lp, sizeof h, cudaMemcpyDeviceToHost, st));
