@@ -139,6 +139,22 @@ int sdf_field_backward(const float* xyzs, uint32_t M, const int* m_dev, const vo
                        const float* g_sigmas /* may be NULL */, const float* g_colors /* may be NULL */, const float* g_normals /* may be NULL */,
                        float* grad_table, float* gw1, float* gb1, float* gw2, float* gb2, float* gw3, float* gb3, void* stream);
 
+/* ------------------------------------------------------------------ SD-1.5-shaped UNet / VAE encoder building blocks
+ * replace the cuDNN / cuBLAS calls underneath guidance/sd_utils.py:95-108 (diffusers UNet2DConditionModel / AutoencoderKL;
+ * module structure per the vendored CompVis code: ldm/modules/diffusionmodules/openaimodel.py:164-277,414-778,
+ * ldm/modules/attention.py:152-275, ldm/modules/diffusionmodules/model.py:82-204,368-460).
+ * Activations are NHWC fp16. */
+
+/* tcgen05 implicit-GEMM plan: out[m, n] = act(alpha * sum_{tap,c} a[pixel(m)+off(tap), c] * wt[n, tap*Cin + c] + bias[n] + temb[img(m), n] + residual[m, n])
+ * taps = 1 (1x1 conv / linear: pass H = 1, Nimg = 1, W = M) or 9 (3x3, stride 1, zero pad 1; tap = ky*3 + kx).
+ * Cin % 64 == 0 (pad channels), lda/ldo/ldr % 8 == 0.  block_n in {64, 128, 160}.  splitk > 1 needs workspace fp32 [M, N].
+ * Returns a plan handle >= 0, or a negative error code. */
+int sdf_gemm_plan_create(const void* a, int lda, const void* wt, int n_rows_w, int Nimg, int H, int W, int Cin, int taps, int N,
+                         void* out, int ldo, const float* bias, const void* temb, int temb_ld, const void* residual, int ldr,
+                         int act, float alpha, int splitk, float* workspace, int block_n);
+int sdf_gemm_run(int plan, void* stream);
+int sdf_gemm_plan_destroy(int plan);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,470 @@
+// sd_gemm.cu — tcgen05 implicit-GEMM convolution / linear kernel for the SD-1.5-shaped UNet and VAE encoder.
+//
+// One persistent, warp-specialised kernel serves every dense contraction on the guidance side
+// (guidance/sd_utils.py:95-108 -> UNet ResBlock / attention projections / GEGLU, VAE conv + data-gradient):
+//
+//     D[m, n] = epilogue( sum_{tap, c}  A[pixel(m) + offset(tap), c] * Wt[n, tap*Cin + c] )
+//
+//   * activations are NHWC fp16; the A tile (128 output pixels x 64 channels) of every filter tap is fetched by
+//     ONE 4-D TMA box load at the tap-shifted coordinate — image borders are zero-filled by the TMA unit, so a 3x3
+//     convolution is 9 x (Cin/64) accumulating MMAs with no im2col buffer; a linear layer is the same with 1 tap;
+//   * weights are packed [Cout, taps*Cin] fp16 (K-major) and fetched with 2-D TMA; both operands land in
+//     128B-swizzled shared memory and feed tcgen05.mma (cta_group::1, M=128, N=BLOCK_N, K=16) through UMMA descriptors;
+//   * accumulators live in TMEM (double-buffered, 2 x BLOCK_N columns) so the epilogue of tile i overlaps the
+//     MMAs of tile i+1; epilogue = tcgen05.ld -> (+bias) (+per-image embedding) (+residual) (SiLU/GELU) -> fp16 store;
+//   * warp roles: warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 epilogue; 5-stage mbarrier pipeline;
+//   * split-K for the low-resolution UNet levels (M = 128..512): partials are reduced with fp32 red.global.add into a
+//     workspace and finished by a tiny epilogue kernel.
+//
+// Roofline: tensor pipe.  FLOPs per launch = 2 * M * N * taps * Cin.
+#include "common.cuh"
+#include <cuda.h>
+#include <mutex>
+#include <vector>
+
+namespace {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;          // 64 fp16 = one 128-byte swizzle row
+constexpr int kUmmaK = 16;
+constexpr int kNumThreads = 192;     // warp 0 producer, warp 1 MMA, warps 2..5 epilogue
+
+enum Act { kActNone = 0, kActSilu = 1, kActGelu = 2 };
+
+struct GemmArgs {
+    int M, N, Cin, taps;             // Cin = channels per tap (multiple of 64)
+    int H, W, Nimg;                  // image geometry (linear: H=1, Nimg=1, W=M)
+    int tw, th, tn;                  // tile rectangle, tw*th*tn == 128
+    int pad;                         // 1 for 3x3 (tap offsets -1..1), 0 for 1x1
+    int splitk;                      // >= 1
+    const float* bias;               // [N] fp32 or null
+    const __half* temb; int temb_ld; // [Nimg, N] or null
+    const __half* residual; int ldr; // [M, N] or null
+    __half* out; int ldo;
+    float* workspace;                // [M, N] fp32 when splitk > 1
+    int act;
+    float alpha;                     // scale applied to the accumulator before bias
+};
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t v[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, 128B-swizzled operand tile: rows of 128 bytes, 8-row groups 1024 bytes apart.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);          // start address
+    d |= (uint64_t)1 << 16;                          // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;                // stride byte offset between 8-row groups
+    d |= (uint64_t)1 << 46;                          // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                          // SWIZZLE_128B
+    return d;
+}
+__device__ __forceinline__ float act_apply(float v, int act) {
+    if (act == kActSilu) return v / (1.f + __expf(-v));
+    if (act == kActGelu) return 0.5f * v * (1.f + erff(v * 0.70710678118654752f));
+    return v;
+}
+
+template <int BLOCK_N>
+struct SmemLayout {
+    static constexpr int kABytes = kBlockM * kBlockK * 2;
+    static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
+    static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kStages = (BLOCK_N <= 64) ? 8 : (BLOCK_N <= 128 ? 6 : 5);
+    static constexpr int kBarrierBytes = (2 * kStages + 4) * 8 + 16;
+    static constexpr int kTotal = kStages * kStageBytes + kBarrierBytes + 1024;   // + alignment slack
+};
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(kNumThreads, 1)
+k_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const GemmArgs g) {
+    using L = SmemLayout<BLOCK_N>;
+    constexpr int kStages = L::kStages;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * L::kStageBytes);
+    uint64_t* empty_bar = full_bar + kStages;
+    uint64_t* tmem_full = empty_bar + kStages;
+    uint64_t* tmem_empty = tmem_full + 2;
+    uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr uint32_t kTmemCols = (2 * BLOCK_N <= 128) ? 128 : (2 * BLOCK_N <= 256 ? 256 : 512);
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < kStages; i++) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+        for (int i = 0; i < 2; i++) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_smem)), "r"(kTmemCols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_base_smem;
+
+    // ---- tile bookkeeping (identical in every role)
+    const int tiles_x = (g.W + g.tw - 1) / g.tw, tiles_y = (g.H + g.th - 1) / g.th, tiles_n_img = (g.Nimg + g.tn - 1) / g.tn;
+    const int m_tiles = tiles_x * tiles_y * tiles_n_img;
+    const int n_tiles = (g.N + BLOCK_N - 1) / BLOCK_N;
+    const int kb_per_tap = g.Cin / kBlockK;
+    const int kb_total = g.taps * kb_per_tap;
+    const int kb_per_split = (kb_total + g.splitk - 1) / g.splitk;
+    const int total_work = m_tiles * n_tiles * g.splitk;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+                const int split = w % g.splitk; const int t2 = w / g.splitk;
+                const int nt = t2 % n_tiles, mt = t2 / n_tiles;
+                const int tx = mt % tiles_x, ty = (mt / tiles_x) % tiles_y, tz = mt / (tiles_x * tiles_y);
+                const int x0 = tx * g.tw, y0 = ty * g.th, i0 = tz * g.tn, n0 = nt * BLOCK_N;
+                const int kb0 = split * kb_per_split, kb1 = min(kb_total, kb0 + kb_per_split);
+                for (int kb = kb0; kb < kb1; kb++) {
+                    const int tap = kb / kb_per_tap, cb = kb - tap * kb_per_tap;
+                    const int dy = g.pad ? tap / 3 - 1 : 0, dx = g.pad ? tap % 3 - 1 : 0;
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    unsigned char* sa = smem + stage * L::kStageBytes;
+                    mbar_expect_tx(&full_bar[stage], L::kStageBytes);
+                    tma_load_4d(&map_a, &full_bar[stage], sa, cb * kBlockK, x0 + dx, y0 + dy, i0);
+                    tma_load_2d(&map_b, &full_bar[stage], sa + L::kABytes, kb * kBlockK, n0);
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
+        int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
+        for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+            const int split = w % g.splitk;
+            const int kb0 = split * kb_per_split, kb1 = min(kb_total, kb0 + kb_per_split);
+            mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+            tcgen05_fence_after();
+            const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+            for (int kb = kb0; kb < kb1; kb++) {
+                mbar_wait(&full_bar[stage], phase);
+                tcgen05_fence_after();
+                if (lane == 0) {
+                    const uint32_t sa = smem_u32(smem + stage * L::kStageBytes);
+                    const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sa + L::kABytes);
+#pragma unroll
+                    for (int k = 0; k < kBlockK / kUmmaK; k++) {
+                        // advance 32 bytes (16 fp16) inside the swizzled row: +2 in 16-byte units
+                        umma_f16(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[stage]);                       // frees the smem slot when the MMAs retire
+                    if (kb == kb1 - 1) umma_commit(&tmem_full[acc]);      // accumulator ready for the epilogue
+                }
+                __syncwarp();
+                if (++stage == kStages) { stage = 0; phase ^= 1; }
+            }
+            if (kb1 <= kb0 && lane == 0) umma_commit(&tmem_full[acc]);      // empty K range (cannot happen with valid args)
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    } else {
+        // ===================== epilogue (4 warps, one TMEM lane quarter each) =====================
+        const int q = warp & 3;                      // TMEM lanes 32q .. 32q+31
+        const int r = q * 32 + lane;                 // row of the tile
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+            const int t2 = w / g.splitk;
+            const int nt = t2 % n_tiles, mt = t2 / n_tiles;
+            const int tx = mt % tiles_x, ty = (mt / tiles_x) % tiles_y, tz = mt / (tiles_x * tiles_y);
+            const int lx = r % g.tw, ly = (r / g.tw) % g.th, li = r / (g.tw * g.th);
+            const int x = tx * g.tw + lx, y = ty * g.th + ly, img = tz * g.tn + li;
+            const bool row_ok = (x < g.W) && (y < g.H) && (img < g.Nimg);
+            const long long m = ((long long)img * g.H + y) * g.W + x;
+            const int n0 = nt * BLOCK_N;
+
+            mbar_wait(&tmem_full[acc], acc_phase);
+            tcgen05_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BLOCK_N;
+#pragma unroll 1
+            for (int c0 = 0; c0 < BLOCK_N; c0 += 16) {
+                uint32_t v[16];
+                tmem_ld16(taddr + c0, v);
+                const int n = n0 + c0;
+                if (!row_ok || n >= g.N) continue;
+                float f[16];
+#pragma unroll
+                for (int j = 0; j < 16; j++) f[j] = __uint_as_float(v[j]) * g.alpha;
+                if (g.splitk > 1) {
+                    float* ws = g.workspace + m * g.N + n;
+#pragma unroll
+                    for (int j = 0; j < 16; j++) if (n + j < g.N) atomicAdd(ws + j, f[j]);
+                    continue;
+                }
+                const bool full16 = (n + 16 <= g.N);
+                if (g.bias) {
+#pragma unroll
+                    for (int j = 0; j < 16; j++) if (full16 || n + j < g.N) f[j] += __ldg(g.bias + n + j);
+                }
+                if (g.temb) {
+                    const __half* te = g.temb + (long long)img * g.temb_ld + n;
+#pragma unroll
+                    for (int j = 0; j < 16; j++) if (full16 || n + j < g.N) f[j] += __half2float(te[j]);
+                }
+                if (g.residual) {
+                    const __half* rs = g.residual + m * g.ldr + n;
+                    if (full16) {
+                        const uint4 r0 = *reinterpret_cast<const uint4*>(rs), r1 = *reinterpret_cast<const uint4*>(rs + 8);
+                        const __half2* h0 = reinterpret_cast<const __half2*>(&r0);
+                        const __half2* h1 = reinterpret_cast<const __half2*>(&r1);
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            const float2 a = __half22float2(h0[j]), b = __half22float2(h1[j]);
+                            f[2 * j] += a.x; f[2 * j + 1] += a.y; f[8 + 2 * j] += b.x; f[8 + 2 * j + 1] += b.y;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; j++) if (n + j < g.N) f[j] += __half2float(rs[j]);
+                    }
+                }
+                if (g.act != kActNone) {
+#pragma unroll
+                    for (int j = 0; j < 16; j++) f[j] = act_apply(f[j], g.act);
+                }
+                __half* o = g.out + m * g.ldo + n;
+                if (full16) {
+                    uint4 o0, o1;
+                    __half2* h0 = reinterpret_cast<__half2*>(&o0);
+                    __half2* h1 = reinterpret_cast<__half2*>(&o1);
+#pragma unroll
+                    for (int j = 0; j < 4; j++) { h0[j] = __floats2half2_rn(f[2 * j], f[2 * j + 1]); h1[j] = __floats2half2_rn(f[8 + 2 * j], f[8 + 2 * j + 1]); }
+                    *reinterpret_cast<uint4*>(o) = o0;
+                    *reinterpret_cast<uint4*>(o + 8) = o1;
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; j++) if (n + j < g.N) o[j] = __float2half_rn(f[j]);
+                }
+            }
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
+    }
+}
+
+// finishes a split-K product: workspace fp32 [M,N] -> epilogue -> fp16 out
+__global__ void k_splitk_epilogue(const float* __restrict__ ws, GemmArgs g) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)g.M * g.N;
+    if (i >= total) return;
+    const long long m = i / g.N; const int n = (int)(i - m * g.N);
+    float v = ws[i];
+    if (g.bias) v += g.bias[n];
+    if (g.temb) { const int img = (int)(m / ((long long)g.H * g.W)); v += __half2float(g.temb[(long long)img * g.temb_ld + n]); }
+    if (g.residual) v += __half2float(g.residual[m * g.ldr + n]);
+    v = act_apply(v, g.act);
+    g.out[m * g.ldo + n] = __float2half_rn(v);
+}
+
+// ------------------------------------------------------------------ host side: plans
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_encodeTiled get_encode() {
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_encodeTiled>(p);
+    }
+    return fn;
+}
+
+struct GemmPlan {
+    CUtensorMap map_a, map_b;
+    GemmArgs args;
+    int block_n;
+    int grid;
+};
+
+std::mutex g_plan_mu;
+std::vector<GemmPlan*> g_plans;
+
+template <int BN>
+int launch_gemm(const GemmPlan& p, cudaStream_t st) {
+    using L = SmemLayout<BN>;
+    static bool attr_set[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 64 && !attr_set[dev]) {
+        SDF_CHECK_CUDA(cudaFuncSetAttribute(k_gemm<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+        attr_set[dev] = true;
+    }
+    k_gemm<BN><<<p.grid, kNumThreads, L::kTotal, st>>>(p.map_a, p.map_b, p.args);
+    return SDF_OK;
+}
+
+}  // namespace
+
+// Creates a reusable plan for D = epilogue(conv/linear(A, Wt)).  Returns a handle >= 0 or a negative error code.
+//   a        : NHWC fp16 activations, pixel (img,y,x) channel c at a[((img*H + y)*W + x)*lda + c]; reads channels [0, Cin)
+//   wt       : packed weights fp16 [n_rows_w, taps*Cin] (row n = output channel; K index = tap*Cin + c; tap = ky*3 + kx);
+//              n_rows_w >= N (extra rows, if any, must be zero or are ignored by the epilogue)
+//   taps     : 1 (1x1 conv / linear) or 9 (3x3, stride 1, zero padding 1)
+//   linear   : pass H = 1, Nimg = 1, W = M
+//   out      : fp16 [M, ldo]; bias fp32 [N] / temb fp16 [Nimg, temb_ld] / residual fp16 [M, ldr] optional (NULL)
+//   act      : 0 none, 1 SiLU, 2 GELU(erf); alpha scales the accumulator first
+//   splitk   : >1 needs workspace fp32 [M, N] (zeroed by sdf_gemm_run)
+SDF_API int sdf_gemm_plan_create(const void* a, int lda, const void* wt, int n_rows_w, int Nimg, int H, int W, int Cin, int taps, int N,
+                                 void* out, int ldo, const float* bias, const void* temb, int temb_ld, const void* residual, int ldr,
+                                 int act, float alpha, int splitk, float* workspace, int block_n) {
+    SDF_CHECK_ARG(a && wt && out, "gemm_plan: null pointer");
+    SDF_CHECK_ARG(Cin > 0 && Cin % kBlockK == 0, "gemm_plan: Cin must be a positive multiple of 64 (pad channels)");
+    SDF_CHECK_ARG(taps == 1 || taps == 9, "gemm_plan: taps must be 1 or 9");
+    SDF_CHECK_ARG(lda % 8 == 0 && ((uintptr_t)a & 15) == 0 && ((uintptr_t)wt & 15) == 0, "gemm_plan: operands must be 16-byte aligned (lda % 8 == 0)");
+    SDF_CHECK_ARG(ldo % 8 == 0 && ((uintptr_t)out & 15) == 0, "gemm_plan: output must be 16-byte aligned (ldo % 8 == 0)");
+    SDF_CHECK_ARG(!residual || (ldr % 8 == 0 && ((uintptr_t)residual & 15) == 0), "gemm_plan: residual must be 16-byte aligned");
+    SDF_CHECK_ARG(block_n == 64 || block_n == 128 || block_n == 160, "gemm_plan: block_n must be 64, 128 or 160");
+    SDF_CHECK_ARG(n_rows_w >= N && N > 0, "gemm_plan: weight rows must cover N");
+    SDF_CHECK_ARG(splitk >= 1 && (splitk == 1 || workspace), "gemm_plan: split-K needs a workspace");
+    PFN_encodeTiled enc = get_encode();
+    if (!enc) { sdf_set_error("gemm_plan: cuTensorMapEncodeTiled unavailable (no CUDA driver?)"); return SDF_ERR_CUDA; }
+
+    GemmPlan* p = new GemmPlan();
+    GemmArgs& g = p->args;
+    g.M = Nimg * H * W; g.N = N; g.Cin = Cin; g.taps = taps; g.H = H; g.W = W; g.Nimg = Nimg;
+    // tile rectangle of 128 pixels: as wide as possible, then rows, then images
+    g.tw = W >= kBlockM ? kBlockM : W;
+    if (kBlockM % g.tw != 0) {   // widths that do not divide 128 (e.g. 154 context tokens use W >= 128 path; 77 would not divide)
+        g.tw = kBlockM; }
+    g.th = 1; g.tn = 1;
+    if (g.tw < kBlockM) {
+        g.th = min(H, kBlockM / g.tw);
+        if (kBlockM % (g.tw * g.th) != 0) { delete p; sdf_set_error("gemm_plan: H x W = %d x %d cannot tile 128 pixels", H, W); return SDF_ERR_ARG; }
+        g.tn = kBlockM / (g.tw * g.th);
+    }
+    g.pad = taps == 9 ? 1 : 0;
+    g.splitk = splitk; g.bias = bias; g.temb = (const __half*)temb; g.temb_ld = temb_ld;
+    g.residual = (const __half*)residual; g.ldr = ldr; g.out = (__half*)out; g.ldo = ldo; g.workspace = workspace;
+    g.act = act; g.alpha = alpha;
+    p->block_n = block_n;
+
+    // A: 4-D map (C, W, H, Nimg), 128B swizzle, zero OOB fill
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)Nimg};
+        cuuint64_t strides[3] = {(cuuint64_t)lda * 2, (cuuint64_t)W * lda * 2, (cuuint64_t)H * W * lda * 2};
+        cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)g.tw, (cuuint32_t)g.th, (cuuint32_t)g.tn};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult r = enc(&p->map_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(a), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { delete p; sdf_set_error("gemm_plan: cuTensorMapEncodeTiled(A) failed (%d)", (int)r); return SDF_ERR_CUDA; }
+    }
+    {
+        const cuuint64_t Ktot = (cuuint64_t)taps * Cin;
+        cuuint64_t dims[2] = {Ktot, (cuuint64_t)n_rows_w};
+        cuuint64_t strides[1] = {Ktot * 2};
+        cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)block_n};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = enc(&p->map_b, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(wt), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { delete p; sdf_set_error("gemm_plan: cuTensorMapEncodeTiled(B) failed (%d)", (int)r); return SDF_ERR_CUDA; }
+    }
+    const int tiles_x = (W + g.tw - 1) / g.tw, tiles_y = (H + g.th - 1) / g.th, tiles_i = (Nimg + g.tn - 1) / g.tn;
+    const int work = tiles_x * tiles_y * tiles_i * ((N + block_n - 1) / block_n) * splitk;
+    p->grid = work < kNumSMs ? work : kNumSMs;
+    std::lock_guard<std::mutex> lk(g_plan_mu);
+    g_plans.push_back(p);
+    return (int)g_plans.size() - 1;
+}
+
+SDF_API int sdf_gemm_run(int plan, void* stream) {
+    GemmPlan* p;
+    {
+        std::lock_guard<std::mutex> lk(g_plan_mu);
+        SDF_CHECK_ARG(plan >= 0 && plan < (int)g_plans.size() && g_plans[plan], "gemm_run: bad plan handle");
+        p = g_plans[plan];
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const GemmArgs& g = p->args;
+    if (g.splitk > 1) SDF_CHECK_CUDA(cudaMemsetAsync(g.workspace, 0, (size_t)g.M * g.N * sizeof(float), st));
+    int rc;
+    if (p->block_n == 64) rc = launch_gemm<64>(*p, st);
+    else if (p->block_n == 128) rc = launch_gemm<128>(*p, st);
+    else rc = launch_gemm<160>(*p, st);
+    if (rc) return rc;
+    SDF_CHECK_LAUNCH("gemm");
+    if (g.splitk > 1) {
+        const long long total = (long long)g.M * g.N;
+        k_splitk_epilogue<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(g.workspace, g);
+        SDF_CHECK_LAUNCH("gemm(split-K epilogue)");
+    }
+    return SDF_OK;
+}
+
+SDF_API int sdf_gemm_plan_destroy(int plan) {
+    std::lock_guard<std::mutex> lk(g_plan_mu);
+    SDF_CHECK_ARG(plan >= 0 && plan < (int)g_plans.size(), "gemm_plan_destroy: bad plan handle");
+    delete g_plans[plan];
+    g_plans[plan] = nullptr;
+    return SDF_OK;
+}

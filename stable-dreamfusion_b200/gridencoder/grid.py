@@ -6,9 +6,6 @@ and GridEncoder(...) with .embeddings [n,C] / .offsets [L+1] / grad_total_variat
 grad_weight_decay — backed by libsdf_b200.so (csrc/gridenc.cu).
 
 What changes underneath:
-  * under autocast the fp16 working copy of the table is cached and refreshed only when
-    the fp32 parameter changes (the reference re-casts all 12.2 M entries on every call,
-    grid.py:46-47 — 7x per lambertian step);
   * outputs are produced directly as [B, L*C] and the gradient is consumed in that layout
     (no permute / .contiguous() kernels, grid.py:64,82);
   * with an fp16 table the table gradient is accumulated in fp32 (atomicAdd on float2)
@@ -27,23 +24,9 @@ from sdf_b200 import _lib
 _gridtype_to_id = {'hash': 0, 'tiled': 1}
 _interp_to_id = {'linear': 0, 'smoothstep': 1}
 
-# fp16 working copies keyed by the parameter's storage; refreshed when ._version moves
-_half_cache = {}
-
-
 def _half_table(embeddings):
-    key = (embeddings.data_ptr(), tuple(embeddings.shape), embeddings.device)
-    ver = embeddings._version
-    hit = _half_cache.get(key)
-    if hit is not None and hit[0] == ver:
-        return hit[1]
-    if hit is not None and hit[1].shape == embeddings.shape:
-        hit[1].copy_(embeddings.detach())
-        h = hit[1]
-    else:
-        h = embeddings.detach().to(torch.half)
-    _half_cache[key] = (ver, h)
-    return h
+    # cast per call, like the reference (grid.py:46-47); a (data_ptr, _version) cache is unsafe under `.data` writes
+    return embeddings.detach().to(torch.half)
 
 
 class _grid_encode(Function):

