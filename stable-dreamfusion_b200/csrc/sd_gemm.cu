@@ -402,6 +402,12 @@ SDF_API int sdf_gemm_plan_create(const void* a, int lda, const void* wt, int n_r
         g.tn = kBlockM / (g.tw * g.th);
     }
     g.pad = taps == 9 ? 1 : 0;
+    {   // no split may own an empty K range: shrink splitk to ceil(kb / ceil(kb / splitk))
+        const int kb_total = taps * (Cin / kBlockK);
+        if (splitk > kb_total) splitk = kb_total;
+        const int per = (kb_total + splitk - 1) / splitk;
+        splitk = (kb_total + per - 1) / per;
+    }
     g.splitk = splitk; g.bias = bias; g.temb = (const __half*)temb; g.temb_ld = temb_ld;
     g.residual = (const __half*)residual; g.ldr = ldr; g.out = (__half*)out; g.ldo = ldo; g.workspace = workspace;
     g.act = act; g.alpha = alpha;

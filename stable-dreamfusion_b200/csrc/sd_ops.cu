@@ -1,0 +1,510 @@
+// sd_ops.cu — memory-bound companions of the tcgen05 GEMM for the SD-1.5-shaped UNet / VAE encoder (NHWC fp16):
+// GroupNorm(+SiLU) forward / backward, LayerNorm, row softmax forward / backward, GEGLU, nearest / bilinear
+// resampling, stride-2 im2col and its scatter (col2im), elementwise glue and the SDS gradient itself.
+// Roofline: HBM.  Every kernel moves 16-byte vectors per thread and keeps statistics in fp32.
+//
+// Reference structure these implement (vendored CompVis code of the reference):
+//   GroupNorm32 / Normalize     ldm/modules/diffusionmodules/util.py:214, model.py:38, attention.py:75
+//   SiLU / swish                 model.py:33-35          LayerNorm       attention.py:204-206
+//   softmax                      attention.py:185, model.py:191         GEGLU  attention.py:37-45
+//   nearest x2                   openaimodel.py:110-120, bilinear 64->512: guidance/sd_utils.py:93
+//   SDS gradient                 guidance/sd_utils.py:103-131,160-161
+#include "common.cuh"
+
+namespace {
+
+__device__ __forceinline__ float silu(float v) { return v / (1.f + __expf(-v)); }
+__device__ __forceinline__ float gelu(float v) { return 0.5f * v * (1.f + erff(v * 0.70710678118654752f)); }
+
+struct H8 { uint4 u; };
+__device__ __forceinline__ void load8(const __half* p, float f[8]) {
+    const uint4 u = *reinterpret_cast<const uint4*>(p);
+    const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+    for (int j = 0; j < 4; j++) { const float2 t = __half22float2(h[j]); f[2 * j] = t.x; f[2 * j + 1] = t.y; }
+}
+__device__ __forceinline__ void store8(__half* p, const float f[8]) {
+    uint4 u;
+    __half2* h = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+    for (int j = 0; j < 4; j++) h[j] = __floats2half2_rn(f[2 * j], f[2 * j + 1]);
+    *reinterpret_cast<uint4*>(p) = u;
+}
+
+// ------------------------------------------------------------------ GroupNorm
+// x: [Nimg, HW, C] (row stride ldx).  stats: [Nimg, G, 2] fp32 (sum, sumsq), zeroed by the caller.
+// One block = (image, slab of pixels); thread = 8 consecutive channels, loops over the slab's pixels.
+__global__ void __launch_bounds__(256) k_gn_stats(const __half* __restrict__ x, int ldx, int HW, int C, int G, int pix_per_block,
+                                                  float* __restrict__ stats) {
+    extern __shared__ float sm[];      // [G][2]
+    const int img = blockIdx.y;
+    const int cpg = C / G;
+    for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) sm[i] = 0.f;
+    __syncthreads();
+    const int vec_per_pix = C / 8;
+    const int p0 = blockIdx.x * pix_per_block, p1 = min(HW, p0 + pix_per_block);
+    const long long base = (long long)img * HW;
+    // consecutive threads walk consecutive 16-byte vectors of the slab
+    const int total = (p1 - p0) * vec_per_pix;
+    float s = 0.f, ss = 0.f;
+    int cur_g = -1;
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+        const int pix = p0 + i / vec_per_pix, v = i % vec_per_pix;
+        const int gidx = (v * 8) / cpg;     // 8 | cpg for every layer here (cpg in {4..60}: handled below when not)
+        float f[8];
+        load8(x + (base + pix) * ldx + v * 8, f);
+        if (cpg % 8 == 0) {
+            if (gidx != cur_g) {
+                if (cur_g >= 0) { atomicAdd(&sm[cur_g * 2], s); atomicAdd(&sm[cur_g * 2 + 1], ss); }
+                cur_g = gidx; s = 0.f; ss = 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < 8; j++) { s += f[j]; ss += f[j] * f[j]; }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const int gj = (v * 8 + j) / cpg;
+                atomicAdd(&sm[gj * 2], f[j]); atomicAdd(&sm[gj * 2 + 1], f[j] * f[j]);
+            }
+        }
+    }
+    if (cur_g >= 0) { atomicAdd(&sm[cur_g * 2], s); atomicAdd(&sm[cur_g * 2 + 1], ss); }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) atomicAdd(&stats[(long long)img * G * 2 + i], sm[i]);
+}
+
+// y = (x - mean) * rstd * gamma + beta, optional SiLU.  Writes y with row stride ldy.
+__global__ void __launch_bounds__(256) k_gn_apply(const __half* __restrict__ x, int ldx, __half* __restrict__ y, int ldy, int HW, int C, int G,
+                                                  const float* __restrict__ stats, const float* __restrict__ gamma,
+                                                  const float* __restrict__ beta, float eps, int act, long long total_vec) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total_vec) return;
+    const int vec_per_pix = C / 8;
+    const long long pix = i / vec_per_pix;
+    const int v = (int)(i - pix * vec_per_pix);
+    const int img = (int)(pix / HW);
+    const int cpg = C / G;
+    const float cnt = (float)HW * cpg;
+    float f[8];
+    load8(x + pix * ldx + v * 8, f);
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const int c = v * 8 + j, gi = c / cpg;
+        const float mean = stats[((long long)img * G + gi) * 2] / cnt;
+        const float var = fmaxf(stats[((long long)img * G + gi) * 2 + 1] / cnt - mean * mean, 0.f);
+        float o = (f[j] - mean) * rsqrtf(var + eps) * gamma[c] + beta[c];
+        f[j] = act ? silu(o) : o;
+    }
+    store8(y + pix * ldy + v * 8, f);
+}
+
+// GroupNorm(+SiLU) backward wrt x (weights frozen).  Pass 1: per (img, group) sums of dy_hat and dy_hat * xhat,
+// where dy_hat = dL/d(normalised*gamma+beta) (after undoing SiLU) * gamma.  Pass 2: dx.
+__global__ void __launch_bounds__(256) k_gn_bwd_stats(const __half* __restrict__ x, int ldx, const __half* __restrict__ dy, int ldd, int HW, int C, int G,
+                                                      int pix_per_block, const float* __restrict__ stats, const float* __restrict__ gamma,
+                                                      const float* __restrict__ beta, float eps, int act, float* __restrict__ bstats) {
+    extern __shared__ float sm[];
+    const int img = blockIdx.y;
+    const int cpg = C / G;
+    const float cnt = (float)HW * cpg;
+    for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) sm[i] = 0.f;
+    __syncthreads();
+    const int vec_per_pix = C / 8;
+    const int p0 = blockIdx.x * pix_per_block, p1 = min(HW, p0 + pix_per_block);
+    const long long base = (long long)img * HW;
+    const int total = (p1 - p0) * vec_per_pix;
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+        const int pix = p0 + i / vec_per_pix, v = i % vec_per_pix;
+        float fx[8], fd[8];
+        load8(x + (base + pix) * ldx + v * 8, fx);
+        load8(dy + (base + pix) * ldd + v * 8, fd);
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const int c = v * 8 + j, gi = c / cpg;
+            const float mean = stats[((long long)img * G + gi) * 2] / cnt;
+            const float var = fmaxf(stats[((long long)img * G + gi) * 2 + 1] / cnt - mean * mean, 0.f);
+            const float xh = (fx[j] - mean) * rsqrtf(var + eps);
+            float g = fd[j];
+            if (act) { const float o = xh * gamma[c] + beta[c]; const float sg = 1.f / (1.f + __expf(-o)); g *= sg * (1.f + o * (1.f - sg)); }
+            g *= gamma[c];
+            atomicAdd(&sm[gi * 2], g); atomicAdd(&sm[gi * 2 + 1], g * xh);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) atomicAdd(&bstats[(long long)img * G * 2 + i], sm[i]);
+}
+
+// dx = rstd * (g - mean(g) - xhat * mean(g*xhat)); if accumulate, dx is added to the existing content of dxo.
+__global__ void __launch_bounds__(256) k_gn_bwd_apply(const __half* __restrict__ x, int ldx, const __half* __restrict__ dy, int ldd,
+                                                      __half* __restrict__ dxo, int ldo, int HW, int C, int G, const float* __restrict__ stats,
+                                                      const float* __restrict__ bstats, const float* __restrict__ gamma,
+                                                      const float* __restrict__ beta, float eps, int act, int accumulate, long long total_vec) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total_vec) return;
+    const int vec_per_pix = C / 8;
+    const long long pix = i / vec_per_pix;
+    const int v = (int)(i - pix * vec_per_pix);
+    const int img = (int)(pix / HW);
+    const int cpg = C / G;
+    const float cnt = (float)HW * cpg;
+    float fx[8], fd[8], fo[8];
+    load8(x + pix * ldx + v * 8, fx);
+    load8(dy + pix * ldd + v * 8, fd);
+    if (accumulate) load8(dxo + pix * ldo + v * 8, fo);
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const int c = v * 8 + j, gi = c / cpg;
+        const long long si = ((long long)img * G + gi) * 2;
+        const float mean = stats[si] / cnt;
+        const float var = fmaxf(stats[si + 1] / cnt - mean * mean, 0.f);
+        const float rstd = rsqrtf(var + eps);
+        const float xh = (fx[j] - mean) * rstd;
+        float g = fd[j];
+        if (act) { const float o = xh * gamma[c] + beta[c]; const float sg = 1.f / (1.f + __expf(-o)); g *= sg * (1.f + o * (1.f - sg)); }
+        g *= gamma[c];
+        const float d = rstd * (g - bstats[si] / cnt - xh * bstats[si + 1] / cnt);
+        fo[j] = accumulate ? fo[j] + d : d;
+    }
+    store8(dxo + pix * ldo + v * 8, fo);
+}
+
+// ------------------------------------------------------------------ LayerNorm (warp per row)
+__global__ void __launch_bounds__(256) k_layernorm(const __half* __restrict__ x, int ldx, __half* __restrict__ y, int ldy, int rows, int C,
+                                                   const float* __restrict__ gamma, const float* __restrict__ beta, float eps) {
+    const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const __half* xr = x + (long long)row * ldx;
+    float s = 0.f, ss = 0.f;
+    for (int c = lane * 8; c < C; c += 256) {
+        float f[8]; load8(xr + c, f);
+#pragma unroll
+        for (int j = 0; j < 8; j++) { s += f[j]; ss += f[j] * f[j]; }
+    }
+    s = warp_sum(s); ss = warp_sum(ss);
+    const float mean = s / C, rstd = rsqrtf(fmaxf(ss / C - mean * mean, 0.f) + eps);
+    __half* yr = y + (long long)row * ldy;
+    for (int c = lane * 8; c < C; c += 256) {
+        float f[8]; load8(xr + c, f);
+#pragma unroll
+        for (int j = 0; j < 8; j++) f[j] = (f[j] - mean) * rstd * gamma[c + j] + beta[c + j];
+        store8(yr + c, f);
+    }
+}
+
+// ------------------------------------------------------------------ softmax over the last dim, in place or out of place
+// one block per row when cols > 1024, else one warp per row
+__global__ void __launch_bounds__(256) k_softmax_rows(const __half* __restrict__ x, __half* __restrict__ y, long long rows, int cols, int ld, float scale) {
+    const long long row = blockIdx.x;
+    const __half* xr = x + row * ld;
+    __half* yr = y + row * ld;
+    __shared__ float red[8];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    float mx = -INFINITY;
+    for (int c = tid * 8; c < cols; c += blockDim.x * 8) {
+        if (c + 8 <= cols) { float f[8]; load8(xr + c, f);
+#pragma unroll
+            for (int j = 0; j < 8; j++) mx = fmaxf(mx, f[j] * scale); }
+        else for (int j = c; j < cols; j++) mx = fmaxf(mx, __half2float(xr[j]) * scale);
+    }
+    mx = warp_max(mx);
+    if (lane == 0) red[wid] = mx;
+    __syncthreads();
+    mx = red[0];
+#pragma unroll
+    for (int i = 1; i < 8; i++) mx = fmaxf(mx, red[i]);
+    __syncthreads();
+    float sum = 0.f;
+    for (int c = tid * 8; c < cols; c += blockDim.x * 8) {
+        if (c + 8 <= cols) { float f[8]; load8(xr + c, f);
+#pragma unroll
+            for (int j = 0; j < 8; j++) sum += __expf(f[j] * scale - mx); }
+        else for (int j = c; j < cols; j++) sum += __expf(__half2float(xr[j]) * scale - mx);
+    }
+    sum = warp_sum(sum);
+    if (lane == 0) red[wid] = sum;
+    __syncthreads();
+    sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; i++) sum += red[i];
+    const float inv = 1.f / sum;
+    for (int c = tid * 8; c < cols; c += blockDim.x * 8) {
+        if (c + 8 <= cols) { float f[8]; load8(xr + c, f);
+#pragma unroll
+            for (int j = 0; j < 8; j++) f[j] = __expf(f[j] * scale - mx) * inv;
+            store8(yr + c, f); }
+        else for (int j = c; j < cols; j++) yr[j] = __float2half_rn(__expf(__half2float(xr[j]) * scale - mx) * inv);
+    }
+}
+
+// dS = scale * P * (dP - sum_j dP_j P_j) per row
+__global__ void __launch_bounds__(256) k_softmax_bwd_rows(const __half* __restrict__ p, const __half* __restrict__ dp, __half* __restrict__ ds,
+                                                          long long rows, int cols, int ld, float scale) {
+    const long long row = blockIdx.x;
+    const __half* pr = p + row * ld; const __half* dr = dp + row * ld; __half* sr = ds + row * ld;
+    __shared__ float red[8];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    float dot = 0.f;
+    for (int c = tid * 8; c < cols; c += blockDim.x * 8) {
+        float a[8], b[8]; load8(pr + c, a); load8(dr + c, b);
+#pragma unroll
+        for (int j = 0; j < 8; j++) dot += a[j] * b[j];
+    }
+    dot = warp_sum(dot);
+    if (lane == 0) red[wid] = dot;
+    __syncthreads();
+    dot = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; i++) dot += red[i];
+    for (int c = tid * 8; c < cols; c += blockDim.x * 8) {
+        float a[8], b[8]; load8(pr + c, a); load8(dr + c, b);
+#pragma unroll
+        for (int j = 0; j < 8; j++) a[j] = scale * a[j] * (b[j] - dot);
+        store8(sr + c, a);
+    }
+}
+
+// ------------------------------------------------------------------ GEGLU: y[m, j] = x[m, j] * gelu(x[m, inner + j])
+__global__ void __launch_bounds__(256) k_geglu(const __half* __restrict__ x, int ldx, __half* __restrict__ y, int ldy, long long rows, int inner) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int vpr = inner / 8;
+    if (i >= rows * vpr) return;
+    const long long m = i / vpr; const int v = (int)(i - m * vpr);
+    float a[8], b[8];
+    load8(x + m * ldx + v * 8, a); load8(x + m * ldx + inner + v * 8, b);
+#pragma unroll
+    for (int j = 0; j < 8; j++) a[j] *= gelu(b[j]);
+    store8(y + m * ldy + v * 8, a);
+}
+
+// ------------------------------------------------------------------ resampling
+// nearest x2: y[img, 2h+a, 2w+b, c] = x[img, h, w, c]
+__global__ void __launch_bounds__(256) k_upsample_nearest2(const __half* __restrict__ x, int ldx, __half* __restrict__ y, int ldy, int Nimg, int H, int W, int C) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int vpp = C / 8;
+    const long long total = (long long)Nimg * 4 * H * W * vpp;
+    if (i >= total) return;
+    const int v = (int)(i % vpp); long long pix = i / vpp;
+    const int ox = (int)(pix % (2 * W)); pix /= 2 * W;
+    const int oy = (int)(pix % (2 * H)); const int img = (int)(pix / (2 * H));
+    const uint4 u = *reinterpret_cast<const uint4*>(x + (((long long)img * H + oy / 2) * W + ox / 2) * ldx + v * 8);
+    *reinterpret_cast<uint4*>(y + (((long long)img * 2 * H + oy) * 2 * W + ox) * ldy + v * 8) = u;
+}
+
+// 3x3 stride-2 patch gather: col[img, oy, ox, tap*C + c] = x[img, 2oy + ky - pt, 2ox + kx - pl, c] (zero outside)
+__global__ void __launch_bounds__(256) k_im2col_s2(const __half* __restrict__ x, int ldx, __half* __restrict__ col, int Nimg, int H, int W, int C,
+                                                   int Ho, int Wo, int pt, int pl) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int vpp = C / 8;
+    const long long total = (long long)Nimg * Ho * Wo * 9 * vpp;
+    if (i >= total) return;
+    const int v = (int)(i % vpp); long long r = i / vpp;
+    const int tap = (int)(r % 9); r /= 9;
+    const int ox = (int)(r % Wo); r /= Wo;
+    const int oy = (int)(r % Ho); const int img = (int)(r / Ho);
+    const int iy = 2 * oy + tap / 3 - pt, ix = 2 * ox + tap % 3 - pl;
+    uint4 u = make_uint4(0, 0, 0, 0);
+    if (iy >= 0 && iy < H && ix >= 0 && ix < W) u = *reinterpret_cast<const uint4*>(x + (((long long)img * H + iy) * W + ix) * ldx + v * 8);
+    *reinterpret_cast<uint4*>(col + ((((long long)img * Ho + oy) * Wo + ox) * 9 + tap) * C + v * 8) = u;
+}
+
+// adjoint of k_im2col_s2: dx[img, iy, ix, c] = sum over the (<= 4) output pixels / taps that read it
+__global__ void __launch_bounds__(256) k_col2im_s2(const __half* __restrict__ dcol, __half* __restrict__ dx, int ldx, int Nimg, int H, int W, int C,
+                                                   int Ho, int Wo, int pt, int pl) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int vpp = C / 8;
+    const long long total = (long long)Nimg * H * W * vpp;
+    if (i >= total) return;
+    const int v = (int)(i % vpp); long long r = i / vpp;
+    const int ix = (int)(r % W); r /= W;
+    const int iy = (int)(r % H); const int img = (int)(r / H);
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int ky = 0; ky < 3; ky++) {
+        const int ny = iy + pt - ky;
+        if (ny < 0 || (ny & 1) || ny / 2 >= Ho) continue;
+#pragma unroll
+        for (int kx = 0; kx < 3; kx++) {
+            const int nx = ix + pl - kx;
+            if (nx < 0 || (nx & 1) || nx / 2 >= Wo) continue;
+            float f[8];
+            load8(dcol + ((((long long)img * Ho + ny / 2) * Wo + nx / 2) * 9 + ky * 3 + kx) * C + v * 8, f);
+#pragma unroll
+            for (int j = 0; j < 8; j++) acc[j] += f[j];
+        }
+    }
+    store8(dx + (((long long)img * H + iy) * W + ix) * ldx + v * 8, acc);
+}
+
+// ------------------------------------------------------------------ elementwise glue
+__global__ void __launch_bounds__(256) k_copy2d(const __half* __restrict__ x, int ldx, __half* __restrict__ y, int ldy, long long rows, int C) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int vpr = C / 8;
+    if (i >= rows * vpr) return;
+    const long long m = i / vpr; const int v = (int)(i - m * vpr);
+    *reinterpret_cast<uint4*>(y + m * ldy + v * 8) = *reinterpret_cast<const uint4*>(x + m * ldx + v * 8);
+}
+__global__ void __launch_bounds__(256) k_add2d(const __half* __restrict__ a, int lda, const __half* __restrict__ b, int ldb, __half* __restrict__ y, int ldy,
+                                               long long rows, int C) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int vpr = C / 8;
+    if (i >= rows * vpr) return;
+    const long long m = i / vpr; const int v = (int)(i - m * vpr);
+    float fa[8], fb[8];
+    load8(a + m * lda + v * 8, fa); load8(b + m * ldb + v * 8, fb);
+#pragma unroll
+    for (int j = 0; j < 8; j++) fa[j] += fb[j];
+    store8(y + m * ldy + v * 8, fa);
+}
+// [rows, C] -> [C, rows] (both dense), 32x32 tiles through shared memory
+__global__ void k_transpose(const __half* __restrict__ x, int ldx, __half* __restrict__ y, int ldy, int rows, int C) {
+    __shared__ __half tile[32][34];
+    const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
+    const long long boff_x = (long long)blockIdx.z * rows * ldx, boff_y = (long long)blockIdx.z * C * ldy;
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const int r = by + j, c = bx + threadIdx.x;
+        tile[j][threadIdx.x] = (r < rows && c < C) ? x[boff_x + (long long)r * ldx + c] : __float2half(0.f);
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const int c = bx + j, r = by + threadIdx.x;
+        if (c < C && r < rows) y[boff_y + (long long)c * ldy + r] = tile[threadIdx.x][j];
+    }
+}
+
+// sinusoidal timestep embedding, cos first (util.py:151-171): out[b, :half] = cos(t f_i), out[b, half:] = sin(t f_i)
+__global__ void k_timestep_embedding(const int* __restrict__ t, int B, int dim, __half* __restrict__ out, int ldo) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int half = dim / 2;
+    if (i >= B * half) return;
+    const int b = i / half, k = i - b * half;
+    const float freq = expf(-logf(10000.f) * (float)k / (float)half);
+    const float a = (float)t[b] * freq;
+    out[(long long)b * ldo + k] = __float2half_rn(cosf(a));
+    out[(long long)b * ldo + half + k] = __float2half_rn(sinf(a));
+}
+
+}  // namespace
+
+#define LAUNCH_1D(kernel, total, st, ...)                                                       \
+    do { const long long t_ = (total); if (t_ > 0) kernel<<<(unsigned)((t_ + 255) / 256), 256, 0, st>>>(__VA_ARGS__); } while (0)
+
+SDF_API int sdf_groupnorm_forward(const void* x, int ldx, void* y, int ldy, int Nimg, int HW, int C, int G, const float* gamma, const float* beta,
+                                  float eps, int silu_act, float* stats /* [Nimg,G,2] scratch, kept for the backward */, void* stream) {
+    SDF_CHECK_ARG(x && y && gamma && beta && stats, "groupnorm_forward: null pointer");
+    SDF_CHECK_ARG(C % 8 == 0 && C % G == 0 && ldx % 8 == 0 && ldy % 8 == 0, "groupnorm_forward: C %% 8, C %% G, ld %% 8 must be 0");
+    cudaStream_t st = (cudaStream_t)stream;
+    SDF_CHECK_CUDA(cudaMemsetAsync(stats, 0, sizeof(float) * 2 * G * Nimg, st));
+    const int ppb = max(1, min(HW, (256 * 16 * 8) / C));       // ~16 vectors per thread
+    dim3 grid((HW + ppb - 1) / ppb, Nimg);
+    k_gn_stats<<<grid, 256, sizeof(float) * 2 * G, st>>>((const __half*)x, ldx, HW, C, G, ppb, stats);
+    SDF_CHECK_LAUNCH("groupnorm(stats)");
+    const long long tv = (long long)Nimg * HW * (C / 8);
+    LAUNCH_1D(k_gn_apply, tv, st, (const __half*)x, ldx, (__half*)y, ldy, HW, C, G, stats, gamma, beta, eps, silu_act, tv);
+    SDF_CHECK_LAUNCH("groupnorm(apply)");
+    return SDF_OK;
+}
+
+SDF_API int sdf_groupnorm_backward(const void* x, int ldx, const void* dy, int ldd, void* dx, int ldo, int Nimg, int HW, int C, int G,
+                                   const float* gamma, const float* beta, float eps, int silu_act, const float* stats, float* bstats,
+                                   int accumulate, void* stream) {
+    SDF_CHECK_ARG(x && dy && dx && gamma && beta && stats && bstats, "groupnorm_backward: null pointer");
+    SDF_CHECK_ARG(C % 8 == 0 && C % G == 0, "groupnorm_backward: C %% 8 and C %% G must be 0");
+    cudaStream_t st = (cudaStream_t)stream;
+    SDF_CHECK_CUDA(cudaMemsetAsync(bstats, 0, sizeof(float) * 2 * G * Nimg, st));
+    const int ppb = max(1, min(HW, (256 * 16 * 8) / C));
+    dim3 grid((HW + ppb - 1) / ppb, Nimg);
+    k_gn_bwd_stats<<<grid, 256, sizeof(float) * 2 * G, st>>>((const __half*)x, ldx, (const __half*)dy, ldd, HW, C, G, ppb, stats, gamma, beta, eps, silu_act, bstats);
+    SDF_CHECK_LAUNCH("groupnorm_backward(stats)");
+    const long long tv = (long long)Nimg * HW * (C / 8);
+    LAUNCH_1D(k_gn_bwd_apply, tv, st, (const __half*)x, ldx, (const __half*)dy, ldd, (__half*)dx, ldo, HW, C, G, stats, bstats, gamma, beta, eps, silu_act, accumulate, tv);
+    SDF_CHECK_LAUNCH("groupnorm_backward(apply)");
+    return SDF_OK;
+}
+
+SDF_API int sdf_layernorm_forward(const void* x, int ldx, void* y, int ldy, int rows, int C, const float* gamma, const float* beta, float eps, void* stream) {
+    if (rows == 0) return SDF_OK;
+    SDF_CHECK_ARG(x && y && gamma && beta && C % 8 == 0, "layernorm_forward: bad arguments");
+    k_layernorm<<<(rows + 7) / 8, 256, 0, (cudaStream_t)stream>>>((const __half*)x, ldx, (__half*)y, ldy, rows, C, gamma, beta, eps);
+    SDF_CHECK_LAUNCH("layernorm_forward");
+    return SDF_OK;
+}
+
+SDF_API int sdf_softmax_rows(const void* x, void* y, long long rows, int cols, int ld, float scale, void* stream) {
+    if (rows == 0) return SDF_OK;
+    SDF_CHECK_ARG(x && y && ld % 8 == 0 && rows < 2147483647LL, "softmax_rows: bad arguments");
+    k_softmax_rows<<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>((const __half*)x, (__half*)y, rows, cols, ld, scale);
+    SDF_CHECK_LAUNCH("softmax_rows");
+    return SDF_OK;
+}
+
+SDF_API int sdf_softmax_rows_backward(const void* p, const void* dp, void* ds, long long rows, int cols, int ld, float scale, void* stream) {
+    if (rows == 0) return SDF_OK;
+    SDF_CHECK_ARG(p && dp && ds && ld % 8 == 0 && cols % 8 == 0, "softmax_rows_backward: bad arguments");
+    k_softmax_bwd_rows<<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>((const __half*)p, (const __half*)dp, (__half*)ds, rows, cols, ld, scale);
+    SDF_CHECK_LAUNCH("softmax_rows_backward");
+    return SDF_OK;
+}
+
+SDF_API int sdf_geglu(const void* x, int ldx, void* y, int ldy, long long rows, int inner, void* stream) {
+    SDF_CHECK_ARG(x && y && inner % 8 == 0, "geglu: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    LAUNCH_1D(k_geglu, rows * (inner / 8), st, (const __half*)x, ldx, (__half*)y, ldy, rows, inner);
+    SDF_CHECK_LAUNCH("geglu");
+    return SDF_OK;
+}
+
+SDF_API int sdf_upsample_nearest2(const void* x, int ldx, void* y, int ldy, int Nimg, int H, int W, int C, void* stream) {
+    SDF_CHECK_ARG(x && y && C % 8 == 0, "upsample_nearest2: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    LAUNCH_1D(k_upsample_nearest2, (long long)Nimg * 4 * H * W * (C / 8), st, (const __half*)x, ldx, (__half*)y, ldy, Nimg, H, W, C);
+    SDF_CHECK_LAUNCH("upsample_nearest2");
+    return SDF_OK;
+}
+
+SDF_API int sdf_im2col_s2(const void* x, int ldx, void* col, int Nimg, int H, int W, int C, int Ho, int Wo, int pad_top, int pad_left, void* stream) {
+    SDF_CHECK_ARG(x && col && C % 8 == 0, "im2col_s2: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    LAUNCH_1D(k_im2col_s2, (long long)Nimg * Ho * Wo * 9 * (C / 8), st, (const __half*)x, ldx, (__half*)col, Nimg, H, W, C, Ho, Wo, pad_top, pad_left);
+    SDF_CHECK_LAUNCH("im2col_s2");
+    return SDF_OK;
+}
+
+SDF_API int sdf_col2im_s2(const void* dcol, void* dx, int ldx, int Nimg, int H, int W, int C, int Ho, int Wo, int pad_top, int pad_left, void* stream) {
+    SDF_CHECK_ARG(dcol && dx && C % 8 == 0, "col2im_s2: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    LAUNCH_1D(k_col2im_s2, (long long)Nimg * H * W * (C / 8), st, (const __half*)dcol, (__half*)dx, ldx, Nimg, H, W, C, Ho, Wo, pad_top, pad_left);
+    SDF_CHECK_LAUNCH("col2im_s2");
+    return SDF_OK;
+}
+
+SDF_API int sdf_copy2d(const void* x, int ldx, void* y, int ldy, long long rows, int C, void* stream) {
+    SDF_CHECK_ARG(x && y && C % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0, "copy2d: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    LAUNCH_1D(k_copy2d, rows * (C / 8), st, (const __half*)x, ldx, (__half*)y, ldy, rows, C);
+    SDF_CHECK_LAUNCH("copy2d");
+    return SDF_OK;
+}
+
+SDF_API int sdf_add2d(const void* a, int lda, const void* b, int ldb, void* y, int ldy, long long rows, int C, void* stream) {
+    SDF_CHECK_ARG(a && b && y && C % 8 == 0, "add2d: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    LAUNCH_1D(k_add2d, rows * (C / 8), st, (const __half*)a, lda, (const __half*)b, ldb, (__half*)y, ldy, rows, C);
+    SDF_CHECK_LAUNCH("add2d");
+    return SDF_OK;
+}
+
+SDF_API int sdf_transpose2d(const void* x, int ldx, void* y, int ldy, int batch, int rows, int C, void* stream) {
+    SDF_CHECK_ARG(x && y, "transpose2d: null pointer");
+    dim3 grid((C + 31) / 32, (rows + 31) / 32, batch), block(32, 8);
+    k_transpose<<<grid, block, 0, (cudaStream_t)stream>>>((const __half*)x, ldx, (__half*)y, ldy, rows, C);
+    SDF_CHECK_LAUNCH("transpose2d");
+    return SDF_OK;
+}
+
+SDF_API int sdf_timestep_embedding(const int* t, int B, int dim, void* out, int ldo, void* stream) {
+    SDF_CHECK_ARG(t && out && dim % 2 == 0, "timestep_embedding: bad arguments");
+    const int total = B * dim / 2;
+    k_timestep_embedding<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(t, B, dim, (__half*)out, ldo);
+    SDF_CHECK_LAUNCH("timestep_embedding");
+    return SDF_OK;
+}
