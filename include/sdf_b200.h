@@ -145,15 +145,41 @@ int sdf_field_backward(const float* xyzs, uint32_t M, const int* m_dev, const vo
  * ldm/modules/attention.py:152-275, ldm/modules/diffusionmodules/model.py:82-204,368-460).
  * Activations are NHWC fp16. */
 
-/* tcgen05 implicit-GEMM plan: out[m, n] = act(alpha * sum_{tap,c} a[pixel(m)+off(tap), c] * wt[n, tap*Cin + c] + bias[n] + temb[img(m), n] + residual[m, n])
- * taps = 1 (1x1 conv / linear: pass H = 1, Nimg = 1, W = M) or 9 (3x3, stride 1, zero pad 1; tap = ky*3 + kx).
- * Cin % 64 == 0 (pad channels), lda/ldo/ldr % 8 == 0.  block_n in {64, 128, 160}.  splitk > 1 needs workspace fp32 [M, N].
+/* tcgen05 implicit-GEMM plan:
+ *   out[img,y,x,n] = act(alpha * sum_{tap,c} a[img, y+dy(tap), x+dx(tap), c] * wt[(img,y,) n, tap*Cin + c] + bias[n] + temb[img,n] + residual[img,y,x,n])
+ * Strides are in fp16 ELEMENTS and multiples of 8.  a: element (img,y,x,c) at img*a_simg + y*a_sy + x*a_sx + c; channels >= a_c_valid
+ * read as zero (TMA fill).  wt: row n, K index k at (img*w_simg + y*w_sy) + n*w_ld + k; k >= w_k_valid / rows >= n_rows_w read as zero;
+ * w_sy = w_simg = 0 -> shared weights (conv / linear); non-zero -> batched product (attention: y = head, img = batch).
+ * Cin = K iterated per tap (multiple of 64); taps = 1 or 9 (3x3, stride 1, zero pad 1; tap = ky*3+kx; packed [n][tap][Cin]).
+ * linear: H = 1, Nimg = 1, W = rows.  block_n in {64,128,160}.  splitk > 1 needs workspace fp32 [Nimg*H*W, N].
  * Returns a plan handle >= 0, or a negative error code. */
-int sdf_gemm_plan_create(const void* a, int lda, const void* wt, int n_rows_w, int Nimg, int H, int W, int Cin, int taps, int N,
-                         void* out, int ldo, const float* bias, const void* temb, int temb_ld, const void* residual, int ldr,
+int sdf_gemm_plan_create(const void* a, long long a_sx, long long a_sy, long long a_simg, int a_c_valid,
+                         const void* wt, long long w_ld, long long w_sy, long long w_simg, int w_k_valid, int n_rows_w,
+                         int Nimg, int H, int W, int Cin, int taps, int N,
+                         void* out, long long o_sx, long long o_sy, long long o_simg,
+                         const float* bias, const void* temb, int temb_ld,
+                         const void* residual, long long r_sx, long long r_sy, long long r_simg,
                          int act, float alpha, int splitk, float* workspace, int block_n);
 int sdf_gemm_run(int plan, void* stream);
 int sdf_gemm_plan_destroy(int plan);
+
+/* memory-bound companions (csrc/sd_ops.cu); x/y are NHWC fp16 with row strides ld* (elements, multiples of 8) */
+int sdf_groupnorm_forward(const void* x, int ldx, void* y, int ldy, int Nimg, int HW, int C, int G, const float* gamma, const float* beta,
+                          float eps, int silu_act, float* stats, void* stream);
+int sdf_groupnorm_backward(const void* x, int ldx, const void* dy, int ldd, void* dx, int ldo, int Nimg, int HW, int C, int G,
+                           const float* gamma, const float* beta, float eps, int silu_act, const float* stats, float* bstats,
+                           int accumulate, void* stream);
+int sdf_layernorm_forward(const void* x, int ldx, void* y, int ldy, int rows, int C, const float* gamma, const float* beta, float eps, void* stream);
+int sdf_softmax_rows(const void* x, void* y, long long rows, int cols, int ld, float scale, void* stream);
+int sdf_softmax_rows_backward(const void* p, const void* dp, void* ds, long long rows, int cols, int ld, float scale, void* stream);
+int sdf_geglu(const void* x, int ldx, void* y, int ldy, long long rows, int inner, void* stream);
+int sdf_upsample_nearest2(const void* x, int ldx, void* y, int ldy, int Nimg, int H, int W, int C, void* stream);
+int sdf_im2col_s2(const void* x, int ldx, void* col, int Nimg, int H, int W, int C, int Ho, int Wo, int pad_top, int pad_left, void* stream);
+int sdf_col2im_s2(const void* dcol, void* dx, int ldx, int Nimg, int H, int W, int C, int Ho, int Wo, int pad_top, int pad_left, void* stream);
+int sdf_copy2d(const void* x, int ldx, void* y, int ldy, long long rows, int C, void* stream);
+int sdf_add2d(const void* a, int lda, const void* b, int ldb, void* y, int ldy, long long rows, int C, void* stream);
+int sdf_transpose2d(const void* x, int ldx, void* y, int ldy, int batch, int rows, int C, void* stream);
+int sdf_timestep_embedding(const int* t, int B, int dim, void* out, int ldo, void* stream);
 
 #ifdef __cplusplus
 }

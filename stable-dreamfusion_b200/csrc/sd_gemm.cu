@@ -19,6 +19,7 @@
 // Roofline: tensor pipe.  FLOPs per launch = 2 * M * N * taps * Cin.
 #include "common.cuh"
 #include <cuda.h>
+#include <algorithm>
 #include <mutex>
 #include <vector>
 
@@ -32,15 +33,16 @@ constexpr int kNumThreads = 192;     // warp 0 producer, warp 1 MMA, warps 2..5 
 enum Act { kActNone = 0, kActSilu = 1, kActGelu = 2 };
 
 struct GemmArgs {
-    int M, N, Cin, taps;             // Cin = channels per tap (multiple of 64)
-    int H, W, Nimg;                  // image geometry (linear: H=1, Nimg=1, W=M)
-    int tw, th, tn;                  // tile rectangle, tw*th*tn == 128
+    int M, N, Cin, taps;             // Cin = K elements iterated per tap (multiple of 64; the TMA zero-fills past the real extent)
+    int H, W, Nimg;                  // A-side geometry: x (pixels / tokens), y (rows / heads), img (images / batch)
+    int tw, th, tn;                  // tile rectangle, tw*th*tn <= 128 rows
     int pad;                         // 1 for 3x3 (tap offsets -1..1), 0 for 1x1
     int splitk;                      // >= 1
+    int w_by, w_bimg;                // B operand indexed by the tile's y / img coordinate (batched products: attention)
     const float* bias;               // [N] fp32 or null
     const __half* temb; int temb_ld; // [Nimg, N] or null
-    const __half* residual; int ldr; // [M, N] or null
-    __half* out; int ldo;
+    const __half* residual; long long r_sx, r_sy, r_simg;   // element strides of the residual, or null
+    __half* out; long long o_sx, o_sy, o_simg;               // element strides of the output
     float* workspace;                // [M, N] fp32 when splitk > 1
     int act;
     float alpha;                     // scale applied to the accumulator before bias
@@ -70,10 +72,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3) {
     asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
                  ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-                 ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -179,9 +177,9 @@ k_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtens
                     const int dy = g.pad ? tap / 3 - 1 : 0, dx = g.pad ? tap % 3 - 1 : 0;
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     unsigned char* sa = smem + stage * L::kStageBytes;
-                    mbar_expect_tx(&full_bar[stage], L::kStageBytes);
+                    mbar_expect_tx(&full_bar[stage], (uint32_t)(g.tw * g.th * g.tn * kBlockK * 2) + L::kBBytes);
                     tma_load_4d(&map_a, &full_bar[stage], sa, cb * kBlockK, x0 + dx, y0 + dy, i0);
-                    tma_load_2d(&map_b, &full_bar[stage], sa + L::kABytes, kb * kBlockK, n0);
+                    tma_load_4d(&map_b, &full_bar[stage], sa + L::kABytes, kb * kBlockK, n0, g.w_by ? y0 : 0, g.w_bimg ? i0 : 0);
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
             }
@@ -227,8 +225,9 @@ k_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtens
             const int tx = mt % tiles_x, ty = (mt / tiles_x) % tiles_y, tz = mt / (tiles_x * tiles_y);
             const int lx = r % g.tw, ly = (r / g.tw) % g.th, li = r / (g.tw * g.th);
             const int x = tx * g.tw + lx, y = ty * g.th + ly, img = tz * g.tn + li;
-            const bool row_ok = (x < g.W) && (y < g.H) && (img < g.Nimg);
+            const bool row_ok = (r < g.tw * g.th * g.tn) && (x < g.W) && (y < g.H) && (img < g.Nimg);
             const long long m = ((long long)img * g.H + y) * g.W + x;
+            const long long o_off = (long long)img * g.o_simg + (long long)y * g.o_sy + (long long)x * g.o_sx;
             const int n0 = nt * BLOCK_N;
 
             mbar_wait(&tmem_full[acc], acc_phase);
@@ -260,7 +259,7 @@ k_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtens
                     for (int j = 0; j < 16; j++) if (full16 || n + j < g.N) f[j] += __half2float(te[j]);
                 }
                 if (g.residual) {
-                    const __half* rs = g.residual + m * g.ldr + n;
+                    const __half* rs = g.residual + (long long)img * g.r_simg + (long long)y * g.r_sy + (long long)x * g.r_sx + n;
                     if (full16) {
                         const uint4 r0 = *reinterpret_cast<const uint4*>(rs), r1 = *reinterpret_cast<const uint4*>(rs + 8);
                         const __half2* h0 = reinterpret_cast<const __half2*>(&r0);
@@ -279,7 +278,7 @@ k_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtens
 #pragma unroll
                     for (int j = 0; j < 16; j++) f[j] = act_apply(f[j], g.act);
                 }
-                __half* o = g.out + m * g.ldo + n;
+                __half* o = g.out + o_off + n;
                 if (full16) {
                     uint4 o0, o1;
                     __half2* h0 = reinterpret_cast<__half2*>(&o0);
@@ -314,12 +313,13 @@ __global__ void k_splitk_epilogue(const float* __restrict__ ws, GemmArgs g) {
     const long long total = (long long)g.M * g.N;
     if (i >= total) return;
     const long long m = i / g.N; const int n = (int)(i - m * g.N);
+    const int x = (int)(m % g.W); const int y = (int)((m / g.W) % g.H); const int img = (int)(m / ((long long)g.W * g.H));
     float v = ws[i];
     if (g.bias) v += g.bias[n];
-    if (g.temb) { const int img = (int)(m / ((long long)g.H * g.W)); v += __half2float(g.temb[(long long)img * g.temb_ld + n]); }
-    if (g.residual) v += __half2float(g.residual[m * g.ldr + n]);
+    if (g.temb) v += __half2float(g.temb[(long long)img * g.temb_ld + n]);
+    if (g.residual) v += __half2float(g.residual[(long long)img * g.r_simg + (long long)y * g.r_sy + (long long)x * g.r_sx + n]);
     v = act_apply(v, g.act);
-    g.out[m * g.ldo + n] = __float2half_rn(v);
+    g.out[(long long)img * g.o_simg + (long long)y * g.o_sy + (long long)x * g.o_sx + n] = __float2half_rn(v);
 }
 
 // ------------------------------------------------------------------ host side: plans
@@ -364,26 +364,38 @@ int launch_gemm(const GemmPlan& p, cudaStream_t st) {
 
 }  // namespace
 
-// Creates a reusable plan for D = epilogue(conv/linear(A, Wt)).  Returns a handle >= 0 or a negative error code.
-//   a        : NHWC fp16 activations, pixel (img,y,x) channel c at a[((img*H + y)*W + x)*lda + c]; reads channels [0, Cin)
-//   wt       : packed weights fp16 [n_rows_w, taps*Cin] (row n = output channel; K index = tap*Cin + c; tap = ky*3 + kx);
-//              n_rows_w >= N (extra rows, if any, must be zero or are ignored by the epilogue)
-//   taps     : 1 (1x1 conv / linear) or 9 (3x3, stride 1, zero padding 1)
-//   linear   : pass H = 1, Nimg = 1, W = M
-//   out      : fp16 [M, ldo]; bias fp32 [N] / temb fp16 [Nimg, temb_ld] / residual fp16 [M, ldr] optional (NULL)
-//   act      : 0 none, 1 SiLU, 2 GELU(erf); alpha scales the accumulator first
-//   splitk   : >1 needs workspace fp32 [M, N] (zeroed by sdf_gemm_run)
-SDF_API int sdf_gemm_plan_create(const void* a, int lda, const void* wt, int n_rows_w, int Nimg, int H, int W, int Cin, int taps, int N,
-                                 void* out, int ldo, const float* bias, const void* temb, int temb_ld, const void* residual, int ldr,
+// Creates a reusable plan for
+//   out[img, y, x, n] = act(alpha * sum_{tap, c} a[img, y + dy(tap), x + dx(tap), c] * wt[(img, y,) n, tap*Cin + c]
+//                           + bias[n] + temb[img, n] + residual[img, y, x, n])
+// All strides are in ELEMENTS (fp16) and must be multiples of 8 (16-byte TMA alignment).
+//   a        : element (img, y, x, c) at a[img*a_simg + y*a_sy + x*a_sx + c]; channels >= a_c_valid read as zero
+//   wt       : row n, K index k at wt[(img*w_simg + y*w_sy) + n*w_ld + k]; k >= w_k_valid and rows >= n_rows_w read as zero.
+//              w_sy / w_simg = 0 -> one weight matrix shared by all tiles (convolution / linear);
+//              non-zero -> batched product (attention: y = head, img = batch); then tiles never span y / img.
+//   Cin      : K elements iterated per tap, multiple of 64 (>= the real extent).  taps = 1, or 9 (3x3, stride 1, zero pad 1,
+//              tap = ky*3 + kx, packed weights [n][tap][Cin]).
+//   linear   : H = 1, Nimg = 1, W = rows.
+//   bias fp32 [N], temb fp16 [Nimg, temb_ld], residual fp16 (strides r_*) optional (NULL).
+//   act      : 0 none, 1 SiLU, 2 GELU(erf).  splitk > 1 needs workspace fp32 [Nimg*H*W, N].  block_n in {64, 128, 160}.
+// Returns a handle >= 0 or a negative error code.
+SDF_API int sdf_gemm_plan_create(const void* a, long long a_sx, long long a_sy, long long a_simg, int a_c_valid,
+                                 const void* wt, long long w_ld, long long w_sy, long long w_simg, int w_k_valid, int n_rows_w,
+                                 int Nimg, int H, int W, int Cin, int taps, int N,
+                                 void* out, long long o_sx, long long o_sy, long long o_simg,
+                                 const float* bias, const void* temb, int temb_ld,
+                                 const void* residual, long long r_sx, long long r_sy, long long r_simg,
                                  int act, float alpha, int splitk, float* workspace, int block_n) {
     SDF_CHECK_ARG(a && wt && out, "gemm_plan: null pointer");
-    SDF_CHECK_ARG(Cin > 0 && Cin % kBlockK == 0, "gemm_plan: Cin must be a positive multiple of 64 (pad channels)");
+    SDF_CHECK_ARG(Cin > 0 && Cin % kBlockK == 0, "gemm_plan: Cin must be a positive multiple of 64");
     SDF_CHECK_ARG(taps == 1 || taps == 9, "gemm_plan: taps must be 1 or 9");
-    SDF_CHECK_ARG(lda % 8 == 0 && ((uintptr_t)a & 15) == 0 && ((uintptr_t)wt & 15) == 0, "gemm_plan: operands must be 16-byte aligned (lda % 8 == 0)");
-    SDF_CHECK_ARG(ldo % 8 == 0 && ((uintptr_t)out & 15) == 0, "gemm_plan: output must be 16-byte aligned (ldo % 8 == 0)");
-    SDF_CHECK_ARG(!residual || (ldr % 8 == 0 && ((uintptr_t)residual & 15) == 0), "gemm_plan: residual must be 16-byte aligned");
+    SDF_CHECK_ARG(a_c_valid > 0 && a_c_valid <= Cin && w_k_valid > 0 && w_k_valid <= taps * Cin, "gemm_plan: bad valid extents");
+    SDF_CHECK_ARG(((uintptr_t)a & 15) == 0 && ((uintptr_t)wt & 15) == 0 && ((uintptr_t)out & 15) == 0, "gemm_plan: pointers must be 16-byte aligned");
+    SDF_CHECK_ARG(a_sx % 8 == 0 && a_sy % 8 == 0 && a_simg % 8 == 0 && w_ld % 8 == 0 && w_sy % 8 == 0 && w_simg % 8 == 0,
+                  "gemm_plan: operand strides must be multiples of 8 elements");
+    SDF_CHECK_ARG(o_sx % 8 == 0 && o_sy % 8 == 0 && o_simg % 8 == 0, "gemm_plan: output strides must be multiples of 8 elements");
+    SDF_CHECK_ARG(!residual || (((uintptr_t)residual & 15) == 0 && r_sx % 8 == 0 && r_sy % 8 == 0 && r_simg % 8 == 0), "gemm_plan: residual alignment");
     SDF_CHECK_ARG(block_n == 64 || block_n == 128 || block_n == 160, "gemm_plan: block_n must be 64, 128 or 160");
-    SDF_CHECK_ARG(n_rows_w >= N && N > 0, "gemm_plan: weight rows must cover N");
+    SDF_CHECK_ARG(N > 0 && n_rows_w > 0 && Nimg > 0 && H > 0 && W > 0, "gemm_plan: bad sizes");
     SDF_CHECK_ARG(splitk >= 1 && (splitk == 1 || workspace), "gemm_plan: split-K needs a workspace");
     PFN_encodeTiled enc = get_encode();
     if (!enc) { sdf_set_error("gemm_plan: cuTensorMapEncodeTiled unavailable (no CUDA driver?)"); return SDF_ERR_CUDA; }
@@ -391,15 +403,13 @@ SDF_API int sdf_gemm_plan_create(const void* a, int lda, const void* wt, int n_r
     GemmPlan* p = new GemmPlan();
     GemmArgs& g = p->args;
     g.M = Nimg * H * W; g.N = N; g.Cin = Cin; g.taps = taps; g.H = H; g.W = W; g.Nimg = Nimg;
-    // tile rectangle of 128 pixels: as wide as possible, then rows, then images
+    const bool batched = (w_sy != 0) || (w_simg != 0);
+    // tile rectangle of up to 128 rows: as wide as possible, then (unless batched) rows, then images
     g.tw = W >= kBlockM ? kBlockM : W;
-    if (kBlockM % g.tw != 0) {   // widths that do not divide 128 (e.g. 154 context tokens use W >= 128 path; 77 would not divide)
-        g.tw = kBlockM; }
     g.th = 1; g.tn = 1;
-    if (g.tw < kBlockM) {
-        g.th = min(H, kBlockM / g.tw);
-        if (kBlockM % (g.tw * g.th) != 0) { delete p; sdf_set_error("gemm_plan: H x W = %d x %d cannot tile 128 pixels", H, W); return SDF_ERR_ARG; }
-        g.tn = kBlockM / (g.tw * g.th);
+    if (!batched && g.tw < kBlockM) {
+        g.th = std::max(1, std::min(H, kBlockM / g.tw));
+        g.tn = std::max(1, std::min(Nimg, kBlockM / (g.tw * g.th)));
     }
     g.pad = taps == 9 ? 1 : 0;
     {   // no split may own an empty K range: shrink splitk to ceil(kb / ceil(kb / splitk))
@@ -408,15 +418,18 @@ SDF_API int sdf_gemm_plan_create(const void* a, int lda, const void* wt, int n_r
         const int per = (kb_total + splitk - 1) / splitk;
         splitk = (kb_total + per - 1) / per;
     }
-    g.splitk = splitk; g.bias = bias; g.temb = (const __half*)temb; g.temb_ld = temb_ld;
-    g.residual = (const __half*)residual; g.ldr = ldr; g.out = (__half*)out; g.ldo = ldo; g.workspace = workspace;
+    g.splitk = splitk; g.w_by = w_sy != 0; g.w_bimg = w_simg != 0;
+    g.bias = bias; g.temb = (const __half*)temb; g.temb_ld = temb_ld;
+    g.residual = (const __half*)residual; g.r_sx = r_sx; g.r_sy = r_sy; g.r_simg = r_simg;
+    g.out = (__half*)out; g.o_sx = o_sx; g.o_sy = o_sy; g.o_simg = o_simg; g.workspace = workspace;
     g.act = act; g.alpha = alpha;
     p->block_n = block_n;
 
-    // A: 4-D map (C, W, H, Nimg), 128B swizzle, zero OOB fill
-    {
-        cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)Nimg};
-        cuuint64_t strides[3] = {(cuuint64_t)lda * 2, (cuuint64_t)W * lda * 2, (cuuint64_t)H * W * lda * 2};
+    auto stride_or = [](long long s, long long fallback) { return (cuuint64_t)((s != 0 ? s : fallback) * 2); };
+    {   // A: 4-D map (c, x, y, img), 128B swizzle, zero OOB fill
+        cuuint64_t dims[4] = {(cuuint64_t)a_c_valid, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)Nimg};
+        const long long fx = a_sx, fy = a_sy ? a_sy : a_sx * W, fi = a_simg ? a_simg : fy * H;
+        cuuint64_t strides[3] = {(cuuint64_t)fx * 2, (cuuint64_t)fy * 2, (cuuint64_t)fi * 2};
         cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)g.tw, (cuuint32_t)g.th, (cuuint32_t)g.tn};
         cuuint32_t estr[4] = {1, 1, 1, 1};
         CUresult r = enc(&p->map_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(a), dims, strides, box, estr,
@@ -424,20 +437,20 @@ SDF_API int sdf_gemm_plan_create(const void* a, int lda, const void* wt, int n_r
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { delete p; sdf_set_error("gemm_plan: cuTensorMapEncodeTiled(A) failed (%d)", (int)r); return SDF_ERR_CUDA; }
     }
-    {
-        const cuuint64_t Ktot = (cuuint64_t)taps * Cin;
-        cuuint64_t dims[2] = {Ktot, (cuuint64_t)n_rows_w};
-        cuuint64_t strides[1] = {Ktot * 2};
-        cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)block_n};
-        cuuint32_t estr[2] = {1, 1};
-        CUresult r = enc(&p->map_b, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(wt), dims, strides, box, estr,
+    {   // B: 4-D map (k, n, y, img); the last two dims have extent 1 unless the product is batched
+        cuuint64_t dims[4] = {(cuuint64_t)w_k_valid, (cuuint64_t)n_rows_w, (cuuint64_t)(g.w_by ? H : 1), (cuuint64_t)(g.w_bimg ? Nimg : 1)};
+        const long long rows_bytes_el = w_ld * (long long)n_rows_w;
+        cuuint64_t strides[3] = {(cuuint64_t)w_ld * 2, stride_or(w_sy, rows_bytes_el), stride_or(w_simg, rows_bytes_el * (g.w_by ? H : 1))};
+        cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)block_n, 1, 1};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult r = enc(&p->map_b, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(wt), dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { delete p; sdf_set_error("gemm_plan: cuTensorMapEncodeTiled(B) failed (%d)", (int)r); return SDF_ERR_CUDA; }
     }
     const int tiles_x = (W + g.tw - 1) / g.tw, tiles_y = (H + g.th - 1) / g.th, tiles_i = (Nimg + g.tn - 1) / g.tn;
-    const int work = tiles_x * tiles_y * tiles_i * ((N + block_n - 1) / block_n) * splitk;
-    p->grid = work < kNumSMs ? work : kNumSMs;
+    const long long work = (long long)tiles_x * tiles_y * tiles_i * ((N + block_n - 1) / block_n) * splitk;
+    p->grid = work < kNumSMs ? (int)work : kNumSMs;
     std::lock_guard<std::mutex> lk(g_plan_mu);
     g_plans.push_back(p);
     return (int)g_plans.size() - 1;

@@ -18,7 +18,7 @@ HEADER_PATH = os.path.join(_REPO_ROOT, "include", "sdf_b200.h")
 
 _SCALARS = {
     "int": C.c_int, "uint32_t": C.c_uint32, "int32_t": C.c_int32, "float": C.c_float, "uint64_t": C.c_uint64,
-    "int64_t": C.c_int64, "size_t": C.c_size_t, "double": C.c_double,
+    "int64_t": C.c_int64, "long long": C.c_longlong, "size_t": C.c_size_t, "double": C.c_double,
 }
 
 

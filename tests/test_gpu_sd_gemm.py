@@ -1,52 +1,38 @@
 """GPU: the tcgen05 implicit-GEMM kernel (csrc/sd_gemm.cu) against an fp32 PyTorch reference of the same op
-(F.conv2d / F.linear on the same fp16-rounded operands).  Tolerance: fp16 inputs, fp32 accumulate, fp16 output ->
+(F.conv2d / F.linear / einsum on the same fp16-rounded operands).  Tolerance: fp16 inputs, fp32 accumulate, fp16 output ->
 rtol 2e-3 + atol 2e-3 * sqrt(K/64) on O(1) data."""
 import math
 
-import numpy as np
 import pytest
 import torch
 import torch.nn.functional as F
 
-from sdf_b200 import _lib
+from sdf_b200 import gemm
 
 pytestmark = pytest.mark.gpu
 
 
-def run_plan(a_nhwc, w_oihw, bias=None, temb=None, residual=None, act=0, alpha=1.0, splitk=1, block_n=128, n_valid=None, lda_extra=0):
-    """a_nhwc [Nimg,H,W,Cin] fp16 cuda; w [Cout,Cin,kh,kw] fp16 -> out [Nimg,H,W,Cout] fp16 via the C ABI"""
+def run_conv(a_nhwc, w_oihw, bias=None, temb=None, residual=None, act=None, alpha=1.0, splitk=1, block_n=128, lda_extra=0):
     dev = a_nhwc.device
     Nimg, H, W, Cin = a_nhwc.shape
     Cout, _, kh, kw = w_oihw.shape
-    taps = kh * kw
     if lda_extra:
-        buf = torch.zeros(Nimg, H, W, Cin + lda_extra, device=dev, dtype=torch.float16)
+        buf = torch.full((Nimg, H, W, Cin + lda_extra), 7.0, device=dev, dtype=torch.float16)   # junk beyond c_valid must be ignored
         buf[..., :Cin] = a_nhwc
-        a_used, lda = buf, Cin + lda_extra
+        a_used = buf
     else:
-        a_used, lda = a_nhwc.contiguous(), Cin
-    rows = ((Cout + block_n - 1) // block_n) * block_n
-    wt = torch.zeros(rows, taps * Cin, device=dev, dtype=torch.float16)
-    wt[:Cout] = w_oihw.permute(0, 2, 3, 1).reshape(Cout, taps * Cin)
-    N = Cout if n_valid is None else n_valid
-    ldo = ((N + 7) // 8) * 8
-    out = torch.full((Nimg * H * W, ldo), float("nan"), device=dev, dtype=torch.float16)
-    ws = torch.empty(Nimg * H * W, N, device=dev, dtype=torch.float32) if splitk > 1 else None
-    res_t = None
-    if residual is not None:
-        res_t = residual.reshape(Nimg * H * W, -1).contiguous()
-    plan = _lib.lib().cdll.sdf_gemm_plan_create(
-        _lib.ptr(a_used), lda, _lib.ptr(wt), rows, Nimg, H, W, Cin, taps, N, _lib.ptr(out), ldo, _lib.ptr(bias),
-        _lib.ptr(temb), 0 if temb is None else temb.shape[1], _lib.ptr(res_t), 0 if res_t is None else res_t.shape[1],
-        act, alpha, splitk, _lib.ptr(ws), block_n)
-    assert plan >= 0, _lib.lib().last_error()
-    _lib.call("sdf_gemm_run", plan, _lib.stream())
+        a_used = a_nhwc.contiguous()
+    wt = gemm.pack_conv_weight(w_oihw)
+    ldo = ((Cout + 7) // 8) * 8
+    out = torch.full((Nimg, H, W, ldo), float("nan"), device=dev, dtype=torch.float16)
+    plan = gemm.conv_plan(a_used, Cin, wt, Cout, out, taps=kh * kw, bias=bias, temb=temb, residual=residual, act=act, alpha=alpha,
+                          splitk=splitk, block_n=block_n)
+    plan.run()
     torch.cuda.synchronize()
-    _lib.call("sdf_gemm_plan_destroy", plan)
-    return out[:, :N].reshape(Nimg, H, W, N)
+    return out[..., :Cout]
 
 
-def ref_conv(a_nhwc, w, bias=None, temb=None, residual=None, act=0, alpha=1.0):
+def ref_conv(a_nhwc, w, bias=None, temb=None, residual=None, act=None, alpha=1.0):
     x = a_nhwc.float().permute(0, 3, 1, 2)
     y = F.conv2d(x, w.float(), None, padding=w.shape[-1] // 2) * alpha
     if bias is not None:
@@ -56,9 +42,9 @@ def ref_conv(a_nhwc, w, bias=None, temb=None, residual=None, act=0, alpha=1.0):
     y = y.permute(0, 2, 3, 1)
     if residual is not None:
         y = y + residual.float()
-    if act == 1:
+    if act == "silu":
         y = F.silu(y)
-    elif act == 2:
+    elif act == "gelu":
         y = F.gelu(y)
     return y
 
@@ -77,23 +63,29 @@ def rnd(*shape, device, scale=1.0, seed=0):
 
 
 @pytest.mark.parametrize("M,K,N,bn", [(8192, 320, 320, 160), (154, 768, 320, 160), (2, 320, 1280, 160), (512, 1280, 1280, 128),
-                                      (4096, 64, 64, 64), (300, 128, 72, 64)])
+                                      (4096, 64, 64, 64), (300, 128, 72, 64), (77, 40, 24, 64)])
 def test_linear(device, M, K, N, bn):
     a = rnd(1, 1, M, K, device=device, seed=1)
     w = rnd(N, K, 1, 1, device=device, scale=1 / math.sqrt(K), seed=2)
     bias = rnd(N, device=device, seed=3).float()
-    out = run_plan(a, w, bias=bias, block_n=bn)
+    out = run_conv(a, w, bias=bias, block_n=bn)
     check(out, ref_conv(a, w, bias=bias), K)
 
 
 @pytest.mark.parametrize("Nimg,H,W,Cin,Cout,bn", [(2, 64, 64, 320, 320, 160), (2, 32, 32, 640, 640, 160), (2, 16, 16, 128, 256, 128),
-                                                   (2, 8, 8, 256, 320, 160), (1, 128, 256, 64, 128, 128), (3, 8, 8, 64, 64, 64)])
+                                                   (2, 8, 8, 256, 320, 160), (1, 128, 256, 64, 128, 128), (3, 8, 8, 64, 64, 64),
+                                                   (1, 8, 8, 64, 64, 64), (2, 64, 64, 4, 320, 160), (1, 32, 32, 320, 4, 64)])
 def test_conv3x3(device, Nimg, H, W, Cin, Cout, bn):
-    a = rnd(Nimg, H, W, Cin, device=device, seed=4)
+    a = rnd(Nimg, H, W, max(Cin, 8), device=device, seed=4)
+    a[..., Cin:] = 3.0            # channels beyond c_valid exist in memory (alignment padding) but must read as zero
     w = rnd(Cout, Cin, 3, 3, device=device, scale=1 / math.sqrt(9 * Cin), seed=5)
     bias = rnd(Cout, device=device, seed=6).float()
-    out = run_plan(a, w, bias=bias, block_n=bn)
-    check(out, ref_conv(a, w, bias=bias), 9 * Cin)
+    wt = gemm.pack_conv_weight(w)
+    ldo = ((Cout + 7) // 8) * 8
+    out = torch.full((Nimg, H, W, ldo), float("nan"), device=device, dtype=torch.float16)
+    gemm.conv_plan(a, Cin, wt, Cout, out, taps=9, bias=bias, block_n=bn).run()
+    torch.cuda.synchronize()
+    check(out[..., :Cout], ref_conv(a[..., :Cin], w, bias=bias), 9 * Cin)
 
 
 def test_epilogue_variants_and_strided_input(device):
@@ -103,21 +95,56 @@ def test_epilogue_variants_and_strided_input(device):
     bias = rnd(Cout, device=device, seed=9).float()
     temb = rnd(Nimg, Cout, device=device, seed=10)
     res = rnd(Nimg, H, W, Cout, device=device, seed=11)
-    for act in (0, 1, 2):
-        out = run_plan(a, w, bias=bias, temb=temb, residual=res, act=act, alpha=0.5, block_n=160, lda_extra=64)
+    for act in (None, "silu", "gelu"):
+        out = run_conv(a, w, bias=bias, temb=temb, residual=res, act=act, alpha=0.5, block_n=160, lda_extra=64)
         check(out, ref_conv(a, w, bias=bias, temb=temb, residual=res, act=act, alpha=0.5), 9 * Cin)
-    # 1x1 conv, output-channel tail (N = 4 valid of a padded weight tile), no bias
     w1 = rnd(4, Cin, 1, 1, device=device, scale=1 / math.sqrt(Cin), seed=12)
-    out = run_plan(a, w1, block_n=64)
+    out = run_conv(a, w1, block_n=64)
     check(out, ref_conv(a, w1), Cin)
 
 
-@pytest.mark.parametrize("splitk", [2, 5, 16])
+@pytest.mark.parametrize("splitk", [2, 5, 16, 64])
 def test_splitk(device, splitk):
     Nimg, H, W, Cin, Cout = 2, 8, 8, 1280, 1280
     a = rnd(Nimg, H, W, Cin, device=device, seed=13)
     w = rnd(Cout, Cin, 3, 3, device=device, scale=1 / math.sqrt(9 * Cin), seed=14)
     bias = rnd(Cout, device=device, seed=15).float()
     res = rnd(Nimg, H, W, Cout, device=device, seed=16)
-    out = run_plan(a, w, bias=bias, residual=res, act=1, splitk=splitk, block_n=160)
-    check(out, ref_conv(a, w, bias=bias, residual=res, act=1), 9 * Cin)
+    out = run_conv(a, w, bias=bias, residual=res, act="silu", splitk=splitk, block_n=160)
+    check(out, ref_conv(a, w, bias=bias, residual=res, act="silu"), 9 * Cin)
+
+
+@pytest.mark.parametrize("B,heads,n,nkv,d", [(2, 8, 1024, 1024, 80), (2, 8, 256, 77, 160), (2, 8, 4096, 77, 40), (2, 8, 64, 64, 160), (1, 1, 4096, 4096, 512)])
+def test_batched_attention_products(device, B, heads, n, nkv, d):
+    """S = scale * Q K^T per (batch, head) straight from [tokens, heads*d] projections (K tail by TMA zero fill), then
+    O = P V with V^T as the weight operand, written back head-interleaved."""
+    C = heads * d
+    q = rnd(B, n, C, device=device, seed=20)
+    k = rnd(B, nkv, C, device=device, seed=21)
+    v = rnd(B, nkv, C, device=device, seed=22)
+    scale = d ** -0.5
+    ld_s = ((nkv + 63) // 64) * 64
+    S = torch.zeros(B, heads, n, ld_s, device=device, dtype=torch.float16)
+    Kit = ((d + 63) // 64) * 64
+    p1 = gemm.GemmPlan(q, (C, d, n * C), d, k, (C, d, nkv * C), d, nkv, B, heads, n, Kit, 1, nkv, S, (ld_s, n * ld_s, heads * n * ld_s),
+                       alpha=scale, block_n=64 if nkv <= 64 else 128)
+    p1.run()
+    torch.cuda.synchronize()
+    qh = q.float().view(B, n, heads, d).permute(0, 2, 1, 3)
+    kh = k.float().view(B, nkv, heads, d).permute(0, 2, 1, 3)
+    vh = v.float().view(B, nkv, heads, d).permute(0, 2, 1, 3)
+    S_ref = torch.einsum("bhid,bhjd->bhij", qh, kh) * scale
+    check(S[..., :nkv], S_ref, d)
+    assert (S[..., nkv:] == 0).all()
+    P = torch.softmax(S_ref, dim=-1).half()
+    Pbuf = torch.zeros(B, heads, n, ld_s, device=device, dtype=torch.float16)
+    Pbuf[..., :nkv] = P
+    vt = torch.zeros(B, C, ld_s, device=device, dtype=torch.float16)          # V^T [b][h*d + j][kv]
+    vt[..., :nkv] = v.permute(0, 2, 1)
+    O = torch.full((B, n, C), float("nan"), device=device, dtype=torch.float16)
+    p2 = gemm.GemmPlan(Pbuf, (ld_s, n * ld_s, heads * n * ld_s), nkv, vt, (ld_s, d * ld_s, C * ld_s), nkv, d, B, heads, n, ld_s, 1, d,
+                       O, (C, d, n * C), block_n=64 if d <= 64 else (160 if d % 160 == 0 else 128))
+    p2.run()
+    torch.cuda.synchronize()
+    O_ref = torch.einsum("bhij,bhjd->bhid", P.float(), vh).permute(0, 2, 1, 3).reshape(B, n, C)
+    check(O, O_ref, nkv)

@@ -5,7 +5,7 @@ import os
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "stable-dreamfusion_b200"))
 import torch
-from sdf_b200 import _lib
+from sdf_b200 import _lib, gemm
 
 dev = torch.device("cuda:0")
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -13,14 +13,12 @@ flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
 def bench(name, Nimg, H, W, Cin, Cout, taps, bn, splitk=1, reps=10):
     a = torch.randn(Nimg, H, W, Cin, device=dev).half()
-    rows = ((Cout + bn - 1) // bn) * bn
-    wt = torch.randn(rows, taps * Cin, device=dev).half() / math.sqrt(taps * Cin)
-    out = torch.empty(Nimg * H * W, Cout, device=dev, dtype=torch.float16)
+    w = torch.randn(Cout, Cin, 3 if taps == 9 else 1, 3 if taps == 9 else 1, device=dev) / math.sqrt(taps * Cin)
+    wt = gemm.pack_conv_weight(w)
+    out = torch.empty(Nimg, H, W, Cout, device=dev, dtype=torch.float16)
     bias = torch.randn(Cout, device=dev)
-    ws = torch.empty(Nimg * H * W, Cout, device=dev) if splitk > 1 else None
-    plan = _lib.lib().cdll.sdf_gemm_plan_create(_lib.ptr(a), Cin, _lib.ptr(wt), rows, Nimg, H, W, Cin, taps, Cout, _lib.ptr(out), Cout,
-                                                _lib.ptr(bias), None, 0, None, 0, 0, 1.0, splitk, _lib.ptr(ws), bn)
-    assert plan >= 0, _lib.lib().last_error()
+    P = gemm.conv_plan(a, Cin, wt, Cout, out, taps=taps, bias=bias, splitk=splitk, block_n=bn)
+    plan = P.handle
     st = _lib.stream()
     for _ in range(3):
         _lib.call("sdf_gemm_run", plan, st)
@@ -37,7 +35,7 @@ def bench(name, Nimg, H, W, Cin, Cout, taps, bn, splitk=1, reps=10):
     ms = sorted(ts)[len(ts) // 2]
     fl = 2.0 * Nimg * H * W * Cout * taps * Cin
     print(f"{name:34s} M={Nimg*H*W:7d} N={Cout:5d} K={taps*Cin:6d} bn={bn:3d} sk={splitk:2d}  {ms*1e3:9.1f} us  {fl/ms/1e9:8.1f} TFLOP/s", flush=True)
-    _lib.call("sdf_gemm_plan_destroy", plan)
+    del P
 
 
 if __name__ == "__main__":
