@@ -181,6 +181,16 @@ int sdf_add2d(const void* a, int lda, const void* b, int ldb, void* y, int ldy, 
 int sdf_transpose2d(const void* x, int ldx, void* y, int ldy, int batch, int rows, int C, void* stream);
 int sdf_timestep_embedding(const int* t, int B, int dim, void* out, int ldo, void* stream);
 
+/* SDS glue (guidance/sd_utils.py:86-163): bilinear 64->512 resize (+ its adjoint), posterior sample + add_noise into the UNet input,
+ * classifier-free guidance + w(t)(eps_hat - eps) + loss value + gradient wrt the VAE moments */
+int sdf_bilinear_forward(const float* src, int B, int Cc, int h, int w, void* dst, int ldd, int H, int W, float a, float b, void* stream);
+int sdf_bilinear_backward(const void* ddst, int ldd, int H, int W, float* dsrc, int B, int Cc, int h, int w, float a, void* stream);
+int sdf_sds_prepare(const void* moments, int ldm, const float* latents_in, const float* eps_post, const float* noise, const int* t,
+                    const float* alphas_cumprod, int Bimg, int HW, float* latents, void* x_in, int ldx, float vae_scale, void* stream);
+int sdf_sds_grad(const void* eps, int lde, const float* noise, const int* t, const float* alphas_cumprod, int Bimg, int HW,
+                 float guidance_scale, float grad_scale, const void* moments, int ldm, const float* eps_post, float vae_scale,
+                 float* grad, void* d_moments, float* loss, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -247,3 +247,609 @@ class RunList:
                 fn()
         self.graph = g
         return self
+
+
+# =============================================================================================== UNet
+UNET_SD15 = dict(in_channels=4, model_channels=320, out_channels=4, num_res_blocks=2, attention_resolutions=(4, 2, 1),
+                 channel_mult=(1, 2, 4, 4), num_heads=8, context_dim=768)
+
+
+def unet_structure(cfg):
+    """Block lists of the CompVis UNetModel constructor (openaimodel.py:530-712): every entry is
+    ('conv_in', cin, cout) | ('res', cin, cout) | ('attn', ch) | ('down', ch) | ('up', ch)."""
+    mc, mult, nrb, ar = cfg['model_channels'], cfg['channel_mult'], cfg['num_res_blocks'], cfg['attention_resolutions']
+    inp = [[('conv_in', cfg['in_channels'], mc)]]
+    chans = [mc]
+    ch, ds = mc, 1
+    for level, m in enumerate(mult):
+        for _ in range(nrb):
+            layers = [('res', ch, m * mc)]
+            ch = m * mc
+            if ds in ar:
+                layers.append(('attn', ch))
+            inp.append(layers)
+            chans.append(ch)
+        if level != len(mult) - 1:
+            inp.append([('down', ch)])
+            chans.append(ch)
+            ds *= 2
+    mid = [('res', ch, ch), ('attn', ch), ('res', ch, ch)]
+    out = []
+    for level, m in list(enumerate(mult))[::-1]:
+        for i in range(nrb + 1):
+            ich = chans.pop()
+            layers = [('res', ch + ich, mc * m)]
+            skip = (ch, ich)
+            ch = mc * m
+            if ds in ar:
+                layers.append(('attn', ch))
+            if level and i == nrb:
+                layers.append(('up', ch))
+                ds //= 2
+            out.append((layers, skip))
+    return inp, mid, out
+
+
+class UNetEngine:
+    """Forward pass of the SD-1.5-shaped UNet for a fixed (batch, latent size, context length).
+
+    inputs  : self.x_in  [B, hw, hw, 8] fp16 (channels 0..3 = noisy latents), self.t_in int32 [B], self.ctx [1,1,B*ctx_len,ctx_dim] fp16
+    output  : self.eps   [B, hw, hw, 8] fp16 (channels 0..3 = predicted noise)
+    """
+
+    def __init__(self, sd, device, cfg=UNET_SD15, batch=2, hw=64, ctx_len=77):
+        self.cfg, self.B, self.hw, self.ctx_len = cfg, batch, hw, ctx_len
+        self.dev = device
+        b = self.b = Builder(device)
+        self.sd = sd
+        self._wcache = {}
+        self._sbuf = {}
+        B, mc = batch, cfg['model_channels']
+        ted = 4 * mc
+        heads = cfg['num_heads']
+        self.heads = heads
+        inp, mid, out = unet_structure(cfg)
+
+        self.x_in = b.buf(B, hw, hw, 8, zero=True)
+        self.t_in = torch.zeros(B, dtype=torch.int32, device=device)
+        self.ctx = b.buf(1, 1, B * ctx_len, cfg['context_dim'], zero=True)
+        ctxv = View(self.ctx)
+
+        # ---- time embedding: sinusoid -> Linear+SiLU -> Linear (+ the SiLU that opens every emb_layers)
+        t0 = b.buf(1, 1, B, mc)
+        b.add('t_emb', lambda: _lib.call('sdf_timestep_embedding', _lib.ptr(self.t_in), B, mc, t0.data_ptr(), mc, _lib.stream()))
+        e1 = b.buf(1, 1, B, ted)
+        b.gemm('time_embed.0', View(t0), mc, self._lin('time_embed.0.weight'), ted, View(e1), bias=self._f32('time_embed.0.bias'), act='silu')
+        emb = b.buf(1, 1, B, ted)
+        b.gemm('time_embed.2', View(e1), ted, self._lin('time_embed.2.weight'), ted, View(emb), bias=self._f32('time_embed.2.bias'), act='silu')
+        # all ResBlock emb_layers as ONE product
+        res_prefixes = []
+        for i, layers in enumerate(inp):
+            for j, l in enumerate(layers):
+                if l[0] == 'res':
+                    res_prefixes.append((f'input_blocks.{i}.{j}', l[2]))
+        for j, l in enumerate(mid):
+            if l[0] == 'res':
+                res_prefixes.append((f'middle_block.{j}', l[2]))
+        for i, (layers, _) in enumerate(out):
+            for j, l in enumerate(layers):
+                if l[0] == 'res':
+                    res_prefixes.append((f'output_blocks.{i}.{j}', l[2]))
+        w_all = torch.cat([sd[p + '.emb_layers.1.weight'] for p, _ in res_prefixes], 0)
+        b_all = torch.cat([sd[p + '.emb_layers.1.bias'] for p, _ in res_prefixes], 0)
+        sumc = w_all.shape[0]
+        self.temb_all = b.buf(1, 1, B, sumc)
+        b.gemm('emb_layers(all)', View(emb), ted, _pack_linear(w_all, device), sumc, View(self.temb_all), bias=_f32(b_all, device))
+        self.temb_off = {}
+        off = 0
+        for p, c in res_prefixes:
+            self.temb_off[p] = off
+            off += c
+
+        # ---- buffers for the skip concatenations: output block k reads cat_k = [h (ch) | skip (ich)]
+        # spatial size of every input block's output
+        sizes = []
+        s = hw
+        for layers in inp:
+            if layers[0][0] == 'down':
+                s //= 2
+            sizes.append(s)
+        cats = []
+        for k, (layers, (chh, ich)) in enumerate(out):
+            j = len(inp) - 1 - k
+            cats.append(b.buf(B, sizes[j], sizes[j], chh + ich))
+        self.cats = cats
+
+        def skip_view(j):      # where input block j must leave its output
+            k = len(inp) - 1 - j
+            chh, ich = out[k][1]
+            return View(cats[k], chh, ich)
+
+        # ---- down path
+        h = None
+        for i, layers in enumerate(inp):
+            dst = skip_view(i)
+            for j, l in enumerate(layers):
+                last = j == len(layers) - 1
+                p = f'input_blocks.{i}.{j}'
+                if l[0] == 'conv_in':
+                    w = pack_conv_weight(sd[p + '.weight'].to(device))
+                    b.gemm(p, View(self.x_in), l[1], w, l[2], dst, taps=9, bias=self._f32(p + '.bias'))
+                    h = dst
+                elif l[0] == 'res':
+                    o = dst if last else View(b.buf(B, h.H, h.W, l[2]))
+                    self._resblock(p, h, l[2], o)
+                    h = o
+                elif l[0] == 'attn':
+                    o = dst if last else View(b.buf(B, h.H, h.W, l[1]))
+                    self._transformer(p, h, o, ctxv)
+                    h = o
+                elif l[0] == 'down':
+                    self._down(p, h, dst)
+                    h = dst
+        # ---- middle
+        dst0 = View(cats[0], 0, out[0][1][0])
+        m0 = View(b.buf(B, h.H, h.W, mid[0][2]))
+        self._resblock('middle_block.0', h, mid[0][2], m0)
+        m1 = View(b.buf(B, h.H, h.W, mid[1][1]))
+        self._transformer('middle_block.1', m0, m1, ctxv)
+        self._resblock('middle_block.2', m1, mid[2][2], dst0)
+        # ---- up path
+        final = None
+        for k, (layers, (chh, ich)) in enumerate(out):
+            h = View(cats[k])
+            last_block = k == len(out) - 1
+            nxt = None if last_block else View(cats[k + 1], 0, out[k + 1][1][0])
+            for j, l in enumerate(layers):
+                last = j == len(layers) - 1
+                p = f'output_blocks.{k}.{j}'
+                if last and not last_block:
+                    o = nxt
+                elif l[0] == 'up':
+                    o = View(b.buf(B, 2 * h.H, 2 * h.W, l[1]))
+                else:
+                    o = View(b.buf(B, h.H, h.W, l[2] if l[0] == 'res' else l[1]))
+                if l[0] == 'res':
+                    self._resblock(p, h, l[2], o)
+                elif l[0] == 'attn':
+                    self._transformer(p, h, o, ctxv)
+                else:
+                    self._up(p, h, o)
+                h = o
+            final = h
+        # ---- out: GroupNorm32 + SiLU + conv3x3
+        tfin = View(b.buf(B, final.H, final.W, final.C))
+        b.groupnorm('out.0', final, tfin, self._f32('out.0.weight'), self._f32('out.0.bias'), 1e-5, True)
+        self.eps = b.buf(B, hw, hw, 8, zero=True)
+        b.gemm('out.2', tfin, final.C, pack_conv_weight(sd['out.2.weight'].to(device)), cfg['out_channels'], View(self.eps), taps=9,
+               bias=self._f32('out.2.bias'))
+        self.runlist = RunList(b.ops)
+        self.flops = b.flops
+        self.sd = None          # fp32 originals are no longer needed
+        self._wcache = None
+
+    # ---------------------------------------------------------------- helpers
+    def _f32(self, key):
+        return _f32(self.sd[key], self.dev)
+
+    def _lin(self, key, rows_multiple=1):
+        return _pack_linear(self.sd[key], self.dev, rows_multiple)
+
+    def _conv1x1_w(self, key):
+        w = self.sd[key]
+        return _pack_linear(w.reshape(w.shape[0], -1), self.dev)
+
+    def _resblock(self, p, x, cout, out):
+        b, sd, dev, B = self.b, self.sd, self.dev, self.B
+        cin = x.C
+        t1 = View(b.buf(B, x.H, x.W, cin))
+        b.groupnorm(p + '.in_layers.0', x, t1, self._f32(p + '.in_layers.0.weight'), self._f32(p + '.in_layers.0.bias'), 1e-5, True)
+        h1 = View(b.buf(B, x.H, x.W, cout))
+        temb = View(self.temb_all, self.temb_off[p], cout)
+        b.gemm(p + '.in_layers.2', t1, cin, pack_conv_weight(sd[p + '.in_layers.2.weight'].to(dev)), cout, h1, taps=9,
+               bias=self._f32(p + '.in_layers.2.bias'), temb=temb, temb_ld=self.temb_all.shape[-1])
+        t2 = View(b.buf(B, x.H, x.W, cout))
+        b.groupnorm(p + '.out_layers.0', h1, t2, self._f32(p + '.out_layers.0.weight'), self._f32(p + '.out_layers.0.bias'), 1e-5, True)
+        if cin != cout:
+            xs = View(b.buf(B, x.H, x.W, cout))
+            b.gemm(p + '.skip_connection', x, cin, self._conv1x1_w(p + '.skip_connection.weight'), cout, xs, bias=self._f32(p + '.skip_connection.bias'))
+        else:
+            xs = x
+        b.gemm(p + '.out_layers.3', t2, cout, pack_conv_weight(sd[p + '.out_layers.3.weight'].to(dev)), cout, out, taps=9,
+               bias=self._f32(p + '.out_layers.3.bias'), residual=xs)
+
+    def _scores(self, n, nkv_pad):
+        key = (n, nkv_pad)
+        if key not in self._sbuf:
+            self._sbuf[key] = torch.zeros(self.B, self.heads, n, nkv_pad, device=self.dev, dtype=torch.float16)
+        return self._sbuf[key]
+
+    def _attention(self, p, ln, kv_src, kv_rows_per_batch, kv_dim, u, C):
+        """u += to_out(softmax(q k^T / sqrt(d)) v);  q from ln [B*n, C]; k, v from kv_src ([B*kv_rows, kv_dim] View)."""
+        b, B, heads, dev = self.b, self.B, self.heads, self.dev
+        n = ln.H * ln.W if ln.Nimg == B else ln.rows // B
+        d = C // heads
+        nkv = kv_rows_per_batch
+        nkv_pad = _r(nkv, 64)
+        q = View(b.buf(1, 1, B * n, C))
+        k = View(b.buf(1, 1, B * nkv, C))
+        lnf = View(ln.t.view(1, 1, B * n, ln.ld), ln.off, ln.C)
+        kvf = View(kv_src.t.view(1, 1, B * nkv, kv_src.ld), kv_src.off, kv_src.C)
+        b.gemm(p + '.to_q', lnf, C, self._lin(p + '.to_q.weight'), C, q)
+        b.gemm(p + '.to_k', kvf, kv_dim, self._lin(p + '.to_k.weight'), C, k)
+        # V^T[b] = Wv . X_b^T : the weight matrix is the A operand, the tokens are the "weights"
+        wv = self._lin(p + '.to_v.weight')                                # [C, kv_dim_iter]
+        vt = torch.zeros(B, C, nkv_pad, device=dev, dtype=torch.float16)
+        for bi in range(B):
+            rows_ptr = _PtrTensor(View(kvf.t, kvf.off, kvf.C))
+            a_holder = _PtrTensor(View(wv.view(1, 1, C, wv.shape[1])))
+            tok = _OffsetPtr(kvf, bi * nkv)
+            outp = _OffsetRaw(vt, bi * C * nkv_pad)
+            b.gemm(f'{p}.to_v^T[{bi}]', a_holder, kv_dim, tok, nkv, outp, geom=(1, 1, C), a_strides=(wv.shape[1], C * wv.shape[1], C * wv.shape[1]),
+                   o_strides=(nkv_pad, C * nkv_pad, C * nkv_pad), w_strides=(kvf.ld, 0, 0), w_k_valid=kv_dim, n_rows_w=nkv, cin_iter=_r(kv_dim, 64),
+                   block_n=64 if nkv <= 64 else 128)
+        S = self._scores(n, nkv_pad)
+        b.gemm(p + '.qk', q, d, k, nkv, S, geom=(B, heads, n), a_strides=(C, d, n * C), o_strides=(nkv_pad, n * nkv_pad, heads * n * nkv_pad),
+               w_strides=(C, d, nkv * C), w_k_valid=d, n_rows_w=nkv, cin_iter=_r(d, 64), alpha=d ** -0.5, block_n=64 if nkv <= 64 else 128)
+        b.softmax(p + '.softmax', S, B * heads * n, nkv, nkv_pad)
+        o = View(b.buf(1, 1, B * n, C))
+        b.gemm(p + '.pv', S, nkv, vt, d, o, geom=(B, heads, n), a_strides=(nkv_pad, n * nkv_pad, heads * n * nkv_pad), o_strides=(C, d, n * C),
+               w_strides=(nkv_pad, d * nkv_pad, C * nkv_pad), w_k_valid=nkv, n_rows_w=d, cin_iter=nkv_pad,
+               block_n=64 if d <= 64 else (160 if d % 160 == 0 else 128))
+        uf = View(u.t.view(1, 1, B * n, u.ld), u.off, u.C)
+        b.gemm(p + '.to_out', o, C, self._lin(p + '.to_out.0.weight'), C, uf, bias=self._f32(p + '.to_out.0.bias'), residual=uf)
+
+    def _transformer(self, p, x, out, ctxv):
+        b, B, dev = self.b, self.B, self.dev
+        C = x.C
+        t = View(b.buf(B, x.H, x.W, C))
+        b.groupnorm(p + '.norm', x, t, self._f32(p + '.norm.weight'), self._f32(p + '.norm.bias'), 1e-6, False)
+        u = View(b.buf(B, x.H, x.W, C))
+        b.gemm(p + '.proj_in', t, C, self._conv1x1_w(p + '.proj_in.weight'), C, u, bias=self._f32(p + '.proj_in.bias'))
+        ln = View(b.buf(B, x.H, x.W, C))
+        tb = p + '.transformer_blocks.0'
+        b.layernorm(tb + '.norm1', u, ln, self._f32(tb + '.norm1.weight'), self._f32(tb + '.norm1.bias'))
+        self._attention(tb + '.attn1', ln, ln, x.H * x.W, C, u, C)
+        b.layernorm(tb + '.norm2', u, ln, self._f32(tb + '.norm2.weight'), self._f32(tb + '.norm2.bias'))
+        self._attention(tb + '.attn2', ln, ctxv, self.ctx_len, self.cfg['context_dim'], u, C)
+        b.layernorm(tb + '.norm3', u, ln, self._f32(tb + '.norm3.weight'), self._f32(tb + '.norm3.bias'))
+        inner = 4 * C
+        n = x.H * x.W
+        f = View(b.buf(1, 1, B * n, 2 * inner))
+        lnf = View(ln.t.view(1, 1, B * n, C))
+        b.gemm(tb + '.ff.net.0.proj', lnf, C, self._lin(tb + '.ff.net.0.proj.weight'), 2 * inner, f, bias=self._f32(tb + '.ff.net.0.proj.bias'))
+        gg = View(b.buf(1, 1, B * n, inner))
+        b.geglu(tb + '.ff.geglu', f, gg, inner)
+        uf = View(u.t.view(1, 1, B * n, C))
+        b.gemm(tb + '.ff.net.2', gg, inner, self._lin(tb + '.ff.net.2.weight'), C, uf, bias=self._f32(tb + '.ff.net.2.bias'), residual=uf)
+        b.gemm(p + '.proj_out', u, C, self._conv1x1_w(p + '.proj_out.weight'), C, out, bias=self._f32(p + '.proj_out.bias'), residual=x)
+
+    def _down(self, p, x, out):
+        b, B = self.b, self.B
+        C = x.C
+        col = torch.empty(B, x.H // 2, x.W // 2, 9 * C, device=self.dev, dtype=torch.float16)
+        b.im2col_s2(p + '.im2col', x, col, 1, 1)
+        w = pack_conv_weight(self.sd[p + '.op.weight'].to(self.dev), cin_iter=C)
+        b.gemm(p + '.op', View(col), 9 * C, w, C, out, bias=self._f32(p + '.op.bias'))
+
+    def _up(self, p, x, out):
+        b, B = self.b, self.B
+        up = View(b.buf(B, 2 * x.H, 2 * x.W, x.C))
+        b.upsample2(p + '.nearest', x, up)
+        b.gemm(p + '.conv', up, x.C, pack_conv_weight(self.sd[p + '.conv.weight'].to(self.dev)), x.C, out, taps=9, bias=self._f32(p + '.conv.bias'))
+
+    # ---------------------------------------------------------------- API
+    def set_inputs(self, latents_nchw, t, context):
+        """latents [B,4,hw,hw], t int [B], context [B, ctx_len, ctx_dim] (any float dtype, on the engine's device)."""
+        self.x_in[..., :latents_nchw.shape[1]].copy_(latents_nchw.permute(0, 2, 3, 1))
+        self.t_in.copy_(t.to(torch.int32))
+        self.ctx.view(self.B, self.ctx_len, -1).copy_(context)
+
+    def forward(self):
+        self.runlist.run()
+        return self.eps[..., :self.cfg['out_channels']].permute(0, 3, 1, 2)
+
+
+class _OffsetPtr:
+    """rows [row0, ...) of a 2-D View (as a pointer holder for GemmPlan)"""
+
+    def __init__(self, view, row0):
+        self.view, self.row0 = view, row0
+        self.device = view.t.device
+
+    def data_ptr(self):
+        return self.view.ptr + 2 * self.row0 * self.view.ld
+
+
+class _OffsetRaw:
+    def __init__(self, t, elem_off):
+        self.t, self.off = t, elem_off
+        self.device = t.device
+
+    def data_ptr(self):
+        return self.t.data_ptr() + 2 * self.off
+
+
+# =============================================================================================== VAE encoder
+VAE_SD15 = dict(ch=128, ch_mult=(1, 2, 4, 4), num_res_blocks=2, in_channels=3, z_channels=4)
+
+
+def _flip_conv_weight(w):
+    """weights of the data-gradient of a stride-1 3x3 convolution: W'[cin, cout, ky, kx] = W[cout, cin, 2-ky, 2-kx]"""
+    return w.flip(2, 3).permute(1, 0, 2, 3).contiguous()
+
+
+class VaeEncoderEngine:
+    """VAE encoder forward (image -> moments) and its data-gradient (d moments -> d image); weights frozen.
+
+    inputs : self.img [B, R, R, 8] fp16 (channels 0..2 = 2*rgb-1)      outputs: self.moments [B, R/8, R/8, 8]
+    backward: self.d_moments [B, R/8, R/8, 8] -> self.d_img [B, R, R, 8]
+    """
+
+    def __init__(self, sd, device, cfg=VAE_SD15, batch=1, res=512):
+        self.cfg, self.B, self.res, self.dev, self.sd = cfg, batch, res, device, sd
+        fb = self.fb = Builder(device)
+        bb = self.bb = Builder(device)
+        self._bwd = []          # closures that append backward ops, run in reverse
+        B, ch = batch, cfg['ch']
+        self.img = fb.buf(B, res, res, 8, zero=True)
+        x = View(fb.buf(B, res, res, ch))
+        fb.gemm('conv_in', View(self.img), cfg['in_channels'], pack_conv_weight(sd['conv_in.weight'].to(device)), ch, x, taps=9, bias=self._f32('conv_in.bias'))
+        x0 = x
+        in_mult = (1,) + tuple(cfg['ch_mult'])
+        nlev = len(cfg['ch_mult'])
+        chain = []              # (kind, prefix, x_in View, x_out View, extras)
+        for i in range(nlev):
+            bin_, bout = ch * in_mult[i], ch * cfg['ch_mult'][i]
+            for j in range(cfg['num_res_blocks']):
+                x = self._res(f'down.{i}.block.{j}', x, bout)
+                bin_ = bout
+            if i != nlev - 1:
+                x = self._down(f'down.{i}.downsample', x)
+        x = self._res('mid.block_1', x, x.C)
+        x = self._attn('mid.attn_1', x)
+        x = self._res('mid.block_2', x, x.C)
+        # norm_out + swish + conv_out + quant_conv
+        tn = View(fb.buf(B, x.H, x.W, x.C))
+        g, be = self._f32('norm_out.weight'), self._f32('norm_out.bias')
+        st = fb.groupnorm('norm_out', x, tn, g, be, 1e-6, True)
+        zc = 2 * cfg['z_channels']
+        co = View(fb.buf(B, x.H, x.W, 8, zero=True))
+        fb.gemm('conv_out', tn, x.C, pack_conv_weight(sd['conv_out.weight'].to(device)), zc, co, taps=9, bias=self._f32('conv_out.bias'))
+        self.moments = fb.buf(B, x.H, x.W, 8, zero=True)
+        wq = sd['quant_conv.weight'].reshape(zc, zc)
+        fb.gemm('quant_conv', co, zc, _pack_linear(wq, device), zc, View(self.moments), bias=self._f32('quant_conv.bias'))
+        self.fwd = RunList(fb.ops)
+
+        # ---------------- backward list
+        self.d_moments = bb.buf(B, x.H, x.W, 8, zero=True)
+        dco = View(bb.buf(B, x.H, x.W, 8, zero=True))
+        bb.gemm('quant_conv^T', View(self.d_moments), zc, _pack_linear(wq.t().contiguous(), device), zc, dco)
+        dtn = View(bb.buf(B, x.H, x.W, x.C))
+        bb.gemm('conv_out^T', dco, zc, pack_conv_weight(_flip_conv_weight(sd['conv_out.weight'].to(device))), x.C, dtn, taps=9)
+        dx = View(bb.buf(B, x.H, x.W, x.C))
+        bb.groupnorm_bwd('norm_out^T', x, dtn, dx, g, be, 1e-6, True, st, 0)
+        for fn in reversed(self._bwd):
+            dx = fn(dx)
+        self.d_img = bb.buf(B, res, res, 8, zero=True)
+        bb.gemm('conv_in^T', dx, ch, pack_conv_weight(_flip_conv_weight(sd['conv_in.weight'].to(device))), cfg['in_channels'], View(self.d_img), taps=9)
+        self.bwd = RunList(bb.ops)
+        self.flops_fwd, self.flops_bwd = fb.flops, bb.flops
+        self.sd = None
+
+    def _f32(self, key):
+        return _f32(self.sd[key], self.dev)
+
+    def _w1x1(self, key, transpose=False):
+        w = self.sd[key].reshape(self.sd[key].shape[0], -1)
+        return _pack_linear(w.t().contiguous() if transpose else w, self.dev)
+
+    def _res(self, p, x, cout):
+        fb, bb, sd, dev, B = self.fb, self.bb, self.sd, self.dev, self.B
+        cin = x.C
+        g1, b1 = self._f32(p + '.norm1.weight'), self._f32(p + '.norm1.bias')
+        g2, b2 = self._f32(p + '.norm2.weight'), self._f32(p + '.norm2.bias')
+        t1 = View(fb.buf(B, x.H, x.W, cin))
+        st1 = fb.groupnorm(p + '.norm1', x, t1, g1, b1, 1e-6, True)
+        h1 = View(fb.buf(B, x.H, x.W, cout))
+        fb.gemm(p + '.conv1', t1, cin, pack_conv_weight(sd[p + '.conv1.weight'].to(dev)), cout, h1, taps=9, bias=self._f32(p + '.conv1.bias'))
+        t2 = t1 if cin == cout else View(fb.buf(B, x.H, x.W, cout))       # t1 is dead once conv1 has run
+        st2 = fb.groupnorm(p + '.norm2', h1, t2, g2, b2, 1e-6, True)
+        if cin != cout:
+            xs = View(fb.buf(B, x.H, x.W, cout))
+            fb.gemm(p + '.nin_shortcut', x, cin, self._w1x1(p + '.nin_shortcut.weight'), cout, xs, bias=self._f32(p + '.nin_shortcut.bias'))
+        else:
+            xs = x
+        out = View(fb.buf(B, x.H, x.W, cout))
+        fb.gemm(p + '.conv2', t2, cout, pack_conv_weight(sd[p + '.conv2.weight'].to(dev)), cout, out, taps=9, bias=self._f32(p + '.conv2.bias'), residual=xs)
+        w2t = pack_conv_weight(_flip_conv_weight(sd[p + '.conv2.weight'].to(dev)))
+        w1t = pack_conv_weight(_flip_conv_weight(sd[p + '.conv1.weight'].to(dev)))
+        wst = self._w1x1(p + '.nin_shortcut.weight', transpose=True) if cin != cout else None
+
+        def backward(dout):
+            dt2 = View(bb.buf(B, x.H, x.W, cout))
+            bb.gemm(p + '.conv2^T', dout, cout, w2t, cout, dt2, taps=9)
+            dh1 = View(bb.buf(B, x.H, x.W, cout))
+            bb.groupnorm_bwd(p + '.norm2^T', h1, dt2, dh1, g2, b2, 1e-6, True, st2, 0)
+            dt1 = View(bb.buf(B, x.H, x.W, cin))
+            bb.gemm(p + '.conv1^T', dh1, cout, w1t, cin, dt1, taps=9)
+            if cin != cout:
+                dxv = View(bb.buf(B, x.H, x.W, cin))
+                bb.gemm(p + '.nin_shortcut^T', dout, cout, wst, cin, dxv)
+            else:
+                dxv = dout
+            bb.groupnorm_bwd(p + '.norm1^T', x, dt1, dxv, g1, b1, 1e-6, True, st1, 1)
+            return dxv
+
+        self._bwd.append(backward)
+        return out
+
+    def _down(self, p, x):
+        fb, bb, dev, B = self.fb, self.bb, self.dev, self.B
+        C = x.C
+        Ho = x.H // 2
+        col = torch.empty(B, Ho, Ho, 9 * C, device=dev, dtype=torch.float16)
+        fb.im2col_s2(p + '.im2col', x, col, 0, 0)                 # (0,1,0,1) zero pad: reads one row / column past the border
+        w = pack_conv_weight(self.sd[p + '.conv.weight'].to(dev), cin_iter=C)     # [C, 9C]
+        out = View(fb.buf(B, Ho, Ho, C))
+        fb.gemm(p + '.conv', View(col), 9 * C, w, C, out, bias=self._f32(p + '.conv.bias'))
+        wt = w[:C].t().contiguous()                                # [9C, C] : d col = d out . W
+
+        def backward(dout):
+            dcol = torch.empty(B, Ho, Ho, 9 * C, device=dev, dtype=torch.float16)
+            bb.gemm(p + '.conv^T', dout, C, _pack_linear(wt, dev), 9 * C, View(dcol))
+            dxv = View(bb.buf(B, x.H, x.W, C))
+            bb.col2im_s2(p + '.col2im', dcol, dxv, 0, 0)
+            return dxv
+
+        self._bwd.append(backward)
+        return out
+
+    def _attn(self, p, x):
+        """single-head self-attention over H*W tokens (model.py:150-204); batch handled per image"""
+        fb, bb, dev, B = self.fb, self.bb, self.dev, self.B
+        C, n = x.C, x.H * x.W
+        scale = float(C) ** -0.5
+        g, be = self._f32(p + '.norm.weight'), self._f32(p + '.norm.bias')
+        hn = View(fb.buf(B, x.H, x.W, C))
+        st = fb.groupnorm(p + '.norm', x, hn, g, be, 1e-6, False)
+        q, k, v = (View(fb.buf(B, x.H, x.W, C)) for _ in range(3))
+        for nm, dst in (('q', q), ('k', k), ('v', v)):
+            fb.gemm(f'{p}.{nm}', hn, C, self._w1x1(f'{p}.{nm}.weight'), C, dst, bias=self._f32(f'{p}.{nm}.bias'))
+        S = torch.empty(B, 1, n, n, device=dev, dtype=torch.float16)
+        geom = (B, 1, n)
+        tokstr = (C, n * C, n * C)
+        sstr = (n, n * n, n * n)
+        fb.gemm(p + '.qk', q, C, k, n, S, geom=geom, a_strides=tokstr, o_strides=sstr, w_strides=(C, 0, n * C), w_k_valid=C, n_rows_w=n, cin_iter=C,
+                alpha=scale, block_n=128)
+        fb.softmax(p + '.softmax', S, B * n, n, n)
+        vt = torch.empty(B, C, n, device=dev, dtype=torch.float16)
+        fb.transpose(p + '.v^T', v.t, C, vt, n, B, n, C)
+        o = View(fb.buf(B, x.H, x.W, C))
+        fb.gemm(p + '.pv', S, n, vt, C, o, geom=geom, a_strides=sstr, o_strides=tokstr, w_strides=(n, 0, C * n), w_k_valid=n, n_rows_w=C, cin_iter=n, block_n=128)
+        out = View(fb.buf(B, x.H, x.W, C))
+        fb.gemm(p + '.proj_out', o, C, self._w1x1(p + '.proj_out.weight'), C, out, bias=self._f32(p + '.proj_out.bias'), residual=x)
+        wp_t = self._w1x1(p + '.proj_out.weight', transpose=True)
+        wq_t, wk_t, wv_t = (self._w1x1(f'{p}.{nm}.weight', transpose=True) for nm in 'qkv')
+
+        def backward(dout):
+            do = View(bb.buf(B, x.H, x.W, C))
+            bb.gemm(p + '.proj_out^T', dout, C, wp_t, C, do)
+            dP = torch.empty(B, 1, n, n, device=dev, dtype=torch.float16)
+            bb.gemm(p + '.dP', do, C, v, n, dP, geom=geom, a_strides=tokstr, o_strides=sstr, w_strides=(C, 0, n * C), w_k_valid=C, n_rows_w=n, cin_iter=C, block_n=128)
+            dS = torch.empty(B, 1, n, n, device=dev, dtype=torch.float16)
+            bb.softmax_bwd(p + '.softmax^T', S, dP, dS, B * n, n, n, scale)
+            kt = torch.empty(B, C, n, device=dev, dtype=torch.float16)
+            qt = torch.empty(B, C, n, device=dev, dtype=torch.float16)
+            dot = torch.empty(B, C, n, device=dev, dtype=torch.float16)
+            bb.transpose(p + '.k^T', k.t, C, kt, n, B, n, C)
+            bb.transpose(p + '.q^T', q.t, C, qt, n, B, n, C)
+            bb.transpose(p + '.dO^T', do.t, C, dot, n, B, n, C)
+            dq, dk, dv = (View(bb.buf(B, x.H, x.W, C)) for _ in range(3))
+            wT = (n, 0, C * n)
+            bb.gemm(p + '.dQ', dS, n, kt, C, dq, geom=geom, a_strides=sstr, o_strides=tokstr, w_strides=wT, w_k_valid=n, n_rows_w=C, cin_iter=n, block_n=128)
+            dSt = dP                                                # dP is dead: reuse it for dS^T, then for P^T
+            bb.transpose(p + '.dS^T', dS, n, dSt, n, B, n, n)
+            bb.gemm(p + '.dK', dSt, n, qt, C, dk, geom=geom, a_strides=sstr, o_strides=tokstr, w_strides=wT, w_k_valid=n, n_rows_w=C, cin_iter=n, block_n=128)
+            Pt = dS                                                 # dS is dead now
+            bb.transpose(p + '.P^T', S, n, Pt, n, B, n, n)
+            bb.gemm(p + '.dV', Pt, n, dot, C, dv, geom=geom, a_strides=sstr, o_strides=tokstr, w_strides=wT, w_k_valid=n, n_rows_w=C, cin_iter=n, block_n=128)
+            dhn = View(bb.buf(B, x.H, x.W, C))
+            bb.gemm(p + '.q^T.w', dq, C, wq_t, C, dhn)
+            bb.gemm(p + '.k^T.w', dk, C, wk_t, C, dhn, residual=dhn)
+            bb.gemm(p + '.v^T.w', dv, C, wv_t, C, dhn, residual=dhn)
+            bb.groupnorm_bwd(p + '.norm^T', x, dhn, dout, g, be, 1e-6, False, st, 1)
+            return dout
+
+        self._bwd.append(backward)
+        return out
+
+
+# =============================================================================================== SDS step
+def alphas_cumprod(n=1000, linear_start=0.00085, linear_end=0.012):
+    """'scaled_linear' betas (sqrt-linear), as DDIMScheduler for SD / ldm make_beta_schedule('linear', ...) (util.py:21-25)"""
+    betas = torch.linspace(linear_start ** 0.5, linear_end ** 0.5, n, dtype=torch.float64) ** 2
+    return torch.cumprod(1.0 - betas, dim=0).float()
+
+
+VAE_SCALING = 0.18215
+
+
+class SDSEngine:
+    """pred_rgb -> (bilinear 512) -> VAE encode -> latents -> add noise -> UNet x2 (CFG) -> SDS gradient -> VAE data-gradient
+    -> d pred_rgb, as three launch lists (encode, unet, backward) around two tiny glue kernels."""
+
+    def __init__(self, unet_sd, vae_sd, device, unet_cfg=UNET_SD15, vae_cfg=VAE_SD15, n_views=1, render_hw=64, ctx_len=77, vae_res=512,
+                 capture=False):
+        self.dev, self.nv, self.rhw, self.vae_res = device, n_views, render_hw, vae_res
+        self.lat_hw = vae_res // 8
+        self.unet = UNetEngine(unet_sd, device, unet_cfg, batch=2 * n_views, hw=self.lat_hw, ctx_len=ctx_len)
+        self.vae = VaeEncoderEngine(vae_sd, device, vae_cfg, batch=n_views, res=vae_res) if vae_sd is not None else None
+        self.acp = alphas_cumprod().to(device)
+        B, hw = n_views, self.lat_hw
+        self.t = torch.zeros(B, dtype=torch.int32, device=device)
+        self.noise = torch.zeros(B, 4, hw, hw, device=device)
+        self.eps_post = torch.zeros(B, 4, hw, hw, device=device)
+        self.latents = torch.zeros(B, 4, hw, hw, device=device)
+        self.latents_in = torch.zeros(B, 4, hw, hw, device=device)
+        self.grad = torch.zeros(B, 4, hw, hw, device=device)
+        self.loss = torch.zeros(1, device=device)
+        self.pred_rgb = torch.zeros(B, 3, render_hw, render_hw, device=device)
+        self.d_pred_rgb = torch.zeros(B, 3, render_hw, render_hw, device=device)
+        self.guidance_scale, self.grad_scale = 100.0, 1.0
+        if capture:
+            self.unet.runlist.capture()
+            if self.vae is not None:
+                self.vae.fwd.capture()
+                self.vae.bwd.capture()
+
+    def set_text(self, text_embeddings):
+        """[2*n_views, ctx_len, ctx_dim]: unconditional rows first, as sd_utils.train_step concatenates them"""
+        self.unet.ctx.view(2 * self.nv, self.unet.ctx_len, -1).copy_(text_embeddings)
+
+    def step(self, as_latent=False):
+        """Consumes self.pred_rgb / self.latents_in, self.t, self.noise, self.eps_post; fills self.loss, self.grad, self.d_pred_rgb."""
+        st = _lib.stream()
+        B, hw = self.nv, self.lat_hw
+        u = self.unet
+        u.t_in[:B].copy_(self.t)
+        u.t_in[B:].copy_(self.t)
+        if as_latent:
+            _lib.call('sdf_sds_prepare', None, 0, _lib.ptr(self.latents_in), None, _lib.ptr(self.noise), _lib.ptr(self.t), _lib.ptr(self.acp), B, hw * hw,
+                      _lib.ptr(self.latents), _lib.ptr(u.x_in), 8, VAE_SCALING, st)
+        else:
+            v = self.vae
+            _lib.call('sdf_bilinear_forward', _lib.ptr(self.pred_rgb), B, 3, self.rhw, self.rhw, _lib.ptr(v.img), 8, self.vae_res, self.vae_res, 2.0, -1.0, st)
+            v.fwd.run()
+            _lib.call('sdf_sds_prepare', _lib.ptr(v.moments), 8, None, _lib.ptr(self.eps_post), _lib.ptr(self.noise), _lib.ptr(self.t), _lib.ptr(self.acp), B,
+                      hw * hw, _lib.ptr(self.latents), _lib.ptr(u.x_in), 8, VAE_SCALING, st)
+        u.runlist.run()
+        if as_latent:
+            _lib.call('sdf_sds_grad', _lib.ptr(u.eps), 8, _lib.ptr(self.noise), _lib.ptr(self.t), _lib.ptr(self.acp), B, hw * hw, float(self.guidance_scale),
+                      float(self.grad_scale), None, 0, None, VAE_SCALING, _lib.ptr(self.grad), None, _lib.ptr(self.loss), st)
+        else:
+            v = self.vae
+            _lib.call('sdf_sds_grad', _lib.ptr(u.eps), 8, _lib.ptr(self.noise), _lib.ptr(self.t), _lib.ptr(self.acp), B, hw * hw, float(self.guidance_scale),
+                      float(self.grad_scale), _lib.ptr(v.moments), 8, _lib.ptr(self.eps_post), VAE_SCALING, _lib.ptr(self.grad), _lib.ptr(v.d_moments),
+                      _lib.ptr(self.loss), st)
+            v.bwd.run()
+            _lib.call('sdf_bilinear_backward', _lib.ptr(v.d_img), 8, self.vae_res, self.vae_res, _lib.ptr(self.d_pred_rgb), B, 3, self.rhw, self.rhw, 2.0, st)
+
+
+def random_state(shapes, device, seed=0, dtype=torch.float16):
+    """Random-init weights of a given {name: shape} table (fan-in scaled uniform, like nn.Conv2d / nn.Linear defaults;
+    norm weights 1, norm/other biases small).  Used by bench.py: synthetic weights of the SD-1.5 architecture."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    out = {}
+    for k, shp in shapes.items():
+        if len(shp) >= 2:
+            fan_in = 1
+            for s_ in shp[1:]:
+                fan_in *= s_
+            bound = 1.0 / math.sqrt(fan_in)
+            out[k] = ((torch.rand(shp, generator=g, device=device) * 2 - 1) * bound).to(dtype)
+        elif 'norm' in k and k.endswith('weight') or k.endswith('in_layers.0.weight') or k.endswith('out_layers.0.weight') or k == 'out.0.weight':
+            out[k] = torch.ones(shp, device=device, dtype=dtype)
+        else:
+            out[k] = ((torch.rand(shp, generator=g, device=device) * 2 - 1) * 0.05).to(dtype)
+    return out

@@ -1,0 +1,135 @@
+"""GPU: the tcgen05 UNet / VAE-encoder engine (sdf_b200/sd_engine.py) against the fp32 PyTorch restatement of the CompVis
+modules (oracle/sd_ref.py, itself pinned to the reference's vendored ldm code by tests/golden/sd_small.npz), same weights.
+
+Tolerances (north star: 'UNet eps / SDS grad: fp16 rtol 2e-2, abs 2e-3 vs the fp32 reference' — scaled by the output range):
+  UNet eps, VAE moments: max |err| <= 2e-2 * max|ref| ;  VAE input gradient, SDS d pred_rgb: relative L2 <= 3e-2."""
+import pytest
+import torch
+
+from oracle import sd_ref
+from sdf_b200 import sd_engine as E
+
+pytestmark = pytest.mark.gpu
+
+SMALL_UNET = dict(in_channels=4, model_channels=64, out_channels=4, num_res_blocks=1, attention_resolutions=(1, 2), channel_mult=(1, 2),
+                  num_heads=2, context_dim=64)
+SMALL_VAE = dict(ch=32, ch_mult=(1, 2, 2), num_res_blocks=1, in_channels=3, z_channels=4)
+
+
+def relmax(a, b):
+    return ((a.float() - b.float()).abs().max() / (b.float().abs().max() + 1e-12)).item()
+
+
+def rell2(a, b):
+    return ((a.float() - b.float()).norm() / (b.float().norm() + 1e-30)).item()
+
+
+def make_unet(cfg, device, seed=0):
+    torch.manual_seed(seed)
+    with torch.device(device):
+        m = sd_ref.UNet(**cfg)
+    sd_ref.reinit_zero_modules(m, seed=seed + 1)
+    return m.to(device).eval()
+
+
+def make_vae(cfg, device, seed=0):
+    torch.manual_seed(seed)
+    with torch.device(device):
+        m = sd_ref.VaeEncoder(**cfg)
+    return m.to(device).eval()
+
+
+@pytest.mark.parametrize("cfg,hw,ctx_len", [(SMALL_UNET, 16, 5), (SMALL_UNET, 32, 77)])
+def test_unet_small(device, cfg, hw, ctx_len):
+    ref = make_unet(cfg, device)
+    eng = E.UNetEngine(ref.state_dict(), device, cfg, batch=2, hw=hw, ctx_len=ctx_len)
+    g = torch.Generator(device="cpu").manual_seed(3)
+    x = torch.randn(2, 4, hw, hw, generator=g).to(device)
+    t = torch.tensor([37, 911], device=device)
+    ctx = torch.randn(2, ctx_len, cfg["context_dim"], generator=g).to(device)
+    eng.set_inputs(x, t, ctx)
+    y = eng.forward().float()
+    with torch.no_grad():
+        y_ref = ref(x.half().float(), t, ctx.half().float())
+    assert torch.isfinite(y).all()
+    assert relmax(y, y_ref) < 2e-2, relmax(y, y_ref)
+    # CUDA-graph replay gives the same answer
+    eng.runlist.capture()
+    y2 = eng.forward().float()
+    assert torch.equal(y, y2)
+
+
+def test_unet_sd15_shape(device):
+    ref = make_unet(sd_ref.UNET_SD15, device, seed=1)
+    eng = E.UNetEngine(ref.state_dict(), device, E.UNET_SD15, batch=2, hw=64, ctx_len=77)
+    g = torch.Generator(device="cpu").manual_seed(4)
+    x = torch.randn(2, 4, 64, 64, generator=g).to(device)
+    t = torch.tensor([500, 500], device=device)
+    ctx = torch.randn(2, 77, 768, generator=g).to(device)
+    eng.set_inputs(x, t, ctx)
+    y = eng.forward().float()
+    with torch.no_grad():
+        y_ref = ref(x.half().float(), t, ctx.half().float())
+    print("UNet SD-1.5 shape: rel-max err", relmax(y, y_ref), "rel-L2", rell2(y, y_ref), "|ref|max", y_ref.abs().max().item(),
+          "GFLOP counted", eng.flops / 1e9)
+    assert relmax(y, y_ref) < 2e-2
+    assert abs(eng.flops / 1e9 - 1606.5) / 1606.5 < 0.05          # SURVEY.md §8d FlopCounter figure for B=2
+
+
+@pytest.mark.parametrize("cfg,res", [(SMALL_VAE, 64), (sd_ref.VAE_SD15, 512)])
+def test_vae_forward_backward(device, cfg, res):
+    ref = make_vae(cfg, device, seed=2)
+    eng = E.VaeEncoderEngine(ref.state_dict(), device, cfg, batch=1, res=res)
+    g = torch.Generator(device="cpu").manual_seed(5)
+    img = (torch.rand(1, 3, res, res, generator=g) * 2 - 1).to(device).half().float()
+    eng.img[..., :3].copy_(img.permute(0, 2, 3, 1))
+    eng.fwd.run()
+    mom = eng.moments.float().permute(0, 3, 1, 2)
+    xin = img.clone().requires_grad_(True)
+    mom_ref = ref(xin)
+    assert relmax(mom, mom_ref) < 2e-2, relmax(mom, mom_ref)
+    gup = torch.randn(mom_ref.shape, generator=g).to(device).half().float()
+    (gi_ref,) = torch.autograd.grad((mom_ref * gup).sum(), xin)
+    eng.d_moments.copy_(gup.permute(0, 2, 3, 1))
+    eng.bwd.run()
+    gi = eng.d_img[..., :3].float().permute(0, 3, 1, 2)
+    print(f"VAE res {res}: moments rel-max {relmax(mom, mom_ref):.3e}; input-grad rel-L2 {rell2(gi, gi_ref):.3e} rel-max {relmax(gi, gi_ref):.3e}; "
+          f"GFLOP fwd {eng.flops_fwd / 1e9:.1f} bwd {eng.flops_bwd / 1e9:.1f}")
+    assert rell2(gi, gi_ref) < 3e-2
+
+
+def test_sds_step_small(device):
+    unet = make_unet(SMALL_UNET, device, seed=5)
+    vae = make_vae(SMALL_VAE, device, seed=6)
+    eng = E.SDSEngine(unet.state_dict(), vae.state_dict(), device, SMALL_UNET, SMALL_VAE, n_views=1, render_hw=16, ctx_len=7, vae_res=128)
+    g = torch.Generator(device="cpu").manual_seed(7)
+    rgb = torch.rand(1, 3, 16, 16, generator=g).to(device)
+    text = torch.randn(2, 7, 64, generator=g).to(device)
+    t = torch.tensor([300], device=device)
+    noise = torch.randn(1, 4, 16, 16, generator=g).to(device)
+    post = torch.randn(1, 4, 16, 16, generator=g).to(device)
+    eng.set_text(text); eng.pred_rgb.copy_(rgb); eng.t.copy_(t.int()); eng.noise.copy_(noise); eng.eps_post.copy_(post)
+    eng.guidance_scale = 7.5
+    eng.step(as_latent=False)
+    rgb_r = rgb.clone().requires_grad_(True)
+    import torch.nn.functional as F
+    rgb512 = F.interpolate(rgb_r, (128, 128), mode="bilinear", align_corners=False)
+    lat = sd_ref.posterior_sample(vae(2 * rgb512 - 1), post) * sd_ref.VAE_SCALING
+    acp = sd_ref.alphas_cumprod().to(device)
+    with torch.no_grad():
+        a = acp[t].view(-1, 1, 1, 1)
+        noisy = a.sqrt() * lat + (1 - a).sqrt() * noise
+        eps = unet(torch.cat([noisy] * 2).half().float(), torch.cat([t] * 2), text.half().float())
+        e_u, e_c = eps.chunk(2)
+        grad = (1 - a) * (e_u + 7.5 * (e_c - e_u) - noise)
+    loss = 0.5 * F.mse_loss(lat, (lat - grad).detach(), reduction="sum")
+    (g_rgb,) = torch.autograd.grad(loss, rgb_r)
+    assert rell2(eng.latents, lat) < 2e-2
+    assert rell2(eng.grad, grad) < 5e-2, rell2(eng.grad, grad)
+    assert abs(eng.loss.item() - loss.item()) < 0.1 * abs(loss.item())
+    print("SDS small: latents", rell2(eng.latents, lat), "grad", rell2(eng.grad, grad), "d_rgb", rell2(eng.d_pred_rgb, g_rgb))
+    assert rell2(eng.d_pred_rgb, g_rgb) < 6e-2
+    # latent mode (first 20 % of the schedule): no VAE
+    eng.latents_in.copy_(lat.detach())
+    eng.step(as_latent=True)
+    assert rell2(eng.grad, grad) < 5e-2
