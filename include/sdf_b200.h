@@ -191,6 +191,16 @@ int sdf_sds_grad(const void* eps, int lde, const float* noise, const int* t, con
                  float guidance_scale, float grad_scale, const void* moments, int ldm, const float* eps_post, float vae_scale,
                  float* grad, void* d_moments, float* loss, void* stream);
 
+/* ------------------------------------------------------------------ fused Adan + GradScaler protocol
+ * replaces optimizer.py:102-258 (Adan.step, _single_tensor_adan) and the unscale / inf-check / skip of nerf/utils.py:1063-1067.
+ * Per optimiser step: sdf_adan_begin(acc) ; sdf_adan_grad_norm(grad_i, ...) for every tensor ; sdf_adan_step(...) for every tensor.
+ * acc: device float[2] = (sum of squared unscaled gradients, non-finite flag).  Nothing is read back to the host. */
+int sdf_adan_begin(float* acc, void* stream);
+int sdf_adan_grad_norm(const float* grad, long long n, float inv_scale, float* acc, void* stream);
+int sdf_adan_step(float* param, float* grad, float* exp_avg, float* exp_avg_diff, float* exp_avg_sq, float* neg_pre_grad, long long n,
+                  float beta1, float beta2, float beta3, int step, float lr, float weight_decay, float eps, float max_grad_norm,
+                  int no_prox, float inv_scale, const float* acc, void* param_half /* may be NULL */, int zero_grad, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -529,7 +529,8 @@ class UNetEngine:
         C = x.C
         col = torch.empty(B, x.H // 2, x.W // 2, 9 * C, device=self.dev, dtype=torch.float16)
         b.im2col_s2(p + '.im2col', x, col, 1, 1)
-        w = pack_conv_weight(self.sd[p + '.op.weight'].to(self.dev), cin_iter=C)
+        w4 = self.sd[p + '.op.weight'].to(self.dev)                                  # [Cout, C, 3, 3] -> [Cout, tap*C + c]
+        w = _pack_linear(w4.permute(0, 2, 3, 1).reshape(w4.shape[0], 9 * C), self.dev)
         b.gemm(p + '.op', View(col), 9 * C, w, C, out, bias=self._f32(p + '.op.bias'))
 
     def _up(self, p, x, out):
@@ -690,10 +691,12 @@ class VaeEncoderEngine:
         Ho = x.H // 2
         col = torch.empty(B, Ho, Ho, 9 * C, device=dev, dtype=torch.float16)
         fb.im2col_s2(p + '.im2col', x, col, 0, 0)                 # (0,1,0,1) zero pad: reads one row / column past the border
-        w = pack_conv_weight(self.sd[p + '.conv.weight'].to(dev), cin_iter=C)     # [C, 9C]
+        w4 = self.sd[p + '.conv.weight'].to(dev)
+        w2 = w4.permute(0, 2, 3, 1).reshape(C, 9 * C)              # [Cout, tap*C + c]
+        w = _pack_linear(w2, dev)
         out = View(fb.buf(B, Ho, Ho, C))
         fb.gemm(p + '.conv', View(col), 9 * C, w, C, out, bias=self._f32(p + '.conv.bias'))
-        wt = w[:C].t().contiguous()                                # [9C, C] : d col = d out . W
+        wt = w2.t().contiguous()                                   # [9C, C] : d col = d out . W
 
         def backward(dout):
             dcol = torch.empty(B, Ho, Ho, 9 * C, device=dev, dtype=torch.float16)

@@ -1,0 +1,165 @@
+"""SDS training step of the -O preset: host-side mirror of the reference loop body
+(nerf/utils.py:1032-1072 train_one_epoch, :439-723 train_step, :725-741 post_train_step; main.py:363-410 wiring), driving the
+B200-native pieces: drop-in raymarching ops, the fused radiance field, the tcgen05 SDS engine and the fused Adan step.
+
+Multi-GPU (new functionality, SURVEY.md §8e — the reference never initialises torch.distributed): one process per GPU, each
+rank renders its own view(s) with its own RNG stream, the NeRF gradients are summed with ONE NCCL all-reduce over a flat fp32
+bucket per step, and the 1/world factor rides in the fused Adan kernel's unscale.  The occupancy grid is refreshed on every rank
+and rank 0's result is broadcast so marching stays identical.
+"""
+import math
+import random
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from . import field, synth
+from .network_grid import NeRFNetwork
+from .optimizer import Adan
+from .renderer import safe_normalize
+
+
+def get_rays_torch(poses, focal, cx, cy, H, W):
+    """nerf/utils.py:113-176 with N=-1: pixel-centre pinhole rays, unnormalised directions.  poses [B,4,4] on the device."""
+    device = poses.device
+    j, i = torch.meshgrid(torch.arange(H, device=device, dtype=torch.float32), torch.arange(W, device=device, dtype=torch.float32), indexing='ij')
+    i = i.reshape(1, H * W) + 0.5
+    j = j.reshape(1, H * W) + 0.5
+    zs = -torch.ones_like(i)
+    xs = -(i - cx) / focal * zs
+    ys = (j - cy) / focal * zs
+    directions = torch.stack((xs, ys, zs), dim=-1).expand(poses.shape[0], H * W, 3)
+    rays_d = directions @ poses[:, :3, :3].transpose(-1, -2)
+    rays_o = poses[..., :3, 3][..., None, :].expand_as(rays_d)
+    return rays_o, rays_d
+
+
+class SDSTrainer:
+    def __init__(self, opt, device, guidance, seed=0, rank=0, world_size=1, fused=True, prompt='a hamburger'):
+        self.opt, self.device, self.guidance = opt, device, guidance
+        self.rank, self.world_size = rank, world_size
+        torch.manual_seed(seed)                       # identical initial parameters on every rank
+        self.model = NeRFNetwork(opt, fused=fused).to(device)
+        self.model.train()
+        field.DIRECT_GRAD_ACCUM = True       # table / MLP gradients are scattered straight into .grad
+        # main.py:368
+        self.optimizer = Adan(self.model.get_params(5 * opt.lr), eps=1e-8, weight_decay=2e-5, max_grad_norm=5.0, foreach=False)
+        self.optimizer.loss_scale = float(world_size)  # all-reduce SUM -> mean
+        self.global_step = 0
+        self.rng = np.random.default_rng(seed * 1000 + rank)       # cameras / schedule: per-rank stream
+        random.seed(seed * 1000 + rank)
+        torch.manual_seed(seed * 1000 + rank + 1)
+        torch.cuda.manual_seed(seed * 1000 + rank + 1)
+        # text embeddings (nerf/utils.py:352-377): uncond + default/front/side/back
+        te = guidance.get_text_embeds
+        self.embeddings = {'uncond': te(['']), 'default': te([prompt])}
+        for d in ('front', 'side', 'back'):
+            self.embeddings[d] = te([f'{prompt}, {d} view'])
+        self._flat = None
+        self.pin_pose = torch.zeros(opt.batch_size, 4, 4).pin_memory()
+        self.last_M = 0
+
+    # ------------------------------------------------------------------ data (nerf/provider.py:248-319 collate)
+    def sample_views(self):
+        B, opt = self.opt.batch_size, self.opt
+        poses, az = [], []
+        for _ in range(B):
+            pose, (r, th, ph) = synth.rand_pose(self.rng, tuple(opt.radius_range), tuple(opt.theta_range), tuple(opt.phi_range))
+            poses.append(pose)
+            a = ph
+            if a > 180:
+                a -= 360
+            az.append(a)
+        fov = self.rng.uniform(*opt.fovy_range)
+        return np.stack(poses), np.array(az, np.float32), float(fov)
+
+    def text_z(self, azimuth):
+        """view-dependent prompt interpolation, nerf/utils.py:597-626"""
+        z = [self.embeddings['uncond']] * len(azimuth)
+        for a in azimuth:
+            if -90 <= a < 90:
+                r = 1 - a / 90 if a >= 0 else 1 + a / 90
+                s, e = self.embeddings['front'], self.embeddings['side']
+            else:
+                r = 1 - (a - 90) / 90 if a >= 0 else 1 + (a + 90) / 90
+                s, e = self.embeddings['side'], self.embeddings['back']
+            z.append(r * s + (1 - r) * e)
+        return torch.cat(z, dim=0)
+
+    # ------------------------------------------------------------------ one optimisation step
+    def train_step(self, views=None, shading=None, read_loss=False):
+        opt, dev = self.opt, self.device
+        if self.global_step % opt.update_extra_interval == 0:
+            self.model.update_extra_state()
+            if self.world_size > 1:
+                from .dist import broadcast_occupancy
+                broadcast_occupancy(self.model, src=0)
+        self.global_step += 1
+        poses_np, azimuth, fov = self.sample_views() if views is None else views
+        # host -> device: the step's only input (pinned staging)
+        self.pin_pose.copy_(torch.from_numpy(poses_np))
+        poses = self.pin_pose.to(dev, non_blocking=True)
+        H, W = opt.h, opt.w
+        focal = H / (2 * math.tan(math.radians(fov) / 2))
+        rays_o, rays_d = get_rays_torch(poses, focal, H / 2, W / 2, H, W)
+        B, N = rays_o.shape[:2]
+
+        # schedule (nerf/utils.py:503-535)
+        exp_iter_ratio = (self.global_step - 1) / opt.iters
+        if shading is None:
+            if exp_iter_ratio <= opt.latent_iter_ratio:
+                ambient_ratio, shading, as_latent, bg_color = 1.0, 'normal', True, None
+            else:
+                if exp_iter_ratio <= opt.albedo_iter_ratio:
+                    ambient_ratio, shading = 1.0, 'albedo'
+                else:
+                    ambient_ratio = opt.min_ambient_ratio + (1.0 - opt.min_ambient_ratio) * random.random()
+                    shading = 'textureless' if random.random() >= (1.0 - opt.textureless_ratio) else 'lambertian'
+                as_latent = False
+                bg_color = None if (opt.bg_radius > 0 and random.random() > 0.5) else torch.rand(3).to(dev)
+        else:
+            as_latent = shading == 'latent'
+            ambient_ratio = 1.0 if shading in ('albedo', 'latent') else 0.55
+            bg_color = None
+            shading = 'normal' if as_latent else shading
+
+        outputs = self.model.render(rays_o, rays_d, None, H, W, staged=False, perturb=True, bg_color=bg_color, ambient_ratio=ambient_ratio,
+                                    shading=shading, binarize=False)
+        if as_latent:
+            pred_rgb = torch.cat([outputs['image'], outputs['weights_sum'].unsqueeze(-1)], dim=-1).reshape(B, H, W, 4).permute(0, 3, 1, 2).contiguous()
+        else:
+            pred_rgb = outputs['image'].reshape(B, H, W, 3).permute(0, 3, 1, 2).contiguous()
+        self.last_M = int(outputs['weights'].shape[0])
+
+        loss = self.guidance.train_step(self.text_z(azimuth), pred_rgb, as_latent=as_latent, guidance_scale=opt.guidance_scale,
+                                        grad_scale=opt.lambda_guidance)
+        # regularisers (nerf/utils.py:686-709)
+        if opt.lambda_opacity > 0:
+            loss = loss + opt.lambda_opacity * (outputs['weights_sum'] ** 2).mean()
+        if opt.lambda_entropy > 0:
+            alphas = outputs['weights'].clamp(1e-5, 1 - 1e-5)
+            loss_entropy = (-alphas * torch.log2(alphas) - (1 - alphas) * torch.log2(1 - alphas)).mean()
+            loss = loss + opt.lambda_entropy * min(1, 2 * self.global_step / opt.iters) * loss_entropy
+        if opt.lambda_orient > 0 and 'loss_orient' in outputs:
+            loss = loss + opt.lambda_orient * outputs['loss_orient']
+
+        loss.backward()
+        if self.world_size > 1:
+            self._allreduce_grads()
+        self.optimizer.step(zero_grad=True)      # gradients are cleared by the fused step: buffers stay allocated (and bucketed)
+        if read_loss:
+            return float(loss.item())          # device -> host read of the step's result (nerf/utils.py:1072)
+        return loss
+
+    def _has_grads(self):
+        return any(p.grad is not None for p in self.model.parameters())
+
+    def _allreduce_grads(self):
+        """ONE NCCL all-reduce per step over the flat gradient bucket (table gradient first, then the MLPs)."""
+        if self._flat is None:
+            from .dist import GradBucket
+            named = dict(self.model.named_parameters())
+            order = [named['encoder.embeddings']] + [p for n, p in named.items() if n != 'encoder.embeddings']
+            self._flat = GradBucket(order)
+        self._flat.all_reduce()

@@ -1,0 +1,69 @@
+"""CPU, world_size 2 over gloo: the data-parallel host logic (sdf_b200/dist.py) — flat gradient bucket + one all-reduce per
+step — gives every rank the SUM of the per-rank gradients (== a single process accumulating both views), keeps .grad views
+inside the bucket across steps, and the occupancy broadcast makes rank 1 adopt rank 0's bitfield."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _worker(rank, world, port, out):
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "stable-dreamfusion_b200"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from sdf_b200.dist import GradBucket, broadcast_occupancy
+    torch.manual_seed(0)
+    model = torch.nn.Sequential(torch.nn.Linear(7, 5), torch.nn.ReLU(), torch.nn.Linear(5, 3))
+    table = torch.nn.Parameter(torch.randn(101, 2))
+    params = [table] + list(model.parameters())
+    bucket = GradBucket(params)
+    results = []
+    for step in range(3):
+        g = torch.Generator().manual_seed(100 * step + rank)          # each rank sees its own "view"
+        x = torch.randn(11, 7, generator=g)
+        idx = torch.randint(0, 101, (11,), generator=g)
+        loss = (model(x) ** 2).sum() + (table[idx] ** 2).sum() * (rank + 1)
+        for p in params:
+            if p.grad is not None:
+                p.grad.zero_()
+        loss.backward()
+        flat = bucket.all_reduce()
+        assert all(p.grad.data_ptr() >= flat.data_ptr() and p.grad.data_ptr() < flat.data_ptr() + flat.numel() * 4 for p in params)
+        results.append([p.grad.clone() for p in params])
+    holder = type("M", (), {})()
+    holder.density_bitfield = torch.full((64,), rank + 1, dtype=torch.uint8)
+    broadcast_occupancy(holder, src=0)
+    assert int(holder.density_bitfield[0]) == 1
+    if rank == 0:
+        torch.save(results, out)
+    dist.destroy_process_group()
+
+
+def test_bucket_allreduce_equals_single_process_sum(tmp_path):
+    out = str(tmp_path / "r0.pt")
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
+    got = torch.load(out)
+    # single-process restatement: accumulate both ranks' losses
+    torch.manual_seed(0)
+    model = torch.nn.Sequential(torch.nn.Linear(7, 5), torch.nn.ReLU(), torch.nn.Linear(5, 3))
+    table = torch.nn.Parameter(torch.randn(101, 2))
+    params = [table] + list(model.parameters())
+    for step in range(3):
+        for p in params:
+            p.grad = None
+        for rank in range(2):
+            g = torch.Generator().manual_seed(100 * step + rank)
+            x = torch.randn(11, 7, generator=g)
+            idx = torch.randint(0, 101, (11,), generator=g)
+            ((model(x) ** 2).sum() + (table[idx] ** 2).sum() * (rank + 1)).backward()
+        for a, p in zip(got[step], params):
+            assert torch.allclose(a, p.grad, atol=1e-5), (step, (a - p.grad).abs().max())

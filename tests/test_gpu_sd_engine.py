@@ -53,10 +53,10 @@ def test_unet_small(device, cfg, hw, ctx_len):
         y_ref = ref(x.half().float(), t, ctx.half().float())
     assert torch.isfinite(y).all()
     assert relmax(y, y_ref) < 2e-2, relmax(y, y_ref)
-    # CUDA-graph replay gives the same answer
+    # CUDA-graph replay gives the same answer (split-K partial sums land in a different order: not bitwise)
     eng.runlist.capture()
     y2 = eng.forward().float()
-    assert torch.equal(y, y2)
+    assert relmax(y2, y) < 2e-3, relmax(y2, y)
 
 
 def test_unet_sd15_shape(device):
