@@ -166,6 +166,12 @@ k_field_backward(FieldParams p, const float* __restrict__ xyzs, const float* __r
         (&s.a2t[kHidden][0])[i] = v;
     }
     for (int i = threadIdx.x; i < 16 * kTStride; i += blockDim.x) (&s.dh3t[0][0])[i] = __float2half_rn(0.f);
+    // rows of a warp that skips a round keep whatever was staged before: make sure that is never NaN garbage
+    for (int i = threadIdx.x; i < kEncDim * kTStride; i += blockDim.x) (&s.enct[0][0])[i] = __float2half_rn(0.f);
+    for (int i = threadIdx.x; i < kHidden * kTStride; i += blockDim.x) {
+        (&s.a1t[0][0])[i] = __float2half_rn(0.f); (&s.a2t[0][0])[i] = __float2half_rn(0.f);
+        (&s.dh1t[0][0])[i] = __float2half_rn(0.f); (&s.dh2t[0][0])[i] = __float2half_rn(0.f);
+    }
     __syncthreads();
 
     const uint32_t M = m_dev ? min((uint32_t)max(*m_dev, 0), M_cap) : M_cap;
@@ -213,8 +219,35 @@ k_field_backward(FieldParams p, const float* __restrict__ xyzs, const float* __r
             }
         }
 
+        // a warp whose 16 samples carry no upstream gradient (early-terminated ray tails, rays that missed) only has to
+        // clear its delta rows; it still meets the CTA barriers because the weight-gradient products span all 256 rows
+        bool mine = false;
+#pragma unroll
+        for (int q = 0; q < 7; q++) mine |= (gsa[q] != 0.f) | (gsb[q] != 0.f);
+        mine |= (gla[0] != 0.f) | (gla[1] != 0.f) | (gla[2] != 0.f) | (glb[0] != 0.f) | (glb[1] != 0.f) | (glb[2] != 0.f);
+        const bool warp_active = __any_sync(0xffffffffu, mine);
+        bool rows_cleared = false;
+
 #pragma unroll 1
         for (int sp = 0; sp < NP; sp++) {
+            if (!warp_active) {
+                if (!rows_cleared) {
+                    const int row_a = warp * 16 + g, row_b = row_a + 8;
+                    if (t < 2) {
+                        st_half(&s.dh3t[0][0], kTStride, 2 * t, row_a, 0.f); st_half(&s.dh3t[0][0], kTStride, 2 * t + 1, row_a, 0.f);
+                        st_half(&s.dh3t[0][0], kTStride, 2 * t, row_b, 0.f); st_half(&s.dh3t[0][0], kTStride, 2 * t + 1, row_b, 0.f);
+                    }
+#pragma unroll
+                    for (int nt = 0; nt < 8; nt++) {
+#pragma unroll
+                        for (int e = 0; e < 2; e++) {
+                            st_half(&s.dh2t[0][0], kTStride, nt * 8 + 2 * t + e, row_a, 0.f); st_half(&s.dh2t[0][0], kTStride, nt * 8 + 2 * t + e, row_b, 0.f);
+                            st_half(&s.dh1t[0][0], kTStride, nt * 8 + 2 * t + e, row_a, 0.f); st_half(&s.dh1t[0][0], kTStride, nt * 8 + 2 * t + e, row_b, 0.f);
+                        }
+                    }
+                    rows_cleared = true;
+                }
+            } else {
             // ---- delta at the logits as an A fragment: k = logit index (0..3), zero beyond
             float d0a = 0.f, d1a = 0.f, d0b = 0.f, d1b = 0.f;     // (k=2t, 2t+1) for rows g and g+8
             {
@@ -318,6 +351,7 @@ k_field_backward(FieldParams p, const float* __restrict__ xyzs, const float* __r
                     if (vb && (c[2] != 0.f || c[3] != 0.f)) scatter_level(grad_table, lv, ub[0], ub[1], ub[2], smooth, c[2], c[3]);
                 }
             }
+            }   // warp_active
             __syncthreads();
 
             // ---- weight gradients over the 256 staged rows

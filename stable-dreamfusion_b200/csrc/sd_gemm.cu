@@ -28,7 +28,8 @@ namespace {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;          // 64 fp16 = one 128-byte swizzle row
 constexpr int kUmmaK = 16;
-constexpr int kNumThreads = 192;     // warp 0 producer, warp 1 MMA, warps 2..5 epilogue
+constexpr int kNumThreads = 320;     // warp 0 producer, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quarter)
+constexpr int kEpiWarps = 8;
 
 enum Act { kActNone = 0, kActSilu = 1, kActGelu = 2 };
 
@@ -85,13 +86,16 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint6
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
 }
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t v[16]) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t v[32]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                   "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                   "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
                  : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major, 128B-swizzled operand tile: rows of 128 bytes, 8-row groups 1024 bytes apart.
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
@@ -141,7 +145,7 @@ k_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtens
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < kStages; i++) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-        for (int i = 0; i < 2; i++) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
+        for (int i = 0; i < 2; i++) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], kEpiWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -215,9 +219,11 @@ k_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtens
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     } else {
-        // ===================== epilogue (4 warps, one TMEM lane quarter each) =====================
+        // ===================== epilogue (8 warps: TMEM lane quarter q = warp % 4, two warps interleave 32-column chunks) ==========
         const int q = warp & 3;                      // TMEM lanes 32q .. 32q+31
+        const int half = (warp - 2) >> 2;            // 0 / 1: even / odd chunks
         const int r = q * 32 + lane;                 // row of the tile
+        constexpr int kChunks = BLOCK_N / 32;        // 2, 4 or 5
         int acc = 0; uint32_t acc_phase = 0;
         for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
             const int t2 = w / g.splitk;
@@ -233,64 +239,76 @@ k_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtens
             mbar_wait(&tmem_full[acc], acc_phase);
             tcgen05_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BLOCK_N;
+            uint32_t va[32], vb[32];
+            if (half < kChunks) { tmem_ld32_nowait(taddr + half * 32, va); tmem_ld_wait(); }
 #pragma unroll 1
-            for (int c0 = 0; c0 < BLOCK_N; c0 += 16) {
-                uint32_t v[16];
-                tmem_ld16(taddr + c0, v);
-                const int n = n0 + c0;
-                if (!row_ok || n >= g.N) continue;
-                float f[16];
+            for (int ch = half; ch < kChunks; ch += 2) {
+                // prefetch this warp's next chunk while the current one is finished and stored
+                const bool odd_iter = ((ch - half) >> 1) & 1;
+                uint32_t* cur = odd_iter ? vb : va;
+                uint32_t* nxt = odd_iter ? va : vb;
+                if (ch + 2 < kChunks) tmem_ld32_nowait(taddr + (ch + 2) * 32, nxt);
+                const int nbase = n0 + ch * 32;
+                if (row_ok && nbase < g.N) {
 #pragma unroll
-                for (int j = 0; j < 16; j++) f[j] = __uint_as_float(v[j]) * g.alpha;
-                if (g.splitk > 1) {
-                    float* ws = g.workspace + m * g.N + n;
+                    for (int hh = 0; hh < 2; hh++) {
+                        const int n = nbase + hh * 16;
+                        if (n >= g.N) break;
+                        float f[16];
 #pragma unroll
-                    for (int j = 0; j < 16; j++) if (n + j < g.N) atomicAdd(ws + j, f[j]);
-                    continue;
-                }
-                const bool full16 = (n + 16 <= g.N);
-                if (g.bias) {
+                        for (int j = 0; j < 16; j++) f[j] = __uint_as_float(cur[hh * 16 + j]) * g.alpha;
+                        if (g.splitk > 1) {
+                            float* ws = g.workspace + m * g.N + n;
 #pragma unroll
-                    for (int j = 0; j < 16; j++) if (full16 || n + j < g.N) f[j] += __ldg(g.bias + n + j);
-                }
-                if (g.temb) {
-                    const __half* te = g.temb + (long long)img * g.temb_ld + n;
-#pragma unroll
-                    for (int j = 0; j < 16; j++) if (full16 || n + j < g.N) f[j] += __half2float(te[j]);
-                }
-                if (g.residual) {
-                    const __half* rs = g.residual + (long long)img * g.r_simg + (long long)y * g.r_sy + (long long)x * g.r_sx + n;
-                    if (full16) {
-                        const uint4 r0 = *reinterpret_cast<const uint4*>(rs), r1 = *reinterpret_cast<const uint4*>(rs + 8);
-                        const __half2* h0 = reinterpret_cast<const __half2*>(&r0);
-                        const __half2* h1 = reinterpret_cast<const __half2*>(&r1);
-#pragma unroll
-                        for (int j = 0; j < 4; j++) {
-                            const float2 a = __half22float2(h0[j]), b = __half22float2(h1[j]);
-                            f[2 * j] += a.x; f[2 * j + 1] += a.y; f[8 + 2 * j] += b.x; f[8 + 2 * j + 1] += b.y;
+                            for (int j = 0; j < 16; j++) if (n + j < g.N) atomicAdd(ws + j, f[j]);
+                            continue;
                         }
-                    } else {
+                        const bool full16 = (n + 16 <= g.N);
+                        if (g.bias) {
 #pragma unroll
-                        for (int j = 0; j < 16; j++) if (n + j < g.N) f[j] += __half2float(rs[j]);
+                            for (int j = 0; j < 16; j++) if (full16 || n + j < g.N) f[j] += __ldg(g.bias + n + j);
+                        }
+                        if (g.temb) {
+                            const __half* te = g.temb + (long long)img * g.temb_ld + n;
+#pragma unroll
+                            for (int j = 0; j < 16; j++) if (full16 || n + j < g.N) f[j] += __half2float(te[j]);
+                        }
+                        if (g.residual) {
+                            const __half* rs = g.residual + (long long)img * g.r_simg + (long long)y * g.r_sy + (long long)x * g.r_sx + n;
+                            if (full16) {
+                                const uint4 r0 = *reinterpret_cast<const uint4*>(rs), r1 = *reinterpret_cast<const uint4*>(rs + 8);
+                                const __half2* h0 = reinterpret_cast<const __half2*>(&r0);
+                                const __half2* h1 = reinterpret_cast<const __half2*>(&r1);
+#pragma unroll
+                                for (int j = 0; j < 4; j++) {
+                                    const float2 a = __half22float2(h0[j]), b = __half22float2(h1[j]);
+                                    f[2 * j] += a.x; f[2 * j + 1] += a.y; f[8 + 2 * j] += b.x; f[8 + 2 * j + 1] += b.y;
+                                }
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 16; j++) if (n + j < g.N) f[j] += __half2float(rs[j]);
+                            }
+                        }
+                        if (g.act != kActNone) {
+#pragma unroll
+                            for (int j = 0; j < 16; j++) f[j] = act_apply(f[j], g.act);
+                        }
+                        __half* o = g.out + o_off + n;
+                        if (full16) {
+                            uint4 o0, o1;
+                            __half2* h0 = reinterpret_cast<__half2*>(&o0);
+                            __half2* h1 = reinterpret_cast<__half2*>(&o1);
+#pragma unroll
+                            for (int j = 0; j < 4; j++) { h0[j] = __floats2half2_rn(f[2 * j], f[2 * j + 1]); h1[j] = __floats2half2_rn(f[8 + 2 * j], f[8 + 2 * j + 1]); }
+                            *reinterpret_cast<uint4*>(o) = o0;
+                            *reinterpret_cast<uint4*>(o + 8) = o1;
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 16; j++) if (n + j < g.N) o[j] = __float2half_rn(f[j]);
+                        }
                     }
                 }
-                if (g.act != kActNone) {
-#pragma unroll
-                    for (int j = 0; j < 16; j++) f[j] = act_apply(f[j], g.act);
-                }
-                __half* o = g.out + o_off + n;
-                if (full16) {
-                    uint4 o0, o1;
-                    __half2* h0 = reinterpret_cast<__half2*>(&o0);
-                    __half2* h1 = reinterpret_cast<__half2*>(&o1);
-#pragma unroll
-                    for (int j = 0; j < 4; j++) { h0[j] = __floats2half2_rn(f[2 * j], f[2 * j + 1]); h1[j] = __floats2half2_rn(f[8 + 2 * j], f[8 + 2 * j + 1]); }
-                    *reinterpret_cast<uint4*>(o) = o0;
-                    *reinterpret_cast<uint4*>(o + 8) = o1;
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 16; j++) if (n + j < g.N) o[j] = __float2half_rn(f[j]);
-                }
+                if (ch + 2 < kChunks) tmem_ld_wait();
             }
             tcgen05_fence_before();
             __syncwarp();

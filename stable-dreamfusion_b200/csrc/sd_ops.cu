@@ -204,19 +204,27 @@ __global__ void __launch_bounds__(256) k_layernorm(const __half* __restrict__ x,
 }
 
 // ------------------------------------------------------------------ softmax over the last dim, in place or out of place
-// one block per row when cols > 1024, else one warp per row
+// One block per row.  Rows up to 256*8*NV columns live entirely in registers: one read and one write of the row.
+template <int NV>     // 16-byte vectors per thread
 __global__ void __launch_bounds__(256) k_softmax_rows(const __half* __restrict__ x, __half* __restrict__ y, long long rows, int cols, int ld, float scale) {
     const long long row = blockIdx.x;
     const __half* xr = x + row * ld;
     __half* yr = y + row * ld;
     __shared__ float red[8];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    float f[NV][8];
     float mx = -INFINITY;
-    for (int c = tid * 8; c < cols; c += blockDim.x * 8) {
-        if (c + 8 <= cols) { float f[8]; load8(xr + c, f);
 #pragma unroll
-            for (int j = 0; j < 8; j++) mx = fmaxf(mx, f[j] * scale); }
-        else for (int j = c; j < cols; j++) mx = fmaxf(mx, __half2float(xr[j]) * scale);
+    for (int v = 0; v < NV; v++) {
+        const int c = (v * 256 + tid) * 8;
+        if (c + 8 <= cols) {
+            load8(xr + c, f[v]);
+#pragma unroll
+            for (int j = 0; j < 8; j++) { f[v][j] *= scale; mx = fmaxf(mx, f[v][j]); }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; j++) { f[v][j] = (c + j < cols) ? __half2float(xr[c + j]) * scale : -INFINITY; mx = fmaxf(mx, f[v][j]); }
+        }
     }
     mx = warp_max(mx);
     if (lane == 0) red[wid] = mx;
@@ -226,12 +234,10 @@ __global__ void __launch_bounds__(256) k_softmax_rows(const __half* __restrict__
     for (int i = 1; i < 8; i++) mx = fmaxf(mx, red[i]);
     __syncthreads();
     float sum = 0.f;
-    for (int c = tid * 8; c < cols; c += blockDim.x * 8) {
-        if (c + 8 <= cols) { float f[8]; load8(xr + c, f);
 #pragma unroll
-            for (int j = 0; j < 8; j++) sum += __expf(f[j] * scale - mx); }
-        else for (int j = c; j < cols; j++) sum += __expf(__half2float(xr[j]) * scale - mx);
-    }
+    for (int v = 0; v < NV; v++)
+#pragma unroll
+        for (int j = 0; j < 8; j++) { f[v][j] = __expf(f[v][j] - mx); sum += f[v][j]; }
     sum = warp_sum(sum);
     if (lane == 0) red[wid] = sum;
     __syncthreads();
@@ -239,13 +245,35 @@ __global__ void __launch_bounds__(256) k_softmax_rows(const __half* __restrict__
 #pragma unroll
     for (int i = 0; i < 8; i++) sum += red[i];
     const float inv = 1.f / sum;
-    for (int c = tid * 8; c < cols; c += blockDim.x * 8) {
-        if (c + 8 <= cols) { float f[8]; load8(xr + c, f);
 #pragma unroll
-            for (int j = 0; j < 8; j++) f[j] = __expf(f[j] * scale - mx) * inv;
-            store8(yr + c, f); }
-        else for (int j = c; j < cols; j++) yr[j] = __float2half_rn(__expf(__half2float(xr[j]) * scale - mx) * inv);
+    for (int v = 0; v < NV; v++) {
+        const int c = (v * 256 + tid) * 8;
+#pragma unroll
+        for (int j = 0; j < 8; j++) f[v][j] *= inv;
+        if (c + 8 <= cols) store8(yr + c, f[v]);
+        else for (int j = 0; j < 8; j++) if (c + j < cols) yr[c + j] = __float2half_rn(f[v][j]);
     }
+}
+
+// warp per row for short rows (cross-attention: 77 keys)
+__global__ void __launch_bounds__(256) k_softmax_rows_warp(const __half* __restrict__ x, __half* __restrict__ y, long long rows, int cols, int ld, float scale) {
+    const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int lane = threadIdx.x & 31;
+    const __half* xr = x + row * ld;
+    __half* yr = y + row * ld;
+    float f[8];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 8; j++) { const int c = lane + 32 * j; f[j] = c < cols ? __half2float(xr[c]) * scale : -INFINITY; mx = fmaxf(mx, f[j]); }
+    mx = warp_max(mx);
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; j++) { f[j] = __expf(f[j] - mx); sum += f[j]; }
+    sum = warp_sum(sum);
+    const float inv = 1.f / sum;
+#pragma unroll
+    for (int j = 0; j < 8; j++) { const int c = lane + 32 * j; if (c < cols) yr[c] = __float2half_rn(f[j] * inv); }
 }
 
 // dS = scale * P * (dP - sum_j dP_j P_j) per row
@@ -552,7 +580,12 @@ SDF_API int sdf_layernorm_forward(const void* x, int ldx, void* y, int ldy, int 
 SDF_API int sdf_softmax_rows(const void* x, void* y, long long rows, int cols, int ld, float scale, void* stream) {
     if (rows == 0) return SDF_OK;
     SDF_CHECK_ARG(x && y && ld % 8 == 0 && rows < 2147483647LL, "softmax_rows: bad arguments");
-    k_softmax_rows<<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>((const __half*)x, (__half*)y, rows, cols, ld, scale);
+    cudaStream_t st = (cudaStream_t)stream;
+    SDF_CHECK_ARG(cols >= 1 && cols <= 256 * 8 * 4, "softmax_rows: at most 8192 columns");
+    if (cols <= 256) k_softmax_rows_warp<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>((const __half*)x, (__half*)y, rows, cols, ld, scale);
+    else if (cols <= 2048) k_softmax_rows<1><<<(unsigned)rows, 256, 0, st>>>((const __half*)x, (__half*)y, rows, cols, ld, scale);
+    else if (cols <= 4096) k_softmax_rows<2><<<(unsigned)rows, 256, 0, st>>>((const __half*)x, (__half*)y, rows, cols, ld, scale);
+    else k_softmax_rows<4><<<(unsigned)rows, 256, 0, st>>>((const __half*)x, (__half*)y, rows, cols, ld, scale);
     SDF_CHECK_LAUNCH("softmax_rows");
     return SDF_OK;
 }

@@ -87,11 +87,12 @@ class _PtrTensor:
 
 
 def _choose_splitk(M, N, kblocks, block_n):
+    """split-K only when the output tiles cannot fill a third of the SMs AND K is long (3x3 convs at 16x16 / 8x8, the M=2
+    embedding products): every split costs a memset + a reduction launch."""
     tiles = ((M + 127) // 128) * ((N + block_n - 1) // block_n)
-    if tiles >= NUM_SMS // 2 or kblocks < 8:
+    if tiles > NUM_SMS // 3 or kblocks < 16:
         return 1
-    want = max(1, min(NUM_SMS // tiles, kblocks // 4))
-    return want
+    return max(1, min(NUM_SMS // tiles, kblocks // 8))
 
 
 class Builder:

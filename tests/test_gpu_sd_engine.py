@@ -100,8 +100,9 @@ def test_vae_forward_backward(device, cfg, res):
 
 def test_sds_step_small(device):
     unet = make_unet(SMALL_UNET, device, seed=5)
-    vae = make_vae(SMALL_VAE, device, seed=6)
-    eng = E.SDSEngine(unet.state_dict(), vae.state_dict(), device, SMALL_UNET, SMALL_VAE, n_views=1, render_hw=16, ctx_len=7, vae_res=128)
+    vae_cfg = dict(SMALL_VAE, ch_mult=(1, 2, 2, 2))          # three downsamplings: latent = image / 8, as the SD VAE
+    vae = make_vae(vae_cfg, device, seed=6)
+    eng = E.SDSEngine(unet.state_dict(), vae.state_dict(), device, SMALL_UNET, vae_cfg, n_views=1, render_hw=16, ctx_len=7, vae_res=128)
     g = torch.Generator(device="cpu").manual_seed(7)
     rgb = torch.rand(1, 3, 16, 16, generator=g).to(device)
     text = torch.randn(2, 7, 64, generator=g).to(device)

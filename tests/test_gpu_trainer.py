@@ -49,9 +49,9 @@ def test_training_steps_all_shadings(device):
     for n, p in tr.model.named_parameters():
         assert torch.isfinite(p).all(), n
         assert (p.detach() - before[n]).abs().max().item() > 0, f"{n} did not move"
-    # the table moved only where samples fell: a small fraction of entries at the fine levels
+    # Adan's decoupled weight decay touches every table entry, sampled or not
     moved = ((tr.model.encoder.embeddings.detach() - before["encoder.embeddings"]).abs().sum(-1) > 0).float().mean().item()
-    assert 0.0 < moved < 1.0
+    assert moved > 0.5
 
 
 def test_schedule_default_path_and_occupancy_refresh(device):
