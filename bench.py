@@ -245,6 +245,26 @@ def run_ours(args):
     except Exception as e:      # never let the auxiliary measurement kill the bench line
         fld = {"error": repr(e)}
 
+    stages = None
+    if args.breakdown:
+        stages = {}
+        for sh in ("latent", "lambertian", "textureless"):
+            acc = {}
+            for rep in range(3):
+                trainer.stage_events = []
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                trainer.train_step(shading=sh)
+                host_ms = (time.perf_counter() - t0) * 1e3
+                torch.cuda.synchronize()
+                ev = trainer.stage_events
+                for (_, a), (name, b_) in zip(ev[:-1], ev[1:]):
+                    acc[name] = acc.get(name, 0.0) + a.elapsed_time(b_) / 3
+                acc["host issue time"] = acc.get("host issue time", 0.0) + host_ms / 3
+                acc["samples"] = trainer.last_M
+            stages[sh] = acc
+        trainer.stage_events = None
+
     if rank == 0:
         # --- CPU baseline (oracle port) on the host cores: bounded sample
         cpu = None
@@ -270,6 +290,8 @@ def run_ours(args):
                 "e2e": {"value": e2e_v, "unit": "steps/s", "h2d_bytes_per_step": 64, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": int(round(launches_per_step * args.steps)),
                 "roofline": roof, "roofline_field": fld, "cpu_baseline": cpu, "clocks": sampler.summary()}
+        if stages is not None:
+            line["stages"] = stages
         print(json.dumps(line), flush=True)
     if world > 1:
         torch.distributed.destroy_process_group()
@@ -282,6 +304,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--breakdown", action="store_true", help="add per-stage CUDA-event times of one step per shading mode ('stages')")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

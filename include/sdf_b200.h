@@ -152,6 +152,8 @@ int sdf_field_backward(const float* xyzs, uint32_t M, const int* m_dev, const vo
  * w_sy = w_simg = 0 -> shared weights (conv / linear); non-zero -> batched product (attention: y = head, img = batch).
  * Cin = K iterated per tap (multiple of 64); taps = 1 or 9 (3x3, stride 1, zero pad 1; tap = ky*3+kx; packed [n][tap][Cin]).
  * linear: H = 1, Nimg = 1, W = rows.  block_n in {64,128,160}.  splitk > 1 needs workspace fp32 [Nimg*H*W, N].
+ * cta_pair = 1: 2-CTA clusters issue tcgen05.mma.cta_group::2 (M = 256), each CTA stages half of the weight tile;
+ * block_n in {128,160,256}; not available for batched products (w_sy / w_simg != 0).
  * Returns a plan handle >= 0, or a negative error code. */
 int sdf_gemm_plan_create(const void* a, long long a_sx, long long a_sy, long long a_simg, int a_c_valid,
                          const void* wt, long long w_ld, long long w_sy, long long w_simg, int w_k_valid, int n_rows_w,
@@ -159,7 +161,7 @@ int sdf_gemm_plan_create(const void* a, long long a_sx, long long a_sy, long lon
                          void* out, long long o_sx, long long o_sy, long long o_simg,
                          const float* bias, const void* temb, int temb_ld,
                          const void* residual, long long r_sx, long long r_sy, long long r_simg,
-                         int act, float alpha, int splitk, float* workspace, int block_n);
+                         int act, float alpha, int splitk, float* workspace, int block_n, int cta_pair);
 int sdf_gemm_run(int plan, void* stream);
 int sdf_gemm_plan_destroy(int plan);
 
@@ -171,6 +173,11 @@ int sdf_groupnorm_backward(const void* x, int ldx, const void* dy, int ldd, void
                            int accumulate, void* stream);
 int sdf_layernorm_forward(const void* x, int ldx, void* y, int ldy, int rows, int C, const float* gamma, const float* beta, float eps, void* stream);
 int sdf_softmax_rows(const void* x, void* y, long long rows, int cols, int ld, float scale, void* stream);
+/* Fused multi-head attention forward, o[b,i,h*d:(h+1)*d] = softmax_j(scale * q[b,i,h].k[b,j,h]) v[b,j,h]; fp16, token-major
+ * [B, tokens, heads*d] with row strides ldq/ldk/ldo (elements).  Replaces einsum + softmax + einsum of CrossAttention.forward,
+ * ldm/modules/attention.py:170-193 (diffusers' attention processor under guidance/sd_utils.py:104).  d in {32, 40, 64, 80, 160}. */
+int sdf_flash_attention(const void* q, const void* k, const void* v, void* o, int B, int heads, int n, int nkv, int d,
+                        int ldq, int ldk, int ldo, float scale, void* stream);
 int sdf_softmax_rows_backward(const void* p, const void* dp, void* ds, long long rows, int cols, int ld, float scale, void* stream);
 int sdf_geglu(const void* x, int ldx, void* y, int ldy, long long rows, int inner, void* stream);
 int sdf_upsample_nearest2(const void* x, int ldx, void* y, int ldy, int Nimg, int H, int W, int C, void* stream);

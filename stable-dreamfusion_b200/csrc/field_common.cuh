@@ -102,38 +102,75 @@ __device__ __forceinline__ void locate_cell(Cell& c, float x, float y, float z, 
     }
 }
 
+// The 8 corners of one (point, level): table indices (relative to the level) and trilinear weights in the reference's corner
+// order (bit 0 = x, bit 1 = y, bit 2 = z; gridencoder.cu:150-175).  ONE branch per level (hashed / dense; lanes of a warp hold
+// different levels, so it only diverges for the 4-level group that straddles the dense->hash switch) and branch-free index
+// arithmetic inside, so the caller can issue all of its gathers back to back.
+struct Corners {
+    uint32_t idx[8];
+    float w[8];
+};
+
+__device__ __forceinline__ void level_corners(Corners& c, const LevelSmem& lv, float x, float y, float z, bool smooth) {
+    Cell cell;
+    locate_cell<false>(cell, x, y, z, lv.res, smooth);
+    const uint32_t x0 = cell.pg[0], y0 = cell.pg[1], z0 = cell.pg[2];
+    const uint32_t x1 = min(x0 + 1, lv.res - 1), y1 = min(y0 + 1, lv.res - 1), z1 = min(z0 + 1, lv.res - 1);
+    const float fx = cell.f[0], fy = cell.f[1], fz = cell.f[2];
+    const float wxy[4] = {(1.f - fx) * (1.f - fy), fx * (1.f - fy), (1.f - fx) * fy, fx * fy};
+#pragma unroll
+    for (int k = 0; k < 8; k++) c.w[k] = wxy[k & 3] * ((k & 4) ? fz : 1.f - fz);
+    if (lv.flags & 1u) {
+        // spatial hash (gridencoder.cu:53-60): x ^ y*2654435761 ^ z*805459861, modulo the level size
+        const uint32_t ya[2] = {y0 * 2654435761u, y1 * 2654435761u}, za[2] = {z0 * 805459861u, z1 * 805459861u};
+        const uint32_t xa[2] = {x0, x1};
+        if (lv.flags & 2u) {
+            const uint32_t mask = lv.size - 1;
+#pragma unroll
+            for (int k = 0; k < 8; k++) c.idx[k] = (xa[k & 1] ^ ya[(k >> 1) & 1] ^ za[k >> 2]) & mask;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; k++) c.idx[k] = (xa[k & 1] ^ ya[(k >> 1) & 1] ^ za[k >> 2]) % lv.size;
+        }
+    } else {
+        // dense levels (flag clear <=> res^3 <= size, load_weights): the reference's `index % size` (gridencoder.cu:79) is the
+        // identity because x + y*res + z*res^2 <= res^3 - 1 < size
+        const uint32_t ya[2] = {y0 * lv.res, y1 * lv.res}, za[2] = {z0 * lv.res * lv.res, z1 * lv.res * lv.res};
+        const uint32_t xa[2] = {x0, x1};
+#pragma unroll
+        for (int k = 0; k < 8; k++) c.idx[k] = xa[k & 1] + ya[(k >> 1) & 1] + za[k >> 2];
+    }
+}
+
 __device__ __forceinline__ uint32_t corner_index(const LevelSmem& lv, uint32_t x, uint32_t y, uint32_t z) {
     if (lv.flags & 1u) {
         const uint32_t h = x ^ (y * 2654435761u) ^ (z * 805459861u);
         return (lv.flags & 2u) ? (h & (lv.size - 1)) : (h % lv.size);
     }
-    // dense levels: the reference adds p_d * stride_d while stride_d <= size
-    uint32_t idx = x, stride = lv.res;
-    if (stride <= lv.size) { idx += y * stride; stride *= lv.res; }
-    if (stride <= lv.size) { idx += z * stride; }
-    return idx % lv.size;
+    return x + (y + z * lv.res) * lv.res;
 }
 
-// Trilinear (smoothstepped) lookup of one level for a point in [0,1]^3; returns the 2 features in fp32.
-__device__ __forceinline__ float2 encode_level(const __half2* __restrict__ table, const LevelSmem& lv,
-                                               float x, float y, float z, bool smooth) {
-    Cell c;
-    locate_cell<false>(c, x, y, z, lv.res, smooth);
+// Trilinear (smoothstepped) lookup of one level for TWO points in [0,1]^3 (the two rows a lane owns): all 16 gathers are issued
+// before the first one is consumed.  Points outside the unit cube (valid == false) still gather (their cell is clamped) and
+// are zeroed afterwards.
+__device__ __forceinline__ void encode_level_pair(const __half2* __restrict__ table, const LevelSmem& lv, const float pa[3], bool va,
+                                                  const float pb[3], bool vb, bool smooth, float2& ea, float2& eb) {
+    Corners ca, cb;
+    level_corners(ca, lv, pa[0], pa[1], pa[2], smooth);
+    level_corners(cb, lv, pb[0], pb[1], pb[2], smooth);
     const __half2* t = table + lv.offset;
-    const uint32_t x0 = c.pg[0], y0 = c.pg[1], z0 = c.pg[2];
-    const uint32_t x1 = min(x0 + 1, lv.res - 1), y1 = min(y0 + 1, lv.res - 1), z1 = min(z0 + 1, lv.res - 1);
-    const float fx = c.f[0], fy = c.f[1], fz = c.f[2];
-    float2 acc = make_float2(0.f, 0.f);
+    __half2 ha[8], hb[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) { ha[k] = __ldg(t + ca.idx[k]); hb[k] = __ldg(t + cb.idx[k]); }
+    float2 aa = make_float2(0.f, 0.f), ab = make_float2(0.f, 0.f);
 #pragma unroll
     for (int k = 0; k < 8; k++) {
-        const uint32_t xi = (k & 1) ? x1 : x0, yi = (k & 2) ? y1 : y0, zi = (k & 4) ? z1 : z0;
-        const float w = ((k & 1) ? fx : 1.f - fx) * ((k & 2) ? fy : 1.f - fy) * ((k & 4) ? fz : 1.f - fz);
-        const __half2 hv = __ldg(t + corner_index(lv, xi, yi, zi));
-        const float2 v = __half22float2(hv);
-        acc.x = fmaf(w, v.x, acc.x);
-        acc.y = fmaf(w, v.y, acc.y);
+        const float2 v = __half22float2(ha[k]), u = __half22float2(hb[k]);
+        aa.x = fmaf(ca.w[k], v.x, aa.x); aa.y = fmaf(ca.w[k], v.y, aa.y);
+        ab.x = fmaf(cb.w[k], u.x, ab.x); ab.y = fmaf(cb.w[k], u.y, ab.y);
     }
-    return acc;
+    ea = va ? aa : make_float2(0.f, 0.f);
+    eb = vb ? ab : make_float2(0.f, 0.f);
 }
 
 // The encoder of one stencil point for the two rows a lane owns, in A-fragment order:
@@ -152,8 +189,7 @@ __device__ __forceinline__ void encode_rows(uint32_t a[2][4], const WeightsSmem&
             float2 ea = make_float2(0.f, 0.f), eb = make_float2(0.f, 0.f);
             if (level < p.n_levels_active) {
                 const LevelSmem lv = s.lv[level];
-                if (va) ea = encode_level(p.table, lv, pa[0], pa[1], pa[2], smooth);
-                if (vb) eb = encode_level(p.table, lv, pb[0], pb[1], pb[2], smooth);
+                encode_level_pair(p.table, lv, pa, va, pb, vb, smooth, ea, eb);
             }
             a[kt][h * 2 + 0] = pack_half2(ea.x, ea.y);
             a[kt][h * 2 + 1] = pack_half2(eb.x, eb.y);

@@ -116,21 +116,14 @@ __device__ __forceinline__ void sample_grads(float gsig[7], float glogit[3], con
     for (int c = 0; c < 3; c++) glogit[c] = galb[c] * alb[c] * (1.f - alb[c]);
 }
 
-// Scatter d(enc) of one (row, level) into the fp32 table gradient (same geometry as encode_level).
+// Scatter d(enc) of one (row, level) into the fp32 table gradient (same corner geometry as the forward gather).
 __device__ __forceinline__ void scatter_level(float* __restrict__ grad_table, const LevelSmem& lv, float x, float y, float z,
                                               bool smooth, float g0, float g1) {
-    Cell c;
-    locate_cell<false>(c, x, y, z, lv.res, smooth);
-    float* t = grad_table + (size_t)lv.offset * 2;
-    const uint32_t x0 = c.pg[0], y0 = c.pg[1], z0 = c.pg[2];
-    const uint32_t x1 = min(x0 + 1, lv.res - 1), y1 = min(y0 + 1, lv.res - 1), z1 = min(z0 + 1, lv.res - 1);
-    const float fx = c.f[0], fy = c.f[1], fz = c.f[2];
+    Corners c;
+    level_corners(c, lv, x, y, z, smooth);
+    float2* t = reinterpret_cast<float2*>(grad_table) + lv.offset;
 #pragma unroll
-    for (int k = 0; k < 8; k++) {
-        const uint32_t xi = (k & 1) ? x1 : x0, yi = (k & 2) ? y1 : y0, zi = (k & 4) ? z1 : z0;
-        const float w = ((k & 1) ? fx : 1.f - fx) * ((k & 2) ? fy : 1.f - fy) * ((k & 4) ? fz : 1.f - fz);
-        atomicAdd(reinterpret_cast<float2*>(t + (size_t)corner_index(lv, xi, yi, zi) * 2), make_float2(w * g0, w * g1));
-    }
+    for (int k = 0; k < 8; k++) atomicAdd(t + c.idx[k], make_float2(c.w[k] * g0, c.w[k] * g1));
 }
 
 __device__ __forceinline__ void st_half(__half* base, int stride, int feat, int row, float v) {

@@ -74,6 +74,34 @@ __device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* ba
     asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
                  ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
+// ---- CTA-pair (cta_group::2) variants: the two CTAs of a cluster share one M=256 MMA; rank 0 issues it.
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t saddr, uint32_t rank) {
+    uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank)); return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load whose completion is signalled on a barrier of the pair's leader CTA (address in the shared::cluster window)
+__device__ __forceinline__ void tma_load_4d_pair(const CUtensorMap* map, uint32_t bar_cluster_addr, void* dst, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {      // arrives on the same barrier offset in both CTAs
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
@@ -113,20 +141,24 @@ __device__ __forceinline__ float act_apply(float v, int act) {
     return v;
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool PAIR>
 struct SmemLayout {
     static constexpr int kABytes = kBlockM * kBlockK * 2;
-    static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
+    static constexpr int kBRows = PAIR ? BLOCK_N / 2 : BLOCK_N;      // a CTA pair splits the B tile between its two CTAs
+    static constexpr int kBBytes = kBRows * kBlockK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
-    static constexpr int kStages = (BLOCK_N <= 64) ? 8 : (BLOCK_N <= 128 ? 6 : 5);
+    static constexpr int kMaxStages = (220 * 1024) / kStageBytes;
+    static constexpr int kStages = kMaxStages > 8 ? 8 : kMaxStages;
     static constexpr int kBarrierBytes = (2 * kStages + 4) * 8 + 16;
     static constexpr int kTotal = kStages * kStageBytes + kBarrierBytes + 1024;   // + alignment slack
+    static_assert(kStageBytes % 1024 == 0, "stages must keep the 1024-byte swizzle-atom alignment");
+    static_assert(kTotal <= 227 * 1024, "shared memory budget");
 };
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool PAIR>
 __global__ void __launch_bounds__(kNumThreads, 1)
 k_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const GemmArgs g) {
-    using L = SmemLayout<BLOCK_N>;
+    using L = SmemLayout<BLOCK_N, PAIR>;
     constexpr int kStages = L::kStages;
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -143,17 +175,25 @@ k_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtens
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
     }
+    // PAIR: rank 0 of the 2-CTA cluster is the leader (issues the M=256 MMAs, owns the full / tmem_empty barriers that count
+    // both CTAs); every CTA owns its empty / tmem_full barriers, which the leader's commits reach by multicast.
+    const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < kStages; i++) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-        for (int i = 0; i < 2; i++) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], kEpiWarps); }
+        for (int i = 0; i < 2; i++) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], PAIR ? 2 * kEpiWarps : kEpiWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_smem)), "r"(kTmemCols));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        if (PAIR) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_smem)), "r"(kTmemCols));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_smem)), "r"(kTmemCols));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        }
     }
     tcgen05_fence_before();
-    __syncthreads();
+    if (PAIR) cluster_sync_all(); else __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_base_smem;
 
@@ -164,35 +204,49 @@ k_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtens
     const int kb_per_tap = g.Cin / kBlockK;
     const int kb_total = g.taps * kb_per_tap;
     const int kb_per_split = (kb_total + g.splitk - 1) / g.splitk;
-    const int total_work = m_tiles * n_tiles * g.splitk;
+    // PAIR: a work item is a pair of consecutive M tiles (this CTA takes 2*pair + rank; a tile past the end is all zero fill)
+    const int m_units = PAIR ? (m_tiles + 1) / 2 : m_tiles;
+    const int total_work = m_units * n_tiles * g.splitk;
+    const int worker = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int n_workers = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
-            for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+            for (int w = worker; w < total_work; w += n_workers) {
                 const int split = w % g.splitk; const int t2 = w / g.splitk;
-                const int nt = t2 % n_tiles, mt = t2 / n_tiles;
+                const int nt = t2 % n_tiles, mt = PAIR ? 2 * (t2 / n_tiles) + (int)cta_rank : t2 / n_tiles;
                 const int tx = mt % tiles_x, ty = (mt / tiles_x) % tiles_y, tz = mt / (tiles_x * tiles_y);
-                const int x0 = tx * g.tw, y0 = ty * g.th, i0 = tz * g.tn, n0 = nt * BLOCK_N;
+                const int x0 = tx * g.tw, y0 = ty * g.th, i0 = tz * g.tn, n0 = nt * BLOCK_N + (PAIR ? (int)cta_rank * L::kBRows : 0);
                 const int kb0 = split * kb_per_split, kb1 = min(kb_total, kb0 + kb_per_split);
+                const uint32_t a_bytes = (uint32_t)(g.tw * g.th * g.tn * kBlockK * 2);
                 for (int kb = kb0; kb < kb1; kb++) {
                     const int tap = kb / kb_per_tap, cb = kb - tap * kb_per_tap;
                     const int dy = g.pad ? tap / 3 - 1 : 0, dx = g.pad ? tap % 3 - 1 : 0;
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     unsigned char* sa = smem + stage * L::kStageBytes;
-                    mbar_expect_tx(&full_bar[stage], (uint32_t)(g.tw * g.th * g.tn * kBlockK * 2) + L::kBBytes);
-                    tma_load_4d(&map_a, &full_bar[stage], sa, cb * kBlockK, x0 + dx, y0 + dy, i0);
-                    tma_load_4d(&map_b, &full_bar[stage], sa + L::kABytes, kb * kBlockK, n0, g.w_by ? y0 : 0, g.w_bimg ? i0 : 0);
+                    if (PAIR) {
+                        // both CTAs' loads complete on the leader's barrier, which expects the bytes of the whole pair
+                        if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * (a_bytes + (uint32_t)L::kBBytes));
+                        const uint32_t bar = map_to_cta(smem_u32(&full_bar[stage]), 0);
+                        tma_load_4d_pair(&map_a, bar, sa, cb * kBlockK, x0 + dx, y0 + dy, i0);
+                        tma_load_4d_pair(&map_b, bar, sa + L::kABytes, kb * kBlockK, n0, 0, 0);
+                    } else {
+                        mbar_expect_tx(&full_bar[stage], a_bytes + L::kBBytes);
+                        tma_load_4d(&map_a, &full_bar[stage], sa, cb * kBlockK, x0 + dx, y0 + dy, i0);
+                        tma_load_4d(&map_b, &full_bar[stage], sa + L::kABytes, kb * kBlockK, n0, g.w_by ? y0 : 0, g.w_bimg ? i0 : 0);
+                    }
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
+      if (cta_rank == 0) {
+        // ===================== MMA issuer (leader CTA only in PAIR mode) =====================
+        constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)((PAIR ? 2 * kBlockM : kBlockM) >> 4) << 24);
         int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
-        for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+        for (int w = worker; w < total_work; w += n_workers) {
             const int split = w % g.splitk;
             const int kb0 = split * kb_per_split, kb1 = min(kb_total, kb0 + kb_per_split);
             mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
@@ -207,17 +261,19 @@ k_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtens
 #pragma unroll
                     for (int k = 0; k < kBlockK / kUmmaK; k++) {
                         // advance 32 bytes (16 fp16) inside the swizzled row: +2 in 16-byte units
-                        umma_f16(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                        if (PAIR) umma_f16_pair(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                        else umma_f16(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb > kb0 || k > 0) ? 1u : 0u);
                     }
-                    umma_commit(&empty_bar[stage]);                       // frees the smem slot when the MMAs retire
-                    if (kb == kb1 - 1) umma_commit(&tmem_full[acc]);      // accumulator ready for the epilogue
+                    // frees the smem slot when the MMAs retire; on the last k-block the accumulator is ready for the epilogue
+                    if (PAIR) { umma_commit_pair(&empty_bar[stage]); if (kb == kb1 - 1) umma_commit_pair(&tmem_full[acc]); }
+                    else { umma_commit(&empty_bar[stage]); if (kb == kb1 - 1) umma_commit(&tmem_full[acc]); }
                 }
                 __syncwarp();
                 if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
-            if (kb1 <= kb0 && lane == 0) umma_commit(&tmem_full[acc]);      // empty K range (cannot happen with valid args)
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
+      }
     } else {
         // ===================== epilogue (8 warps: TMEM lane quarter q = warp % 4, two warps interleave 32-column chunks) ==========
         const int q = warp & 3;                      // TMEM lanes 32q .. 32q+31
@@ -225,9 +281,9 @@ k_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtens
         const int r = q * 32 + lane;                 // row of the tile
         constexpr int kChunks = BLOCK_N / 32;        // 2, 4 or 5
         int acc = 0; uint32_t acc_phase = 0;
-        for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+        for (int w = worker; w < total_work; w += n_workers) {
             const int t2 = w / g.splitk;
-            const int nt = t2 % n_tiles, mt = t2 / n_tiles;
+            const int nt = t2 % n_tiles, mt = PAIR ? 2 * (t2 / n_tiles) + (int)cta_rank : t2 / n_tiles;
             const int tx = mt % tiles_x, ty = (mt / tiles_x) % tiles_y, tz = mt / (tiles_x * tiles_y);
             const int lx = r % g.tw, ly = (r / g.tw) % g.th, li = r / (g.tw * g.th);
             const int x = tx * g.tw + lx, y = ty * g.th + ly, img = tz * g.tn + li;
@@ -312,16 +368,20 @@ k_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtens
             }
             tcgen05_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            if (lane == 0) {
+                if (PAIR) mbar_arrive_cluster(map_to_cta(smem_u32(&tmem_empty[acc]), 0));      // the leader's MMA warp waits for both CTAs
+                else mbar_arrive(&tmem_empty[acc]);
+            }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     }
 
     tcgen05_fence_before();
-    __syncthreads();
+    if (PAIR) cluster_sync_all(); else __syncthreads();      // PAIR: neither CTA may leave while its partner still uses its smem / TMEM / barriers
     if (warp == 2) {
         tcgen05_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
+        if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
     }
 }
 
@@ -360,23 +420,34 @@ struct GemmPlan {
     CUtensorMap map_a, map_b;
     GemmArgs args;
     int block_n;
+    int pair;        // 1: 2-CTA clusters (cta_group::2), grid is even
     int grid;
 };
 
 std::mutex g_plan_mu;
 std::vector<GemmPlan*> g_plans;
 
-template <int BN>
+template <int BN, bool PAIR>
 int launch_gemm(const GemmPlan& p, cudaStream_t st) {
-    using L = SmemLayout<BN>;
+    using L = SmemLayout<BN, PAIR>;
     static bool attr_set[64] = {false};
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 64 && !attr_set[dev]) {
-        SDF_CHECK_CUDA(cudaFuncSetAttribute(k_gemm<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+        SDF_CHECK_CUDA(cudaFuncSetAttribute(k_gemm<BN, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
         attr_set[dev] = true;
     }
-    k_gemm<BN><<<p.grid, kNumThreads, L::kTotal, st>>>(p.map_a, p.map_b, p.args);
+    if (!PAIR) {
+        k_gemm<BN, PAIR><<<p.grid, kNumThreads, L::kTotal, st>>>(p.map_a, p.map_b, p.args);
+        return SDF_OK;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(p.grid); cfg.blockDim = dim3(kNumThreads); cfg.dynamicSmemBytes = L::kTotal; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    SDF_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k_gemm<BN, PAIR>, p.map_a, p.map_b, p.args));
     return SDF_OK;
 }
 
@@ -395,6 +466,8 @@ int launch_gemm(const GemmPlan& p, cudaStream_t st) {
 //   linear   : H = 1, Nimg = 1, W = rows.
 //   bias fp32 [N], temb fp16 [Nimg, temb_ld], residual fp16 (strides r_*) optional (NULL).
 //   act      : 0 none, 1 SiLU, 2 GELU(erf).  splitk > 1 needs workspace fp32 [Nimg*H*W, N].  block_n in {64, 128, 160}.
+//   cta_pair : 1 -> 2-CTA clusters (tcgen05 cta_group::2, M = 256 per MMA, each CTA stages half of the weight tile);
+//              block_n in {128, 160, 256}; not for batched products.
 // Returns a handle >= 0 or a negative error code.
 SDF_API int sdf_gemm_plan_create(const void* a, long long a_sx, long long a_sy, long long a_simg, int a_c_valid,
                                  const void* wt, long long w_ld, long long w_sy, long long w_simg, int w_k_valid, int n_rows_w,
@@ -402,7 +475,7 @@ SDF_API int sdf_gemm_plan_create(const void* a, long long a_sx, long long a_sy, 
                                  void* out, long long o_sx, long long o_sy, long long o_simg,
                                  const float* bias, const void* temb, int temb_ld,
                                  const void* residual, long long r_sx, long long r_sy, long long r_simg,
-                                 int act, float alpha, int splitk, float* workspace, int block_n) {
+                                 int act, float alpha, int splitk, float* workspace, int block_n, int cta_pair) {
     SDF_CHECK_ARG(a && wt && out, "gemm_plan: null pointer");
     SDF_CHECK_ARG(Cin > 0 && Cin % kBlockK == 0, "gemm_plan: Cin must be a positive multiple of 64");
     SDF_CHECK_ARG(taps == 1 || taps == 9, "gemm_plan: taps must be 1 or 9");
@@ -412,7 +485,9 @@ SDF_API int sdf_gemm_plan_create(const void* a, long long a_sx, long long a_sy, 
                   "gemm_plan: operand strides must be multiples of 8 elements");
     SDF_CHECK_ARG(o_sx % 8 == 0 && o_sy % 8 == 0 && o_simg % 8 == 0, "gemm_plan: output strides must be multiples of 8 elements");
     SDF_CHECK_ARG(!residual || (((uintptr_t)residual & 15) == 0 && r_sx % 8 == 0 && r_sy % 8 == 0 && r_simg % 8 == 0), "gemm_plan: residual alignment");
-    SDF_CHECK_ARG(block_n == 64 || block_n == 128 || block_n == 160, "gemm_plan: block_n must be 64, 128 or 160");
+    SDF_CHECK_ARG(cta_pair ? (block_n == 128 || block_n == 160 || block_n == 256) : (block_n == 64 || block_n == 128 || block_n == 160),
+                  "gemm_plan: block_n must be 64, 128 or 160 (128, 160 or 256 with cta_pair)");
+    SDF_CHECK_ARG(!cta_pair || (w_sy == 0 && w_simg == 0), "gemm_plan: cta_pair needs one weight matrix shared by all tiles (not a batched product)");
     SDF_CHECK_ARG(N > 0 && n_rows_w > 0 && Nimg > 0 && H > 0 && W > 0, "gemm_plan: bad sizes");
     SDF_CHECK_ARG(splitk >= 1 && (splitk == 1 || workspace), "gemm_plan: split-K needs a workspace");
     PFN_encodeTiled enc = get_encode();
@@ -442,6 +517,7 @@ SDF_API int sdf_gemm_plan_create(const void* a, long long a_sx, long long a_sy, 
     g.out = (__half*)out; g.o_sx = o_sx; g.o_sy = o_sy; g.o_simg = o_simg; g.workspace = workspace;
     g.act = act; g.alpha = alpha;
     p->block_n = block_n;
+    p->pair = cta_pair ? 1 : 0;
 
     auto stride_or = [](long long s, long long fallback) { return (cuuint64_t)((s != 0 ? s : fallback) * 2); };
     {   // A: 4-D map (c, x, y, img), 128B swizzle, zero OOB fill
@@ -459,7 +535,7 @@ SDF_API int sdf_gemm_plan_create(const void* a, long long a_sx, long long a_sy, 
         cuuint64_t dims[4] = {(cuuint64_t)w_k_valid, (cuuint64_t)n_rows_w, (cuuint64_t)(g.w_by ? H : 1), (cuuint64_t)(g.w_bimg ? Nimg : 1)};
         const long long rows_bytes_el = w_ld * (long long)n_rows_w;
         cuuint64_t strides[3] = {(cuuint64_t)w_ld * 2, stride_or(w_sy, rows_bytes_el), stride_or(w_simg, rows_bytes_el * (g.w_by ? H : 1))};
-        cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)block_n, 1, 1};
+        cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)(cta_pair ? block_n / 2 : block_n), 1, 1};
         cuuint32_t estr[4] = {1, 1, 1, 1};
         CUresult r = enc(&p->map_b, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(wt), dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -467,8 +543,10 @@ SDF_API int sdf_gemm_plan_create(const void* a, long long a_sx, long long a_sy, 
         if (r != CUDA_SUCCESS) { delete p; sdf_set_error("gemm_plan: cuTensorMapEncodeTiled(B) failed (%d)", (int)r); return SDF_ERR_CUDA; }
     }
     const int tiles_x = (W + g.tw - 1) / g.tw, tiles_y = (H + g.th - 1) / g.th, tiles_i = (Nimg + g.tn - 1) / g.tn;
-    const long long work = (long long)tiles_x * tiles_y * tiles_i * ((N + block_n - 1) / block_n) * splitk;
-    p->grid = work < kNumSMs ? (int)work : kNumSMs;
+    const long long m_tiles = (long long)tiles_x * tiles_y * tiles_i;
+    const long long work = (cta_pair ? (m_tiles + 1) / 2 : m_tiles) * ((N + block_n - 1) / block_n) * splitk;
+    if (cta_pair) p->grid = 2 * (int)std::min<long long>(work, kNumSMs / 2);
+    else p->grid = work < kNumSMs ? (int)work : kNumSMs;
     std::lock_guard<std::mutex> lk(g_plan_mu);
     g_plans.push_back(p);
     return (int)g_plans.size() - 1;
@@ -485,9 +563,15 @@ SDF_API int sdf_gemm_run(int plan, void* stream) {
     const GemmArgs& g = p->args;
     if (g.splitk > 1) SDF_CHECK_CUDA(cudaMemsetAsync(g.workspace, 0, (size_t)g.M * g.N * sizeof(float), st));
     int rc;
-    if (p->block_n == 64) rc = launch_gemm<64>(*p, st);
-    else if (p->block_n == 128) rc = launch_gemm<128>(*p, st);
-    else rc = launch_gemm<160>(*p, st);
+    if (p->pair) {
+        if (p->block_n == 128) rc = launch_gemm<128, true>(*p, st);
+        else if (p->block_n == 160) rc = launch_gemm<160, true>(*p, st);
+        else rc = launch_gemm<256, true>(*p, st);
+    } else {
+        if (p->block_n == 64) rc = launch_gemm<64, false>(*p, st);
+        else if (p->block_n == 128) rc = launch_gemm<128, false>(*p, st);
+        else rc = launch_gemm<160, false>(*p, st);
+    }
     if (rc) return rc;
     SDF_CHECK_LAUNCH("gemm");
     if (g.splitk > 1) {

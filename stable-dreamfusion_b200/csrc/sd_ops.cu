@@ -13,7 +13,10 @@
 
 namespace {
 
-__device__ __forceinline__ float silu(float v) { return v / (1.f + __expf(-v)); }
+__device__ __forceinline__ float tanh_approx(float v) { float r; asm("tanh.approx.f32 %0, %1;" : "=f"(r) : "f"(v)); return r; }
+// sigmoid(v) = 0.5 tanh(v/2) + 0.5: one MUFU op instead of ex2 + rcp (the apply kernels are otherwise MUFU-limited)
+__device__ __forceinline__ float sigmoid_fast(float v) { return fmaf(0.5f, tanh_approx(0.5f * v), 0.5f); }
+__device__ __forceinline__ float silu(float v) { const float h = 0.5f * v; return fmaf(h, tanh_approx(h), h); }
 __device__ __forceinline__ float gelu(float v) { return 0.5f * v * (1.f + erff(v * 0.70710678118654752f)); }
 
 struct H8 { uint4 u; };
@@ -76,29 +79,58 @@ __global__ void __launch_bounds__(256) k_gn_stats(const __half* __restrict__ x, 
     for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) atomicAdd(&stats[(long long)img * G * 2 + i], sm[i]);
 }
 
-// y = (x - mean) * rstd * gamma + beta, optional SiLU.  Writes y with row stride ldy.
-__global__ void __launch_bounds__(256) k_gn_apply(const __half* __restrict__ x, int ldx, __half* __restrict__ y, int ldy, int HW, int C, int G,
-                                                  const float* __restrict__ stats, const float* __restrict__ gamma,
-                                                  const float* __restrict__ beta, float eps, int act, long long total_vec) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total_vec) return;
-    const int vec_per_pix = C / 8;
-    const long long pix = i / vec_per_pix;
-    const int v = (int)(i - pix * vec_per_pix);
-    const int img = (int)(pix / HW);
-    const int cpg = C / G;
-    const float cnt = (float)HW * cpg;
-    float f[8];
-    load8(x + pix * ldx + v * 8, f);
+// Per-thread channel constants of one 16-byte channel vector: mean / rstd of each channel's group.
+__device__ __forceinline__ void gn_channel_stats(const float* __restrict__ stats, int img, int G, int cpg, float inv_cnt, float eps, int v,
+                                                 float mean[8], float rstd[8]) {
 #pragma unroll
     for (int j = 0; j < 8; j++) {
-        const int c = v * 8 + j, gi = c / cpg;
-        const float mean = stats[((long long)img * G + gi) * 2] / cnt;
-        const float var = fmaxf(stats[((long long)img * G + gi) * 2 + 1] / cnt - mean * mean, 0.f);
-        float o = (f[j] - mean) * rsqrtf(var + eps) * gamma[c] + beta[c];
-        f[j] = act ? silu(o) : o;
+        const int gi = (v * 8 + j) / cpg;
+        const float m = stats[((long long)img * G + gi) * 2] * inv_cnt;
+        const float var = fmaxf(stats[((long long)img * G + gi) * 2 + 1] * inv_cnt - m * m, 0.f);
+        mean[j] = m; rstd[j] = rsqrtf(var + eps);
     }
-    store8(y + pix * ldy + v * 8, f);
+}
+
+// y = (x - mean) * rstd * gamma + beta, optional SiLU.  Same slab decomposition as k_gn_stats: a thread owns one channel vector,
+// folds the normalisation into y = x * a + b once, and streams its pixels (4 independent 16-byte loads in flight).
+template <bool ACT>
+__global__ void __launch_bounds__(256) k_gn_apply(const __half* __restrict__ x, int ldx, __half* __restrict__ y, int ldy, int HW, int C, int G,
+                                                  int pix_per_block, const float* __restrict__ stats, const float* __restrict__ gamma,
+                                                  const float* __restrict__ beta, float eps) {
+    const int img = blockIdx.y;
+    const int cpg = C / G, vpp = C / 8;
+    const float inv_cnt = 1.f / ((float)HW * cpg);
+    const int p0 = blockIdx.x * pix_per_block, p1 = min(HW, p0 + pix_per_block);
+    const long long base = (long long)img * HW;
+    const int ngroups = max(1, (int)blockDim.x / vpp);
+    for (int idx = threadIdx.x; idx < vpp * ngroups; idx += blockDim.x) {
+        const int v = idx % vpp, pg = idx / vpp;
+        float a[8], b[8];
+        gn_channel_stats(stats, img, G, cpg, inv_cnt, eps, v, b, a);
+#pragma unroll
+        for (int j = 0; j < 8; j++) { a[j] *= gamma[v * 8 + j]; b[j] = fmaf(-b[j], a[j], beta[v * 8 + j]); }
+        const __half* xp = x + v * 8;
+        __half* yp = y + v * 8;
+        int pix = p0 + pg;
+        for (; pix + 3 * ngroups < p1; pix += 4 * ngroups) {
+            float f[4][8];
+#pragma unroll
+            for (int u = 0; u < 4; u++) load8(xp + (base + pix + u * ngroups) * ldx, f[u]);
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+#pragma unroll
+                for (int j = 0; j < 8; j++) { const float o = fmaf(f[u][j], a[j], b[j]); f[u][j] = ACT ? silu(o) : o; }
+                store8(yp + (base + pix + u * ngroups) * ldy, f[u]);
+            }
+        }
+        for (; pix < p1; pix += ngroups) {
+            float f[8];
+            load8(xp + (base + pix) * ldx, f);
+#pragma unroll
+            for (int j = 0; j < 8; j++) { const float o = fmaf(f[j], a[j], b[j]); f[j] = ACT ? silu(o) : o; }
+            store8(yp + (base + pix) * ldy, f);
+        }
+    }
 }
 
 // GroupNorm(+SiLU) backward wrt x (weights frozen).  Pass 1: per (img, group) sums of dy_hat and dy_hat * xhat,
@@ -120,25 +152,35 @@ __global__ void __launch_bounds__(256) k_gn_bwd_stats(const __half* __restrict__
     for (int idx = threadIdx.x; idx < vpp * ngroups; idx += blockDim.x) {
         const int v = idx % vpp, pg = idx / vpp;
         float mean[8], rstd[8], gam[8], bet[8], s[8], ss[8];
+        gn_channel_stats(stats, img, G, cpg, 1.f / cnt, eps, v, mean, rstd);
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
-            const int c = v * 8 + j, gi = c / cpg;
-            mean[j] = stats[((long long)img * G + gi) * 2] / cnt;
-            const float var = fmaxf(stats[((long long)img * G + gi) * 2 + 1] / cnt - mean[j] * mean[j], 0.f);
-            rstd[j] = rsqrtf(var + eps); gam[j] = gamma[c]; bet[j] = beta[c]; s[j] = ss[j] = 0.f;
-        }
-        for (int pix = p0 + pg; pix < p1; pix += ngroups) {
-            float fx[8], fd[8];
-            load8(x + (base + pix) * ldx + v * 8, fx);
-            load8(dy + (base + pix) * ldd + v * 8, fd);
+        for (int j = 0; j < 8; j++) { gam[j] = gamma[v * 8 + j]; bet[j] = beta[v * 8 + j]; s[j] = ss[j] = 0.f; }
+        int pix = p0 + pg;
+        auto accumulate = [&](const float fx[8], const float fd[8]) {
 #pragma unroll
             for (int j = 0; j < 8; j++) {
                 const float xh = (fx[j] - mean[j]) * rstd[j];
                 float g = fd[j];
-                if (act) { const float o = xh * gam[j] + bet[j]; const float sg = 1.f / (1.f + __expf(-o)); g *= sg * (1.f + o * (1.f - sg)); }
+                if (act) { const float o = fmaf(xh, gam[j], bet[j]); const float sg = sigmoid_fast(o); g *= sg * fmaf(o, 1.f - sg, 1.f); }
                 g *= gam[j];
                 s[j] += g; ss[j] = fmaf(g, xh, ss[j]);
             }
+        };
+        for (; pix + ngroups < p1; pix += 2 * ngroups) {
+            float fx[2][8], fd[2][8];
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                load8(x + (base + pix + u * ngroups) * ldx + v * 8, fx[u]);
+                load8(dy + (base + pix + u * ngroups) * ldd + v * 8, fd[u]);
+            }
+            accumulate(fx[0], fd[0]);
+            accumulate(fx[1], fd[1]);
+        }
+        for (; pix < p1; pix += ngroups) {
+            float fx[8], fd[8];
+            load8(x + (base + pix) * ldx + v * 8, fx);
+            load8(dy + (base + pix) * ldd + v * 8, fd);
+            accumulate(fx, fd);
         }
         gn_flush(sm, v, cpg, s, ss);
     }
@@ -147,37 +189,49 @@ __global__ void __launch_bounds__(256) k_gn_bwd_stats(const __half* __restrict__
 }
 
 // dx = rstd * (g - mean(g) - xhat * mean(g*xhat)); if accumulate, dx is added to the existing content of dxo.
+// Slab decomposition as above: the per-channel constants are computed once per thread.
+template <bool ACT, bool ACCUM>
 __global__ void __launch_bounds__(256) k_gn_bwd_apply(const __half* __restrict__ x, int ldx, const __half* __restrict__ dy, int ldd,
-                                                      __half* __restrict__ dxo, int ldo, int HW, int C, int G, const float* __restrict__ stats,
-                                                      const float* __restrict__ bstats, const float* __restrict__ gamma,
-                                                      const float* __restrict__ beta, float eps, int act, int accumulate, long long total_vec) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total_vec) return;
-    const int vec_per_pix = C / 8;
-    const long long pix = i / vec_per_pix;
-    const int v = (int)(i - pix * vec_per_pix);
-    const int img = (int)(pix / HW);
-    const int cpg = C / G;
-    const float cnt = (float)HW * cpg;
-    float fx[8], fd[8], fo[8];
-    load8(x + pix * ldx + v * 8, fx);
-    load8(dy + pix * ldd + v * 8, fd);
-    if (accumulate) load8(dxo + pix * ldo + v * 8, fo);
+                                                      __half* __restrict__ dxo, int ldo, int HW, int C, int G, int pix_per_block,
+                                                      const float* __restrict__ stats, const float* __restrict__ bstats,
+                                                      const float* __restrict__ gamma, const float* __restrict__ beta, float eps) {
+    const int img = blockIdx.y;
+    const int cpg = C / G, vpp = C / 8;
+    const float inv_cnt = 1.f / ((float)HW * cpg);
+    const int p0 = blockIdx.x * pix_per_block, p1 = min(HW, p0 + pix_per_block);
+    const long long base = (long long)img * HW;
+    const int ngroups = max(1, (int)blockDim.x / vpp);
+    for (int idx = threadIdx.x; idx < vpp * ngroups; idx += blockDim.x) {
+        const int v = idx % vpp, pg = idx / vpp;
+        float mean[8], rstd[8], gam[8], bet[8], m1[8], m2[8];
+        gn_channel_stats(stats, img, G, cpg, inv_cnt, eps, v, mean, rstd);
 #pragma unroll
-    for (int j = 0; j < 8; j++) {
-        const int c = v * 8 + j, gi = c / cpg;
-        const long long si = ((long long)img * G + gi) * 2;
-        const float mean = stats[si] / cnt;
-        const float var = fmaxf(stats[si + 1] / cnt - mean * mean, 0.f);
-        const float rstd = rsqrtf(var + eps);
-        const float xh = (fx[j] - mean) * rstd;
-        float g = fd[j];
-        if (act) { const float o = xh * gamma[c] + beta[c]; const float sg = 1.f / (1.f + __expf(-o)); g *= sg * (1.f + o * (1.f - sg)); }
-        g *= gamma[c];
-        const float d = rstd * (g - bstats[si] / cnt - xh * bstats[si + 1] / cnt);
-        fo[j] = accumulate ? fo[j] + d : d;
+        for (int j = 0; j < 8; j++) {
+            const int c = v * 8 + j, gi = c / cpg;
+            gam[j] = gamma[c]; bet[j] = beta[c];
+            m1[j] = bstats[((long long)img * G + gi) * 2] * inv_cnt;
+            m2[j] = bstats[((long long)img * G + gi) * 2 + 1] * inv_cnt;
+        }
+        auto one = [&](int pix) {
+            float fx[8], fd[8], fo[8];
+            load8(x + (base + pix) * ldx + v * 8, fx);
+            load8(dy + (base + pix) * ldd + v * 8, fd);
+            if (ACCUM) load8(dxo + (base + pix) * ldo + v * 8, fo);
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const float xh = (fx[j] - mean[j]) * rstd[j];
+                float g = fd[j];
+                if (ACT) { const float o = fmaf(xh, gam[j], bet[j]); const float sg = sigmoid_fast(o); g *= sg * fmaf(o, 1.f - sg, 1.f); }
+                g *= gam[j];
+                const float d = rstd[j] * (g - m1[j] - xh * m2[j]);
+                fo[j] = ACCUM ? fo[j] + d : d;
+            }
+            store8(dxo + (base + pix) * ldo + v * 8, fo);
+        };
+        int pix = p0 + pg;
+        for (; pix + ngroups < p1; pix += 2 * ngroups) { one(pix); one(pix + ngroups); }
+        for (; pix < p1; pix += ngroups) one(pix);
     }
-    store8(dxo + pix * ldo + v * 8, fo);
 }
 
 // ------------------------------------------------------------------ LayerNorm (warp per row)
@@ -546,8 +600,8 @@ SDF_API int sdf_groupnorm_forward(const void* x, int ldx, void* y, int ldy, int 
     dim3 grid((HW + ppb - 1) / ppb, Nimg);
     k_gn_stats<<<grid, 256, sizeof(float) * 2 * G, st>>>((const __half*)x, ldx, HW, C, G, ppb, stats);
     SDF_CHECK_LAUNCH("groupnorm(stats)");
-    const long long tv = (long long)Nimg * HW * (C / 8);
-    LAUNCH_1D(k_gn_apply, tv, st, (const __half*)x, ldx, (__half*)y, ldy, HW, C, G, stats, gamma, beta, eps, silu_act, tv);
+    if (silu_act) k_gn_apply<true><<<grid, 256, 0, st>>>((const __half*)x, ldx, (__half*)y, ldy, HW, C, G, ppb, stats, gamma, beta, eps);
+    else k_gn_apply<false><<<grid, 256, 0, st>>>((const __half*)x, ldx, (__half*)y, ldy, HW, C, G, ppb, stats, gamma, beta, eps);
     SDF_CHECK_LAUNCH("groupnorm(apply)");
     return SDF_OK;
 }
@@ -563,8 +617,10 @@ SDF_API int sdf_groupnorm_backward(const void* x, int ldx, const void* dy, int l
     dim3 grid((HW + ppb - 1) / ppb, Nimg);
     k_gn_bwd_stats<<<grid, 256, sizeof(float) * 2 * G, st>>>((const __half*)x, ldx, (const __half*)dy, ldd, HW, C, G, ppb, stats, gamma, beta, eps, silu_act, bstats);
     SDF_CHECK_LAUNCH("groupnorm_backward(stats)");
-    const long long tv = (long long)Nimg * HW * (C / 8);
-    LAUNCH_1D(k_gn_bwd_apply, tv, st, (const __half*)x, ldx, (const __half*)dy, ldd, (__half*)dx, ldo, HW, C, G, stats, bstats, gamma, beta, eps, silu_act, accumulate, tv);
+#define GN_BWD_APPLY(A, B) k_gn_bwd_apply<A, B><<<grid, 256, 0, st>>>((const __half*)x, ldx, (const __half*)dy, ldd, (__half*)dx, ldo, HW, C, G, ppb, stats, bstats, gamma, beta, eps)
+    if (silu_act) { if (accumulate) GN_BWD_APPLY(true, true); else GN_BWD_APPLY(true, false); }
+    else { if (accumulate) GN_BWD_APPLY(false, true); else GN_BWD_APPLY(false, false); }
+#undef GN_BWD_APPLY
     SDF_CHECK_LAUNCH("groupnorm_backward(apply)");
     return SDF_OK;
 }

@@ -22,9 +22,12 @@ import math
 import torch
 
 from . import _lib
-from .gemm import GemmPlan, conv_plan, linear_plan, pack_conv_weight, pick_block_n
+import os
+
+from .gemm import GemmPlan, conv_plan, linear_plan, pack_conv_weight, pick_block_n, pick_tile
 
 NUM_SMS = 148
+USE_CTA_PAIRS = os.environ.get('SDF_GEMM_CTA_PAIRS', '1') != '0'      # A/B switch for the cta_group::2 GEMM variant
 
 
 def _r(x, m):
@@ -86,13 +89,15 @@ class _PtrTensor:
         return self.view.ptr
 
 
-def _choose_splitk(M, N, kblocks, block_n):
-    """split-K only when the output tiles cannot fill a third of the SMs AND K is long (3x3 convs at 16x16 / 8x8, the M=2
-    embedding products): every split costs a memset + a reduction launch."""
-    tiles = ((M + 127) // 128) * ((N + block_n - 1) // block_n)
-    if tiles > NUM_SMS // 3 or kblocks < 16:
+def _choose_splitk(M, N, kblocks, block_n, pair=0):
+    """split-K only when the output tiles cannot fill a third of the SMs (CTA pairs: of the 74 pairs) AND K is long (3x3 convs at
+    16x16 / 8x8, the M=2 embedding products): every split costs a memset + a reduction launch."""
+    m_tiles = (M + 127) // 128
+    units = ((m_tiles + 1) // 2 if pair else m_tiles) * ((N + block_n - 1) // block_n)
+    workers = NUM_SMS // 2 if pair else NUM_SMS
+    if units > workers // 3 or kblocks < 16:
         return 1
-    return max(1, min(NUM_SMS // tiles, kblocks // 8))
+    return max(1, min(workers // units, kblocks // 8))
 
 
 class Builder:
@@ -102,6 +107,7 @@ class Builder:
         self.device = device
         self.ops = []
         self.flops = 0.0
+        self.flops_attn = 0.0
         self.bytes_act = 0
 
     def buf(self, Nimg, H, W, C, zero=False):
@@ -131,15 +137,19 @@ class Builder:
         if cin_iter is None:
             cin_iter = wt.shape[-1] // taps
         w_str = w_strides if w_strides is not None else (wt.shape[-1], 0, 0)
-        bn = pick_block_n(N) if block_n is None else block_n
         M = Nimg * H * W
+        batched = w_str[1] != 0 or w_str[2] != 0
+        if block_n is None:
+            bn, pair = pick_tile(M, N, batched) if USE_CTA_PAIRS else (pick_block_n(N), 0)
+        else:
+            bn, pair = block_n, 0
         kb = taps * cin_iter // 64
-        sk = _choose_splitk(M, N, kb, bn) if splitk is None else splitk
+        sk = _choose_splitk(M, N, kb, bn, pair) if splitk is None else splitk
         wrap = lambda v: _PtrTensor(v) if isinstance(v, View) else v
         plan = GemmPlan(wrap(a), a_str, c_valid, wrap(wt), w_str, (taps * cin_iter if w_k_valid is None else w_k_valid),
                         (wt.shape[0] if n_rows_w is None else n_rows_w), Nimg, H, W, cin_iter, taps, N, wrap(out), o_str, bias=bias,
                         temb=wrap(temb) if temb is not None else None, temb_ld=temb_ld, residual=wrap(residual) if residual is not None else None,
-                        r_strides=r_str, act=act, alpha=alpha, splitk=sk, block_n=bn)
+                        r_strides=r_str, act=act, alpha=alpha, splitk=sk, block_n=bn, cta_pair=pair)
         self.flops += 2.0 * M * N * taps * c_valid
         self.add(name, plan.run)
         return plan
@@ -167,6 +177,12 @@ class Builder:
     def softmax(self, name, s, rows, cols, ld, scale=1.0):
         args = (s.data_ptr(), s.data_ptr(), rows, cols, ld, float(scale))
         self.add(name, lambda a=args, k=s: _lib.call('sdf_softmax_rows', *a, _lib.stream()))
+
+    def flash_attention(self, name, q, k, v, o, B, heads, n, nkv, d):
+        args = (q.ptr, k.ptr, v.ptr, o.ptr, B, heads, n, nkv, d, q.ld, k.ld, o.ld, float(d) ** -0.5)
+        assert k.ld == v.ld
+        self.flops_attn += 4.0 * B * heads * n * nkv * d
+        self.add(name, lambda a=args, keep=(q, k, v, o): _lib.call('sdf_flash_attention', *a, _lib.stream()))
 
     def softmax_bwd(self, name, p, dp, ds, rows, cols, ld, scale):
         args = (p.data_ptr(), dp.data_ptr(), ds.data_ptr(), rows, cols, ld, float(scale))
@@ -425,7 +441,8 @@ class UNetEngine:
         b.gemm('out.2', tfin, final.C, pack_conv_weight(sd['out.2.weight'].to(device)), cfg['out_channels'], View(self.eps), taps=9,
                bias=self._f32('out.2.bias'))
         self.runlist = RunList(b.ops)
-        self.flops = b.flops
+        self.flops = b.flops + b.flops_attn
+        self.flops_gemm, self.flops_attn = b.flops, b.flops_attn
         self.sd = None          # fp32 originals are no longer needed
         self._wcache = None
 
@@ -459,44 +476,32 @@ class UNetEngine:
         b.gemm(p + '.out_layers.3', t2, cout, pack_conv_weight(sd[p + '.out_layers.3.weight'].to(dev)), cout, out, taps=9,
                bias=self._f32(p + '.out_layers.3.bias'), residual=xs)
 
-    def _scores(self, n, nkv_pad):
-        key = (n, nkv_pad)
-        if key not in self._sbuf:
-            self._sbuf[key] = torch.zeros(self.B, self.heads, n, nkv_pad, device=self.dev, dtype=torch.float16)
-        return self._sbuf[key]
+    def _lin_cat(self, keys):
+        """rows of several linear weights stacked (one GEMM produces q|k|v or k|v side by side)"""
+        return torch.cat([self._lin(k) for k in keys], 0).contiguous()
 
     def _attention(self, p, ln, kv_src, kv_rows_per_batch, kv_dim, u, C):
-        """u += to_out(softmax(q k^T / sqrt(d)) v);  q from ln [B*n, C]; k, v from kv_src ([B*kv_rows, kv_dim] View)."""
-        b, B, heads, dev = self.b, self.B, self.heads, self.dev
+        """u += to_out(softmax(q k^T / sqrt(d)) v);  q from ln [B*n, C]; k, v from kv_src ([B*kv_rows, kv_dim] View).
+        Projections are one GEMM (q|k|v for self-attention, q and k|v for cross-attention); the attention itself is the fused
+        flash kernel on the [tokens, heads*d] layout (ldm/modules/attention.py:170-193)."""
+        b, B, heads = self.b, self.B, self.heads
         n = ln.H * ln.W if ln.Nimg == B else ln.rows // B
         d = C // heads
         nkv = kv_rows_per_batch
-        nkv_pad = _r(nkv, 64)
-        q = View(b.buf(1, 1, B * n, C))
-        k = View(b.buf(1, 1, B * nkv, C))
         lnf = View(ln.t.view(1, 1, B * n, ln.ld), ln.off, ln.C)
-        kvf = View(kv_src.t.view(1, 1, B * nkv, kv_src.ld), kv_src.off, kv_src.C)
-        b.gemm(p + '.to_q', lnf, C, self._lin(p + '.to_q.weight'), C, q)
-        b.gemm(p + '.to_k', kvf, kv_dim, self._lin(p + '.to_k.weight'), C, k)
-        # V^T[b] = Wv . X_b^T : the weight matrix is the A operand, the tokens are the "weights"
-        wv = self._lin(p + '.to_v.weight')                                # [C, kv_dim_iter]
-        vt = torch.zeros(B, C, nkv_pad, device=dev, dtype=torch.float16)
-        for bi in range(B):
-            rows_ptr = _PtrTensor(View(kvf.t, kvf.off, kvf.C))
-            a_holder = _PtrTensor(View(wv.view(1, 1, C, wv.shape[1])))
-            tok = _OffsetPtr(kvf, bi * nkv)
-            outp = _OffsetRaw(vt, bi * C * nkv_pad)
-            b.gemm(f'{p}.to_v^T[{bi}]', a_holder, kv_dim, tok, nkv, outp, geom=(1, 1, C), a_strides=(wv.shape[1], C * wv.shape[1], C * wv.shape[1]),
-                   o_strides=(nkv_pad, C * nkv_pad, C * nkv_pad), w_strides=(kvf.ld, 0, 0), w_k_valid=kv_dim, n_rows_w=nkv, cin_iter=_r(kv_dim, 64),
-                   block_n=64 if nkv <= 64 else 128)
-        S = self._scores(n, nkv_pad)
-        b.gemm(p + '.qk', q, d, k, nkv, S, geom=(B, heads, n), a_strides=(C, d, n * C), o_strides=(nkv_pad, n * nkv_pad, heads * n * nkv_pad),
-               w_strides=(C, d, nkv * C), w_k_valid=d, n_rows_w=nkv, cin_iter=_r(d, 64), alpha=d ** -0.5, block_n=64 if nkv <= 64 else 128)
-        b.softmax(p + '.softmax', S, B * heads * n, nkv, nkv_pad)
+        if kv_src is ln:
+            qkv = View(b.buf(1, 1, B * n, 3 * C))
+            b.gemm(p + '.to_qkv', lnf, C, self._lin_cat([p + '.to_q.weight', p + '.to_k.weight', p + '.to_v.weight']), 3 * C, qkv)
+            q, k, v = qkv.sub(0, C), qkv.sub(C, C), qkv.sub(2 * C, C)
+        else:
+            kvf = View(kv_src.t.view(1, 1, B * nkv, kv_src.ld), kv_src.off, kv_src.C)
+            q = View(b.buf(1, 1, B * n, C))
+            kv = View(b.buf(1, 1, B * nkv, 2 * C))
+            b.gemm(p + '.to_q', lnf, C, self._lin(p + '.to_q.weight'), C, q)
+            b.gemm(p + '.to_kv', kvf, kv_dim, self._lin_cat([p + '.to_k.weight', p + '.to_v.weight']), 2 * C, kv)
+            k, v = kv.sub(0, C), kv.sub(C, C)
         o = View(b.buf(1, 1, B * n, C))
-        b.gemm(p + '.pv', S, nkv, vt, d, o, geom=(B, heads, n), a_strides=(nkv_pad, n * nkv_pad, heads * n * nkv_pad), o_strides=(C, d, n * C),
-               w_strides=(nkv_pad, d * nkv_pad, C * nkv_pad), w_k_valid=nkv, n_rows_w=d, cin_iter=nkv_pad,
-               block_n=64 if d <= 64 else (160 if d % 160 == 0 else 128))
+        b.flash_attention(p + '.attention', q, k, v, o, B, heads, n, nkv, d)
         uf = View(u.t.view(1, 1, B * n, u.ld), u.off, u.C)
         b.gemm(p + '.to_out', o, C, self._lin(p + '.to_out.0.weight'), C, uf, bias=self._f32(p + '.to_out.0.bias'), residual=uf)
 

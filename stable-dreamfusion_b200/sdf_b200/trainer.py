@@ -59,6 +59,13 @@ class SDSTrainer:
         self._flat = None
         self.pin_pose = torch.zeros(opt.batch_size, 4, 4).pin_memory()
         self.last_M = 0
+        self.stage_events = None         # set to [] to record (name, cuda event) marks of the next step (bench.py --breakdown)
+
+    def _mark(self, name):
+        if self.stage_events is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            self.stage_events.append((name, ev))
 
     # ------------------------------------------------------------------ data (nerf/provider.py:248-319 collate)
     def sample_views(self):
@@ -90,6 +97,7 @@ class SDSTrainer:
     # ------------------------------------------------------------------ one optimisation step
     def train_step(self, views=None, shading=None, read_loss=False):
         opt, dev = self.opt, self.device
+        self._mark('start')
         if self.global_step % opt.update_extra_interval == 0:
             self.model.update_extra_state()
             if self.world_size > 1:
@@ -131,9 +139,11 @@ class SDSTrainer:
         else:
             pred_rgb = outputs['image'].reshape(B, H, W, 3).permute(0, 3, 1, 2).contiguous()
         self.last_M = int(outputs['weights'].shape[0])
+        self._mark('render (rays, march, field forward, composite)')
 
         loss = self.guidance.train_step(self.text_z(azimuth), pred_rgb, as_latent=as_latent, guidance_scale=opt.guidance_scale,
                                         grad_scale=opt.lambda_guidance)
+        self._mark('guidance (VAE encode, UNet, SDS gradient, VAE data-gradient)')
         # regularisers (nerf/utils.py:686-709)
         if opt.lambda_opacity > 0:
             loss = loss + opt.lambda_opacity * (outputs['weights_sum'] ** 2).mean()
@@ -144,10 +154,14 @@ class SDSTrainer:
         if opt.lambda_orient > 0 and 'loss_orient' in outputs:
             loss = loss + opt.lambda_orient * outputs['loss_orient']
 
+        self._mark('regularisers')
         loss.backward()
+        self._mark('backward (composite, field backward)')
         if self.world_size > 1:
             self._allreduce_grads()
+            self._mark('all-reduce')
         self.optimizer.step(zero_grad=True)      # gradients are cleared by the fused step: buffers stay allocated (and bucketed)
+        self._mark('Adan step')
         if read_loss:
             return float(loss.item())          # device -> host read of the step's result (nerf/utils.py:1072)
         return loss

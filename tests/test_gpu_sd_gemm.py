@@ -12,7 +12,7 @@ from sdf_b200 import gemm
 pytestmark = pytest.mark.gpu
 
 
-def run_conv(a_nhwc, w_oihw, bias=None, temb=None, residual=None, act=None, alpha=1.0, splitk=1, block_n=128, lda_extra=0):
+def run_conv(a_nhwc, w_oihw, bias=None, temb=None, residual=None, act=None, alpha=1.0, splitk=1, block_n=128, lda_extra=0, cta_pair=0):
     dev = a_nhwc.device
     Nimg, H, W, Cin = a_nhwc.shape
     Cout, _, kh, kw = w_oihw.shape
@@ -26,7 +26,7 @@ def run_conv(a_nhwc, w_oihw, bias=None, temb=None, residual=None, act=None, alph
     ldo = ((Cout + 7) // 8) * 8
     out = torch.full((Nimg, H, W, ldo), float("nan"), device=dev, dtype=torch.float16)
     plan = gemm.conv_plan(a_used, Cin, wt, Cout, out, taps=kh * kw, bias=bias, temb=temb, residual=residual, act=act, alpha=alpha,
-                          splitk=splitk, block_n=block_n)
+                          splitk=splitk, block_n=block_n, cta_pair=cta_pair)
     plan.run()
     torch.cuda.synchronize()
     return out[..., :Cout]
@@ -148,3 +148,34 @@ def test_batched_attention_products(device, B, heads, n, nkv, d):
     torch.cuda.synchronize()
     O_ref = torch.einsum("bhij,bhjd->bhid", P.float(), vh).permute(0, 2, 1, 3).reshape(B, n, C)
     check(O, O_ref, nkv)
+
+
+# ---- CTA-pair variant (tcgen05 cta_group::2): same contract, M = 256 per MMA, weight tile split across the two CTAs
+@pytest.mark.parametrize("M,K,N,bn", [(8192, 320, 320, 160), (8192, 320, 2560, 256), (154, 768, 320, 160), (512, 1280, 1280, 256),
+                                      (4096, 64, 128, 128), (300, 128, 72, 128), (129, 64, 384, 256), (100000, 192, 256, 256)])
+def test_linear_cta_pair(device, M, K, N, bn):
+    a = rnd(1, 1, M, K, device=device, seed=1)
+    w = rnd(N, K, 1, 1, device=device, scale=1 / math.sqrt(K), seed=2)
+    bias = rnd(N, device=device, seed=3).float()
+    out = run_conv(a, w, bias=bias, block_n=bn, cta_pair=1)
+    check(out, ref_conv(a, w, bias=bias), K)
+
+
+@pytest.mark.parametrize("Nimg,H,W,Cin,Cout,bn,sk", [(2, 64, 64, 320, 320, 160, 1), (2, 32, 32, 640, 640, 160, 1), (2, 16, 16, 128, 256, 256, 1),
+                                                      (2, 16, 16, 1280, 1280, 256, 4), (1, 128, 256, 64, 128, 128, 1), (3, 8, 8, 64, 128, 128, 1),
+                                                      (1, 96, 96, 128, 256, 256, 1), (2, 64, 64, 4, 320, 160, 1), (3, 24, 40, 72, 200, 256, 2)])
+def test_conv3x3_cta_pair(device, Nimg, H, W, Cin, Cout, bn, sk):
+    a = rnd(Nimg, H, W, max(Cin, 8), device=device, seed=4)
+    a[..., Cin:] = 3.0
+    w = rnd(Cout, Cin, 3, 3, device=device, scale=1 / math.sqrt(9 * Cin), seed=5)
+    bias = rnd(Cout, device=device, seed=6).float()
+    temb = rnd(Nimg, Cout, device=device, seed=7)
+    res = rnd(Nimg, H, W, Cout, device=device, seed=8)
+    dev = a.device
+    wt = gemm.pack_conv_weight(w)
+    out = torch.full((Nimg, H, W, Cout), float("nan"), device=dev, dtype=torch.float16)
+    plan = gemm.conv_plan(a, Cin, wt, Cout, out, taps=9, bias=bias, temb=temb, residual=res, act="silu", splitk=sk, block_n=bn, cta_pair=1)
+    for _ in range(3):            # persistent barriers / TMEM hand-over must survive repeated launches
+        plan.run()
+    torch.cuda.synchronize()
+    check(out, ref_conv(a[..., :Cin], w, bias=bias, temb=temb, residual=res, act="silu"), 9 * Cin)

@@ -114,3 +114,26 @@ def test_resample_im2col_glue(device):
     a3 = rnd(3, 100, 96, device=device, seed=12)
     _lib.call("sdf_transpose2d", _lib.ptr(a3), 96, _lib.ptr(tr), 104, 3, 100, 96, _lib.stream())
     assert torch.equal(tr[:, :, :100], a3.permute(0, 2, 1))
+
+
+@pytest.mark.parametrize("B,heads,n,nkv,d,fused", [(2, 8, 4096, 4096, 40, True), (2, 8, 1024, 1024, 80, True), (2, 8, 256, 256, 160, True),
+                                                    (2, 8, 64, 64, 160, True), (2, 8, 4096, 77, 40, False), (2, 8, 256, 77, 160, False),
+                                                    (1, 4, 100, 5, 32, False), (1, 2, 70, 130, 64, False)])
+def test_flash_attention(device, B, heads, n, nkv, d, fused):
+    """csrc/flash_attn.cu vs softmax(q k^T / sqrt(d)) v in fp32 on the same fp16 inputs (ldm/modules/attention.py:170-193).
+    P is rounded to fp16 before the P V product (as the reference does under autocast): atol 2e-3 of max|v|."""
+    C = heads * d
+    if fused:                                  # q|k|v side by side as the fused projection GEMM writes them
+        qkv = rnd(B, n, 3 * C, device=device, seed=3, scale=1.5)
+        q, k, v = qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:]
+    else:
+        q = rnd(B, n, C, device=device, seed=4, scale=1.5)
+        kv = rnd(B, nkv, 2 * C, device=device, seed=5, scale=1.5)
+        k, v = kv[..., :C], kv[..., C:]
+    o = torch.zeros(B, n, C, device=device, dtype=torch.float16)
+    _lib.call("sdf_flash_attention", q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), B, heads, n, nkv, d,
+              q.stride(1), k.stride(1), C, d ** -0.5, _lib.stream())
+    qf, kf, vf = (t.float().reshape(B, -1, heads, d).permute(0, 2, 1, 3) for t in (q, k, v))
+    ref = torch.softmax(qf @ kf.transpose(-1, -2) * d ** -0.5, -1) @ vf
+    ref = ref.permute(0, 2, 1, 3).reshape(B, n, C)
+    close(o, ref, rtol=4e-3, atol=4e-3)
