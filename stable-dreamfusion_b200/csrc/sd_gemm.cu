@@ -156,7 +156,7 @@ struct SmemLayout {
 };
 
 template <int BLOCK_N, bool PAIR>
-__global__ void __launch_bounds__(kNumThreads, 1)
+__global__ void __launch_bounds__(kNumThreads, 1)      // 10 warps -> 3 on one SM sub-partition -> 168 registers per thread at most
 k_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const GemmArgs g) {
     using L = SmemLayout<BLOCK_N, PAIR>;
     constexpr int kStages = L::kStages;
@@ -292,79 +292,122 @@ k_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtens
             const long long o_off = (long long)img * g.o_simg + (long long)y * g.o_sy + (long long)x * g.o_sx;
             const int n0 = nt * BLOCK_N;
 
+            // Addends of a full 32-column chunk (bias fp32, per-image embedding fp16, residual fp16) are fetched with 16-byte loads
+            // BEFORE the accumulator is waited for, so their latency hides behind the main loop / the TMEM read.
+            const __half* res_row = g.residual ? g.residual + (long long)img * g.r_simg + (long long)y * g.r_sy + (long long)x * g.r_sx : nullptr;
+            const __half* temb_row = g.temb ? g.temb + (long long)img * g.temb_ld : nullptr;
+            __half* out_row = g.out + o_off;
+            const bool direct = (g.splitk == 1);
+            const bool vec_ok = direct && row_ok && ((g.N & 7) == 0);
+            const bool st32_ok = ((reinterpret_cast<uintptr_t>(out_row) & 31) == 0);
+            uint4 cr[4];
+            auto fetch_addends = [&](int nbase) {      // the residual row segment of a full chunk (64 bytes)
+                if (!(vec_ok && res_row && nbase + 32 <= g.N)) return;
+#pragma unroll
+                for (int j = 0; j < 4; j++) cr[j] = *(reinterpret_cast<const uint4*>(res_row + nbase) + j);
+            };
+            if (half < kChunks) fetch_addends(n0 + half * 32);
+
             mbar_wait(&tmem_full[acc], acc_phase);
             tcgen05_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BLOCK_N;
             uint32_t va[32], vb[32];
             if (half < kChunks) { tmem_ld32_nowait(taddr + half * 32, va); tmem_ld_wait(); }
-#pragma unroll 1
-            for (int ch = half; ch < kChunks; ch += 2) {
-                // prefetch this warp's next chunk while the current one is finished and stored
-                const bool odd_iter = ((ch - half) >> 1) & 1;
-                uint32_t* cur = odd_iter ? vb : va;
-                uint32_t* nxt = odd_iter ? va : vb;
-                if (ch + 2 < kChunks) tmem_ld32_nowait(taddr + (ch + 2) * 32, nxt);
+            auto process_chunk = [&](const uint32_t (&cur)[32], int ch) {
                 const int nbase = n0 + ch * 32;
                 if (row_ok && nbase < g.N) {
+                    if (vec_ok && nbase + 32 <= g.N) {
+                        // ---- fast path: whole chunk, 16-byte aligned operands
+                        float f[32];
 #pragma unroll
-                    for (int hh = 0; hh < 2; hh++) {
-                        const int n = nbase + hh * 16;
-                        if (n >= g.N) break;
-                        float f[16];
-#pragma unroll
-                        for (int j = 0; j < 16; j++) f[j] = __uint_as_float(cur[hh * 16 + j]) * g.alpha;
-                        if (g.splitk > 1) {
-                            float* ws = g.workspace + m * g.N + n;
-#pragma unroll
-                            for (int j = 0; j < 16; j++) if (n + j < g.N) atomicAdd(ws + j, f[j]);
-                            continue;
-                        }
-                        const bool full16 = (n + 16 <= g.N);
+                        for (int j = 0; j < 32; j++) f[j] = __uint_as_float(cur[j]) * g.alpha;
                         if (g.bias) {
 #pragma unroll
-                            for (int j = 0; j < 16; j++) if (full16 || n + j < g.N) f[j] += __ldg(g.bias + n + j);
+                            for (int j = 0; j < 8; j++) {
+                                const float4 b4 = __ldg(reinterpret_cast<const float4*>(g.bias + nbase) + j);
+                                f[4 * j] += b4.x; f[4 * j + 1] += b4.y; f[4 * j + 2] += b4.z; f[4 * j + 3] += b4.w;
+                            }
                         }
-                        if (g.temb) {
-                            const __half* te = g.temb + (long long)img * g.temb_ld + n;
+                        if (temb_row) {
 #pragma unroll
-                            for (int j = 0; j < 16; j++) if (full16 || n + j < g.N) f[j] += __half2float(te[j]);
+                            for (int j = 0; j < 4; j++) {
+                                const uint4 t4 = __ldg(reinterpret_cast<const uint4*>(temb_row + nbase) + j);
+                                const __half2* h = reinterpret_cast<const __half2*>(&t4);
+#pragma unroll
+                                for (int k = 0; k < 4; k++) { const float2 t2 = __half22float2(h[k]); f[8 * j + 2 * k] += t2.x; f[8 * j + 2 * k + 1] += t2.y; }
+                            }
                         }
-                        if (g.residual) {
-                            const __half* rs = g.residual + (long long)img * g.r_simg + (long long)y * g.r_sy + (long long)x * g.r_sx + n;
-                            if (full16) {
-                                const uint4 r0 = *reinterpret_cast<const uint4*>(rs), r1 = *reinterpret_cast<const uint4*>(rs + 8);
-                                const __half2* h0 = reinterpret_cast<const __half2*>(&r0);
-                                const __half2* h1 = reinterpret_cast<const __half2*>(&r1);
+                        if (res_row) {
 #pragma unroll
-                                for (int j = 0; j < 4; j++) {
-                                    const float2 a = __half22float2(h0[j]), b = __half22float2(h1[j]);
-                                    f[2 * j] += a.x; f[2 * j + 1] += a.y; f[8 + 2 * j] += b.x; f[8 + 2 * j + 1] += b.y;
-                                }
-                            } else {
+                            for (int j = 0; j < 4; j++) {
+                                const __half2* h = reinterpret_cast<const __half2*>(&cr[j]);
 #pragma unroll
-                                for (int j = 0; j < 16; j++) if (n + j < g.N) f[j] += __half2float(rs[j]);
+                                for (int k = 0; k < 4; k++) { const float2 t2 = __half22float2(h[k]); f[8 * j + 2 * k] += t2.x; f[8 * j + 2 * k + 1] += t2.y; }
                             }
                         }
                         if (g.act != kActNone) {
 #pragma unroll
-                            for (int j = 0; j < 16; j++) f[j] = act_apply(f[j], g.act);
+                            for (int j = 0; j < 32; j++) f[j] = act_apply(f[j], g.act);
                         }
-                        __half* o = g.out + o_off + n;
-                        if (full16) {
-                            uint4 o0, o1;
-                            __half2* h0 = reinterpret_cast<__half2*>(&o0);
-                            __half2* h1 = reinterpret_cast<__half2*>(&o1);
+                        uint32_t pk[16];
 #pragma unroll
-                            for (int j = 0; j < 4; j++) { h0[j] = __floats2half2_rn(f[2 * j], f[2 * j + 1]); h1[j] = __floats2half2_rn(f[8 + 2 * j], f[8 + 2 * j + 1]); }
-                            *reinterpret_cast<uint4*>(o) = o0;
-                            *reinterpret_cast<uint4*>(o + 8) = o1;
+                        for (int j = 0; j < 16; j++) { const __half2 h2 = __floats2half2_rn(f[2 * j], f[2 * j + 1]); pk[j] = *reinterpret_cast<const uint32_t*>(&h2); }
+                        __half* o = out_row + nbase;
+                        if (st32_ok) {       // two full 32-byte sectors per thread
+                            asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(o), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]),
+                                         "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7]) : "memory");
+                            asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(o + 16), "r"(pk[8]), "r"(pk[9]), "r"(pk[10]), "r"(pk[11]),
+                                         "r"(pk[12]), "r"(pk[13]), "r"(pk[14]), "r"(pk[15]) : "memory");
                         } else {
 #pragma unroll
-                            for (int j = 0; j < 16; j++) if (n + j < g.N) o[j] = __float2half_rn(f[j]);
+                            for (int j = 0; j < 4; j++) *reinterpret_cast<uint4*>(o + 8 * j) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+                        }
+                        if (ch + 2 < kChunks) fetch_addends(n0 + (ch + 2) * 32);      // next chunk's addends fly during the TMEM wait
+                    } else {
+                        // ---- general path: split-K partial sums, ragged N, unaligned rows
+#pragma unroll
+                        for (int hh = 0; hh < 2; hh++) {
+                            const int n = nbase + hh * 16;
+                            if (n >= g.N) continue;
+                            float f[16];
+#pragma unroll
+                            for (int j = 0; j < 16; j++) f[j] = __uint_as_float(cur[hh * 16 + j]) * g.alpha;
+                            if (!direct) {
+                                float* ws = g.workspace + m * g.N + n;
+                                if (n + 16 <= g.N && ((g.N & 3) == 0)) {
+#pragma unroll
+                                    for (int j = 0; j < 4; j++) atomicAdd(reinterpret_cast<float4*>(ws) + j, make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]));
+                                } else {
+#pragma unroll
+                                    for (int j = 0; j < 16; j++) if (n + j < g.N) atomicAdd(ws + j, f[j]);
+                                }
+                                    continue;
+                            }
+#pragma unroll
+                            for (int j = 0; j < 16; j++) {
+                                if (n + j < g.N) {
+                                    if (g.bias) f[j] += __ldg(g.bias + n + j);
+                                    if (temb_row) f[j] += __half2float(temb_row[n + j]);
+                                    if (res_row) f[j] += __half2float(res_row[n + j]);
+                                    out_row[n + j] = __float2half_rn(act_apply(f[j], g.act));
+                                }
+                            }
                         }
                     }
                 }
-                if (ch + 2 < kChunks) tmem_ld_wait();
+            };
+            // two chunks per trip so that the current / prefetched register sets are compile-time (no local-memory arrays):
+            // the next chunk's TMEM read is in flight while the current one is finished and stored
+#pragma unroll 1
+            for (int ch = half; ch < kChunks; ch += 4) {
+                if (ch + 2 < kChunks) tmem_ld32_nowait(taddr + (ch + 2) * 32, vb);
+                process_chunk(va, ch);
+                if (ch + 2 < kChunks) {
+                    tmem_ld_wait();
+                    if (ch + 4 < kChunks) tmem_ld32_nowait(taddr + (ch + 4) * 32, va);
+                    process_chunk(vb, ch + 2);
+                    if (ch + 4 < kChunks) tmem_ld_wait();
+                }
             }
             tcgen05_fence_before();
             __syncwarp();

@@ -14,18 +14,51 @@ def pick_block_n(N):
     return 128
 
 
-def pick_tile(M, N, batched=False):
-    """(block_n, cta_pair): CTA pairs (tcgen05 cta_group::2, M = 256) whenever the product has at least two M tiles and one shared
-    weight matrix — the pair stages each weight tile once for 256 rows, which is what the L2 -> SM fabric needs."""
-    if batched or M <= 128 or N <= 64:
-        return pick_block_n(N), 0
-    if N % 256 == 0:
-        return 256, 1
+NUM_SMS = 148
+
+# Cost model of one plan launch, fitted to tools/gemm_sweep.py on a B200 (profiles/r01_gemm_sweep.txt): the persistent kernel
+# retires one 64-deep k-block per CTA every ~0.32 us whatever the tile width (0.44 us for the 256-wide CTA-pair tile), a tile's
+# epilogue costs 2.5-7 us when it cannot hide behind the next tile, and split-K adds a memset + a reduction launch.
+_T_KB = {(64, 0): 0.30, (128, 0): 0.32, (160, 0): 0.33, (128, 1): 0.33, (160, 1): 0.33, (256, 1): 0.44}
+_T_EPI = {64: 2.5, 128: 4.5, 160: 5.5, 256: 7.0}
+
+
+def estimate_us(M, N, kb, bn, pair, sk):
+    m_tiles = (M + 127) // 128
+    units = ((m_tiles + 1) // 2 if pair else m_tiles) * ((N + bn - 1) // bn) * sk
+    workers = NUM_SMS // 2 if pair else NUM_SMS
+    waves = (units + workers - 1) // workers
+    kb_per = (kb + sk - 1) // sk
+    t = 4.0 + waves * kb_per * _T_KB[(bn, pair)] + _T_EPI[bn] + (waves - 1) * max(0.0, _T_EPI[bn] - kb_per * _T_KB[(bn, pair)])
+    if sk > 1:
+        t += 5.0 + 2.0 * M * N * 4 * (sk + 1) / 3.0e6          # memset + atomics + reduction pass at ~3 TB/s of L2 traffic
+    return t
+
+
+def choose_config(M, N, kb, batched=False, allow_pair=True):
+    """(block_n, cta_pair, splitk) minimising the modelled launch time.  kb = K / 64."""
+    cands = [(64, 0), (128, 0)]
     if N % 160 == 0:
-        return 160, 1
-    if N % 128 == 0 or N < 256:
-        return 128, 1
-    return 256, 1
+        cands.append((160, 0))
+    if allow_pair and not batched and M > 128 and N % 256 == 0:
+        cands.append((256, 1))
+    if N <= 64:
+        cands = [(64, 0)]
+    best = None
+    for bn, pair in cands:
+        for sk in (1, 2, 3, 4, 6, 8, 12, 16):
+            if sk > 1 and (kb // sk < 8 or batched):
+                continue
+            t = estimate_us(M, N, kb, bn, pair, sk)
+            if best is None or t < best[0] - 1e-9:
+                best = (t, bn, pair, sk)
+    return best[1], best[2], best[3]
+
+
+def pick_tile(M, N, batched=False):
+    """(block_n, cta_pair) for callers that fix split-K themselves."""
+    bn, pair, _ = choose_config(M, N, 64, batched)
+    return bn, pair
 
 
 def pack_conv_weight(w, cin_iter=None, rows_multiple=1):

@@ -24,7 +24,7 @@ import torch
 from . import _lib
 import os
 
-from .gemm import GemmPlan, conv_plan, linear_plan, pack_conv_weight, pick_block_n, pick_tile
+from .gemm import GemmPlan, choose_config, conv_plan, linear_plan, pack_conv_weight, pick_block_n
 
 NUM_SMS = 148
 USE_CTA_PAIRS = os.environ.get('SDF_GEMM_CTA_PAIRS', '1') != '0'      # A/B switch for the cta_group::2 GEMM variant
@@ -139,12 +139,12 @@ class Builder:
         w_str = w_strides if w_strides is not None else (wt.shape[-1], 0, 0)
         M = Nimg * H * W
         batched = w_str[1] != 0 or w_str[2] != 0
-        if block_n is None:
-            bn, pair = pick_tile(M, N, batched) if USE_CTA_PAIRS else (pick_block_n(N), 0)
-        else:
-            bn, pair = block_n, 0
         kb = taps * cin_iter // 64
-        sk = _choose_splitk(M, N, kb, bn, pair) if splitk is None else splitk
+        if block_n is None and splitk is None:
+            bn, pair, sk = choose_config(M, N, kb, batched, allow_pair=USE_CTA_PAIRS)
+        else:
+            bn, pair = (pick_block_n(N) if block_n is None else block_n), 0
+            sk = _choose_splitk(M, N, kb, bn, pair) if splitk is None else splitk
         wrap = lambda v: _PtrTensor(v) if isinstance(v, View) else v
         plan = GemmPlan(wrap(a), a_str, c_valid, wrap(wt), w_str, (taps * cin_iter if w_k_valid is None else w_k_valid),
                         (wt.shape[0] if n_rows_w is None else n_rows_w), Nimg, H, W, cin_iter, taps, N, wrap(out), o_str, bias=bias,
