@@ -74,6 +74,23 @@ __device__ __forceinline__ void mma16816(float c[4], const uint32_t a[4], uint32
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+// Four 8x8 b16 matrices from shared memory in one instruction: lane l supplies the address of row (l & 7) of matrix (l >> 3);
+// thread (g, t) receives M_i[g][2t..2t+1] in r[i] — exactly the mma.sync B fragment of a [n][k] (k contiguous) operand, or
+// the A fragment of a [m][k] operand.  Replaces four 32-bit LDS per lane (the kernels are shared-memory-issue bound).
+__device__ __forceinline__ void ldsm_x4(uint32_t r[4], const void* smem_row) {
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(smem_row);
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+// B fragments of TWO consecutive k-steps (k0 .. k0+31) of the n-tile whose first row is `rows` (row stride in halfs):
+// r[0], r[1] = (b0, b1) of k-step 0; r[2], r[3] = (b0, b1) of k-step 1.
+__device__ __forceinline__ void ldsm_b2(uint32_t r[4], const __half* rows, int stride, int k0, int lane) {
+    ldsm_x4(r, rows + (lane & 7) * stride + k0 + (lane >> 3) * 8);
+}
+// A fragment (a0..a3) of the 16 x 16 block at (rows, k0) of a [m][k] operand.
+__device__ __forceinline__ void ldsm_a(uint32_t r[4], const __half* rows, int stride, int k0, int lane) {
+    ldsm_x4(r, rows + ((lane & 7) + ((lane >> 3) & 1) * 8) * stride + k0 + (lane >> 4) * 8);
+}
+
 // Corner geometry of one (point, level): base cell, interpolation fractions (after smoothstep) and
 // whether the point is inside the unit cube.
 struct Cell {
@@ -203,21 +220,18 @@ __device__ __forceinline__ void encode_rows(uint32_t a[2][4], const WeightsSmem&
 template <bool KEEP>
 __device__ __forceinline__ void mlp_forward(float out[4], const uint32_t a0[2][4], const WeightsSmem& s, int lane,
                                             uint32_t act1[4][4], uint32_t act2[4][4]) {
-    const int g = lane >> 2, t = lane & 3;
+    const int t = lane & 3;
     uint32_t a1[4][4];
     // layer 1
 #pragma unroll
     for (int nt = 0; nt < 8; nt++) {
-        const int n = nt * 8 + g;
         float c[4];
         c[0] = c[2] = s.b1[nt * 8 + 2 * t];
         c[1] = c[3] = s.b1[nt * 8 + 2 * t + 1];
-#pragma unroll
-        for (int kt = 0; kt < 2; kt++) {
-            const uint32_t b0 = *reinterpret_cast<const uint32_t*>(&s.w1[n][kt * 16 + 2 * t]);
-            const uint32_t b1 = *reinterpret_cast<const uint32_t*>(&s.w1[n][kt * 16 + 2 * t + 8]);
-            mma16816(c, a0[kt], b0, b1);
-        }
+        uint32_t wb[4];
+        ldsm_b2(wb, &s.w1[nt * 8][0], kW1Stride, 0, lane);
+        mma16816(c, a0[0], wb[0], wb[1]);
+        mma16816(c, a0[1], wb[2], wb[3]);
         // fp16 output of the linear layer, ReLU, straight into the next layer's A fragment
         const int kt2 = nt >> 1, hi = (nt & 1) * 2;
         a1[kt2][hi + 0] = pack_half2(fmaxf(c[0], 0.f), fmaxf(c[1], 0.f));
@@ -226,15 +240,15 @@ __device__ __forceinline__ void mlp_forward(float out[4], const uint32_t a0[2][4
     uint32_t a2[4][4];
 #pragma unroll
     for (int nt = 0; nt < 8; nt++) {
-        const int n = nt * 8 + g;
         float c[4];
         c[0] = c[2] = s.b2[nt * 8 + 2 * t];
         c[1] = c[3] = s.b2[nt * 8 + 2 * t + 1];
 #pragma unroll
-        for (int kt = 0; kt < 4; kt++) {
-            const uint32_t b0 = *reinterpret_cast<const uint32_t*>(&s.w2[n][kt * 16 + 2 * t]);
-            const uint32_t b1 = *reinterpret_cast<const uint32_t*>(&s.w2[n][kt * 16 + 2 * t + 8]);
-            mma16816(c, a1[kt], b0, b1);
+        for (int kp = 0; kp < 2; kp++) {
+            uint32_t wb[4];
+            ldsm_b2(wb, &s.w2[nt * 8][0], kW2Stride, kp * 32, lane);
+            mma16816(c, a1[2 * kp], wb[0], wb[1]);
+            mma16816(c, a1[2 * kp + 1], wb[2], wb[3]);
         }
         const int kt2 = nt >> 1, hi = (nt & 1) * 2;
         a2[kt2][hi + 0] = pack_half2(fmaxf(c[0], 0.f), fmaxf(c[1], 0.f));
@@ -243,10 +257,11 @@ __device__ __forceinline__ void mlp_forward(float out[4], const uint32_t a0[2][4
     out[0] = out[2] = s.b3[2 * t];
     out[1] = out[3] = s.b3[2 * t + 1];
 #pragma unroll
-    for (int kt = 0; kt < 4; kt++) {
-        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(&s.w3[g][kt * 16 + 2 * t]);
-        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(&s.w3[g][kt * 16 + 2 * t + 8]);
-        mma16816(out, a2[kt], b0, b1);
+    for (int kp = 0; kp < 2; kp++) {
+        uint32_t wb[4];
+        ldsm_b2(wb, &s.w3[0][0], kW2Stride, kp * 32, lane);
+        mma16816(out, a2[2 * kp], wb[0], wb[1]);
+        mma16816(out, a2[2 * kp + 1], wb[2], wb[3]);
     }
     if (KEEP) {
 #pragma unroll

@@ -14,6 +14,7 @@
 // Algorithmic bytes: forward 540 B per point-eval (12 B xyz + 128 half2
 // corner reads + 16 B out).  Roofline: HBM.
 #include "field_common.cuh"
+#include <cstdlib>
 
 using namespace field;
 
@@ -33,12 +34,12 @@ __device__ __forceinline__ float nan_to_num(float v) {
 
 // stencil point p of a sample at x (clamped to the scene box, network_grid.py:83-88)
 __device__ __forceinline__ void stencil_point(float out[3], const float x[3], int p, float bound) {
-    out[0] = x[0]; out[1] = x[1]; out[2] = x[2];
-    if (p > 0) {
-        const int axis = (p - 1) >> 1;
-        const float e = ((p - 1) & 1) ? -kFdEps : kFdEps;
-        out[axis] = fminf(fmaxf(x[axis] + e, -bound), bound);
-    }
+    // p = 0: the sample itself; p = 1..6: +eps / -eps along x, y, z (nerf/network_grid.py:92-100).  Branch-free so that a
+    // rolled stencil loop keeps the point in registers.
+    const int axis = p > 0 ? (p - 1) >> 1 : -1;
+    const float e = ((p - 1) & 1) ? -kFdEps : kFdEps;
+#pragma unroll
+    for (int d = 0; d < 3; d++) out[d] = (d == axis) ? fminf(fmaxf(x[d] + e, -bound), bound) : x[d];
 }
 
 __device__ __forceinline__ bool to_unit(float u[3], const float x[3], float bound) {
@@ -49,8 +50,8 @@ __device__ __forceinline__ bool to_unit(float u[3], const float x[3], float boun
     return ok;
 }
 
-template <int SHADING>
-__global__ void __launch_bounds__(256, 2)
+template <int SHADING, int OCC>
+__global__ void __launch_bounds__(256, OCC)
 k_field_forward(FieldParams p, const float* __restrict__ xyzs, const float* __restrict__ light_d, int light_per_sample,
                 float ratio, uint32_t M_cap, const int* __restrict__ m_dev,
                 float* __restrict__ sigmas, float* __restrict__ colors, float* __restrict__ normals, float* __restrict__ aux) {
@@ -72,9 +73,12 @@ k_field_forward(FieldParams p, const float* __restrict__ xyzs, const float* __re
         if (ina) { xa[0] = xyzs[(size_t)sa * 3]; xa[1] = xyzs[(size_t)sa * 3 + 1]; xa[2] = xyzs[(size_t)sa * 3 + 2]; }
         if (inb) { xb[0] = xyzs[(size_t)sb * 3]; xb[1] = xyzs[(size_t)sb * 3 + 1]; xb[2] = xyzs[(size_t)sb * 3 + 2]; }
 
-        float sig_a[NP], sig_b[NP];
+        // The stencil loop stays rolled (7 unrolled copies of gather + MLP are ~400 KB of SASS: instruction-cache misses showed
+        // up as the third stall reason): densities go straight to the stash, the finite differences accumulate as they come.
+        float sig0_a = 0.f, sig0_b = 0.f;
+        float nda[3] = {0.f, 0.f, 0.f}, ndb[3] = {0.f, 0.f, 0.f};      // sigma(+eps) - sigma(-eps) per axis
         float alb_a[3] = {0.f, 0.f, 0.f}, alb_b[3] = {0.f, 0.f, 0.f};
-#pragma unroll
+#pragma unroll 1
         for (int sp = 0; sp < NP; sp++) {
             float pa[3], pb[3], ua[3], ub[3];
             stencil_point(pa, xa, sp, p.bound);
@@ -85,13 +89,25 @@ k_field_forward(FieldParams p, const float* __restrict__ xyzs, const float* __re
             float h[4];
             mlp_forward<false>(h, a0, s, lane, nullptr, nullptr);
             // lanes t==0: h[0],h[1] = logits 0,1 of row g ; h[2],h[3] = of row g+8.  lanes t==1: logits 2,3.
-            sig_a[sp] = __expf(round_h(h[0]) + blob(p, pa));
-            sig_b[sp] = __expf(round_h(h[2]) + blob(p, pb));
+            const float sga = __expf(round_h(h[0]) + blob(p, pa));
+            const float sgb = __expf(round_h(h[2]) + blob(p, pb));
+            if (aux && t == 0) {      // saved for the backward pass: the stencil densities
+                if (ina) aux[(size_t)sa * kAuxStride + sp] = sga;
+                if (inb) aux[(size_t)sb * kAuxStride + sp] = sgb;
+            }
             if (sp == 0) {
+                sig0_a = sga; sig0_b = sgb;
                 const float h2a = __shfl_down_sync(0xffffffffu, h[0], 1), h3a = __shfl_down_sync(0xffffffffu, h[1], 1);
                 const float h2b = __shfl_down_sync(0xffffffffu, h[2], 1), h3b = __shfl_down_sync(0xffffffffu, h[3], 1);
                 alb_a[0] = round_h(1.f / (1.f + __expf(-round_h(h[1])))); alb_a[1] = round_h(1.f / (1.f + __expf(-round_h(h2a)))); alb_a[2] = round_h(1.f / (1.f + __expf(-round_h(h3a))));
                 alb_b[0] = round_h(1.f / (1.f + __expf(-round_h(h[3])))); alb_b[1] = round_h(1.f / (1.f + __expf(-round_h(h2b)))); alb_b[2] = round_h(1.f / (1.f + __expf(-round_h(h3b))));
+            } else {
+                const int axis = (sp - 1) >> 1;
+                const bool plus = (sp & 1) != 0;                 // sp = 1, 3, 5 are the +eps points
+#pragma unroll
+                for (int d = 0; d < 3; d++) {
+                    if (d == axis) { nda[d] = plus ? sga : nda[d] - sga; ndb[d] = plus ? sgb : ndb[d] - sgb; }
+                }
             }
         }
         if (t != 0) continue;
@@ -100,21 +116,21 @@ k_field_forward(FieldParams p, const float* __restrict__ xyzs, const float* __re
         for (int r = 0; r < 2; r++) {
             const uint32_t si = r ? sb : sa;
             if (!(r ? inb : ina)) continue;
-            const float* sg = r ? sig_b : sig_a;
+            const float* nd = r ? ndb : nda;
             const float* al = r ? alb_b : alb_a;
-            sigmas[si] = sg[0];
-            if (aux) {      // saved for the backward pass: the stencil densities and the albedo
+            sigmas[si] = r ? sig0_b : sig0_a;
+            if (aux) {      // the rest of the stash: unused stencil slots (albedo mode) and the albedo
                 float* ax = aux + (size_t)si * kAuxStride;
 #pragma unroll
-                for (int q = 0; q < 7; q++) ax[q] = q < NP ? sg[q] : 0.f;
+                for (int q = NP; q < 7; q++) ax[q] = 0.f;
                 ax[7] = al[0]; ax[8] = al[1]; ax[9] = al[2];
             }
             float col[3] = {al[0], al[1], al[2]};
             if (SHADING != kAlbedo) {
                 float n[3];
-                n[0] = -(0.5f * (sg[1] - sg[2]) / kFdEps);
-                n[1] = -(0.5f * (sg[3] - sg[4]) / kFdEps);
-                n[2] = -(0.5f * (sg[5] - sg[6]) / kFdEps);
+                n[0] = -(0.5f * nd[0] / kFdEps);
+                n[1] = -(0.5f * nd[1] / kFdEps);
+                n[2] = -(0.5f * nd[2] / kFdEps);
                 const float inv = 1.f / sqrtf(fmaxf(n[0] * n[0] + n[1] * n[1] + n[2] * n[2], 1e-20f));   // safe_normalize (nerf/utils.py:110)
                 n[0] = nan_to_num(n[0] * inv); n[1] = nan_to_num(n[1] * inv); n[2] = nan_to_num(n[2] * inv);
                 const float* l = light_d + (light_per_sample ? (size_t)si * 3 : 0);
@@ -161,10 +177,13 @@ SDF_API int sdf_field_forward(const float* xyzs, uint32_t M, const int* m_dev, c
     const size_t smem = sizeof(WeightsSmem);
     static_assert(sizeof(WeightsSmem) <= 48 * 1024, "forward weights must fit the default dynamic smem window");
     const uint32_t groups = (M + 15) / 16;
-    const uint32_t blocks = min((uint32_t)(kNumSMs * 2), (groups + 7) / 8);
+    // resident CTAs per SM: 2 (128 registers; measured 1.18 ms at 432k shaded samples) or 3 (80 registers; 1.34 ms); SDF_FIELD_OCC=3 selects the latter
+    static const int occ = [] { const char* e = getenv("SDF_FIELD_OCC"); return (e && e[0] == '3') ? 3 : 2; }();
+    const uint32_t blocks = min((uint32_t)(kNumSMs * occ), (groups + 7) / 8);
 #define LAUNCH(SH)                                                                                                   \
     do {                                                                                                             \
-        k_field_forward<SH><<<blocks, 256, smem, st>>>(p, xyzs, light_d, light_per_sample, ambient_ratio, M, m_dev, sigmas, colors, normals, aux); \
+        if (occ == 2) k_field_forward<SH, 2><<<blocks, 256, smem, st>>>(p, xyzs, light_d, light_per_sample, ambient_ratio, M, m_dev, sigmas, colors, normals, aux); \
+        else k_field_forward<SH, 3><<<blocks, 256, smem, st>>>(p, xyzs, light_d, light_per_sample, ambient_ratio, M, m_dev, sigmas, colors, normals, aux); \
     } while (0)
     switch (shading) {
         case 0: LAUNCH(kAlbedo); break;

@@ -45,12 +45,12 @@ struct BwdSmem {
 };
 
 __device__ __forceinline__ void stencil_point(float out[3], const float x[3], int p, float bound) {
-    out[0] = x[0]; out[1] = x[1]; out[2] = x[2];
-    if (p > 0) {
-        const int axis = (p - 1) >> 1;
-        const float e = ((p - 1) & 1) ? -kFdEps : kFdEps;
-        out[axis] = fminf(fmaxf(x[axis] + e, -bound), bound);
-    }
+    // p = 0: the sample itself; p = 1..6: +eps / -eps along x, y, z (nerf/network_grid.py:92-100).  Branch-free so that a
+    // rolled stencil loop keeps the point in registers.
+    const int axis = p > 0 ? (p - 1) >> 1 : -1;
+    const float e = ((p - 1) & 1) ? -kFdEps : kFdEps;
+#pragma unroll
+    for (int d = 0; d < 3; d++) out[d] = (d == axis) ? fminf(fmaxf(x[d] + e, -bound), bound) : x[d];
 }
 __device__ __forceinline__ bool to_unit(float u[3], const float x[3], float bound) {
     const float inv = 1.f / (2.f * bound);
@@ -126,13 +126,27 @@ __device__ __forceinline__ void scatter_level(float* __restrict__ grad_table, co
     for (int k = 0; k < 8; k++) atomicAdd(t + c.idx[k], make_float2(c.w[k] * g0, c.w[k] * g1));
 }
 
-__device__ __forceinline__ void st_half(__half* base, int stride, int feat, int row, float v) {
-    base[feat * stride + row] = __float2half_rn(v);
+// Staging for the weight-gradient products is [feature][row].  A register in A-fragment block layout (lane (g, t) holds
+// X[row0 + g][f0 + 2t .. 2t+1]) is transposed across the warp with movmatrix, after which lane (g, t) holds
+// X[row0 + 2t .. 2t+1][f0 + g]: one conflict-free 32-bit store per register instead of two 16-bit ones.
+__device__ __forceinline__ uint32_t movm_trans(uint32_t a) {
+    uint32_t d;
+    asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(d) : "r"(a));
+    return d;
 }
-__device__ __forceinline__ void st_half2regs(__half* base, int stride, int feat, int row, uint32_t packed) {
-    const __half2 h = *reinterpret_cast<const __half2*>(&packed);
-    base[feat * stride + row] = __low2half(h);
-    base[(feat + 1) * stride + row] = __high2half(h);
+__device__ __forceinline__ void stage_block(__half* buf, int f0, int row0, uint32_t reg, int g, int t) {
+    *reinterpret_cast<uint32_t*>(buf + (f0 + g) * kTStride + row0 + 2 * t) = movm_trans(reg);
+}
+// all four blocks of one A-fragment k-tile (16 rows x 16 features)
+__device__ __forceinline__ void stage_frag(__half* buf, int f0, int row0, const uint32_t a[4], int g, int t) {
+    stage_block(buf, f0, row0, a[0], g, t);
+    stage_block(buf, f0, row0 + 8, a[1], g, t);
+    stage_block(buf, f0 + 8, row0, a[2], g, t);
+    stage_block(buf, f0 + 8, row0 + 8, a[3], g, t);
+}
+__device__ __forceinline__ void clear_rows(__half* buf, int n_feat, int row0, int lane) {
+    // 16 staged rows (32 bytes) of every feature: 8 x 32-bit per feature
+    for (int i = lane; i < n_feat * 8; i += 32) *reinterpret_cast<uint32_t*>(buf + (i >> 3) * kTStride + row0 + (i & 7) * 2) = 0u;
 }
 
 template <int SHADING>
@@ -177,8 +191,10 @@ k_field_backward(FieldParams p, const float* __restrict__ xyzs, const float* __r
 
     // ---- weight-gradient tile assignment: 65 (m-tile, n-tile) pairs over 16 warps
     //   q in [0,36): layer 2  (4 m-tiles x 9 n-tiles; n-tile 8 = ones row -> bias)
-    //   q in [36,56): layer 1 (4 x 5)           q in [56,65): layer 3 (1 x 9)
-    constexpr int kPairs = 65, kMaxPerWarp = 5;
+    //   q in [36,56): layer 1 (4 x 5)           q in [56,64): layer 3 (1 x 8; its bias gradient is summed in registers below,
+    //   which leaves exactly 4 pairs per warp)
+    constexpr int kPairs = 64, kMaxPerWarp = 4;
+    float gb3_acc[2] = {0.f, 0.f};      // lanes t == 0: logits 0, 1; t == 1: logits 2, 3
     float wacc[kMaxPerWarp][4];
 #pragma unroll
     for (int j = 0; j < kMaxPerWarp; j++) wacc[j][0] = wacc[j][1] = wacc[j][2] = wacc[j][3] = 0.f;
@@ -225,19 +241,9 @@ k_field_backward(FieldParams p, const float* __restrict__ xyzs, const float* __r
         for (int sp = 0; sp < NP; sp++) {
             if (!warp_active) {
                 if (!rows_cleared) {
-                    const int row_a = warp * 16 + g, row_b = row_a + 8;
-                    if (t < 2) {
-                        st_half(&s.dh3t[0][0], kTStride, 2 * t, row_a, 0.f); st_half(&s.dh3t[0][0], kTStride, 2 * t + 1, row_a, 0.f);
-                        st_half(&s.dh3t[0][0], kTStride, 2 * t, row_b, 0.f); st_half(&s.dh3t[0][0], kTStride, 2 * t + 1, row_b, 0.f);
-                    }
-#pragma unroll
-                    for (int nt = 0; nt < 8; nt++) {
-#pragma unroll
-                        for (int e = 0; e < 2; e++) {
-                            st_half(&s.dh2t[0][0], kTStride, nt * 8 + 2 * t + e, row_a, 0.f); st_half(&s.dh2t[0][0], kTStride, nt * 8 + 2 * t + e, row_b, 0.f);
-                            st_half(&s.dh1t[0][0], kTStride, nt * 8 + 2 * t + e, row_a, 0.f); st_half(&s.dh1t[0][0], kTStride, nt * 8 + 2 * t + e, row_b, 0.f);
-                        }
-                    }
+                    clear_rows(&s.dh3t[0][0], 8, warp * 16, lane);
+                    clear_rows(&s.dh2t[0][0], kHidden, warp * 16, lane);
+                    clear_rows(&s.dh1t[0][0], kHidden, warp * 16, lane);
                     rows_cleared = true;
                 }
             } else {
@@ -265,47 +271,37 @@ k_field_backward(FieldParams p, const float* __restrict__ xyzs, const float* __r
             float hdummy[4];
             mlp_forward<true>(hdummy, a0, s.w, lane, a1, a2);
 
-            const int row_a = warp * 16 + g, row_b = row_a + 8;
-            // stage dh3^T (logit deltas) and the layer-3 input a2^T
-            if (t < 2) {
-                st_half(&s.dh3t[0][0], kTStride, 2 * t, row_a, d0a); st_half(&s.dh3t[0][0], kTStride, 2 * t + 1, row_a, d1a);
-                st_half(&s.dh3t[0][0], kTStride, 2 * t, row_b, d0b); st_half(&s.dh3t[0][0], kTStride, 2 * t + 1, row_b, d1b);
-            }
+            const int row0 = warp * 16;
+            gb3_acc[0] += d0a + d0b; gb3_acc[1] += d1a + d1b;
+            // stage dh3^T (logit deltas), the layer inputs a2^T, a1^T and enc^T
+            uint32_t d3frag[4] = {pack_half2(d0a, d1a), pack_half2(d0b, d1b), 0u, 0u};
+            stage_block(&s.dh3t[0][0], 0, row0, d3frag[0], g, t);
+            stage_block(&s.dh3t[0][0], 0, row0 + 8, d3frag[1], g, t);
 #pragma unroll
             for (int kt = 0; kt < 4; kt++) {
-                st_half2regs(&s.a2t[0][0], kTStride, kt * 16 + 2 * t, row_a, a2[kt][0]);
-                st_half2regs(&s.a2t[0][0], kTStride, kt * 16 + 2 * t, row_b, a2[kt][1]);
-                st_half2regs(&s.a2t[0][0], kTStride, kt * 16 + 2 * t + 8, row_a, a2[kt][2]);
-                st_half2regs(&s.a2t[0][0], kTStride, kt * 16 + 2 * t + 8, row_b, a2[kt][3]);
-                st_half2regs(&s.a1t[0][0], kTStride, kt * 16 + 2 * t, row_a, a1[kt][0]);
-                st_half2regs(&s.a1t[0][0], kTStride, kt * 16 + 2 * t, row_b, a1[kt][1]);
-                st_half2regs(&s.a1t[0][0], kTStride, kt * 16 + 2 * t + 8, row_a, a1[kt][2]);
-                st_half2regs(&s.a1t[0][0], kTStride, kt * 16 + 2 * t + 8, row_b, a1[kt][3]);
+                stage_frag(&s.a2t[0][0], kt * 16, row0, a2[kt], g, t);
+                stage_frag(&s.a1t[0][0], kt * 16, row0, a1[kt], g, t);
             }
 #pragma unroll
-            for (int kt = 0; kt < 2; kt++) {
-                st_half2regs(&s.enct[0][0], kTStride, kt * 16 + 2 * t, row_a, a0[kt][0]);
-                st_half2regs(&s.enct[0][0], kTStride, kt * 16 + 2 * t, row_b, a0[kt][1]);
-                st_half2regs(&s.enct[0][0], kTStride, kt * 16 + 2 * t + 8, row_a, a0[kt][2]);
-                st_half2regs(&s.enct[0][0], kTStride, kt * 16 + 2 * t + 8, row_b, a0[kt][3]);
-            }
+            for (int kt = 0; kt < 2; kt++) stage_frag(&s.enct[0][0], kt * 16, row0, a0[kt], g, t);
 
             // ---- dh2 = (dh3 . W3) * relu'(a2)    A = dh3 [16 x 16(k: 4 valid)], B[k][n] = W3[k][n] = w3t[n][k]
-            uint32_t d3frag[4] = {pack_half2(d0a, d1a), pack_half2(d0b, d1b), 0u, 0u};
             uint32_t dh2[4][4];
+            uint32_t w3b[8];       // b0 of the 8 n-tiles (k = logit 0..7): matrix i of an x4 = rows 8i..8i+7 of w3t, 16 bytes each
+            ldsm_x4(w3b, &s.w3t[lane][0]);
+            ldsm_x4(w3b + 4, &s.w3t[32 + lane][0]);
 #pragma unroll
             for (int nt = 0; nt < 8; nt++) {
                 float c[4] = {0.f, 0.f, 0.f, 0.f};
-                const uint32_t b0 = *reinterpret_cast<const uint32_t*>(&s.w3t[nt * 8 + g][2 * t]);
-                mma16816(c, d3frag, b0, 0u);
+                mma16816(c, d3frag, w3b[nt], 0u);
                 const int kt2 = nt >> 1, hi = (nt & 1) * 2;
                 const float2 ma = unpack_half2(a2[kt2][hi + 0]), mb = unpack_half2(a2[kt2][hi + 1]);
                 c[0] = ma.x > 0.f ? c[0] : 0.f; c[1] = ma.y > 0.f ? c[1] : 0.f;
                 c[2] = mb.x > 0.f ? c[2] : 0.f; c[3] = mb.y > 0.f ? c[3] : 0.f;
                 dh2[kt2][hi + 0] = pack_half2(c[0], c[1]);
                 dh2[kt2][hi + 1] = pack_half2(c[2], c[3]);
-                st_half(&s.dh2t[0][0], kTStride, nt * 8 + 2 * t, row_a, c[0]); st_half(&s.dh2t[0][0], kTStride, nt * 8 + 2 * t + 1, row_a, c[1]);
-                st_half(&s.dh2t[0][0], kTStride, nt * 8 + 2 * t, row_b, c[2]); st_half(&s.dh2t[0][0], kTStride, nt * 8 + 2 * t + 1, row_b, c[3]);
+                stage_block(&s.dh2t[0][0], nt * 8, row0, dh2[kt2][hi + 0], g, t);
+                stage_block(&s.dh2t[0][0], nt * 8, row0 + 8, dh2[kt2][hi + 1], g, t);
             }
             // ---- dh1 = (dh2 . W2) * relu'(a1)    B[k][n] = W2[k][n] = w2t[n][k]
             uint32_t dh1[4][4];
@@ -313,10 +309,11 @@ k_field_backward(FieldParams p, const float* __restrict__ xyzs, const float* __r
             for (int nt = 0; nt < 8; nt++) {
                 float c[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-                for (int kt = 0; kt < 4; kt++) {
-                    const uint32_t b0 = *reinterpret_cast<const uint32_t*>(&s.w2t[nt * 8 + g][kt * 16 + 2 * t]);
-                    const uint32_t b1 = *reinterpret_cast<const uint32_t*>(&s.w2t[nt * 8 + g][kt * 16 + 2 * t + 8]);
-                    mma16816(c, dh2[kt], b0, b1);
+                for (int kp = 0; kp < 2; kp++) {
+                    uint32_t wb[4];
+                    ldsm_b2(wb, &s.w2t[nt * 8][0], kWtStride, kp * 32, lane);
+                    mma16816(c, dh2[2 * kp], wb[0], wb[1]);
+                    mma16816(c, dh2[2 * kp + 1], wb[2], wb[3]);
                 }
                 const int kt2 = nt >> 1, hi = (nt & 1) * 2;
                 const float2 ma = unpack_half2(a1[kt2][hi + 0]), mb = unpack_half2(a1[kt2][hi + 1]);
@@ -324,18 +321,19 @@ k_field_backward(FieldParams p, const float* __restrict__ xyzs, const float* __r
                 c[2] = mb.x > 0.f ? c[2] : 0.f; c[3] = mb.y > 0.f ? c[3] : 0.f;
                 dh1[kt2][hi + 0] = pack_half2(c[0], c[1]);
                 dh1[kt2][hi + 1] = pack_half2(c[2], c[3]);
-                st_half(&s.dh1t[0][0], kTStride, nt * 8 + 2 * t, row_a, c[0]); st_half(&s.dh1t[0][0], kTStride, nt * 8 + 2 * t + 1, row_a, c[1]);
-                st_half(&s.dh1t[0][0], kTStride, nt * 8 + 2 * t, row_b, c[2]); st_half(&s.dh1t[0][0], kTStride, nt * 8 + 2 * t + 1, row_b, c[3]);
+                stage_block(&s.dh1t[0][0], nt * 8, row0, dh1[kt2][hi + 0], g, t);
+                stage_block(&s.dh1t[0][0], nt * 8, row0 + 8, dh1[kt2][hi + 1], g, t);
             }
             // ---- d(enc) = dh1 . W1 ; n-tile nt covers levels 4nt..4nt+3: lane gets (row g / g+8, level 4nt + t)
 #pragma unroll
             for (int nt = 0; nt < 4; nt++) {
                 float c[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-                for (int kt = 0; kt < 4; kt++) {
-                    const uint32_t b0 = *reinterpret_cast<const uint32_t*>(&s.w1t[nt * 8 + g][kt * 16 + 2 * t]);
-                    const uint32_t b1 = *reinterpret_cast<const uint32_t*>(&s.w1t[nt * 8 + g][kt * 16 + 2 * t + 8]);
-                    mma16816(c, dh1[kt], b0, b1);
+                for (int kp = 0; kp < 2; kp++) {
+                    uint32_t wb[4];
+                    ldsm_b2(wb, &s.w1t[nt * 8][0], kWtStride, kp * 32, lane);
+                    mma16816(c, dh1[2 * kp], wb[0], wb[1]);
+                    mma16816(c, dh1[2 * kp + 1], wb[2], wb[3]);
                 }
                 const uint32_t level = nt * 4 + t;
                 if (level < p.n_levels_active) {
@@ -357,19 +355,16 @@ k_field_backward(FieldParams p, const float* __restrict__ xyzs, const float* __r
                     if (q < 36) { mt = q / 9; nt = q % 9; A = &s.dh2t[0][0]; B = &s.a1t[0][0]; }
                     else if (q < 56) { mt = (q - 36) / 5; nt = (q - 36) % 5; A = &s.dh1t[0][0]; B = &s.enct[0][0]; }
                     else { mt = 0; nt = q - 56; A = &s.dh3t[0][0]; B = &s.a2t[0][0]; }
-                    const __half* Ar0 = A + (mt * 16 + g) * kTStride;
-                    const __half* Ar1 = Ar0 + 8 * kTStride;
-                    const __half* Br = B + (nt * 8 + g) * kTStride;
+                    const __half* Ar = A + (mt * 16) * kTStride;
+                    const __half* Br = B + (nt * 8) * kTStride;
 #pragma unroll 4
-                    for (int kt = 0; kt < kRows / 16; kt++) {
-                        uint32_t af[4];
-                        af[0] = *reinterpret_cast<const uint32_t*>(Ar0 + kt * 16 + 2 * t);
-                        af[1] = *reinterpret_cast<const uint32_t*>(Ar1 + kt * 16 + 2 * t);
-                        af[2] = *reinterpret_cast<const uint32_t*>(Ar0 + kt * 16 + 2 * t + 8);
-                        af[3] = *reinterpret_cast<const uint32_t*>(Ar1 + kt * 16 + 2 * t + 8);
-                        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(Br + kt * 16 + 2 * t);
-                        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(Br + kt * 16 + 2 * t + 8);
-                        mma16816(wacc[j], af, b0, b1);
+                    for (int kp = 0; kp < kRows / 32; kp++) {      // two k-steps (32 staged rows) per trip: 3 ldmatrix.x4 for 2 MMAs
+                        uint32_t af0[4], af1[4], bf[4];
+                        ldsm_a(af0, Ar, kTStride, kp * 32, lane);
+                        ldsm_a(af1, Ar, kTStride, kp * 32 + 16, lane);
+                        ldsm_b2(bf, Br, kTStride, kp * 32, lane);
+                        mma16816(wacc[j], af0, bf[0], bf[1]);
+                        mma16816(wacc[j], af1, bf[2], bf[3]);
                     }
                 }
             }
@@ -377,6 +372,13 @@ k_field_backward(FieldParams p, const float* __restrict__ xyzs, const float* __r
         }
     }
 
+    // ---- layer-3 bias gradient: sum the per-lane partials over the 8 row groups of the warp
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+        float v = gb3_acc[e];
+        v += __shfl_xor_sync(0xffffffffu, v, 4); v += __shfl_xor_sync(0xffffffffu, v, 8); v += __shfl_xor_sync(0xffffffffu, v, 16);
+        if (g == 0 && t < 2 && v != 0.f) atomicAdd(gb3 + 2 * t + e, v);
+    }
     // ---- flush the weight-gradient accumulators: wacc[j] = (out = 16mt + g (+8), in = 8nt + 2t (+1))
 #pragma unroll
     for (int j = 0; j < kMaxPerWarp; j++) {
