@@ -166,6 +166,8 @@ int sdf_gemm_run(int plan, void* stream);
 int sdf_gemm_plan_destroy(int plan);
 
 /* memory-bound companions (csrc/sd_ops.cu); x/y are NHWC fp16 with row strides ld* (elements, multiples of 8) */
+/* GroupNorm(+SiLU), ldm/modules/diffusionmodules/util.py:214 / model.py:38.  stats: fp32 scratch [Nimg,G,2] (sums / sums of squares,
+ * kept for sdf_groupnorm_backward). */
 int sdf_groupnorm_forward(const void* x, int ldx, void* y, int ldy, int Nimg, int HW, int C, int G, const float* gamma, const float* beta,
                           float eps, int silu_act, float* stats, void* stream);
 int sdf_groupnorm_backward(const void* x, int ldx, const void* dy, int ldd, void* dx, int ldo, int Nimg, int HW, int C, int G,

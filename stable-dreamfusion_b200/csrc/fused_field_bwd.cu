@@ -117,13 +117,27 @@ __device__ __forceinline__ void sample_grads(float gsig[7], float glogit[3], con
 }
 
 // Scatter d(enc) of one (row, level) into the fp32 table gradient (same corner geometry as the forward gather).
+// The kernel is bound by the LSU's scattered-reduction rate (~1.3 cycles per active lane per SM), so the two x-neighbours of
+// a corner pair share ONE 16-byte reduction whenever they sit in the same aligned pair of table entries: always for hashed
+// levels when x0 is even (x1 = x0 ^ 1 flips only bit 0 of the hash) and for dense levels when the linear index is even.
 __device__ __forceinline__ void scatter_level(float* __restrict__ grad_table, const LevelSmem& lv, float x, float y, float z,
                                               bool smooth, float g0, float g1) {
     Corners c;
     level_corners(c, lv, x, y, z, smooth);
-    float2* t = reinterpret_cast<float2*>(grad_table) + lv.offset;
+    float2* t = reinterpret_cast<float2*>(grad_table) + lv.offset;       // level offsets are multiples of 8 entries: pairs stay 16-byte aligned
 #pragma unroll
-    for (int k = 0; k < 8; k++) atomicAdd(t + c.idx[k], make_float2(c.w[k] * g0, c.w[k] * g1));
+    for (int j = 0; j < 4; j++) {
+        const uint32_t i0 = c.idx[2 * j], i1 = c.idx[2 * j + 1];
+        const float w0 = c.w[2 * j], w1 = c.w[2 * j + 1];
+        if ((i0 ^ i1) == 1u) {
+            const bool lo = (i0 & 1u) == 0u;                                 // which corner owns the even slot
+            const float wa = lo ? w0 : w1, wb = lo ? w1 : w0;
+            atomicAdd(reinterpret_cast<float4*>(t + (i0 & ~1u)), make_float4(wa * g0, wa * g1, wb * g0, wb * g1));
+        } else {
+            atomicAdd(t + i0, make_float2(w0 * g0, w0 * g1));
+            atomicAdd(t + i1, make_float2(w1 * g0, w1 * g1));
+        }
+    }
 }
 
 // Staging for the weight-gradient products is [feature][row].  A register in A-fragment block layout (lane (g, t) holds

@@ -23,7 +23,8 @@ def close(a, b, rtol=2e-3, atol=2e-3):
     assert err.max().item() <= 0, f"max violation {err.max().item():.3g}, max abs err {(a - b).abs().max().item():.3g}"
 
 
-@pytest.mark.parametrize("Nimg,HW,C,act", [(2, 4096, 320, 1), (2, 256, 1280, 0), (1, 16384, 128, 1), (2, 64, 2560, 1), (1, 1024, 960, 1)])
+@pytest.mark.parametrize("Nimg,HW,C,act", [(2, 4096, 320, 1), (2, 256, 1280, 0), (1, 16384, 128, 1), (2, 64, 2560, 1), (1, 1024, 960, 1),
+                                           (2, 4096, 640, 1), (1, 65536, 128, 1), (2, 4096, 960, 0), (3, 100, 64, 1)])
 def test_groupnorm_fwd_bwd(device, Nimg, HW, C, act):
     x = rnd(Nimg, HW, C, device=device, seed=1, shift=0.3)
     gamma = torch.randn(C, device=device) * 0.5 + 1
