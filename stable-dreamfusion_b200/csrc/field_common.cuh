@@ -214,6 +214,65 @@ __device__ __forceinline__ void encode_rows(uint32_t a[2][4], const WeightsSmem&
     }
 }
 
+// Split form of encode_rows for software pipelining (fused_field_bwd.cu): gather_issue() computes the corner indices of the
+// lane's two FINE levels (8 + t, 12 + t: the hashed ones that miss L1) x 2 rows and issues those 32 gathers into `raw`
+// (nothing waits on them); gather_finish() gathers the two coarse levels as usual, recomputes the trilinear weights of the
+// fine ones (pure ALU) and folds the values that arrived meanwhile into the A fragments.  (Prefetching all four level
+// groups needs 64 live registers and spills under the 128-register budget of the 16-warp CTA.)
+__device__ __forceinline__ void gather_issue(__half2 raw[2][16], const WeightsSmem& s, const FieldParams& p, int lane,
+                                             const float pa[3], const float pb[3]) {
+    const int t = lane & 3;
+    const bool smooth = p.interp_smoothstep != 0;
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const uint32_t level = 8 + t + h * 4;
+        if (level < p.n_levels_active) {
+            const LevelSmem lv = s.lv[level];
+            Corners ca, cb;
+            level_corners(ca, lv, pa[0], pa[1], pa[2], smooth);
+            level_corners(cb, lv, pb[0], pb[1], pb[2], smooth);
+            const __half2* tb = p.table + lv.offset;
+#pragma unroll
+            for (int k = 0; k < 8; k++) { raw[h][k] = __ldg(tb + ca.idx[k]); raw[h][8 + k] = __ldg(tb + cb.idx[k]); }
+        }
+    }
+}
+
+__device__ __forceinline__ void gather_finish(uint32_t a[2][4], const __half2 raw[2][16], const WeightsSmem& s, const FieldParams& p, int lane,
+                                              const float pa[3], bool va, const float pb[3], bool vb) {
+    const int t = lane & 3;
+    const bool smooth = p.interp_smoothstep != 0;
+#pragma unroll
+    for (int h = 0; h < 2; h++) {            // coarse levels t, t + 4: gathered now (mostly L1 hits)
+        const uint32_t level = t + h * 4;
+        float2 ea = make_float2(0.f, 0.f), eb = make_float2(0.f, 0.f);
+        if (level < p.n_levels_active) encode_level_pair(p.table, s.lv[level], pa, va, pb, vb, smooth, ea, eb);
+        a[0][h * 2 + 0] = pack_half2(ea.x, ea.y);
+        a[0][h * 2 + 1] = pack_half2(eb.x, eb.y);
+    }
+#pragma unroll
+    for (int h = 0; h < 2; h++) {            // fine levels: values were prefetched
+        const uint32_t level = 8 + t + h * 4;
+        float2 ea = make_float2(0.f, 0.f), eb = make_float2(0.f, 0.f);
+        if (level < p.n_levels_active) {
+            const LevelSmem lv = s.lv[level];
+            Corners ca, cb;          // only the weights are used: the index arithmetic is dead code here
+            level_corners(ca, lv, pa[0], pa[1], pa[2], smooth);
+            level_corners(cb, lv, pb[0], pb[1], pb[2], smooth);
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const float2 v = __half22float2(raw[h][k]), u = __half22float2(raw[h][8 + k]);
+                ea.x = fmaf(ca.w[k], v.x, ea.x); ea.y = fmaf(ca.w[k], v.y, ea.y);
+                eb.x = fmaf(cb.w[k], u.x, eb.x); eb.y = fmaf(cb.w[k], u.y, eb.y);
+            }
+            if (!va) ea = make_float2(0.f, 0.f);
+            if (!vb) eb = make_float2(0.f, 0.f);
+        }
+        a[1][h * 2 + 0] = pack_half2(ea.x, ea.y);
+        a[1][h * 2 + 1] = pack_half2(eb.x, eb.y);
+    }
+}
+
 // 32 -> 64 -> 64 -> 4 MLP for a 16-row tile held as A fragments.  Returns the layer-3 accumulator tile
 // (cols 0..7; lane holds (row g, cols 2t,2t+1) in c[0],c[1] and (row g+8, ...) in c[2],c[3]).
 // When KEEP is set the post-ReLU activations of both hidden layers are returned as A fragments.

@@ -16,6 +16,7 @@
 // Algorithmic bytes: 1 052 B per point-eval (12 B xyz + 16 B upstream + 128 float2/half2
 // RMWs counted 8 B each).  Roofline: HBM (L2 atomics in practice).
 #include "field_common.cuh"
+#include <cstdlib>
 
 using namespace field;
 
@@ -163,7 +164,7 @@ __device__ __forceinline__ void clear_rows(__half* buf, int n_feat, int row0, in
     for (int i = lane; i < n_feat * 8; i += 32) *reinterpret_cast<uint32_t*>(buf + (i >> 3) * kTStride + row0 + (i & 7) * 2) = 0u;
 }
 
-template <int SHADING>
+template <int SHADING, bool PREFETCH>
 __global__ void __launch_bounds__(kWarps * 32, 1)
 k_field_backward(FieldParams p, const float* __restrict__ xyzs, const float* __restrict__ light_d, int light_per_sample,
                  float ratio, uint32_t M_cap, const int* __restrict__ m_dev, const float* __restrict__ aux,
@@ -251,6 +252,17 @@ k_field_backward(FieldParams p, const float* __restrict__ xyzs, const float* __r
         const bool warp_active = __any_sync(0xffffffffu, mine);
         bool rows_cleared = false;
 
+        // software pipeline over the stencil points: the 32 fine-level gathers of point sp+1 are issued before the CTA barrier and the
+        // weight-gradient products of point sp, so their latency is hidden behind tensor-core work instead of being exposed
+        __half2 raw[2][16];
+        if (PREFETCH && warp_active) {
+            float pa[3], pb[3], ua[3], ub[3];
+            stencil_point(pa, xa, 0, p.bound);
+            stencil_point(pb, xb, 0, p.bound);
+            to_unit(ua, pa, p.bound); to_unit(ub, pb, p.bound);
+            gather_issue(raw, s.w, p, lane, ua, ub);
+        }
+
 #pragma unroll 1
         for (int sp = 0; sp < NP; sp++) {
             if (!warp_active) {
@@ -281,7 +293,8 @@ k_field_backward(FieldParams p, const float* __restrict__ xyzs, const float* __r
             stencil_point(pb, xb, sp, p.bound);
             const bool va = to_unit(ua, pa, p.bound) && ina, vb = to_unit(ub, pb, p.bound) && inb;
             uint32_t a0[2][4], a1[4][4], a2[4][4];
-            encode_rows(a0, s.w, p, lane, ua, va, ub, vb);
+            if (PREFETCH) gather_finish(a0, raw, s.w, p, lane, ua, va, ub, vb);
+            else encode_rows(a0, s.w, p, lane, ua, va, ub, vb);
             float hdummy[4];
             mlp_forward<true>(hdummy, a0, s.w, lane, a1, a2);
 
@@ -355,6 +368,13 @@ k_field_backward(FieldParams p, const float* __restrict__ xyzs, const float* __r
                     if (va && (c[0] != 0.f || c[1] != 0.f)) scatter_level(grad_table, lv, ua[0], ua[1], ua[2], smooth, c[0], c[1]);
                     if (vb && (c[2] != 0.f || c[3] != 0.f)) scatter_level(grad_table, lv, ub[0], ub[1], ub[2], smooth, c[2], c[3]);
                 }
+            }
+            if (PREFETCH && sp + 1 < NP) {      // next stencil point's gathers fly during the barrier + weight-gradient phase
+                float qa[3], qb[3], wa[3], wb[3];
+                stencil_point(qa, xa, sp + 1, p.bound);
+                stencil_point(qb, xb, sp + 1, p.bound);
+                to_unit(wa, qa, p.bound); to_unit(wb, qb, p.bound);
+                gather_issue(raw, s.w, p, lane, wa, wb);
             }
             }   // warp_active
             __syncthreads();
@@ -446,17 +466,20 @@ SDF_API int sdf_field_backward(const float* xyzs, uint32_t M, const int* m_dev, 
     const int smem = (int)sizeof(BwdSmem);
     const uint32_t n_super = ((M + 15) / 16 + kWarps - 1) / kWarps;
     const uint32_t blocks = min((uint32_t)kNumSMs, n_super);
-#define LAUNCH(SH)                                                                                                        \
+    // SDF_FIELD_BWD_PREFETCH=0 selects the variant without the software-pipelined fine-level gathers (A/B experiments)
+    static const bool prefetch = [] { const char* e = getenv("SDF_FIELD_BWD_PREFETCH"); return !(e && e[0] == '0'); }();
+#define LAUNCH_V(SH, PF)                                                                                                  \
     do {                                                                                                                  \
         static bool attr_set[64] = {false};                                                                               \
         int dev = 0; cudaGetDevice(&dev);                                                                                 \
         if (dev < 64 && !attr_set[dev]) {                                                                                 \
-            SDF_CHECK_CUDA(cudaFuncSetAttribute(k_field_backward<SH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+            SDF_CHECK_CUDA(cudaFuncSetAttribute(k_field_backward<SH, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
             attr_set[dev] = true;                                                                                         \
         }                                                                                                                 \
-        k_field_backward<SH><<<blocks, kWarps * 32, smem, st>>>(p, xyzs, light_d, light_per_sample, ambient_ratio, M, m_dev, aux, \
-                                                               g_sigmas, g_colors, g_normals, grad_table, gw1, gb1, gw2, gb2, gw3, gb3); \
+        k_field_backward<SH, PF><<<blocks, kWarps * 32, smem, st>>>(p, xyzs, light_d, light_per_sample, ambient_ratio, M, m_dev, aux, \
+                                                                   g_sigmas, g_colors, g_normals, grad_table, gw1, gb1, gw2, gb2, gw3, gb3); \
     } while (0)
+#define LAUNCH(SH) do { if (prefetch) LAUNCH_V(SH, true); else LAUNCH_V(SH, false); } while (0)
     switch (shading) {
         case 0: LAUNCH(kAlbedo); break;
         case 1: LAUNCH(kLambertian); break;
@@ -464,6 +487,7 @@ SDF_API int sdf_field_backward(const float* xyzs, uint32_t M, const int* m_dev, 
         default: LAUNCH(kNormal); break;
     }
 #undef LAUNCH
+#undef LAUNCH_V
     SDF_CHECK_LAUNCH("field_backward");
     return SDF_OK;
 }
