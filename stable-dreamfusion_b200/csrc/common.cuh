@@ -31,6 +31,30 @@ static inline uint64_t cdiv64(uint64_t a, uint64_t b) { return (a + b - 1) / b; 
 
 constexpr int kNumSMs = 148;   // B200
 
+// ---- programmatic dependent launch (PDL).  The SD launch lists are ~950 small dependent kernels per step; with PDL the next
+// kernel's CTAs are scheduled as soon as the previous grid's CTAs have all STARTED (every kernel triggers at its first
+// instruction), run their prologue (barrier init, TMEM allocation, tensor-map prefetch, index math) and then block in
+// griddepcontrol.wait until the previous grid has completed and flushed — launch latency and prologues leave the critical path.
+// Contract for a PDL-aware kernel: pdl_prologue() (or trigger + wait) before the first global-memory access.
+// SDF_PDL=0 in the environment launches everything with full stream serialisation (the wait is then a no-op).
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_prologue() { pdl_trigger(); pdl_wait(); }
+bool sdf_pdl_enabled();
+
+// Launch `kernel` so that it may overlap the tail of its stream predecessor (which must be a kernel: callers use a plain
+// <<<>>> launch right after a memset).
+template <typename... KArgs, typename... Args>
+inline cudaError_t sdf_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = sdf_pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -14,3 +14,9 @@ void sdf_set_error(const char* fmt, ...) {
 SDF_API const char* sdf_last_error(void) { return g_err; }
 
 SDF_API int sdf_abi_version(void) { return 1; }
+
+#include <cstdlib>
+bool sdf_pdl_enabled() {
+    static const bool on = [] { const char* e = getenv("SDF_PDL"); return !(e && e[0] == '0'); }();
+    return on;
+}

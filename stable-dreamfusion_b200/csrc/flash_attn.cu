@@ -53,6 +53,7 @@ template <int D>
 __global__ void __launch_bounds__(128) k_flash_attn(const __half* __restrict__ q, const __half* __restrict__ k, const __half* __restrict__ v,
                                                     __half* __restrict__ o, int n, int nkv, int heads, int ldq, int ldk, int ldo, float scale_log2e) {
     using C = Cfg<D>;
+    pdl_prologue();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __half* sK = reinterpret_cast<__half*>(smem_raw);                 // [2][kBN][kStride]
     __half* sV = sK + 2 * kBN * C::kStride;                           // [2][kBN][kStride]
@@ -201,7 +202,7 @@ int launch_flash(const __half* q, const __half* k, const __half* v, __half* o, i
         attr_set[dev] = true;
     }
     dim3 grid((n + kBM - 1) / kBM, B * heads);
-    k_flash_attn<D><<<grid, 128, smem, st>>>(q, k, v, o, n, nkv, heads, ldq, ldk, ldo, scale * 1.4426950408889634f);
+    sdf_launch_pdl(k_flash_attn<D>, grid, dim3(128), (size_t)smem, st, q, k, v, o, n, nkv, heads, ldq, ldk, ldo, scale * 1.4426950408889634f);
     return SDF_OK;
 }
 

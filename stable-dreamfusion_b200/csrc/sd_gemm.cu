@@ -168,6 +168,7 @@ k_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtens
     uint64_t* tmem_empty = tmem_full + 2;
     uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
+    pdl_trigger();        // the next kernel of the stream may be scheduled (it blocks in its own griddepcontrol.wait)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr uint32_t kTmemCols = (2 * BLOCK_N <= 128) ? 128 : (2 * BLOCK_N <= 256 ? 256 : 512);
 
@@ -196,6 +197,7 @@ k_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtens
     if (PAIR) cluster_sync_all(); else __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_base_smem;
+    pdl_wait();           // everything above overlapped the previous kernel's tail; its results are visible from here on
 
     // ---- tile bookkeeping (identical in every role)
     const int tiles_x = (g.W + g.tw - 1) / g.tw, tiles_y = (g.H + g.th - 1) / g.th, tiles_n_img = (g.Nimg + g.tn - 1) / g.tn;
@@ -430,6 +432,7 @@ k_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtens
 
 // finishes a split-K product: workspace fp32 [M,N] -> epilogue -> fp16 out
 __global__ void k_splitk_epilogue(const float* __restrict__ ws, GemmArgs g) {
+    pdl_prologue();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long total = (long long)g.M * g.N;
     if (i >= total) return;
@@ -480,16 +483,23 @@ int launch_gemm(const GemmPlan& p, cudaStream_t st) {
         SDF_CHECK_CUDA(cudaFuncSetAttribute(k_gemm<BN, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
         attr_set[dev] = true;
     }
-    if (!PAIR) {
-        k_gemm<BN, PAIR><<<p.grid, kNumThreads, L::kTotal, st>>>(p.map_a, p.map_b, p.args);
-        return SDF_OK;
-    }
+    // split-K plans follow their workspace memset: programmatic launch needs a kernel as stream predecessor
+    const bool pdl = sdf_pdl_enabled() && p.args.splitk == 1;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(p.grid); cfg.blockDim = dim3(kNumThreads); cfg.dynamicSmemBytes = L::kTotal; cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (PAIR) {
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = 2; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+        na++;
+    }
+    if (pdl) {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        na++;
+    }
+    cfg.attrs = attr; cfg.numAttrs = na;
     SDF_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k_gemm<BN, PAIR>, p.map_a, p.map_b, p.args));
     return SDF_OK;
 }
@@ -619,7 +629,7 @@ SDF_API int sdf_gemm_run(int plan, void* stream) {
     SDF_CHECK_LAUNCH("gemm");
     if (g.splitk > 1) {
         const long long total = (long long)g.M * g.N;
-        k_splitk_epilogue<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(g.workspace, g);
+        sdf_launch_pdl(k_splitk_epilogue, dim3((unsigned)((total + 255) / 256)), dim3(256), (size_t)0, st, (const float*)g.workspace, g);
         SDF_CHECK_LAUNCH("gemm(split-K epilogue)");
     }
     return SDF_OK;

@@ -54,6 +54,7 @@ __device__ __forceinline__ void gn_flush(float* sm, int v, int cpg, const float 
 
 __global__ void __launch_bounds__(256) k_gn_stats(const __half* __restrict__ x, int ldx, int HW, int C, int G, int pix_per_block,
                                                   float* __restrict__ stats) {
+    pdl_prologue();
     extern __shared__ float sm[];      // [G][2]
     const int img = blockIdx.y;
     const int cpg = C / G;
@@ -109,6 +110,7 @@ template <bool ACT>
 __global__ void __launch_bounds__(256) k_gn_apply(const __half* __restrict__ x, int ldx, __half* __restrict__ y, int ldy, int HW, int C, int G,
                                                   int pix_per_block, const float* __restrict__ stats, const float* __restrict__ gamma,
                                                   const float* __restrict__ beta, float eps) {
+    pdl_prologue();
     const int img = blockIdx.y;
     const int cpg = C / G, vpp = C / 8;
     const float inv_cnt = 1.f / ((float)HW * cpg);
@@ -151,6 +153,7 @@ __global__ void __launch_bounds__(256) k_gn_apply(const __half* __restrict__ x, 
 __global__ void __launch_bounds__(256) k_gn_bwd_stats(const __half* __restrict__ x, int ldx, const __half* __restrict__ dy, int ldd, int HW, int C, int G,
                                                       int pix_per_block, const float* __restrict__ stats, const float* __restrict__ gamma,
                                                       const float* __restrict__ beta, float eps, int act, float* __restrict__ bstats) {
+    pdl_prologue();
     extern __shared__ float sm[];
     const int img = blockIdx.y;
     const int cpg = C / G;
@@ -207,6 +210,7 @@ __global__ void __launch_bounds__(256) k_gn_bwd_apply(const __half* __restrict__
                                                       __half* __restrict__ dxo, int ldo, int HW, int C, int G, int pix_per_block,
                                                       const float* __restrict__ stats, const float* __restrict__ bstats,
                                                       const float* __restrict__ gamma, const float* __restrict__ beta, float eps) {
+    pdl_prologue();
     const int img = blockIdx.y;
     const int cpg = C / G, vpp = C / 8;
     const float inv_cnt = 1.f / ((float)HW * cpg);
@@ -249,6 +253,7 @@ __global__ void __launch_bounds__(256) k_gn_bwd_apply(const __half* __restrict__
 // ------------------------------------------------------------------ LayerNorm (warp per row)
 __global__ void __launch_bounds__(256) k_layernorm(const __half* __restrict__ x, int ldx, __half* __restrict__ y, int ldy, int rows, int C,
                                                    const float* __restrict__ gamma, const float* __restrict__ beta, float eps) {
+    pdl_prologue();
     const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (row >= rows) return;
     const __half* xr = x + (long long)row * ldx;
@@ -273,6 +278,7 @@ __global__ void __launch_bounds__(256) k_layernorm(const __half* __restrict__ x,
 // One block per row.  Rows up to 256*8*NV columns live entirely in registers: one read and one write of the row.
 template <int NV>     // 16-byte vectors per thread
 __global__ void __launch_bounds__(256) k_softmax_rows(const __half* __restrict__ x, __half* __restrict__ y, long long rows, int cols, int ld, float scale) {
+    pdl_prologue();
     const long long row = blockIdx.x;
     const __half* xr = x + row * ld;
     __half* yr = y + row * ld;
@@ -323,6 +329,7 @@ __global__ void __launch_bounds__(256) k_softmax_rows(const __half* __restrict__
 
 // warp per row for short rows (cross-attention: 77 keys)
 __global__ void __launch_bounds__(256) k_softmax_rows_warp(const __half* __restrict__ x, __half* __restrict__ y, long long rows, int cols, int ld, float scale) {
+    pdl_prologue();
     const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (row >= rows) return;
     const int lane = threadIdx.x & 31;
@@ -345,6 +352,7 @@ __global__ void __launch_bounds__(256) k_softmax_rows_warp(const __half* __restr
 // dS = scale * P * (dP - sum_j dP_j P_j) per row
 __global__ void __launch_bounds__(256) k_softmax_bwd_rows(const __half* __restrict__ p, const __half* __restrict__ dp, __half* __restrict__ ds,
                                                           long long rows, int cols, int ld, float scale) {
+    pdl_prologue();
     const long long row = blockIdx.x;
     const __half* pr = p + row * ld; const __half* dr = dp + row * ld; __half* sr = ds + row * ld;
     __shared__ float red[8];
@@ -371,6 +379,7 @@ __global__ void __launch_bounds__(256) k_softmax_bwd_rows(const __half* __restri
 
 // ------------------------------------------------------------------ GEGLU: y[m, j] = x[m, j] * gelu(x[m, inner + j])
 __global__ void __launch_bounds__(256) k_geglu(const __half* __restrict__ x, int ldx, __half* __restrict__ y, int ldy, long long rows, int inner) {
+    pdl_prologue();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int vpr = inner / 8;
     if (i >= rows * vpr) return;
@@ -385,6 +394,7 @@ __global__ void __launch_bounds__(256) k_geglu(const __half* __restrict__ x, int
 // ------------------------------------------------------------------ resampling
 // nearest x2: y[img, 2h+a, 2w+b, c] = x[img, h, w, c]
 __global__ void __launch_bounds__(256) k_upsample_nearest2(const __half* __restrict__ x, int ldx, __half* __restrict__ y, int ldy, int Nimg, int H, int W, int C) {
+    pdl_prologue();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int vpp = C / 8;
     const long long total = (long long)Nimg * 4 * H * W * vpp;
@@ -399,6 +409,7 @@ __global__ void __launch_bounds__(256) k_upsample_nearest2(const __half* __restr
 // 3x3 stride-2 patch gather: col[img, oy, ox, tap*C + c] = x[img, 2oy + ky - pt, 2ox + kx - pl, c] (zero outside)
 __global__ void __launch_bounds__(256) k_im2col_s2(const __half* __restrict__ x, int ldx, __half* __restrict__ col, int Nimg, int H, int W, int C,
                                                    int Ho, int Wo, int pt, int pl) {
+    pdl_prologue();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int vpp = C / 8;
     const long long total = (long long)Nimg * Ho * Wo * 9 * vpp;
@@ -416,6 +427,7 @@ __global__ void __launch_bounds__(256) k_im2col_s2(const __half* __restrict__ x,
 // adjoint of k_im2col_s2: dx[img, iy, ix, c] = sum over the (<= 4) output pixels / taps that read it
 __global__ void __launch_bounds__(256) k_col2im_s2(const __half* __restrict__ dcol, __half* __restrict__ dx, int ldx, int Nimg, int H, int W, int C,
                                                    int Ho, int Wo, int pt, int pl) {
+    pdl_prologue();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int vpp = C / 8;
     const long long total = (long long)Nimg * H * W * vpp;
@@ -443,6 +455,7 @@ __global__ void __launch_bounds__(256) k_col2im_s2(const __half* __restrict__ dc
 
 // ------------------------------------------------------------------ elementwise glue
 __global__ void __launch_bounds__(256) k_copy2d(const __half* __restrict__ x, int ldx, __half* __restrict__ y, int ldy, long long rows, int C) {
+    pdl_prologue();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int vpr = C / 8;
     if (i >= rows * vpr) return;
@@ -451,6 +464,7 @@ __global__ void __launch_bounds__(256) k_copy2d(const __half* __restrict__ x, in
 }
 __global__ void __launch_bounds__(256) k_add2d(const __half* __restrict__ a, int lda, const __half* __restrict__ b, int ldb, __half* __restrict__ y, int ldy,
                                                long long rows, int C) {
+    pdl_prologue();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int vpr = C / 8;
     if (i >= rows * vpr) return;
@@ -463,6 +477,7 @@ __global__ void __launch_bounds__(256) k_add2d(const __half* __restrict__ a, int
 }
 // [rows, C] -> [C, rows] (both dense), 32x32 tiles through shared memory
 __global__ void k_transpose(const __half* __restrict__ x, int ldx, __half* __restrict__ y, int ldy, int rows, int C) {
+    pdl_prologue();
     __shared__ __half tile[32][34];
     const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
     const long long boff_x = (long long)blockIdx.z * rows * ldx, boff_y = (long long)blockIdx.z * C * ldy;
@@ -479,6 +494,7 @@ __global__ void k_transpose(const __half* __restrict__ x, int ldx, __half* __res
 
 // sinusoidal timestep embedding, cos first (util.py:151-171): out[b, :half] = cos(t f_i), out[b, half:] = sin(t f_i)
 __global__ void k_timestep_embedding(const int* __restrict__ t, int B, int dim, __half* __restrict__ out, int ldo) {
+    pdl_prologue();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int half = dim / 2;
     if (i >= B * half) return;
@@ -500,6 +516,7 @@ __device__ __forceinline__ void bilin_coeff(int o, float scale, int n, int& i0, 
 }
 __global__ void k_bilinear_fwd(const float* __restrict__ src, int B, int Cc, int h, int w, __half* __restrict__ dst, int ldd, int H, int W,
                                float a, float b) {
+    pdl_prologue();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (long long)B * H * W) return;
     const int ox = (int)(i % W); const int oy = (int)((i / W) % H); const int img = (int)(i / ((long long)W * H));
@@ -519,6 +536,7 @@ __global__ void k_bilinear_fwd(const float* __restrict__ src, int B, int Cc, int
 }
 // adjoint: dsrc[img,c,y,x] = a * sum over destination pixels of their bilinear weight on (y,x)
 __global__ void k_bilinear_bwd(const __half* __restrict__ ddst, int ldd, int H, int W, float* __restrict__ dsrc, int B, int Cc, int h, int w, float a) {
+    pdl_prologue();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (long long)B * Cc * h * w) return;
     const int x = (int)(i % w); const int y = (int)((i / w) % h); const int c = (int)((i / ((long long)w * h)) % Cc); const int img = (int)(i / ((long long)w * h * Cc));
@@ -547,6 +565,7 @@ __global__ void k_bilinear_bwd(const __half* __restrict__ ddst, int ldd, int H, 
 __global__ void k_sds_prepare(const __half* __restrict__ moments, int ldm, const float* __restrict__ latents_in, const float* __restrict__ eps_post,
                               const float* __restrict__ noise, const int* __restrict__ t, const float* __restrict__ acp, int Bimg, int HW,
                               float* __restrict__ latents, __half* __restrict__ x_in, int ldx, float vae_scale) {
+    pdl_prologue();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= Bimg * HW * 4) return;
     const int c = i % 4, pix = (i / 4) % HW, img = i / (4 * HW);
@@ -572,6 +591,7 @@ __global__ void k_sds_grad(const __half* __restrict__ eps, int lde, const float*
                            const float* __restrict__ acp, int Bimg, int HW, float guidance_scale, float grad_scale,
                            const __half* __restrict__ moments, int ldm, const float* __restrict__ eps_post, float vae_scale,
                            float* __restrict__ grad, __half* __restrict__ d_moments, float* __restrict__ loss) {
+    pdl_prologue();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     float g = 0.f;
     if (i < Bimg * HW * 4) {
@@ -600,7 +620,7 @@ __global__ void k_sds_grad(const __half* __restrict__ eps, int lde, const float*
 }  // namespace
 
 #define LAUNCH_1D(kernel, total, st, ...)                                                       \
-    do { const long long t_ = (total); if (t_ > 0) kernel<<<(unsigned)((t_ + 255) / 256), 256, 0, st>>>(__VA_ARGS__); } while (0)
+    do { const long long t_ = (total); if (t_ > 0) sdf_launch_pdl(kernel, dim3((unsigned)((t_ + 255) / 256)), dim3(256), (size_t)0, st, __VA_ARGS__); } while (0)
 
 // stats: fp32 scratch [Nimg, G, 2] (sum, sum of squares), kept for the backward.
 // (A single-pass variant — rows held in registers, grid-wide arrival counter between the statistics and the normalisation —
@@ -621,8 +641,8 @@ SDF_API int sdf_groupnorm_forward(const void* x, int ldx, void* y, int ldy, int 
     dim3 grid((HW + ppb - 1) / ppb, Nimg);
     k_gn_stats<<<grid, 256, sizeof(float) * 2 * G, st>>>((const __half*)x, ldx, HW, C, G, ppb, stats);
     SDF_CHECK_LAUNCH("groupnorm(stats)");
-    if (silu_act) k_gn_apply<true><<<grid, 256, 0, st>>>((const __half*)x, ldx, (__half*)y, ldy, HW, C, G, ppb, stats, gamma, beta, eps);
-    else k_gn_apply<false><<<grid, 256, 0, st>>>((const __half*)x, ldx, (__half*)y, ldy, HW, C, G, ppb, stats, gamma, beta, eps);
+    if (silu_act) sdf_launch_pdl(k_gn_apply<true>, dim3(grid), dim3(256), (size_t)(0), st, (const __half*)x, ldx, (__half*)y, ldy, HW, C, G, ppb, stats, gamma, beta, eps);
+    else sdf_launch_pdl(k_gn_apply<false>, dim3(grid), dim3(256), (size_t)(0), st, (const __half*)x, ldx, (__half*)y, ldy, HW, C, G, ppb, stats, gamma, beta, eps);
     SDF_CHECK_LAUNCH("groupnorm(apply)");
     return SDF_OK;
 }
@@ -643,7 +663,7 @@ SDF_API int sdf_groupnorm_backward(const void* x, int ldx, const void* dy, int l
     dim3 grid((HW + ppb - 1) / ppb, Nimg);
     k_gn_bwd_stats<<<grid, 256, sizeof(float) * 2 * G, st>>>((const __half*)x, ldx, (const __half*)dy, ldd, HW, C, G, ppb, stats, gamma, beta, eps, silu_act, bstats);
     SDF_CHECK_LAUNCH("groupnorm_backward(stats)");
-#define GN_BWD_APPLY(A, B) k_gn_bwd_apply<A, B><<<grid, 256, 0, st>>>((const __half*)x, ldx, (const __half*)dy, ldd, (__half*)dx, ldo, HW, C, G, ppb, stats, bstats, gamma, beta, eps)
+#define GN_BWD_APPLY(A, B) sdf_launch_pdl(k_gn_bwd_apply<A, B>, dim3(grid), dim3(256), (size_t)(0), st, (const __half*)x, ldx, (const __half*)dy, ldd, (__half*)dx, ldo, HW, C, G, ppb, stats, bstats, gamma, beta, eps)
     if (silu_act) { if (accumulate) GN_BWD_APPLY(true, true); else GN_BWD_APPLY(true, false); }
     else { if (accumulate) GN_BWD_APPLY(false, true); else GN_BWD_APPLY(false, false); }
 #undef GN_BWD_APPLY
@@ -654,7 +674,7 @@ SDF_API int sdf_groupnorm_backward(const void* x, int ldx, const void* dy, int l
 SDF_API int sdf_layernorm_forward(const void* x, int ldx, void* y, int ldy, int rows, int C, const float* gamma, const float* beta, float eps, void* stream) {
     if (rows == 0) return SDF_OK;
     SDF_CHECK_ARG(x && y && gamma && beta && C % 8 == 0, "layernorm_forward: bad arguments");
-    k_layernorm<<<(rows + 7) / 8, 256, 0, (cudaStream_t)stream>>>((const __half*)x, ldx, (__half*)y, ldy, rows, C, gamma, beta, eps);
+    sdf_launch_pdl(k_layernorm, dim3((rows + 7) / 8), dim3(256), (size_t)(0), (cudaStream_t)stream, (const __half*)x, ldx, (__half*)y, ldy, rows, C, gamma, beta, eps);
     SDF_CHECK_LAUNCH("layernorm_forward");
     return SDF_OK;
 }
@@ -664,10 +684,10 @@ SDF_API int sdf_softmax_rows(const void* x, void* y, long long rows, int cols, i
     SDF_CHECK_ARG(x && y && ld % 8 == 0 && rows < 2147483647LL, "softmax_rows: bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
     SDF_CHECK_ARG(cols >= 1 && cols <= 256 * 8 * 4, "softmax_rows: at most 8192 columns");
-    if (cols <= 256) k_softmax_rows_warp<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>((const __half*)x, (__half*)y, rows, cols, ld, scale);
-    else if (cols <= 2048) k_softmax_rows<1><<<(unsigned)rows, 256, 0, st>>>((const __half*)x, (__half*)y, rows, cols, ld, scale);
-    else if (cols <= 4096) k_softmax_rows<2><<<(unsigned)rows, 256, 0, st>>>((const __half*)x, (__half*)y, rows, cols, ld, scale);
-    else k_softmax_rows<4><<<(unsigned)rows, 256, 0, st>>>((const __half*)x, (__half*)y, rows, cols, ld, scale);
+    if (cols <= 256) sdf_launch_pdl(k_softmax_rows_warp, dim3((unsigned)((rows + 7) / 8)), dim3(256), (size_t)(0), st, (const __half*)x, (__half*)y, rows, cols, ld, scale);
+    else if (cols <= 2048) sdf_launch_pdl(k_softmax_rows<1>, dim3((unsigned)rows), dim3(256), (size_t)(0), st, (const __half*)x, (__half*)y, rows, cols, ld, scale);
+    else if (cols <= 4096) sdf_launch_pdl(k_softmax_rows<2>, dim3((unsigned)rows), dim3(256), (size_t)(0), st, (const __half*)x, (__half*)y, rows, cols, ld, scale);
+    else sdf_launch_pdl(k_softmax_rows<4>, dim3((unsigned)rows), dim3(256), (size_t)(0), st, (const __half*)x, (__half*)y, rows, cols, ld, scale);
     SDF_CHECK_LAUNCH("softmax_rows");
     return SDF_OK;
 }
@@ -675,7 +695,7 @@ SDF_API int sdf_softmax_rows(const void* x, void* y, long long rows, int cols, i
 SDF_API int sdf_softmax_rows_backward(const void* p, const void* dp, void* ds, long long rows, int cols, int ld, float scale, void* stream) {
     if (rows == 0) return SDF_OK;
     SDF_CHECK_ARG(p && dp && ds && ld % 8 == 0 && cols % 8 == 0, "softmax_rows_backward: bad arguments");
-    k_softmax_bwd_rows<<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>((const __half*)p, (const __half*)dp, (__half*)ds, rows, cols, ld, scale);
+    sdf_launch_pdl(k_softmax_bwd_rows, dim3((unsigned)rows), dim3(256), (size_t)(0), (cudaStream_t)stream, (const __half*)p, (const __half*)dp, (__half*)ds, rows, cols, ld, scale);
     SDF_CHECK_LAUNCH("softmax_rows_backward");
     return SDF_OK;
 }
@@ -731,7 +751,7 @@ SDF_API int sdf_add2d(const void* a, int lda, const void* b, int ldb, void* y, i
 SDF_API int sdf_transpose2d(const void* x, int ldx, void* y, int ldy, int batch, int rows, int C, void* stream) {
     SDF_CHECK_ARG(x && y, "transpose2d: null pointer");
     dim3 grid((C + 31) / 32, (rows + 31) / 32, batch), block(32, 8);
-    k_transpose<<<grid, block, 0, (cudaStream_t)stream>>>((const __half*)x, ldx, (__half*)y, ldy, rows, C);
+    sdf_launch_pdl(k_transpose, dim3(grid), dim3(block), (size_t)(0), (cudaStream_t)stream, (const __half*)x, ldx, (__half*)y, ldy, rows, C);
     SDF_CHECK_LAUNCH("transpose2d");
     return SDF_OK;
 }
@@ -739,7 +759,7 @@ SDF_API int sdf_transpose2d(const void* x, int ldx, void* y, int ldy, int batch,
 SDF_API int sdf_timestep_embedding(const int* t, int B, int dim, void* out, int ldo, void* stream) {
     SDF_CHECK_ARG(t && out && dim % 2 == 0, "timestep_embedding: bad arguments");
     const int total = B * dim / 2;
-    k_timestep_embedding<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(t, B, dim, (__half*)out, ldo);
+    sdf_launch_pdl(k_timestep_embedding, dim3((total + 255) / 256), dim3(256), (size_t)(0), (cudaStream_t)stream, t, B, dim, (__half*)out, ldo);
     SDF_CHECK_LAUNCH("timestep_embedding");
     return SDF_OK;
 }
@@ -765,7 +785,7 @@ SDF_API int sdf_sds_prepare(const void* moments, int ldm, const float* latents_i
     SDF_CHECK_ARG((moments || latents_in) && noise && t && alphas_cumprod && latents && x_in, "sds_prepare: null pointer");
     SDF_CHECK_ARG(!moments || eps_post, "sds_prepare: posterior noise required with moments");
     const int total = Bimg * HW * 4;
-    k_sds_prepare<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>((const __half*)moments, ldm, latents_in, eps_post, noise, t, alphas_cumprod,
+    sdf_launch_pdl(k_sds_prepare, dim3((total + 255) / 256), dim3(256), (size_t)(0), (cudaStream_t)stream, (const __half*)moments, ldm, latents_in, eps_post, noise, t, alphas_cumprod,
                                                                        Bimg, HW, latents, (__half*)x_in, ldx, vae_scale);
     SDF_CHECK_LAUNCH("sds_prepare");
     return SDF_OK;
