@@ -328,8 +328,10 @@ def run_ours(args):
                 "config": {"workload": "-O instant-NGP backbone, 64x64 render, 1 view/step/GPU, SD-1.5-shaped UNet (B=2 CFG) + VAE encoder 512x512, "
                                        "reference shading schedule mix (20% latent, 64% lambertian, 16% textureless), Adan step, grid refresh every 16 steps",
                            "rays_per_view": 4096, "samples_last_step": trainer.last_M, "l2": "per-step working set (UNet weights 1.7 GB + activations) exceeds the 126 MB L2",
-                           "parallelism": f"dp{world}"},
-                "e2e": {"value": e2e_v, "unit": "steps/s", "h2d_bytes_per_step": 64, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
+                           "parallelism": f"dp{world}" + (" (one view per GPU for the UNet/VAE; every GPU renders 1/N of the rays of every view, pixels and pixel "
+                                                         "gradients exchanged by all-to-all; one gradient all-reduce)" if world > 1 else "")},
+                "e2e": {"value": e2e_v, "unit": "steps/s", "h2d_bytes_per_step": 64 * (world if trainer.ray_parallel else 1), "d2h_bytes_per_step": 4,
+                        "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": int(round(launches_per_step * args.steps)),
                 "roofline": roof, "roofline_field": fld, "cpu_baseline": cpu, "clocks": sampler.summary()}
         if stages is not None:

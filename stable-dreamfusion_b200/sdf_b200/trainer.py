@@ -59,7 +59,15 @@ class SDSTrainer:
         for d in ('front', 'side', 'back'):
             self.embeddings[d] = te([f'{prompt}, {d} view'])
         self._flat = None
-        self.pin_pose = torch.zeros(opt.batch_size, 4, 4).pin_memory()
+        # multi-GPU: every rank renders 1/W of the rays of every view (balanced sample counts), guidance stays view-parallel;
+        # cameras / lights / background colours then come from a stream that is identical on all ranks
+        self.ray_parallel = world_size > 1 and (opt.h * opt.w) % world_size == 0
+        self.rng_shared = np.random.default_rng(seed * 1000 + 999)
+        # pinned staging ring for the poses: the host may run several steps ahead of the GPU, so a slot is only rewritten after
+        # the copy that read it has completed (event per slot)
+        n_pose = opt.batch_size * (world_size if self.ray_parallel else 1)
+        self.pin_ring = [torch.zeros(n_pose, 4, 4).pin_memory() for _ in range(4)]
+        self.pin_events = [None] * len(self.pin_ring)
         self.last_M = 0
         self.stage_events = None         # set to [] to record (name, cuda event) marks of the next step (bench.py --breakdown)
 
@@ -70,17 +78,19 @@ class SDSTrainer:
             self.stage_events.append((name, ev))
 
     # ------------------------------------------------------------------ data (nerf/provider.py:248-319 collate)
-    def sample_views(self):
-        B, opt = self.opt.batch_size, self.opt
+    def sample_views(self, n=None, rng=None):
+        opt = self.opt
+        B = opt.batch_size if n is None else n
+        rng = self.rng if rng is None else rng
         poses, az = [], []
         for _ in range(B):
-            pose, (r, th, ph) = synth.rand_pose(self.rng, tuple(opt.radius_range), tuple(opt.theta_range), tuple(opt.phi_range))
+            pose, (r, th, ph) = synth.rand_pose(rng, tuple(opt.radius_range), tuple(opt.theta_range), tuple(opt.phi_range))
             poses.append(pose)
             a = ph
             if a > 180:
                 a -= 360
             az.append(a)
-        fov = self.rng.uniform(*opt.fovy_range)
+        fov = rng.uniform(*opt.fovy_range)
         return np.stack(poses), np.array(az, np.float32), float(fov)
 
     def text_z(self, azimuth):
@@ -106,14 +116,36 @@ class SDSTrainer:
                 from .dist import broadcast_occupancy
                 broadcast_occupancy(self.model, src=0)
         self.global_step += 1
-        poses_np, azimuth, fov = self.sample_views() if views is None else views
-        # host -> device: the step's only input (pinned staging)
-        self.pin_pose.copy_(torch.from_numpy(poses_np))
-        poses = self.pin_pose.to(dev, non_blocking=True)
+        ray_par = self.ray_parallel and views is None
         H, W = opt.h, opt.w
+        if ray_par:
+            # all W * B views of the step, identical on every rank; this rank owns views [rank * B, rank * B + B)
+            WS, Bv = self.world_size, opt.batch_size
+            poses_np, az_all, fov = self.sample_views(WS * Bv, self.rng_shared)
+            azimuth = az_all[self.rank * Bv:(self.rank + 1) * Bv]
+            light_off = torch.from_numpy(self.rng_shared.standard_normal((WS * Bv, 1, 3)).astype(np.float32)).to(dev)
+            bg_shared = torch.from_numpy(self.rng_shared.random(3).astype(np.float32)).to(dev)
+            bg_coin = float(self.rng_shared.random())
+        else:
+            poses_np, azimuth, fov = self.sample_views() if views is None else views
+        # host -> device: the step's only input (pinned staging)
+        slot = self.global_step % len(self.pin_ring)
+        if self.pin_events[slot] is not None:
+            self.pin_events[slot].synchronize()
+        self.pin_ring[slot][:poses_np.shape[0]].copy_(torch.from_numpy(poses_np))
+        poses = self.pin_ring[slot][:poses_np.shape[0]].to(dev, non_blocking=True)
+        if dev.type == 'cuda':
+            self.pin_events[slot] = torch.cuda.Event()
+            self.pin_events[slot].record()
         focal = H / (2 * math.tan(math.radians(fov) / 2))
         rays_o, rays_d = get_rays_torch(poses, focal, H / 2, W / 2, H, W)
-        B, N = rays_o.shape[:2]
+        light_d = None
+        if ray_par:
+            # pixels rank, rank + W, ... of every view; per-view light as in nerf/renderer.py:759 (rays_o + randn(3))
+            light_d = safe_normalize(rays_o[:, self.rank::WS] + light_off).reshape(-1, 3)
+            rays_o = rays_o[:, self.rank::WS].reshape(1, -1, 3)
+            rays_d = rays_d[:, self.rank::WS].reshape(1, -1, 3)
+        B, N = (opt.batch_size, H * W) if ray_par else rays_o.shape[:2]
 
         # schedule (nerf/utils.py:503-535)
         exp_iter_ratio = (self.global_step - 1) / opt.iters
@@ -124,10 +156,15 @@ class SDSTrainer:
                 if exp_iter_ratio <= opt.albedo_iter_ratio:
                     ambient_ratio, shading = 1.0, 'albedo'
                 else:
-                    ambient_ratio = opt.min_ambient_ratio + (1.0 - opt.min_ambient_ratio) * random.random()
-                    shading = 'textureless' if random.random() >= (1.0 - opt.textureless_ratio) else 'lambertian'
+                    # one draw per step for the whole batch, like the reference; ray-parallel ranks must agree on it
+                    u1, u2 = (float(self.rng_shared.random()), float(self.rng_shared.random())) if ray_par else (random.random(), random.random())
+                    ambient_ratio = opt.min_ambient_ratio + (1.0 - opt.min_ambient_ratio) * u1
+                    shading = 'textureless' if u2 >= (1.0 - opt.textureless_ratio) else 'lambertian'
                 as_latent = False
-                bg_color = None if (opt.bg_radius > 0 and random.random() > 0.5) else torch.rand(3).to(dev)
+                if ray_par:
+                    bg_color = None if (opt.bg_radius > 0 and bg_coin > 0.5) else bg_shared
+                else:
+                    bg_color = None if (opt.bg_radius > 0 and random.random() > 0.5) else torch.rand(3).to(dev)
         else:
             as_latent = shading == 'latent'
             ambient_ratio = 1.0 if shading in ('albedo', 'latent') else 0.55
@@ -135,8 +172,15 @@ class SDSTrainer:
             shading = 'normal' if as_latent else shading
 
         outputs = self.model.render(rays_o, rays_d, None, H, W, staged=False, perturb=True, bg_color=bg_color, ambient_ratio=ambient_ratio,
-                                    shading=shading, binarize=False)
-        if as_latent:
+                                    shading=shading, binarize=False, light_d=light_d)
+        if ray_par:
+            # rendered pixels travel to the rank that owns their view; the SDS pixel gradients come back the same way
+            from .dist import exchange_pixels
+            local = torch.cat([outputs['image'], outputs['weights_sum'].unsqueeze(-1)], dim=-1).reshape(WS, Bv, (H * W) // WS, 4)
+            full = exchange_pixels(local, WS)                                # [B, HW, 4] complete images of my views
+            chans = full if as_latent else full[..., :3]
+            pred_rgb = chans.reshape(B, H, W, chans.shape[-1]).permute(0, 3, 1, 2).contiguous()
+        elif as_latent:
             pred_rgb = torch.cat([outputs['image'], outputs['weights_sum'].unsqueeze(-1)], dim=-1).reshape(B, H, W, 4).permute(0, 3, 1, 2).contiguous()
         else:
             pred_rgb = outputs['image'].reshape(B, H, W, 3).permute(0, 3, 1, 2).contiguous()

@@ -67,3 +67,49 @@ def test_bucket_allreduce_equals_single_process_sum(tmp_path):
             ((model(x) ** 2).sum() + (table[idx] ** 2).sum() * (rank + 1)).backward()
         for a, p in zip(got[step], params):
             assert torch.allclose(a, p.grad, atol=1e-5), (step, (a - p.grad).abs().max())
+
+
+def _worker_exchange(rank, world, port, out):
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "stable-dreamfusion_b200"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from sdf_b200.dist import exchange_pixels
+    B, HW, C = 2, 12, 4
+    P = HW // world
+    # the "scene": pixel p of global view v has value f(v, p, c) * theta; every rank renders pixels rank::world of all views
+    theta = torch.tensor(1.5, requires_grad=True)
+    v = torch.arange(world * B).view(world, B, 1, 1).float()
+    p_idx = (torch.arange(P) * world + rank).view(1, 1, P, 1).float()
+    c = torch.arange(C).view(1, 1, 1, C).float()
+    local = (100 * v + p_idx + 0.1 * c) * theta                       # [W, B, P, C]
+    full = exchange_pixels(local, world)                              # [B, HW, C] complete images of my views
+    my_v = (torch.arange(B) + rank * B).view(B, 1, 1).float()
+    expect = (100 * my_v + torch.arange(HW).view(1, HW, 1).float() + 0.1 * torch.arange(C).view(1, 1, C).float()) * 1.5
+    assert torch.allclose(full.detach(), expect), (rank, full, expect)
+    # per-view loss on the owner; its gradient must come back to the ranks that rendered the pixels
+    w = torch.linspace(0.5, 2.0, HW).view(1, HW, 1) * (rank + 1)
+    (full * w).sum().backward()
+    g = theta.grad.clone()
+    dist.all_reduce(g)                                                # what the gradient bucket does for the NeRF parameters
+    if rank == 0:
+        torch.save(g, out)
+    dist.destroy_process_group()
+
+
+def test_pixel_exchange_forward_and_gradient(tmp_path):
+    """ray-parallel rendering: all-to-all of rendered pixels reassembles whole views on their owner, and the summed parameter
+    gradient equals the single-process gradient of the same per-view losses"""
+    out = str(tmp_path / "g.pt")
+    world, B, HW, C = 2, 2, 12, 4
+    mp.spawn(_worker_exchange, args=(world, _free_port(), out), nprocs=world, join=True)
+    got = torch.load(out)
+    theta = torch.tensor(1.5, requires_grad=True)
+    total = 0.0
+    for r in range(world):
+        my_v = (torch.arange(B) + r * B).view(B, 1, 1).float()
+        img = (100 * my_v + torch.arange(HW).view(1, HW, 1).float() + 0.1 * torch.arange(C).view(1, 1, C).float()) * theta
+        total = total + (img * (torch.linspace(0.5, 2.0, HW).view(1, HW, 1) * (r + 1))).sum()
+    total.backward()
+    assert torch.allclose(got, theta.grad, rtol=1e-6), (got, theta.grad)
