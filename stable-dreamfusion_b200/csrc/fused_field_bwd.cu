@@ -24,18 +24,15 @@ namespace {
 
 constexpr float kFdEps = 1e-2f;
 constexpr int kAuxStride = 10;
-constexpr int kWarps = 16;
-constexpr int kRows = kWarps * 16;          // rows per CTA round
-constexpr int kTStride = kRows + 8;         // halfs; row stride of the transposed staging buffers
-constexpr int kWtStride = kHidden + 8;
-
 enum Shading { kAlbedo = 0, kLambertian = 1, kTextureless = 2, kNormal = 3 };
 
-struct BwdSmem {
-    WeightsSmem w;
-    __half w3t[kHidden][8];                 // W3^T [in][out(4, zero padded to 8)]
-    __half w2t[kHidden][kWtStride];         // W2^T [in][out]
-    __half w1t[kEncDim][kWtStride];         // W1^T [in][out]
+// WARPS = 16: one CTA per SM, 256 point-evals per round.  WARPS = 8: two CTAs per SM (~105 KB each), 128 per round — the
+// gather / scatter (LSU-bound) phase of one CTA overlaps the weight-gradient (tensor-bound) phase and the barriers of the other.
+template <int WARPS>
+struct BwdSmemT {
+    static constexpr int kRows = WARPS * 16;        // rows per CTA round
+    static constexpr int kTStride = kRows + 8;      // halfs; row stride of the transposed staging buffers
+    WeightsSmem w;                                  // forward-orientation weights; the data-gradient products read them through ldmatrix.trans
     // staging for the weight gradients, all [feature][row]
     __half enct[kEncDim + 8][kTStride];     // + ones row (bias) + zero rows up to a full n-tile
     __half a1t[kHidden + 8][kTStride];
@@ -149,38 +146,46 @@ __device__ __forceinline__ uint32_t movm_trans(uint32_t a) {
     asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(d) : "r"(a));
     return d;
 }
-__device__ __forceinline__ void stage_block(__half* buf, int f0, int row0, uint32_t reg, int g, int t) {
-    *reinterpret_cast<uint32_t*>(buf + (f0 + g) * kTStride + row0 + 2 * t) = movm_trans(reg);
+__device__ __forceinline__ void stage_block(__half* buf, int stride, int f0, int row0, uint32_t reg, int g, int t) {
+    *reinterpret_cast<uint32_t*>(buf + (f0 + g) * stride + row0 + 2 * t) = movm_trans(reg);
 }
 // all four blocks of one A-fragment k-tile (16 rows x 16 features)
-__device__ __forceinline__ void stage_frag(__half* buf, int f0, int row0, const uint32_t a[4], int g, int t) {
-    stage_block(buf, f0, row0, a[0], g, t);
-    stage_block(buf, f0, row0 + 8, a[1], g, t);
-    stage_block(buf, f0 + 8, row0, a[2], g, t);
-    stage_block(buf, f0 + 8, row0 + 8, a[3], g, t);
+__device__ __forceinline__ void stage_frag(__half* buf, int stride, int f0, int row0, const uint32_t a[4], int g, int t) {
+    stage_block(buf, stride, f0, row0, a[0], g, t);
+    stage_block(buf, stride, f0, row0 + 8, a[1], g, t);
+    stage_block(buf, stride, f0 + 8, row0, a[2], g, t);
+    stage_block(buf, stride, f0 + 8, row0 + 8, a[3], g, t);
 }
-__device__ __forceinline__ void clear_rows(__half* buf, int n_feat, int row0, int lane) {
+__device__ __forceinline__ void clear_rows(__half* buf, int stride, int n_feat, int row0, int lane) {
     // 16 staged rows (32 bytes) of every feature: 8 x 32-bit per feature
-    for (int i = lane; i < n_feat * 8; i += 32) *reinterpret_cast<uint32_t*>(buf + (i >> 3) * kTStride + row0 + (i & 7) * 2) = 0u;
+    for (int i = lane; i < n_feat * 8; i += 32) *reinterpret_cast<uint32_t*>(buf + (i >> 3) * stride + row0 + (i & 7) * 2) = 0u;
+}
+// B fragments of one k-step (k0 .. k0+15) for the TWO n-tiles at n0 and n0 + 8 of an operand stored [k][n] (n contiguous):
+// r[0], r[1] = (b0, b1) of n-tile n0; r[2], r[3] = of n-tile n0 + 8.  This is how the data-gradient products read the
+// forward-orientation weights W[out = k][in = n] without a transposed copy.
+__device__ __forceinline__ void ldsm_bt2(uint32_t r[4], const __half* base, int stride, int k0, int n0, int lane) {
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(base + (k0 + (lane & 7) + ((lane >> 3) & 1) * 8) * stride + n0 + (lane >> 4) * 8);
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+// b0 of FOUR consecutive n-tiles (n0, n0+8, n0+16, n0+24) for the k rows k0 .. k0+7 of a [k][n] operand.
+__device__ __forceinline__ void ldsm_bt_k8(uint32_t r[4], const __half* base, int stride, int k0, int n0, int lane) {
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(base + (k0 + (lane & 7)) * stride + n0 + (lane >> 3) * 8);
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
 }
 
-template <int SHADING, bool PREFETCH>
-__global__ void __launch_bounds__(kWarps * 32, 1)
+template <int SHADING, bool PREFETCH, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, WARPS == 16 ? 1 : 2)
 k_field_backward(FieldParams p, const float* __restrict__ xyzs, const float* __restrict__ light_d, int light_per_sample,
                  float ratio, uint32_t M_cap, const int* __restrict__ m_dev, const float* __restrict__ aux,
                  const float* __restrict__ g_sigmas, const float* __restrict__ g_colors, const float* __restrict__ g_normals,
                  float* __restrict__ grad_table, float* __restrict__ gw1, float* __restrict__ gb1, float* __restrict__ gw2,
                  float* __restrict__ gb2, float* __restrict__ gw3, float* __restrict__ gb3) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    BwdSmem& s = *reinterpret_cast<BwdSmem*>(smem_raw);
+    using Smem = BwdSmemT<WARPS>;
+    constexpr int kWarps = WARPS, kRows = Smem::kRows, kTStride = Smem::kTStride;
+    Smem& s = *reinterpret_cast<Smem*>(smem_raw);
     load_weights(s.w, p);
-    // transposed copies for the data-gradient products, constant rows of the staging buffers
-    for (int i = threadIdx.x; i < kHidden * 8; i += blockDim.x) {
-        const int in = i / 8, out = i % 8;
-        s.w3t[in][out] = out < kOut ? __float2half_rn(p.w3[out * kHidden + in]) : __float2half_rn(0.f);
-    }
-    for (int i = threadIdx.x; i < kHidden * kHidden; i += blockDim.x) s.w2t[i % kHidden][i / kHidden] = __float2half_rn(p.w2[i]);
-    for (int i = threadIdx.x; i < kHidden * kEncDim; i += blockDim.x) s.w1t[i % kEncDim][i / kEncDim] = __float2half_rn(p.w1[i]);
+    // constant rows of the staging buffers
     for (int i = threadIdx.x; i < 8 * kTStride; i += blockDim.x) {
         const __half v = __float2half_rn((i / kTStride) == 0 ? 1.f : 0.f);
         (&s.enct[kEncDim][0])[i] = v;
@@ -204,11 +209,11 @@ k_field_backward(FieldParams p, const float* __restrict__ xyzs, const float* __r
     const uint32_t n_groups = (M + 15) / 16;
     const uint32_t n_super = (n_groups + kWarps - 1) / kWarps;     // CTA rounds of 16 groups
 
-    // ---- weight-gradient tile assignment: 65 (m-tile, n-tile) pairs over 16 warps
+    // ---- weight-gradient tile assignment: 64 (m-tile, n-tile) pairs over the CTA's warps
     //   q in [0,36): layer 2  (4 m-tiles x 9 n-tiles; n-tile 8 = ones row -> bias)
     //   q in [36,56): layer 1 (4 x 5)           q in [56,64): layer 3 (1 x 8; its bias gradient is summed in registers below,
-    //   which leaves exactly 4 pairs per warp)
-    constexpr int kPairs = 64, kMaxPerWarp = 4;
+    //   which leaves exactly 4 (16 warps) or 8 (8 warps) pairs per warp)
+    constexpr int kPairs = 64, kMaxPerWarp = kPairs / kWarps;
     float gb3_acc[2] = {0.f, 0.f};      // lanes t == 0: logits 0, 1; t == 1: logits 2, 3
     float wacc[kMaxPerWarp][4];
 #pragma unroll
@@ -267,9 +272,9 @@ k_field_backward(FieldParams p, const float* __restrict__ xyzs, const float* __r
         for (int sp = 0; sp < NP; sp++) {
             if (!warp_active) {
                 if (!rows_cleared) {
-                    clear_rows(&s.dh3t[0][0], 8, warp * 16, lane);
-                    clear_rows(&s.dh2t[0][0], kHidden, warp * 16, lane);
-                    clear_rows(&s.dh1t[0][0], kHidden, warp * 16, lane);
+                    clear_rows(&s.dh3t[0][0], kTStride, 8, warp * 16, lane);
+                    clear_rows(&s.dh2t[0][0], kTStride, kHidden, warp * 16, lane);
+                    clear_rows(&s.dh1t[0][0], kTStride, kHidden, warp * 16, lane);
                     rows_cleared = true;
                 }
             } else {
@@ -302,21 +307,21 @@ k_field_backward(FieldParams p, const float* __restrict__ xyzs, const float* __r
             gb3_acc[0] += d0a + d0b; gb3_acc[1] += d1a + d1b;
             // stage dh3^T (logit deltas), the layer inputs a2^T, a1^T and enc^T
             uint32_t d3frag[4] = {pack_half2(d0a, d1a), pack_half2(d0b, d1b), 0u, 0u};
-            stage_block(&s.dh3t[0][0], 0, row0, d3frag[0], g, t);
-            stage_block(&s.dh3t[0][0], 0, row0 + 8, d3frag[1], g, t);
+            stage_block(&s.dh3t[0][0], kTStride, 0, row0, d3frag[0], g, t);
+            stage_block(&s.dh3t[0][0], kTStride, 0, row0 + 8, d3frag[1], g, t);
 #pragma unroll
             for (int kt = 0; kt < 4; kt++) {
-                stage_frag(&s.a2t[0][0], kt * 16, row0, a2[kt], g, t);
-                stage_frag(&s.a1t[0][0], kt * 16, row0, a1[kt], g, t);
+                stage_frag(&s.a2t[0][0], kTStride, kt * 16, row0, a2[kt], g, t);
+                stage_frag(&s.a1t[0][0], kTStride, kt * 16, row0, a1[kt], g, t);
             }
 #pragma unroll
-            for (int kt = 0; kt < 2; kt++) stage_frag(&s.enct[0][0], kt * 16, row0, a0[kt], g, t);
+            for (int kt = 0; kt < 2; kt++) stage_frag(&s.enct[0][0], kTStride, kt * 16, row0, a0[kt], g, t);
 
-            // ---- dh2 = (dh3 . W3) * relu'(a2)    A = dh3 [16 x 16(k: 4 valid)], B[k][n] = W3[k][n] = w3t[n][k]
+            // ---- dh2 = (dh3 . W3) * relu'(a2)    A = dh3 [16 x 16(k: 4 valid)], B[k = logit][n = hidden] = W3[k][n] (rows 4..7 zero)
             uint32_t dh2[4][4];
-            uint32_t w3b[8];       // b0 of the 8 n-tiles (k = logit 0..7): matrix i of an x4 = rows 8i..8i+7 of w3t, 16 bytes each
-            ldsm_x4(w3b, &s.w3t[lane][0]);
-            ldsm_x4(w3b + 4, &s.w3t[32 + lane][0]);
+            uint32_t w3b[8];       // b0 of the 8 n-tiles (k = logit 0..7; b1 = 0)
+            ldsm_bt_k8(w3b, &s.w.w3[0][0], kW2Stride, 0, 0, lane);
+            ldsm_bt_k8(w3b + 4, &s.w.w3[0][0], kW2Stride, 0, 32, lane);
 #pragma unroll
             for (int nt = 0; nt < 8; nt++) {
                 float c[4] = {0.f, 0.f, 0.f, 0.f};
@@ -327,46 +332,53 @@ k_field_backward(FieldParams p, const float* __restrict__ xyzs, const float* __r
                 c[2] = mb.x > 0.f ? c[2] : 0.f; c[3] = mb.y > 0.f ? c[3] : 0.f;
                 dh2[kt2][hi + 0] = pack_half2(c[0], c[1]);
                 dh2[kt2][hi + 1] = pack_half2(c[2], c[3]);
-                stage_block(&s.dh2t[0][0], nt * 8, row0, dh2[kt2][hi + 0], g, t);
-                stage_block(&s.dh2t[0][0], nt * 8, row0 + 8, dh2[kt2][hi + 1], g, t);
+                stage_block(&s.dh2t[0][0], kTStride, nt * 8, row0, dh2[kt2][hi + 0], g, t);
+                stage_block(&s.dh2t[0][0], kTStride, nt * 8, row0 + 8, dh2[kt2][hi + 1], g, t);
             }
-            // ---- dh1 = (dh2 . W2) * relu'(a1)    B[k][n] = W2[k][n] = w2t[n][k]
+            // ---- dh1 = (dh2 . W2) * relu'(a1)    B[k = out][n = in] = W2[k][n]: forward weights through ldmatrix.trans,
+            //      two n-tiles per load
             uint32_t dh1[4][4];
 #pragma unroll
-            for (int nt = 0; nt < 8; nt++) {
-                float c[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int np = 0; np < 4; np++) {
+                float c[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
 #pragma unroll
-                for (int kp = 0; kp < 2; kp++) {
+                for (int kt = 0; kt < 4; kt++) {
                     uint32_t wb[4];
-                    ldsm_b2(wb, &s.w2t[nt * 8][0], kWtStride, kp * 32, lane);
-                    mma16816(c, dh2[2 * kp], wb[0], wb[1]);
-                    mma16816(c, dh2[2 * kp + 1], wb[2], wb[3]);
+                    ldsm_bt2(wb, &s.w.w2[0][0], kW2Stride, kt * 16, np * 16, lane);
+                    mma16816(c[0], dh2[kt], wb[0], wb[1]);
+                    mma16816(c[1], dh2[kt], wb[2], wb[3]);
                 }
-                const int kt2 = nt >> 1, hi = (nt & 1) * 2;
-                const float2 ma = unpack_half2(a1[kt2][hi + 0]), mb = unpack_half2(a1[kt2][hi + 1]);
-                c[0] = ma.x > 0.f ? c[0] : 0.f; c[1] = ma.y > 0.f ? c[1] : 0.f;
-                c[2] = mb.x > 0.f ? c[2] : 0.f; c[3] = mb.y > 0.f ? c[3] : 0.f;
-                dh1[kt2][hi + 0] = pack_half2(c[0], c[1]);
-                dh1[kt2][hi + 1] = pack_half2(c[2], c[3]);
-                stage_block(&s.dh1t[0][0], nt * 8, row0, dh1[kt2][hi + 0], g, t);
-                stage_block(&s.dh1t[0][0], nt * 8, row0 + 8, dh1[kt2][hi + 1], g, t);
+#pragma unroll
+                for (int e = 0; e < 2; e++) {
+                    const int nt = np * 2 + e;                      // kt2 = np, hi = 2 e
+                    const float2 ma = unpack_half2(a1[np][2 * e + 0]), mb = unpack_half2(a1[np][2 * e + 1]);
+                    c[e][0] = ma.x > 0.f ? c[e][0] : 0.f; c[e][1] = ma.y > 0.f ? c[e][1] : 0.f;
+                    c[e][2] = mb.x > 0.f ? c[e][2] : 0.f; c[e][3] = mb.y > 0.f ? c[e][3] : 0.f;
+                    dh1[np][2 * e + 0] = pack_half2(c[e][0], c[e][1]);
+                    dh1[np][2 * e + 1] = pack_half2(c[e][2], c[e][3]);
+                    stage_block(&s.dh1t[0][0], kTStride, nt * 8, row0, dh1[np][2 * e + 0], g, t);
+                    stage_block(&s.dh1t[0][0], kTStride, nt * 8, row0 + 8, dh1[np][2 * e + 1], g, t);
+                }
             }
             // ---- d(enc) = dh1 . W1 ; n-tile nt covers levels 4nt..4nt+3: lane gets (row g / g+8, level 4nt + t)
 #pragma unroll
-            for (int nt = 0; nt < 4; nt++) {
-                float c[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int np = 0; np < 2; np++) {
+                float c[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
 #pragma unroll
-                for (int kp = 0; kp < 2; kp++) {
+                for (int kt = 0; kt < 4; kt++) {
                     uint32_t wb[4];
-                    ldsm_b2(wb, &s.w1t[nt * 8][0], kWtStride, kp * 32, lane);
-                    mma16816(c, dh1[2 * kp], wb[0], wb[1]);
-                    mma16816(c, dh1[2 * kp + 1], wb[2], wb[3]);
+                    ldsm_bt2(wb, &s.w.w1[0][0], kW1Stride, kt * 16, np * 16, lane);
+                    mma16816(c[0], dh1[kt], wb[0], wb[1]);
+                    mma16816(c[1], dh1[kt], wb[2], wb[3]);
                 }
-                const uint32_t level = nt * 4 + t;
-                if (level < p.n_levels_active) {
-                    const LevelSmem lv = s.w.lv[level];
-                    if (va && (c[0] != 0.f || c[1] != 0.f)) scatter_level(grad_table, lv, ua[0], ua[1], ua[2], smooth, c[0], c[1]);
-                    if (vb && (c[2] != 0.f || c[3] != 0.f)) scatter_level(grad_table, lv, ub[0], ub[1], ub[2], smooth, c[2], c[3]);
+#pragma unroll
+                for (int e = 0; e < 2; e++) {
+                    const uint32_t level = (np * 2 + e) * 4 + t;
+                    if (level < p.n_levels_active) {
+                        const LevelSmem lv = s.w.lv[level];
+                        if (va && (c[e][0] != 0.f || c[e][1] != 0.f)) scatter_level(grad_table, lv, ua[0], ua[1], ua[2], smooth, c[e][0], c[e][1]);
+                        if (vb && (c[e][2] != 0.f || c[e][3] != 0.f)) scatter_level(grad_table, lv, ub[0], ub[1], ub[2], smooth, c[e][2], c[e][3]);
+                    }
                 }
             }
             if (PREFETCH && sp + 1 < NP) {      // next stencil point's gathers fly during the barrier + weight-gradient phase
@@ -463,23 +475,30 @@ SDF_API int sdf_field_backward(const float* xyzs, uint32_t M, const int* m_dev, 
     p.w1 = w1; p.b1 = b1; p.w2 = w2; p.b2 = b2; p.w3 = w3; p.b3 = b3;
     p.lp = lp; p.bound = bound; p.n_levels_active = n_levels_active;
     p.blob_density = blob_density; p.blob_radius = blob_radius; p.interp_smoothstep = interp_smoothstep;
-    const int smem = (int)sizeof(BwdSmem);
-    const uint32_t n_super = ((M + 15) / 16 + kWarps - 1) / kWarps;
-    const uint32_t blocks = min((uint32_t)kNumSMs, n_super);
-    // SDF_FIELD_BWD_PREFETCH=0 selects the variant without the software-pipelined fine-level gathers (A/B experiments)
-    static const bool prefetch = [] { const char* e = getenv("SDF_FIELD_BWD_PREFETCH"); return !(e && e[0] == '0'); }();
-#define LAUNCH_V(SH, PF)                                                                                                  \
+    // Measured at 432 k shaded samples (tools/bench_field.py): 16 warps 3.32 ms, 16 warps + prefetch 3.35 ms, 2 x 8 warps 4.03 ms,
+    // 2 x 8 warps + prefetch 4.31 ms.  The default is the first; SDF_FIELD_BWD_WARPS=8 / SDF_FIELD_BWD_PREFETCH=1 select the others.
+    static const bool prefetch = [] { const char* e = getenv("SDF_FIELD_BWD_PREFETCH"); return e && e[0] == '1'; }();
+    static const int warps = [] { const char* e = getenv("SDF_FIELD_BWD_WARPS"); return (e && atoi(e) == 8) ? 8 : 16; }();
+    const uint32_t n_groups = (M + 15) / 16;
+#define LAUNCH_V(SH, PF, WP)                                                                                              \
     do {                                                                                                                  \
+        const int smem = (int)sizeof(BwdSmemT<WP>);                                                                       \
+        const uint32_t n_super = (n_groups + WP - 1) / WP;                                                                \
+        const uint32_t blocks = min((uint32_t)(kNumSMs * (WP == 16 ? 1 : 2)), n_super);                                   \
         static bool attr_set[64] = {false};                                                                               \
         int dev = 0; cudaGetDevice(&dev);                                                                                 \
         if (dev < 64 && !attr_set[dev]) {                                                                                 \
-            SDF_CHECK_CUDA(cudaFuncSetAttribute(k_field_backward<SH, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+            SDF_CHECK_CUDA(cudaFuncSetAttribute(k_field_backward<SH, PF, WP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
             attr_set[dev] = true;                                                                                         \
         }                                                                                                                 \
-        k_field_backward<SH, PF><<<blocks, kWarps * 32, smem, st>>>(p, xyzs, light_d, light_per_sample, ambient_ratio, M, m_dev, aux, \
+        k_field_backward<SH, PF, WP><<<blocks, WP * 32, smem, st>>>(p, xyzs, light_d, light_per_sample, ambient_ratio, M, m_dev, aux, \
                                                                    g_sigmas, g_colors, g_normals, grad_table, gw1, gb1, gw2, gb2, gw3, gb3); \
     } while (0)
-#define LAUNCH(SH) do { if (prefetch) LAUNCH_V(SH, true); else LAUNCH_V(SH, false); } while (0)
+#define LAUNCH(SH)                                                                           \
+    do {                                                                                     \
+        if (warps == 16) { if (prefetch) LAUNCH_V(SH, true, 16); else LAUNCH_V(SH, false, 16); } \
+        else { if (prefetch) LAUNCH_V(SH, true, 8); else LAUNCH_V(SH, false, 8); }           \
+    } while (0)
     switch (shading) {
         case 0: LAUNCH(kAlbedo); break;
         case 1: LAUNCH(kLambertian); break;
