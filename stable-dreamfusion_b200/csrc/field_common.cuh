@@ -86,6 +86,11 @@ __device__ __forceinline__ void ldsm_x4(uint32_t r[4], const void* smem_row) {
 __device__ __forceinline__ void ldsm_b2(uint32_t r[4], const __half* rows, int stride, int k0, int lane) {
     ldsm_x4(r, rows + (lane & 7) * stride + k0 + (lane >> 3) * 8);
 }
+// B fragments of ONE k-step (k0 .. k0+15) for the TWO n-tiles at n0 and n0 + 8 of an operand stored [n][k] (k contiguous):
+// r[0], r[1] = (b0, b1) of n-tile n0; r[2], r[3] = of n-tile n0 + 8.
+__device__ __forceinline__ void ldsm_b_nn(uint32_t r[4], const __half* base, int stride, int n0, int k0, int lane) {
+    ldsm_x4(r, base + (n0 + (lane & 7) + (lane >> 4) * 8) * stride + k0 + ((lane >> 3) & 1) * 8);
+}
 // A fragment (a0..a3) of the 16 x 16 block at (rows, k0) of a [m][k] operand.
 __device__ __forceinline__ void ldsm_a(uint32_t r[4], const __half* rows, int stride, int k0, int lane) {
     ldsm_x4(r, rows + ((lane & 7) + ((lane >> 3) & 1) * 8) * stride + k0 + (lane >> 4) * 8);
@@ -281,38 +286,51 @@ __device__ __forceinline__ void mlp_forward(float out[4], const uint32_t a0[2][4
                                             uint32_t act1[4][4], uint32_t act2[4][4]) {
     const int t = lane & 3;
     uint32_t a1[4][4];
-    // layer 1
+    // Every layer runs k-step outer / n-tile inner: 8 independent accumulator chains (a chain of dependent mma.sync stalls the
+    // warp for the whole MMA latency).  One ldmatrix.x4 feeds two n-tiles of one k-step.
+    {   // layer 1: 32 -> 64
+        float c[8][4];
 #pragma unroll
-    for (int nt = 0; nt < 8; nt++) {
-        float c[4];
-        c[0] = c[2] = s.b1[nt * 8 + 2 * t];
-        c[1] = c[3] = s.b1[nt * 8 + 2 * t + 1];
-        uint32_t wb[4];
-        ldsm_b2(wb, &s.w1[nt * 8][0], kW1Stride, 0, lane);
-        mma16816(c, a0[0], wb[0], wb[1]);
-        mma16816(c, a0[1], wb[2], wb[3]);
+        for (int nt = 0; nt < 8; nt++) { c[nt][0] = c[nt][2] = s.b1[nt * 8 + 2 * t]; c[nt][1] = c[nt][3] = s.b1[nt * 8 + 2 * t + 1]; }
+#pragma unroll
+        for (int kt = 0; kt < 2; kt++) {
+#pragma unroll
+            for (int np = 0; np < 4; np++) {
+                uint32_t wb[4];
+                ldsm_b_nn(wb, &s.w1[0][0], kW1Stride, np * 16, kt * 16, lane);
+                mma16816(c[2 * np], a0[kt], wb[0], wb[1]);
+                mma16816(c[2 * np + 1], a0[kt], wb[2], wb[3]);
+            }
+        }
         // fp16 output of the linear layer, ReLU, straight into the next layer's A fragment
-        const int kt2 = nt >> 1, hi = (nt & 1) * 2;
-        a1[kt2][hi + 0] = pack_half2(fmaxf(c[0], 0.f), fmaxf(c[1], 0.f));
-        a1[kt2][hi + 1] = pack_half2(fmaxf(c[2], 0.f), fmaxf(c[3], 0.f));
+#pragma unroll
+        for (int nt = 0; nt < 8; nt++) {
+            a1[nt >> 1][(nt & 1) * 2 + 0] = pack_half2(fmaxf(c[nt][0], 0.f), fmaxf(c[nt][1], 0.f));
+            a1[nt >> 1][(nt & 1) * 2 + 1] = pack_half2(fmaxf(c[nt][2], 0.f), fmaxf(c[nt][3], 0.f));
+        }
     }
     uint32_t a2[4][4];
+    {   // layer 2: 64 -> 64
+        float c[8][4];
 #pragma unroll
-    for (int nt = 0; nt < 8; nt++) {
-        float c[4];
-        c[0] = c[2] = s.b2[nt * 8 + 2 * t];
-        c[1] = c[3] = s.b2[nt * 8 + 2 * t + 1];
+        for (int nt = 0; nt < 8; nt++) { c[nt][0] = c[nt][2] = s.b2[nt * 8 + 2 * t]; c[nt][1] = c[nt][3] = s.b2[nt * 8 + 2 * t + 1]; }
 #pragma unroll
-        for (int kp = 0; kp < 2; kp++) {
-            uint32_t wb[4];
-            ldsm_b2(wb, &s.w2[nt * 8][0], kW2Stride, kp * 32, lane);
-            mma16816(c, a1[2 * kp], wb[0], wb[1]);
-            mma16816(c, a1[2 * kp + 1], wb[2], wb[3]);
+        for (int kt = 0; kt < 4; kt++) {
+#pragma unroll
+            for (int np = 0; np < 4; np++) {
+                uint32_t wb[4];
+                ldsm_b_nn(wb, &s.w2[0][0], kW2Stride, np * 16, kt * 16, lane);
+                mma16816(c[2 * np], a1[kt], wb[0], wb[1]);
+                mma16816(c[2 * np + 1], a1[kt], wb[2], wb[3]);
+            }
         }
-        const int kt2 = nt >> 1, hi = (nt & 1) * 2;
-        a2[kt2][hi + 0] = pack_half2(fmaxf(c[0], 0.f), fmaxf(c[1], 0.f));
-        a2[kt2][hi + 1] = pack_half2(fmaxf(c[2], 0.f), fmaxf(c[3], 0.f));
+#pragma unroll
+        for (int nt = 0; nt < 8; nt++) {
+            a2[nt >> 1][(nt & 1) * 2 + 0] = pack_half2(fmaxf(c[nt][0], 0.f), fmaxf(c[nt][1], 0.f));
+            a2[nt >> 1][(nt & 1) * 2 + 1] = pack_half2(fmaxf(c[nt][2], 0.f), fmaxf(c[nt][3], 0.f));
+        }
     }
+    // layer 3: 64 -> 4 (one n-tile, rows 4..7 of w3 are zero): a single chain of 4
     out[0] = out[2] = s.b3[2 * t];
     out[1] = out[3] = s.b3[2 * t + 1];
 #pragma unroll

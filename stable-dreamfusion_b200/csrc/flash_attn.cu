@@ -118,13 +118,16 @@ __global__ void __launch_bounds__(128) k_flash_attn(const __half* __restrict__ q
         const __half* tV = sV + (size_t)stage * kBN * C::kStride;
 
         // ---- S = Q K^T  (16 x 64 per warp)
+        // k-step outer, key tile inner: 8 independent accumulator chains keep the tensor pipe busy (a single chain of
+        // dependent mma.sync stalls the warp for the full MMA latency between instructions)
         float s[8][4];
 #pragma unroll
-        for (int nt = 0; nt < 8; nt++) {
-            s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
-            const __half* krow = tK + (size_t)(nt * 8 + g) * C::kStride;
+        for (int nt = 0; nt < 8; nt++) s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
 #pragma unroll
-            for (int ks = 0; ks < C::kKSteps; ks++) {
+        for (int ks = 0; ks < C::kKSteps; ks++) {
+#pragma unroll
+            for (int nt = 0; nt < 8; nt++) {
+                const __half* krow = tK + (size_t)(nt * 8 + g) * C::kStride;
                 const uint32_t b0 = *reinterpret_cast<const uint32_t*>(krow + ks * 16 + 2 * t);
                 const uint32_t b1 = *reinterpret_cast<const uint32_t*>(krow + ks * 16 + 2 * t + 8);
                 mma16816(s[nt], qf[ks], b0, b1);
@@ -162,9 +165,9 @@ __global__ void __launch_bounds__(128) k_flash_attn(const __half* __restrict__ q
         for (int i = 0; i < C::kNTilesO; i++) { oacc[i][0] *= corr0; oacc[i][1] *= corr0; oacc[i][2] *= corr1; oacc[i][3] *= corr1; }
         // ---- O += P V   (V tile row-major [key][d]: transposed fragments through ldmatrix)
 #pragma unroll
-        for (int i = 0; i < C::kNTilesO; i++) {
+        for (int kt = 0; kt < 4; kt++) {                 // key step outer: kNTilesO independent accumulator chains
 #pragma unroll
-            for (int kt = 0; kt < 4; kt++) {
+            for (int i = 0; i < C::kNTilesO; i++) {
                 uint32_t b0, b1;
                 // lanes 0..7 address keys kt*16 + 0..7, lanes 8..15 keys kt*16 + 8..15 (x2: lanes 16..31 ignored but must be valid)
                 const int krow = kt * 16 + (lane & 15);

@@ -391,24 +391,28 @@ k_field_backward(FieldParams p, const float* __restrict__ xyzs, const float* __r
             }   // warp_active
             __syncthreads();
 
-            // ---- weight gradients over the 256 staged rows
+            // ---- weight gradients over the staged rows: k (row) step outer, the warp's tile pairs inner, so the kMaxPerWarp
+            //      accumulator chains are independent back-to-back MMAs
+            {
+                const __half* Aj[kMaxPerWarp]; const __half* Bj[kMaxPerWarp];
 #pragma unroll
-            for (int j = 0; j < kMaxPerWarp; j++) {
-                const int q = warp + j * kWarps;
-                if (q < kPairs) {
-                    const __half* A; const __half* B;
-                    int mt, nt;
+                for (int j = 0; j < kMaxPerWarp; j++) {
+                    const int q = warp + j * kWarps;
+                    int mt, nt; const __half* A; const __half* B;
                     if (q < 36) { mt = q / 9; nt = q % 9; A = &s.dh2t[0][0]; B = &s.a1t[0][0]; }
                     else if (q < 56) { mt = (q - 36) / 5; nt = (q - 36) % 5; A = &s.dh1t[0][0]; B = &s.enct[0][0]; }
                     else { mt = 0; nt = q - 56; A = &s.dh3t[0][0]; B = &s.a2t[0][0]; }
-                    const __half* Ar = A + (mt * 16) * kTStride;
-                    const __half* Br = B + (nt * 8) * kTStride;
-#pragma unroll 4
-                    for (int kp = 0; kp < kRows / 32; kp++) {      // two k-steps (32 staged rows) per trip: 3 ldmatrix.x4 for 2 MMAs
+                    Aj[j] = A + (mt * 16) * kTStride;
+                    Bj[j] = B + (nt * 8) * kTStride;
+                }
+#pragma unroll 2
+                for (int kp = 0; kp < kRows / 32; kp++) {          // two k-steps (32 staged rows) per trip: 3 ldmatrix.x4 for 2 MMAs
+#pragma unroll
+                    for (int j = 0; j < kMaxPerWarp; j++) {
                         uint32_t af0[4], af1[4], bf[4];
-                        ldsm_a(af0, Ar, kTStride, kp * 32, lane);
-                        ldsm_a(af1, Ar, kTStride, kp * 32 + 16, lane);
-                        ldsm_b2(bf, Br, kTStride, kp * 32, lane);
+                        ldsm_a(af0, Aj[j], kTStride, kp * 32, lane);
+                        ldsm_a(af1, Aj[j], kTStride, kp * 32 + 16, lane);
+                        ldsm_b2(bf, Bj[j], kTStride, kp * 32, lane);
                         mma16816(wacc[j], af0, bf[0], bf[1]);
                         mma16816(wacc[j], af1, bf[2], bf[3]);
                     }
