@@ -12,6 +12,7 @@
 //
 // Roofline: tensor (legacy mma.sync).  FLOPs per launch = 4 * B * heads * n * nkv * d.
 #include "common.cuh"
+#include <cstdlib>
 
 namespace {
 
@@ -48,8 +49,19 @@ struct Cfg {
     static_assert(D % 8 == 0, "head dim must be a multiple of 8");
 };
 
+__device__ __forceinline__ void ldsm_x4(uint32_t r[4], const void* smem) {
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(smem);
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t r[4], const void* smem) {
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(smem);
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+
 // q: [B, n, ldq] head h at columns [h*D, h*D + D); k, v: [B, nkv, ldk]; o: [B, n, ldo].
-template <int D>
+// MT = 16-row query tiles per warp: with MT = 2 every K / V fragment read from shared memory feeds two MMAs (the kernel is
+// bound by shared-memory bandwidth + issue slots, not by the tensor pipe), at the price of ~190 registers (2 CTAs per SM).
+template <int D, int MT>
 __global__ void __launch_bounds__(128) k_flash_attn(const __half* __restrict__ q, const __half* __restrict__ k, const __half* __restrict__ v,
                                                     __half* __restrict__ o, int n, int nkv, int heads, int ldq, int ldk, int ldo, float scale_log2e) {
     using C = Cfg<D>;
@@ -59,16 +71,18 @@ __global__ void __launch_bounds__(128) k_flash_attn(const __half* __restrict__ q
     __half* sV = sK + 2 * kBN * C::kStride;                           // [2][kBN][kStride]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
     const int bh = blockIdx.y, b = bh / heads, h = bh % heads;
-    const int q0 = blockIdx.x * kBM;
+    const int q0 = blockIdx.x * (kBM * MT);
     const __half* qb = q + ((size_t)b * n) * ldq + h * D;
     const __half* kb = k + ((size_t)b * nkv) * ldk + h * D;
     const __half* vb = v + ((size_t)b * nkv) * ldk + h * D;
 
-    // zero the padding columns [D, kStride) of both stages once (they are read by the last k-step when D % 16 != 0)
-    for (int i = tid; i < 2 * 2 * kBN * (C::kStride - D) / 8; i += 128) {
-        const int per_row = (C::kStride - D) / 8;
-        const int row = i / per_row, c = i % per_row;
-        *reinterpret_cast<uint4*>((row < 2 * kBN ? sK : sV - 2 * kBN * C::kStride) + (size_t)row * C::kStride + D + c * 8) = make_uint4(0, 0, 0, 0);
+    // zero the padding columns [D, kStride) of both stages of K and V once (read by the last k-step when D % 16 != 0)
+    {
+        constexpr int per_row = (C::kStride - D) / 8;
+        for (int i = tid; i < 4 * kBN * per_row; i += 128) {
+            const int row = i / per_row, c = i % per_row;
+            *reinterpret_cast<uint4*>(sK + (size_t)row * C::kStride + D + c * 8) = make_uint4(0, 0, 0, 0);
+        }
     }
 
     auto load_tile = [&](int stage, int kv0) {
@@ -87,23 +101,29 @@ __global__ void __launch_bounds__(128) k_flash_attn(const __half* __restrict__ q
         }
     };
 
-    // ---- Q fragments (A operand), loaded straight from global memory
-    uint32_t qf[C::kKSteps][4];
-    {
-        const int r0 = q0 + warp * 16 + g, r1 = r0 + 8;
+    // ---- Q fragments (A operand), loaded straight from global memory; query tile mt of this warp starts at row_base(mt)
+    auto row_base = [&](int mt) { return q0 + (warp * MT + mt) * 16; };
+    uint32_t qf[MT][C::kKSteps][4];
+#pragma unroll
+    for (int mt = 0; mt < MT; mt++) {
+        const int r0 = row_base(mt) + g, r1 = r0 + 8;
 #pragma unroll
         for (int ks = 0; ks < C::kKSteps; ks++) {
             const int c0 = ks * 16 + 2 * t, c1 = c0 + 8;
-            qf[ks][0] = (r0 < n && c0 < D) ? *reinterpret_cast<const uint32_t*>(qb + (size_t)r0 * ldq + c0) : 0u;
-            qf[ks][1] = (r1 < n && c0 < D) ? *reinterpret_cast<const uint32_t*>(qb + (size_t)r1 * ldq + c0) : 0u;
-            qf[ks][2] = (r0 < n && c1 < D) ? *reinterpret_cast<const uint32_t*>(qb + (size_t)r0 * ldq + c1) : 0u;
-            qf[ks][3] = (r1 < n && c1 < D) ? *reinterpret_cast<const uint32_t*>(qb + (size_t)r1 * ldq + c1) : 0u;
+            qf[mt][ks][0] = (r0 < n && c0 < D) ? *reinterpret_cast<const uint32_t*>(qb + (size_t)r0 * ldq + c0) : 0u;
+            qf[mt][ks][1] = (r1 < n && c0 < D) ? *reinterpret_cast<const uint32_t*>(qb + (size_t)r1 * ldq + c0) : 0u;
+            qf[mt][ks][2] = (r0 < n && c1 < D) ? *reinterpret_cast<const uint32_t*>(qb + (size_t)r0 * ldq + c1) : 0u;
+            qf[mt][ks][3] = (r1 < n && c1 < D) ? *reinterpret_cast<const uint32_t*>(qb + (size_t)r1 * ldq + c1) : 0u;
         }
     }
-    float oacc[C::kNTilesO][4];
+    float oacc[MT][C::kNTilesO][4];
+    float mrow[MT][2], lrow[MT][2];                                 // running max / sum for rows g and g+8 of each query tile
 #pragma unroll
-    for (int i = 0; i < C::kNTilesO; i++) oacc[i][0] = oacc[i][1] = oacc[i][2] = oacc[i][3] = 0.f;
-    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;       // running max / sum for rows g and g+8
+    for (int mt = 0; mt < MT; mt++) {
+#pragma unroll
+        for (int i = 0; i < C::kNTilesO; i++) oacc[mt][i][0] = oacc[mt][i][1] = oacc[mt][i][2] = oacc[mt][i][3] = 0.f;
+        mrow[mt][0] = mrow[mt][1] = -INFINITY; lrow[mt][0] = lrow[mt][1] = 0.f;
+    }
 
     const int n_tiles = (nkv + kBN - 1) / kBN;
     load_tile(0, 0);
@@ -117,82 +137,105 @@ __global__ void __launch_bounds__(128) k_flash_attn(const __half* __restrict__ q
         const __half* tK = sK + (size_t)stage * kBN * C::kStride;
         const __half* tV = sV + (size_t)stage * kBN * C::kStride;
 
-        // ---- S = Q K^T  (16 x 64 per warp)
-        // k-step outer, key tile inner: 8 independent accumulator chains keep the tensor pipe busy (a single chain of
-        // dependent mma.sync stalls the warp for the full MMA latency between instructions)
-        float s[8][4];
+        // ---- S = Q K^T  (MT x 16 x 64 per warp): k-step outer, key-tile pairs inner; one ldmatrix.x4 = the B fragments of two
+        //      key tiles, shared by the MT query tiles
+        float s[MT][8][4];
 #pragma unroll
-        for (int nt = 0; nt < 8; nt++) s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+        for (int mt = 0; mt < MT; mt++)
+#pragma unroll
+            for (int nt = 0; nt < 8; nt++) s[mt][nt][0] = s[mt][nt][1] = s[mt][nt][2] = s[mt][nt][3] = 0.f;
 #pragma unroll
         for (int ks = 0; ks < C::kKSteps; ks++) {
 #pragma unroll
-            for (int nt = 0; nt < 8; nt++) {
-                const __half* krow = tK + (size_t)(nt * 8 + g) * C::kStride;
-                const uint32_t b0 = *reinterpret_cast<const uint32_t*>(krow + ks * 16 + 2 * t);
-                const uint32_t b1 = *reinterpret_cast<const uint32_t*>(krow + ks * 16 + 2 * t + 8);
-                mma16816(s[nt], qf[ks], b0, b1);
+            for (int np = 0; np < 4; np++) {
+                uint32_t kf[4];
+                ldsm_x4(kf, tK + (size_t)(np * 16 + (lane & 7) + (lane >> 4) * 8) * C::kStride + ks * 16 + ((lane >> 3) & 1) * 8);
+#pragma unroll
+                for (int mt = 0; mt < MT; mt++) {
+                    mma16816(s[mt][2 * np], qf[mt][ks], kf[0], kf[1]);
+                    mma16816(s[mt][2 * np + 1], qf[mt][ks], kf[2], kf[3]);
+                }
             }
         }
-        // ---- mask the key tail, online softmax (base-2 exponent with the scale folded in)
+        // ---- mask the key tail, online softmax (base-2 exponent with the scale folded in), P as A fragments
         const int kv0 = it * kBN;
-        float mx0 = -INFINITY, mx1 = -INFINITY;
+        const bool partial_tile = kv0 + kBN > nkv;
+        uint32_t pf[MT][4][4];
 #pragma unroll
-        for (int nt = 0; nt < 8; nt++) {
-            const int c = kv0 + nt * 8 + 2 * t;
-            if (c >= nkv) { s[nt][0] = -INFINITY; s[nt][2] = -INFINITY; }
-            if (c + 1 >= nkv) { s[nt][1] = -INFINITY; s[nt][3] = -INFINITY; }
-            mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
-            mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
+        for (int mt = 0; mt < MT; mt++) {
+            float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+            for (int nt = 0; nt < 8; nt++) {
+                if (partial_tile) {                      // uniform: only the last key tile can be ragged
+                    const int c = kv0 + nt * 8 + 2 * t;
+                    if (c >= nkv) { s[mt][nt][0] = -INFINITY; s[mt][nt][2] = -INFINITY; }
+                    if (c + 1 >= nkv) { s[mt][nt][1] = -INFINITY; s[mt][nt][3] = -INFINITY; }
+                }
+                mx0 = fmaxf(mx0, fmaxf(s[mt][nt][0], s[mt][nt][1]));
+                mx1 = fmaxf(mx1, fmaxf(s[mt][nt][2], s[mt][nt][3]));
+            }
+            mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+            mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+            const float mn0 = fmaxf(mrow[mt][0], mx0 * scale_log2e), mn1 = fmaxf(mrow[mt][1], mx1 * scale_log2e);
+            const float corr0 = exp2f(mrow[mt][0] - mn0), corr1 = exp2f(mrow[mt][1] - mn1);     // exp2f(-inf) = 0 on the first tile
+            mrow[mt][0] = mn0; mrow[mt][1] = mn1;
+            float rs0 = 0.f, rs1 = 0.f;
+#pragma unroll
+            for (int nt = 0; nt < 8; nt++) {
+                const float p0 = exp2f(fmaf(s[mt][nt][0], scale_log2e, -mn0)), p1 = exp2f(fmaf(s[mt][nt][1], scale_log2e, -mn0));
+                const float p2 = exp2f(fmaf(s[mt][nt][2], scale_log2e, -mn1)), p3 = exp2f(fmaf(s[mt][nt][3], scale_log2e, -mn1));
+                rs0 += p0 + p1; rs1 += p2 + p3;
+                const int kt = nt >> 1, hi = (nt & 1) * 2;
+                pf[mt][kt][hi + 0] = pack_half2(p0, p1);
+                pf[mt][kt][hi + 1] = pack_half2(p2, p3);
+            }
+            lrow[mt][0] = lrow[mt][0] * corr0 + rs0; lrow[mt][1] = lrow[mt][1] * corr1 + rs1;
+#pragma unroll
+            for (int i = 0; i < C::kNTilesO; i++) { oacc[mt][i][0] *= corr0; oacc[mt][i][1] *= corr0; oacc[mt][i][2] *= corr1; oacc[mt][i][3] *= corr1; }
         }
-        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
-        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-        const float mn0 = fmaxf(m0, mx0 * scale_log2e), mn1 = fmaxf(m1, mx1 * scale_log2e);
-        const float corr0 = exp2f(m0 - mn0), corr1 = exp2f(m1 - mn1);     // exp2f(-inf) = 0 on the first tile
-        m0 = mn0; m1 = mn1;
-        float rs0 = 0.f, rs1 = 0.f;
-        uint32_t pf[4][4];
+        // ---- O += P V   (V tile row-major [key][d]: transposed fragments through ldmatrix; x4 = two d-tiles of one key step)
 #pragma unroll
-        for (int nt = 0; nt < 8; nt++) {
-            const float p0 = exp2f(s[nt][0] * scale_log2e - mn0), p1 = exp2f(s[nt][1] * scale_log2e - mn0);
-            const float p2 = exp2f(s[nt][2] * scale_log2e - mn1), p3 = exp2f(s[nt][3] * scale_log2e - mn1);
-            rs0 += p0 + p1; rs1 += p2 + p3;
-            const int kt = nt >> 1, hi = (nt & 1) * 2;
-            pf[kt][hi + 0] = pack_half2(p0, p1);
-            pf[kt][hi + 1] = pack_half2(p2, p3);
-        }
-        l0 = l0 * corr0 + rs0; l1 = l1 * corr1 + rs1;
+        for (int kt = 0; kt < 4; kt++) {
 #pragma unroll
-        for (int i = 0; i < C::kNTilesO; i++) { oacc[i][0] *= corr0; oacc[i][1] *= corr0; oacc[i][2] *= corr1; oacc[i][3] *= corr1; }
-        // ---- O += P V   (V tile row-major [key][d]: transposed fragments through ldmatrix)
+            for (int ip = 0; ip < C::kNTilesO / 2; ip++) {
+                uint32_t vf[4];
+                ldsm_x4_trans(vf, tV + (size_t)(kt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * C::kStride + ip * 16 + (lane >> 4) * 8);
 #pragma unroll
-        for (int kt = 0; kt < 4; kt++) {                 // key step outer: kNTilesO independent accumulator chains
-#pragma unroll
-            for (int i = 0; i < C::kNTilesO; i++) {
+                for (int mt = 0; mt < MT; mt++) {
+                    mma16816(oacc[mt][2 * ip], pf[mt][kt], vf[0], vf[1]);
+                    mma16816(oacc[mt][2 * ip + 1], pf[mt][kt], vf[2], vf[3]);
+                }
+            }
+            if (C::kNTilesO & 1) {
+                constexpr int i = C::kNTilesO - 1;
                 uint32_t b0, b1;
-                // lanes 0..7 address keys kt*16 + 0..7, lanes 8..15 keys kt*16 + 8..15 (x2: lanes 16..31 ignored but must be valid)
-                const int krow = kt * 16 + (lane & 15);
-                ldmatrix_x2_trans(b0, b1, tV + (size_t)krow * C::kStride + i * 8);
-                mma16816(oacc[i], pf[kt], b0, b1);
+                ldmatrix_x2_trans(b0, b1, tV + (size_t)(kt * 16 + (lane & 15)) * C::kStride + i * 8);
+#pragma unroll
+                for (int mt = 0; mt < MT; mt++) mma16816(oacc[mt][i], pf[mt][kt], b0, b1);
             }
         }
         __syncthreads();      // everyone is done with this stage before it is refilled
     }
     cp_async_wait<0>();
     // ---- finalise: row sums across the lane quad, normalise, store
-    l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
-    l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-    const float inv0 = 1.f / l0, inv1 = 1.f / l1;
-    const int r0 = q0 + warp * 16 + g, r1 = r0 + 8;
     __half* ob = o + ((size_t)b * n) * ldo + h * D;
 #pragma unroll
-    for (int i = 0; i < C::kNTilesO; i++) {
-        const int c = i * 8 + 2 * t;
-        if (r0 < n) *reinterpret_cast<uint32_t*>(ob + (size_t)r0 * ldo + c) = pack_half2(oacc[i][0] * inv0, oacc[i][1] * inv0);
-        if (r1 < n) *reinterpret_cast<uint32_t*>(ob + (size_t)r1 * ldo + c) = pack_half2(oacc[i][2] * inv1, oacc[i][3] * inv1);
+    for (int mt = 0; mt < MT; mt++) {
+        float l0 = lrow[mt][0], l1 = lrow[mt][1];
+        l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+        l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+        const float inv0 = 1.f / l0, inv1 = 1.f / l1;
+        const int r0 = row_base(mt) + g, r1 = r0 + 8;
+#pragma unroll
+        for (int i = 0; i < C::kNTilesO; i++) {
+            const int c = i * 8 + 2 * t;
+            if (r0 < n) *reinterpret_cast<uint32_t*>(ob + (size_t)r0 * ldo + c) = pack_half2(oacc[mt][i][0] * inv0, oacc[mt][i][1] * inv0);
+            if (r1 < n) *reinterpret_cast<uint32_t*>(ob + (size_t)r1 * ldo + c) = pack_half2(oacc[mt][i][2] * inv1, oacc[mt][i][3] * inv1);
+        }
     }
 }
 
-template <int D>
+template <int D, int MT>
 int launch_flash(const __half* q, const __half* k, const __half* v, __half* o, int B, int heads, int n, int nkv, int ldq, int ldk, int ldo,
                  float scale, cudaStream_t st) {
     using C = Cfg<D>;
@@ -201,11 +244,11 @@ int launch_flash(const __half* q, const __half* k, const __half* v, __half* o, i
     int dev = 0;
     cudaGetDevice(&dev);
     if (smem > 48 * 1024 && dev < 64 && !attr_set[dev]) {
-        SDF_CHECK_CUDA(cudaFuncSetAttribute(k_flash_attn<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        SDF_CHECK_CUDA(cudaFuncSetAttribute(k_flash_attn<D, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_set[dev] = true;
     }
-    dim3 grid((n + kBM - 1) / kBM, B * heads);
-    sdf_launch_pdl(k_flash_attn<D>, grid, dim3(128), (size_t)smem, st, q, k, v, o, n, nkv, heads, ldq, ldk, ldo, scale * 1.4426950408889634f);
+    dim3 grid((n + kBM * MT - 1) / (kBM * MT), B * heads);
+    sdf_launch_pdl(k_flash_attn<D, MT>, grid, dim3(128), (size_t)smem, st, q, k, v, o, n, nkv, heads, ldq, ldk, ldo, scale * 1.4426950408889634f);
     return SDF_OK;
 }
 
@@ -220,14 +263,19 @@ SDF_API int sdf_flash_attention(const void* q, const void* k, const void* v, voi
                   "flash_attention: q/k/v must be 16-byte aligned with row strides multiple of 8");
     cudaStream_t st = (cudaStream_t)stream;
     int rc;
+#define FLASH(DD, MM) rc = launch_flash<DD, MM>((const __half*)q, (const __half*)k, (const __half*)v, (__half*)o, B, heads, n, nkv, ldq, ldk, ldo, scale, st)
+    // two query tiles per warp where the grid stays large enough to fill the GPU (the 64x64 / 32x32 self-attention layers)
+    static const bool allow_mt2 = [] { const char* e = getenv("SDF_FLASH_MT2"); return !(e && e[0] == '0'); }();
+    const bool mt2 = allow_mt2 && (long long)B * heads * ((n + 127) / 128) >= 2 * kNumSMs;
     switch (d) {
-        case 40: rc = launch_flash<40>((const __half*)q, (const __half*)k, (const __half*)v, (__half*)o, B, heads, n, nkv, ldq, ldk, ldo, scale, st); break;
-        case 80: rc = launch_flash<80>((const __half*)q, (const __half*)k, (const __half*)v, (__half*)o, B, heads, n, nkv, ldq, ldk, ldo, scale, st); break;
-        case 160: rc = launch_flash<160>((const __half*)q, (const __half*)k, (const __half*)v, (__half*)o, B, heads, n, nkv, ldq, ldk, ldo, scale, st); break;
-        case 32: rc = launch_flash<32>((const __half*)q, (const __half*)k, (const __half*)v, (__half*)o, B, heads, n, nkv, ldq, ldk, ldo, scale, st); break;
-        case 64: rc = launch_flash<64>((const __half*)q, (const __half*)k, (const __half*)v, (__half*)o, B, heads, n, nkv, ldq, ldk, ldo, scale, st); break;
+        case 40: if (mt2) FLASH(40, 2); else FLASH(40, 1); break;
+        case 80: FLASH(80, 1); break;                      // two query tiles need 255 registers at d = 80: not worth it
+        case 160: FLASH(160, 1); break;
+        case 32: FLASH(32, 1); break;
+        case 64: FLASH(64, 1); break;
         default: sdf_set_error("flash_attention: head dim %d not instantiated (32, 40, 64, 80, 160)", d); return SDF_ERR_UNSUPPORTED;
     }
+#undef FLASH
     if (rc) return rc;
     SDF_CHECK_LAUNCH("flash_attention");
     return SDF_OK;

@@ -56,7 +56,7 @@ def test_unet_small(device, cfg, hw, ctx_len):
     # CUDA-graph replay gives the same answer (split-K partial sums land in a different order: not bitwise)
     eng.runlist.capture()
     y2 = eng.forward().float()
-    assert relmax(y2, y) < 2e-3, relmax(y2, y)
+    assert relmax(y2, y) < 5e-3, relmax(y2, y)
 
 
 def test_unet_sd15_shape(device):
