@@ -150,14 +150,19 @@ __global__ void __launch_bounds__(256) k_gn_apply(const __half* __restrict__ x, 
 // GroupNorm(+SiLU) backward wrt x (weights frozen).  Pass 1: per (img, group) sums of dy_hat and dy_hat * xhat,
 // where dy_hat = dL/d(normalised*gamma+beta) (after undoing SiLU) * gamma.  Pass 2: dx.
 // GroupNorm(+SiLU) backward wrt x (weights frozen).  Pass 1: per (img, group) sums of g and g * xhat, g = dL/d(xhat) .
-__global__ void __launch_bounds__(256) k_gn_bwd_stats(const __half* __restrict__ x, int ldx, const __half* __restrict__ dy, int ldd, int HW, int C, int G,
-                                                      int pix_per_block, const float* __restrict__ stats, const float* __restrict__ gamma,
-                                                      const float* __restrict__ beta, float eps, int act, float* __restrict__ bstats) {
+// Per channel the backward needs  o = x*a + b  (pre-activation output, a = rstd*gamma, b = beta - mean*a),
+// g = dy * silu'(o) * gamma  and  xhat = (x - mean) * rstd.  The statistics pass accumulates sum(g_raw) and sum(g_raw * x)
+// with g_raw = dy * silu'(o) and converts them when it flushes:  sum(g) = gamma * S,  sum(g * xhat) = gamma * rstd * (SX - mean * S)
+// — two constant arrays live in the loop instead of four, which is what lets three CTAs share an SM.
+template <bool ACT>
+__global__ void __launch_bounds__(256, 3) k_gn_bwd_stats(const __half* __restrict__ x, int ldx, const __half* __restrict__ dy, int ldd, int HW, int C, int G,
+                                                         int pix_per_block, const float* __restrict__ stats, const float* __restrict__ gamma,
+                                                         const float* __restrict__ beta, float eps, float* __restrict__ bstats) {
     pdl_prologue();
     extern __shared__ float sm[];
     const int img = blockIdx.y;
     const int cpg = C / G;
-    const float cnt = (float)HW * cpg;
+    const float inv_cnt = 1.f / ((float)HW * cpg);
     for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) sm[i] = 0.f;
     __syncthreads();
     const int vpp = C / 8;
@@ -166,50 +171,70 @@ __global__ void __launch_bounds__(256) k_gn_bwd_stats(const __half* __restrict__
     const int ngroups = max(1, (int)blockDim.x / vpp);
     for (int idx = threadIdx.x; idx < vpp * ngroups; idx += blockDim.x) {
         const int v = idx % vpp, pg = idx / vpp;
-        float mean[8], rstd[8], gam[8], bet[8], s[8], ss[8];
-        gn_channel_stats(stats, img, G, cpg, 1.f / cnt, eps, v, mean, rstd);
+        float a[8], b[8], s[8], sx[8];
+        {
+            float mean[8], rstd[8];
+            gn_channel_stats(stats, img, G, cpg, inv_cnt, eps, v, mean, rstd);
 #pragma unroll
-        for (int j = 0; j < 8; j++) { gam[j] = gamma[v * 8 + j]; bet[j] = beta[v * 8 + j]; s[j] = ss[j] = 0.f; }
-        int pix = p0 + pg;
-        auto accumulate = [&](const float fx[8], const float fd[8]) {
+            for (int j = 0; j < 8; j++) { a[j] = rstd[j] * gamma[v * 8 + j]; b[j] = fmaf(-mean[j], a[j], beta[v * 8 + j]); s[j] = sx[j] = 0.f; }
+        }
+        auto accumulate = [&](const uint4& rx, const uint4& rd) {
+            const __half2* hx = reinterpret_cast<const __half2*>(&rx);
+            const __half2* hd = reinterpret_cast<const __half2*>(&rd);
 #pragma unroll
-            for (int j = 0; j < 8; j++) {
-                const float xh = (fx[j] - mean[j]) * rstd[j];
-                float g = fd[j];
-                if (act) { const float o = fmaf(xh, gam[j], bet[j]); const float sg = sigmoid_fast(o); g *= sg * fmaf(o, 1.f - sg, 1.f); }
-                g *= gam[j];
-                s[j] += g; ss[j] = fmaf(g, xh, ss[j]);
+            for (int j = 0; j < 4; j++) {
+                const float2 fx = __half22float2(hx[j]), fd = __half22float2(hd[j]);
+                float g0 = fd.x, g1 = fd.y;
+                if (ACT) {
+                    const float o0 = fmaf(fx.x, a[2 * j], b[2 * j]), o1 = fmaf(fx.y, a[2 * j + 1], b[2 * j + 1]);
+                    const float s0 = sigmoid_fast(o0), s1 = sigmoid_fast(o1);
+                    g0 *= s0 * fmaf(o0, 1.f - s0, 1.f); g1 *= s1 * fmaf(o1, 1.f - s1, 1.f);
+                }
+                s[2 * j] += g0; sx[2 * j] = fmaf(g0, fx.x, sx[2 * j]);
+                s[2 * j + 1] += g1; sx[2 * j + 1] = fmaf(g1, fx.y, sx[2 * j + 1]);
             }
         };
-        for (; pix + ngroups < p1; pix += 2 * ngroups) {
-            float fx[2][8], fd[2][8];
+        int pix = p0 + pg;
+        for (; pix + 3 * ngroups < p1; pix += 4 * ngroups) {        // 8 independent 16-byte loads in flight
+            uint4 rx[4], rd[4];
 #pragma unroll
-            for (int u = 0; u < 2; u++) {
-                load8(x + (base + pix + u * ngroups) * ldx + v * 8, fx[u]);
-                load8(dy + (base + pix + u * ngroups) * ldd + v * 8, fd[u]);
+            for (int u = 0; u < 4; u++) {
+                rx[u] = *reinterpret_cast<const uint4*>(x + (base + pix + u * ngroups) * ldx + v * 8);
+                rd[u] = *reinterpret_cast<const uint4*>(dy + (base + pix + u * ngroups) * ldd + v * 8);
             }
-            accumulate(fx[0], fd[0]);
-            accumulate(fx[1], fd[1]);
+#pragma unroll
+            for (int u = 0; u < 4; u++) accumulate(rx[u], rd[u]);
         }
         for (; pix < p1; pix += ngroups) {
-            float fx[8], fd[8];
-            load8(x + (base + pix) * ldx + v * 8, fx);
-            load8(dy + (base + pix) * ldd + v * 8, fd);
-            accumulate(fx, fd);
+            const uint4 rx = *reinterpret_cast<const uint4*>(x + (base + pix) * ldx + v * 8);
+            const uint4 rd = *reinterpret_cast<const uint4*>(dy + (base + pix) * ldd + v * 8);
+            accumulate(rx, rd);
         }
-        gn_flush(sm, v, cpg, s, ss);
+        // convert to sum(g), sum(g * xhat) per channel, then fold channels into groups
+        {
+            float mean[8], rstd[8];
+            gn_channel_stats(stats, img, G, cpg, inv_cnt, eps, v, mean, rstd);
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const float gm = gamma[v * 8 + j];
+                const float S = s[j], SX = sx[j];
+                s[j] = gm * S;
+                sx[j] = gm * rstd[j] * (SX - mean[j] * S);
+            }
+        }
+        gn_flush(sm, v, cpg, s, sx);
     }
     __syncthreads();
     for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) atomicAdd(&bstats[(long long)img * G * 2 + i], sm[i]);
 }
 
 // dx = rstd * (g - mean(g) - xhat * mean(g*xhat)); if accumulate, dx is added to the existing content of dxo.
-// Slab decomposition as above: the per-channel constants are computed once per thread.
+// With m1 = mean(g), m2 = mean(g * xhat):  dx = g_raw * (rstd*gamma) + x * c3 + c4,  c3 = -rstd^2 * m2,  c4 = -rstd*m1 + rstd^2*mean*m2.
 template <bool ACT, bool ACCUM>
-__global__ void __launch_bounds__(256) k_gn_bwd_apply(const __half* __restrict__ x, int ldx, const __half* __restrict__ dy, int ldd,
-                                                      __half* __restrict__ dxo, int ldo, int HW, int C, int G, int pix_per_block,
-                                                      const float* __restrict__ stats, const float* __restrict__ bstats,
-                                                      const float* __restrict__ gamma, const float* __restrict__ beta, float eps) {
+__global__ void __launch_bounds__(256, 3) k_gn_bwd_apply(const __half* __restrict__ x, int ldx, const __half* __restrict__ dy, int ldd,
+                                                         __half* __restrict__ dxo, int ldo, int HW, int C, int G, int pix_per_block,
+                                                         const float* __restrict__ stats, const float* __restrict__ bstats,
+                                                         const float* __restrict__ gamma, const float* __restrict__ beta, float eps) {
     pdl_prologue();
     const int img = blockIdx.y;
     const int cpg = C / G, vpp = C / 8;
@@ -219,33 +244,49 @@ __global__ void __launch_bounds__(256) k_gn_bwd_apply(const __half* __restrict__
     const int ngroups = max(1, (int)blockDim.x / vpp);
     for (int idx = threadIdx.x; idx < vpp * ngroups; idx += blockDim.x) {
         const int v = idx % vpp, pg = idx / vpp;
-        float mean[8], rstd[8], gam[8], bet[8], m1[8], m2[8];
-        gn_channel_stats(stats, img, G, cpg, inv_cnt, eps, v, mean, rstd);
-#pragma unroll
-        for (int j = 0; j < 8; j++) {
-            const int c = v * 8 + j, gi = c / cpg;
-            gam[j] = gamma[c]; bet[j] = beta[c];
-            m1[j] = bstats[((long long)img * G + gi) * 2] * inv_cnt;
-            m2[j] = bstats[((long long)img * G + gi) * 2 + 1] * inv_cnt;
-        }
-        auto one = [&](int pix) {
-            float fx[8], fd[8], fo[8];
-            load8(x + (base + pix) * ldx + v * 8, fx);
-            load8(dy + (base + pix) * ldd + v * 8, fd);
-            if (ACCUM) load8(dxo + (base + pix) * ldo + v * 8, fo);
+        float a[8], b[8], rg[8], c3[8], c4[8];
+        {
+            float mean[8], rstd[8];
+            gn_channel_stats(stats, img, G, cpg, inv_cnt, eps, v, mean, rstd);
 #pragma unroll
             for (int j = 0; j < 8; j++) {
-                const float xh = (fx[j] - mean[j]) * rstd[j];
-                float g = fd[j];
-                if (ACT) { const float o = fmaf(xh, gam[j], bet[j]); const float sg = sigmoid_fast(o); g *= sg * fmaf(o, 1.f - sg, 1.f); }
-                g *= gam[j];
-                const float d = rstd[j] * (g - m1[j] - xh * m2[j]);
-                fo[j] = ACCUM ? fo[j] + d : d;
+                const int c = v * 8 + j, gi = c / cpg;
+                const float gm = gamma[c];
+                const float m1 = bstats[((long long)img * G + gi) * 2] * inv_cnt;
+                const float m2 = bstats[((long long)img * G + gi) * 2 + 1] * inv_cnt;
+                a[j] = rstd[j] * gm; b[j] = fmaf(-mean[j], a[j], beta[c]);
+                rg[j] = a[j];
+                c3[j] = -rstd[j] * rstd[j] * m2;
+                c4[j] = -rstd[j] * m1 - c3[j] * mean[j];
+            }
+        }
+        auto one = [&](int pix) {
+            const uint4 rx = *reinterpret_cast<const uint4*>(x + (base + pix) * ldx + v * 8);
+            const uint4 rd = *reinterpret_cast<const uint4*>(dy + (base + pix) * ldd + v * 8);
+            uint4 ro = make_uint4(0, 0, 0, 0);
+            if (ACCUM) ro = *reinterpret_cast<const uint4*>(dxo + (base + pix) * ldo + v * 8);
+            const __half2* hx = reinterpret_cast<const __half2*>(&rx);
+            const __half2* hd = reinterpret_cast<const __half2*>(&rd);
+            const __half2* ho = reinterpret_cast<const __half2*>(&ro);
+            float fo[8];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const float2 fx = __half22float2(hx[j]), fd = __half22float2(hd[j]), fa = __half22float2(ho[j]);
+                float g0 = fd.x, g1 = fd.y;
+                if (ACT) {
+                    const float o0 = fmaf(fx.x, a[2 * j], b[2 * j]), o1 = fmaf(fx.y, a[2 * j + 1], b[2 * j + 1]);
+                    const float s0 = sigmoid_fast(o0), s1 = sigmoid_fast(o1);
+                    g0 *= s0 * fmaf(o0, 1.f - s0, 1.f); g1 *= s1 * fmaf(o1, 1.f - s1, 1.f);
+                }
+                const float d0 = fmaf(g0, rg[2 * j], fmaf(fx.x, c3[2 * j], c4[2 * j]));
+                const float d1 = fmaf(g1, rg[2 * j + 1], fmaf(fx.y, c3[2 * j + 1], c4[2 * j + 1]));
+                fo[2 * j] = ACCUM ? fa.x + d0 : d0;
+                fo[2 * j + 1] = ACCUM ? fa.y + d1 : d1;
             }
             store8(dxo + (base + pix) * ldo + v * 8, fo);
         };
         int pix = p0 + pg;
-        for (; pix + ngroups < p1; pix += 2 * ngroups) { one(pix); one(pix + ngroups); }
+        for (; pix + 3 * ngroups < p1; pix += 4 * ngroups) { one(pix); one(pix + ngroups); one(pix + 2 * ngroups); one(pix + 3 * ngroups); }
         for (; pix < p1; pix += ngroups) one(pix);
     }
 }
@@ -661,7 +702,8 @@ SDF_API int sdf_groupnorm_backward(const void* x, int ldx, const void* dy, int l
         if (ppb_small < ppb) ppb = ppb_small;
     }
     dim3 grid((HW + ppb - 1) / ppb, Nimg);
-    k_gn_bwd_stats<<<grid, 256, sizeof(float) * 2 * G, st>>>((const __half*)x, ldx, (const __half*)dy, ldd, HW, C, G, ppb, stats, gamma, beta, eps, silu_act, bstats);
+    if (silu_act) k_gn_bwd_stats<true><<<grid, 256, sizeof(float) * 2 * G, st>>>((const __half*)x, ldx, (const __half*)dy, ldd, HW, C, G, ppb, stats, gamma, beta, eps, bstats);
+    else k_gn_bwd_stats<false><<<grid, 256, sizeof(float) * 2 * G, st>>>((const __half*)x, ldx, (const __half*)dy, ldd, HW, C, G, ppb, stats, gamma, beta, eps, bstats);
     SDF_CHECK_LAUNCH("groupnorm_backward(stats)");
 #define GN_BWD_APPLY(A, B) sdf_launch_pdl(k_gn_bwd_apply<A, B>, dim3(grid), dim3(256), (size_t)(0), st, (const __half*)x, ldx, (const __half*)dy, ldd, (__half*)dx, ldo, HW, C, G, ppb, stats, bstats, gamma, beta, eps)
     if (silu_act) { if (accumulate) GN_BWD_APPLY(true, true); else GN_BWD_APPLY(true, false); }
