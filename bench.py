@@ -170,6 +170,34 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------------------------------------ reference, CUDA path (SURVEY §8d arm A)
+def run_reference_cuda(args):
+    import torch
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    from oracle import ref_cuda_path
+    from sdf_b200.options import default_opt
+    tr = ref_cuda_path.build_reference_trainer(default_opt(h=64, w=64, batch_size=1), dev, seed=0)
+    for i in range(max(3, args.warmup)):
+        tr.train_step(shading=CYCLE[i % len(CYCLE)], read_loss=False)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        tr.train_step(shading=CYCLE[(args.warmup + i) % len(CYCLE)], read_loss=False)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    v = args.steps / (ms * 1e-3)
+    print(json.dumps({"metric": METRIC, "value": v, "unit": "steps/s", "impl": "reference-cuda", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+                      "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+                      "config": {"workload": "reference -O path on this GPU: its own CUDA extensions (oracle/_ref, unmodified sources) + PyTorch fp16 "
+                                             "UNet/VAE (cuDNN/cuBLAS/SDPA) + per-tensor PyTorch Adan; same schedule mix, 64x64, 1 view/step; no GradScaler/EMA/logging",
+                                 "samples_last_step": tr.last_M}}), flush=True)
+
+
 # ------------------------------------------------------------------------------------------------ ours
 def run_ours(args):
     import numpy as np
@@ -346,12 +374,16 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-cuda"],
+                    help="reference = the reference's CPU path (driver contract); reference-cuda = arm (A) of SURVEY.md §8d: the reference's own "
+                         "CUDA extensions + PyTorch fp16 UNet/VAE on this GPU (oracle/ref_cuda_path.py)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--breakdown", action="store_true", help="add per-stage CUDA-event times of one step per shading mode ('stages')")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.impl == "reference-cuda":
+        run_reference_cuda(args)
     else:
         run_ours(args)
 

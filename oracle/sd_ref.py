@@ -60,6 +60,8 @@ class ResBlock(nn.Module):
 
 
 class CrossAttention(nn.Module):
+    use_sdpa = False
+
     def __init__(self, query_dim, context_dim, heads, dim_head):
         super().__init__()
         inner = heads * dim_head
@@ -76,6 +78,10 @@ class CrossAttention(nn.Module):
         context = x if context is None else context
         q, k, v = self.to_q(x), self.to_k(context), self.to_v(context)
         b, n, _ = q.shape
+        if self.use_sdpa:        # what diffusers' default attention processor dispatches to on torch 2 (GPU reference arm only)
+            heads = lambda t: t.view(b, t.shape[1], h, -1).transpose(1, 2)
+            out = F.scaled_dot_product_attention(heads(q), heads(k), heads(v), scale=self.scale)
+            return self.to_out(out.transpose(1, 2).reshape(b, n, -1))
         split = lambda t: t.view(b, t.shape[1], h, -1).permute(0, 2, 1, 3).reshape(b * h, t.shape[1], -1)
         q, k, v = split(q), split(k), split(v)
         sim = torch.einsum('b i d, b j d -> b i j', q, k) * self.scale
