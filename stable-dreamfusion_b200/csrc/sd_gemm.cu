@@ -31,7 +31,7 @@ constexpr int kUmmaK = 16;
 constexpr int kNumThreads = 320;     // warp 0 producer, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quarter)
 constexpr int kEpiWarps = 8;
 
-enum Act { kActNone = 0, kActSilu = 1, kActGelu = 2 };
+enum Act { kActNone = 0, kActSilu = 1, kActGelu = 2, kActGeglu = 3 };    // GEGLU: columns come in 32-wide chunks [16 x | 16 gate], out = x * gelu(gate), N/2 wide
 
 struct GemmArgs {
     int M, N, Cin, taps;             // Cin = K elements iterated per tap (multiple of 64; the TMA zero-fills past the real extent)
@@ -347,6 +347,26 @@ k_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtens
                                 for (int k = 0; k < 4; k++) { const float2 t2 = __half22float2(h[k]); f[8 * j + 2 * k] += t2.x; f[8 * j + 2 * k + 1] += t2.y; }
                             }
                         }
+                        if (g.act == kActGeglu) {
+                            // ldm/modules/attention.py:37-45 fused into the projection: the weight rows were interleaved at pack time so
+                            // that this chunk holds 16 values and their 16 gates; the 16 products go to columns nbase/2 .. nbase/2 + 15
+                            uint32_t pg[8];
+#pragma unroll
+                            for (int j = 0; j < 8; j++) {
+                                const __half2 h2 = __floats2half2_rn(f[2 * j] * act_apply(f[16 + 2 * j], kActGelu), f[2 * j + 1] * act_apply(f[16 + 2 * j + 1], kActGelu));
+                                pg[j] = *reinterpret_cast<const uint32_t*>(&h2);
+                            }
+                            __half* og = out_row + (nbase >> 1);
+                            if (st32_ok) {
+                                asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(og), "r"(pg[0]), "r"(pg[1]), "r"(pg[2]), "r"(pg[3]),
+                                             "r"(pg[4]), "r"(pg[5]), "r"(pg[6]), "r"(pg[7]) : "memory");
+                            } else {
+                                *reinterpret_cast<uint4*>(og) = make_uint4(pg[0], pg[1], pg[2], pg[3]);
+                                *reinterpret_cast<uint4*>(og + 8) = make_uint4(pg[4], pg[5], pg[6], pg[7]);
+                            }
+                            if (ch + 2 < kChunks) fetch_addends(n0 + (ch + 2) * 32);
+                            return;
+                        }
                         if (g.act != kActNone) {
 #pragma unroll
                             for (int j = 0; j < 32; j++) f[j] = act_apply(f[j], g.act);
@@ -518,7 +538,7 @@ int launch_gemm(const GemmPlan& p, cudaStream_t st) {
 //              tap = ky*3 + kx, packed weights [n][tap][Cin]).
 //   linear   : H = 1, Nimg = 1, W = rows.
 //   bias fp32 [N], temb fp16 [Nimg, temb_ld], residual fp16 (strides r_*) optional (NULL).
-//   act      : 0 none, 1 SiLU, 2 GELU(erf).  splitk > 1 needs workspace fp32 [Nimg*H*W, N].  block_n in {64, 128, 160}.
+//   act      : 0 none, 1 SiLU, 2 GELU(erf), 3 GEGLU (weight rows interleaved in 32-row chunks [16 value | 16 gate]; output N/2 wide).  splitk > 1 needs workspace fp32 [Nimg*H*W, N].  block_n in {64, 128, 160}.
 //   cta_pair : 1 -> 2-CTA clusters (tcgen05 cta_group::2, M = 256 per MMA, each CTA stages half of the weight tile);
 //              block_n in {128, 160, 256}; not for batched products.
 // Returns a handle >= 0 or a negative error code.
@@ -543,6 +563,7 @@ SDF_API int sdf_gemm_plan_create(const void* a, long long a_sx, long long a_sy, 
     SDF_CHECK_ARG(!cta_pair || (w_sy == 0 && w_simg == 0), "gemm_plan: cta_pair needs one weight matrix shared by all tiles (not a batched product)");
     SDF_CHECK_ARG(N > 0 && n_rows_w > 0 && Nimg > 0 && H > 0 && W > 0, "gemm_plan: bad sizes");
     SDF_CHECK_ARG(splitk >= 1 && (splitk == 1 || workspace), "gemm_plan: split-K needs a workspace");
+    SDF_CHECK_ARG(act != kActGeglu || (N % 32 == 0 && splitk == 1 && !residual && !temb), "gemm_plan: GEGLU epilogue needs N %% 32 == 0, no split-K, no residual / embedding");
     PFN_encodeTiled enc = get_encode();
     if (!enc) { sdf_set_error("gemm_plan: cuTensorMapEncodeTiled unavailable (no CUDA driver?)"); return SDF_ERR_CUDA; }
 

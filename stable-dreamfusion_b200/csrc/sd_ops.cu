@@ -292,26 +292,39 @@ __global__ void __launch_bounds__(256, 3) k_gn_bwd_apply(const __half* __restric
 }
 
 // ------------------------------------------------------------------ LayerNorm (warp per row)
+// The row stays in registers (NV 16-byte vectors per lane): one global read, statistics by shuffles, normalise, one write.
+template <int NV>
 __global__ void __launch_bounds__(256) k_layernorm(const __half* __restrict__ x, int ldx, __half* __restrict__ y, int ldy, int rows, int C,
                                                    const float* __restrict__ gamma, const float* __restrict__ beta, float eps) {
     pdl_prologue();
     const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (row >= rows) return;
     const __half* xr = x + (long long)row * ldx;
+    float f[NV][8];
     float s = 0.f, ss = 0.f;
-    for (int c = lane * 8; c < C; c += 256) {
-        float f[8]; load8(xr + c, f);
 #pragma unroll
-        for (int j = 0; j < 8; j++) { s += f[j]; ss += f[j] * f[j]; }
+    for (int u = 0; u < NV; u++) {
+        const int c = (lane + 32 * u) * 8;
+        if (c < C) {
+            load8(xr + c, f[u]);
+#pragma unroll
+            for (int j = 0; j < 8; j++) { s += f[u][j]; ss = fmaf(f[u][j], f[u][j], ss); }
+        }
     }
     s = warp_sum(s); ss = warp_sum(ss);
     const float mean = s / C, rstd = rsqrtf(fmaxf(ss / C - mean * mean, 0.f) + eps);
     __half* yr = y + (long long)row * ldy;
-    for (int c = lane * 8; c < C; c += 256) {
-        float f[8]; load8(xr + c, f);
 #pragma unroll
-        for (int j = 0; j < 8; j++) f[j] = (f[j] - mean) * rstd * gamma[c + j] + beta[c + j];
-        store8(yr + c, f);
+    for (int u = 0; u < NV; u++) {
+        const int c = (lane + 32 * u) * 8;
+        if (c < C) {
+            const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + c) + 1);
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c)), b1 = __ldg(reinterpret_cast<const float4*>(beta + c) + 1);
+            const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w}, bt[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int j = 0; j < 8; j++) f[u][j] = (f[u][j] - mean) * rstd * gm[j] + bt[j];
+            store8(yr + c, f[u]);
+        }
     }
 }
 
@@ -715,8 +728,13 @@ SDF_API int sdf_groupnorm_backward(const void* x, int ldx, const void* dy, int l
 
 SDF_API int sdf_layernorm_forward(const void* x, int ldx, void* y, int ldy, int rows, int C, const float* gamma, const float* beta, float eps, void* stream) {
     if (rows == 0) return SDF_OK;
-    SDF_CHECK_ARG(x && y && gamma && beta && C % 8 == 0, "layernorm_forward: bad arguments");
-    sdf_launch_pdl(k_layernorm, dim3((rows + 7) / 8), dim3(256), (size_t)(0), (cudaStream_t)stream, (const __half*)x, ldx, (__half*)y, ldy, rows, C, gamma, beta, eps);
+    SDF_CHECK_ARG(x && y && gamma && beta && C % 8 == 0 && C <= 2048 && ((uintptr_t)gamma & 15) == 0 && ((uintptr_t)beta & 15) == 0,
+                  "layernorm_forward: C must be a multiple of 8 up to 2048, gamma / beta 16-byte aligned");
+    const dim3 lgrid((rows + 7) / 8);
+    cudaStream_t lst = (cudaStream_t)stream;
+    if (C <= 512) sdf_launch_pdl(k_layernorm<2>, lgrid, dim3(256), (size_t)0, lst, (const __half*)x, ldx, (__half*)y, ldy, rows, C, gamma, beta, eps);
+    else if (C <= 1024) sdf_launch_pdl(k_layernorm<4>, lgrid, dim3(256), (size_t)0, lst, (const __half*)x, ldx, (__half*)y, ldy, rows, C, gamma, beta, eps);
+    else sdf_launch_pdl(k_layernorm<8>, lgrid, dim3(256), (size_t)0, lst, (const __half*)x, ldx, (__half*)y, ldy, rows, C, gamma, beta, eps);
     SDF_CHECK_LAUNCH("layernorm_forward");
     return SDF_OK;
 }

@@ -3,7 +3,7 @@ import torch
 
 from . import _lib
 
-ACT = {None: 0, 'none': 0, 'silu': 1, 'gelu': 2}
+ACT = {None: 0, 'none': 0, 'silu': 1, 'gelu': 2, 'geglu': 3}
 
 
 def pick_block_n(N):

@@ -27,7 +27,8 @@ import os
 from .gemm import GemmPlan, choose_config, conv_plan, linear_plan, pack_conv_weight, pick_block_n
 
 NUM_SMS = 148
-USE_CTA_PAIRS = os.environ.get('SDF_GEMM_CTA_PAIRS', '1') != '0'      # A/B switch for the cta_group::2 GEMM variant
+USE_CTA_PAIRS = os.environ.get('SDF_GEMM_CTA_PAIRS', '1') != '0'
+FUSE_GEGLU = os.environ.get('SDF_FUSE_GEGLU', '1') != '0'                 # A/B switch: GEGLU in the projection GEMM's epilogue      # A/B switch for the cta_group::2 GEMM variant
 
 
 def _r(x, m):
@@ -142,6 +143,10 @@ class Builder:
         kb = taps * cin_iter // 64
         if block_n is None and splitk is None:
             bn, pair, sk = choose_config(M, N, kb, batched, allow_pair=USE_CTA_PAIRS)
+        elif block_n is None and splitk == 1:
+            bn, pair, sk = choose_config(M, N, kb, True, allow_pair=False)[0], 0, 1      # batched=True disables split-K in the model
+            if USE_CTA_PAIRS and not batched and M > 128 and N % 256 == 0:
+                bn, pair = 256, 1
         else:
             bn, pair = (pick_block_n(N) if block_n is None else block_n), 0
             sk = _choose_splitk(M, N, kb, bn, pair) if splitk is None else splitk
@@ -223,6 +228,13 @@ class Builder:
 
 def _f32(t, device):
     return t.detach().to(device=device, dtype=torch.float32).contiguous()
+
+
+def geglu_row_permutation(inner, device):
+    """row order of a [2*inner, k] GEGLU projection for the fused epilogue: chunk c = rows [16c, 16c+16) of the value half followed
+    by the same rows of the gate half"""
+    idx = torch.arange(inner, device=device).view(-1, 16)
+    return torch.cat([idx, idx + inner], dim=1).reshape(-1)
 
 
 def _pack_linear(w, device, rows_multiple=1):
@@ -521,11 +533,20 @@ class UNetEngine:
         b.layernorm(tb + '.norm3', u, ln, self._f32(tb + '.norm3.weight'), self._f32(tb + '.norm3.bias'))
         inner = 4 * C
         n = x.H * x.W
-        f = View(b.buf(1, 1, B * n, 2 * inner))
         lnf = View(ln.t.view(1, 1, B * n, C))
-        b.gemm(tb + '.ff.net.0.proj', lnf, C, self._lin(tb + '.ff.net.0.proj.weight'), 2 * inner, f, bias=self._f32(tb + '.ff.net.0.proj.bias'))
         gg = View(b.buf(1, 1, B * n, inner))
-        b.geglu(tb + '.ff.geglu', f, gg, inner)
+        if FUSE_GEGLU and inner % 16 == 0:
+            # GEGLU inside the projection's epilogue (ldm/modules/attention.py:37-45): weight / bias rows interleaved in 32-row chunks
+            # [16 value | 16 gate], so the [tokens, 2*inner] intermediate (42 MB per 64x64 layer) never exists
+            perm = geglu_row_permutation(inner, self.dev)
+            wp = self._lin(tb + '.ff.net.0.proj.weight')[perm].contiguous()
+            bp = self._f32(tb + '.ff.net.0.proj.bias')[perm].contiguous()
+            b.gemm(tb + '.ff.net.0.proj+geglu', lnf, C, wp, 2 * inner, gg, bias=bp, act='geglu', splitk=1,
+                   block_n=None)
+        else:
+            f = View(b.buf(1, 1, B * n, 2 * inner))
+            b.gemm(tb + '.ff.net.0.proj', lnf, C, self._lin(tb + '.ff.net.0.proj.weight'), 2 * inner, f, bias=self._f32(tb + '.ff.net.0.proj.bias'))
+            b.geglu(tb + '.ff.geglu', f, gg, inner)
         uf = View(u.t.view(1, 1, B * n, C))
         b.gemm(tb + '.ff.net.2', gg, inner, self._lin(tb + '.ff.net.2.weight'), C, uf, bias=self._f32(tb + '.ff.net.2.bias'), residual=uf)
         b.gemm(p + '.proj_out', u, C, self._conv1x1_w(p + '.proj_out.weight'), C, out, bias=self._f32(p + '.proj_out.bias'), residual=x)

@@ -179,3 +179,22 @@ def test_conv3x3_cta_pair(device, Nimg, H, W, Cin, Cout, bn, sk):
         plan.run()
     torch.cuda.synchronize()
     check(out, ref_conv(a[..., :Cin], w, bias=bias, temb=temb, residual=res, act="silu"), 9 * Cin)
+
+
+@pytest.mark.parametrize("M,K,inner,bn,pair", [(300, 128, 160, 160, 0), (8192, 320, 1280, 256, 1), (512, 1280, 5120, 128, 0)])
+def test_geglu_epilogue(device, M, K, inner, bn, pair):
+    """GEGLU fused into the projection (ldm/modules/attention.py:37-45): rows interleaved [16 value | 16 gate] per 32-row chunk"""
+    from sdf_b200.sd_engine import geglu_row_permutation
+    a = rnd(1, 1, M, K, device=device, seed=11)
+    w = rnd(2 * inner, K, device=device, scale=1 / math.sqrt(K), seed=12)
+    bias = rnd(2 * inner, device=device, seed=13).float()
+    perm = geglu_row_permutation(inner, device)
+    wt = gemm.pack_conv_weight(w[perm].reshape(2 * inner, K, 1, 1))
+    out = torch.full((1, 1, M, inner), float("nan"), device=device, dtype=torch.float16)
+    plan = gemm.GemmPlan(a, (K, M * K, M * K), K, wt, (wt.shape[1], 0, 0), wt.shape[1], 2 * inner, 1, 1, M, wt.shape[1], 1, 2 * inner,
+                         out, (inner, M * inner, M * inner), bias=bias[perm].contiguous(), act="geglu", block_n=bn, cta_pair=pair)
+    plan.run()
+    torch.cuda.synchronize()
+    y = a.float().view(M, K) @ w.float().t() + bias
+    ref = y[:, :inner] * F.gelu(y[:, inner:])
+    check(out.view(M, inner), ref, K)
