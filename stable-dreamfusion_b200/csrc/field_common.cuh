@@ -175,21 +175,49 @@ __device__ __forceinline__ uint32_t corner_index(const LevelSmem& lv, uint32_t x
 // Trilinear (smoothstepped) lookup of one level for TWO points in [0,1]^3 (the two rows a lane owns): all 16 gathers are issued
 // before the first one is consumed.  Points outside the unit cube (valid == false) still gather (their cell is clamped) and
 // are zeroed afterwards.
+// Gather of one x-neighbour corner pair (corners 2j, 2j+1).  When both entries sit in the same aligned 8-byte pair of the table
+// (always on hashed levels with even x0: x1 = x0 ^ 1 only flips bit 0 of the hash; on dense levels when the linear index is
+// even) ONE 8-byte load replaces two 4-byte ones — the kernels are bound by the number of scattered lanes the LSU / L1 has to
+// serve, not by bytes.  Predicated loads, no branches: all gathers of a level pair still issue back to back.
+struct PairLoad { uint32_t lo, hi, a, b, sel; };
+__device__ __forceinline__ void pair_issue(PairLoad& r, const __half2* t, uint32_t i0, uint32_t i1) {
+    const uint32_t merged = ((i0 ^ i1) == 1u) ? 1u : 0u;
+    r.sel = merged | ((i0 & 1u) << 1);
+    r.lo = r.hi = r.a = r.b = 0u;
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %7, 0;\n\t"
+                 "@p ld.global.nc.v2.u32 {%0, %1}, [%4];\n\t"
+                 "@!p ld.global.nc.u32 %2, [%5];\n\t"
+                 "@!p ld.global.nc.u32 %3, [%6];\n\t}"
+                 : "+r"(r.lo), "+r"(r.hi), "+r"(r.a), "+r"(r.b)
+                 : "l"(t + (i0 & ~1u)), "l"(t + i0), "l"(t + i1), "r"(merged));
+}
+__device__ __forceinline__ void pair_values(const PairLoad& r, float2& v0, float2& v1) {
+    const bool merged = r.sel & 1u, odd = r.sel & 2u;
+    const uint32_t u0 = merged ? (odd ? r.hi : r.lo) : r.a;
+    const uint32_t u1 = merged ? (odd ? r.lo : r.hi) : r.b;
+    v0 = __half22float2(*reinterpret_cast<const __half2*>(&u0));
+    v1 = __half22float2(*reinterpret_cast<const __half2*>(&u1));
+}
+
 __device__ __forceinline__ void encode_level_pair(const __half2* __restrict__ table, const LevelSmem& lv, const float pa[3], bool va,
                                                   const float pb[3], bool vb, bool smooth, float2& ea, float2& eb) {
     Corners ca, cb;
     level_corners(ca, lv, pa[0], pa[1], pa[2], smooth);
     level_corners(cb, lv, pb[0], pb[1], pb[2], smooth);
-    const __half2* t = table + lv.offset;
-    __half2 ha[8], hb[8];
+    const __half2* t = table + lv.offset;          // level offsets are multiples of 8 entries: entry pairs stay 8-byte aligned
+    PairLoad la[4], lb[4];
 #pragma unroll
-    for (int k = 0; k < 8; k++) { ha[k] = __ldg(t + ca.idx[k]); hb[k] = __ldg(t + cb.idx[k]); }
+    for (int j = 0; j < 4; j++) { pair_issue(la[j], t, ca.idx[2 * j], ca.idx[2 * j + 1]); pair_issue(lb[j], t, cb.idx[2 * j], cb.idx[2 * j + 1]); }
     float2 aa = make_float2(0.f, 0.f), ab = make_float2(0.f, 0.f);
 #pragma unroll
-    for (int k = 0; k < 8; k++) {
-        const float2 v = __half22float2(ha[k]), u = __half22float2(hb[k]);
-        aa.x = fmaf(ca.w[k], v.x, aa.x); aa.y = fmaf(ca.w[k], v.y, aa.y);
-        ab.x = fmaf(cb.w[k], u.x, ab.x); ab.y = fmaf(cb.w[k], u.y, ab.y);
+    for (int j = 0; j < 4; j++) {
+        float2 v0, v1, u0, u1;
+        pair_values(la[j], v0, v1);
+        pair_values(lb[j], u0, u1);
+        aa.x = fmaf(ca.w[2 * j], v0.x, aa.x); aa.y = fmaf(ca.w[2 * j], v0.y, aa.y);
+        aa.x = fmaf(ca.w[2 * j + 1], v1.x, aa.x); aa.y = fmaf(ca.w[2 * j + 1], v1.y, aa.y);
+        ab.x = fmaf(cb.w[2 * j], u0.x, ab.x); ab.y = fmaf(cb.w[2 * j], u0.y, ab.y);
+        ab.x = fmaf(cb.w[2 * j + 1], u1.x, ab.x); ab.y = fmaf(cb.w[2 * j + 1], u1.y, ab.y);
     }
     ea = va ? aa : make_float2(0.f, 0.f);
     eb = vb ? ab : make_float2(0.f, 0.f);
