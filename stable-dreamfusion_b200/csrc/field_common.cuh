@@ -133,10 +133,11 @@ struct Corners {
     float w[8];
 };
 
-__device__ __forceinline__ void level_corners(Corners& c, const LevelSmem& lv, float x, float y, float z, bool smooth) {
+__device__ __forceinline__ uint32_t level_corners(Corners& c, const LevelSmem& lv, float x, float y, float z, bool smooth) {
     Cell cell;
     locate_cell<false>(cell, x, y, z, lv.res, smooth);
     const uint32_t x0 = cell.pg[0], y0 = cell.pg[1], z0 = cell.pg[2];
+    const uint32_t cell_key = x0 | (y0 << 10) | (z0 << 20);          // unique while res <= 1024 (used on the coarse levels only)
     const uint32_t x1 = min(x0 + 1, lv.res - 1), y1 = min(y0 + 1, lv.res - 1), z1 = min(z0 + 1, lv.res - 1);
     const float fx = cell.f[0], fy = cell.f[1], fz = cell.f[2];
     const float wxy[4] = {(1.f - fx) * (1.f - fy), fx * (1.f - fy), (1.f - fx) * fy, fx * fy};
@@ -162,6 +163,7 @@ __device__ __forceinline__ void level_corners(Corners& c, const LevelSmem& lv, f
 #pragma unroll
         for (int k = 0; k < 8; k++) c.idx[k] = xa[k & 1] + ya[(k >> 1) & 1] + za[k >> 2];
     }
+    return cell_key;
 }
 
 __device__ __forceinline__ uint32_t corner_index(const LevelSmem& lv, uint32_t x, uint32_t y, uint32_t z) {
@@ -221,6 +223,92 @@ __device__ __forceinline__ void encode_level_pair(const __half2* __restrict__ ta
     }
     ea = va ? aa : make_float2(0.f, 0.f);
     eb = vb ? ab : make_float2(0.f, 0.f);
+}
+
+// Corner values of the CENTRE point (stencil point 0) on the lane's two coarse levels (t and t + 4), kept across the 7 stencil
+// evaluations of a sample: the +-eps points fall into the centre's cell ~85 % (levels 0-3) / ~50 % (levels 4-7) of the time and
+// then need no gather at all, only new weights.  The arrays live in local memory if registers run out — a coalesced spill
+// access costs the LSU 1/32 of a scattered gather, which is the resource these kernels are bound by.
+struct CornerCache {
+    uint32_t key[2][2];          // [coarse level slot][row]
+    uint32_t val[2][2][8];
+};
+
+// pair_issue with an extra predicate: nothing is loaded when the cached corner values can be used
+__device__ __forceinline__ void pair_issue_if(PairLoad& r, const __half2* t, uint32_t i0, uint32_t i1, bool need) {
+    const uint32_t m = ((i0 ^ i1) == 1u) ? 1u : 0u;
+    r.sel = m | ((i0 & 1u) << 1);
+    r.lo = r.hi = r.a = r.b = 0u;
+    const uint32_t pm = (need && m) ? 1u : 0u, ps = (need && !m) ? 1u : 0u;
+    asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.u32 p, %7, 0;\n\tsetp.ne.u32 q, %8, 0;\n\t"
+                 "@p ld.global.nc.v2.u32 {%0, %1}, [%4];\n\t"
+                 "@q ld.global.nc.u32 %2, [%5];\n\t"
+                 "@q ld.global.nc.u32 %3, [%6];\n\t}"
+                 : "+r"(r.lo), "+r"(r.hi), "+r"(r.a), "+r"(r.b)
+                 : "l"(t + (i0 & ~1u)), "l"(t + i0), "l"(t + i1), "r"(pm), "r"(ps));
+}
+__device__ __forceinline__ void pair_raw(const PairLoad& r, uint32_t& u0, uint32_t& u1) {
+    const bool merged = r.sel & 1u, odd = r.sel & 2u;
+    u0 = merged ? (odd ? r.hi : r.lo) : r.a;
+    u1 = merged ? (odd ? r.lo : r.hi) : r.b;
+}
+
+// encode_level_pair for a coarse level slot with the centre-cell cache: `centre` = this is stencil point 0 (fill the cache).
+__device__ __forceinline__ void encode_level_pair_cached(const __half2* __restrict__ table, const LevelSmem& lv, const float pa[3], bool va,
+                                                         const float pb[3], bool vb, bool smooth, float2& ea, float2& eb,
+                                                         uint32_t ckey[2], uint32_t cval[2][8], bool centre) {
+    Corners ca, cb;
+    const uint32_t ka = level_corners(ca, lv, pa[0], pa[1], pa[2], smooth);
+    const uint32_t kb = level_corners(cb, lv, pb[0], pb[1], pb[2], smooth);
+    const bool need_a = centre || ka != ckey[0], need_b = centre || kb != ckey[1];
+    const __half2* t = table + lv.offset;
+    PairLoad la[4], lb[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        pair_issue_if(la[j], t, ca.idx[2 * j], ca.idx[2 * j + 1], need_a);
+        pair_issue_if(lb[j], t, cb.idx[2 * j], cb.idx[2 * j + 1], need_b);
+    }
+    if (centre) { ckey[0] = ka; ckey[1] = kb; }
+    float2 aa = make_float2(0.f, 0.f), ab = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        uint32_t a0, a1, b0, b1;
+        pair_raw(la[j], a0, a1);
+        pair_raw(lb[j], b0, b1);
+        a0 = need_a ? a0 : cval[0][2 * j]; a1 = need_a ? a1 : cval[0][2 * j + 1];
+        b0 = need_b ? b0 : cval[1][2 * j]; b1 = need_b ? b1 : cval[1][2 * j + 1];
+        if (centre) { cval[0][2 * j] = a0; cval[0][2 * j + 1] = a1; cval[1][2 * j] = b0; cval[1][2 * j + 1] = b1; }
+        const float2 v0 = __half22float2(*reinterpret_cast<const __half2*>(&a0)), v1 = __half22float2(*reinterpret_cast<const __half2*>(&a1));
+        const float2 u0 = __half22float2(*reinterpret_cast<const __half2*>(&b0)), u1 = __half22float2(*reinterpret_cast<const __half2*>(&b1));
+        aa.x = fmaf(ca.w[2 * j], v0.x, aa.x); aa.y = fmaf(ca.w[2 * j], v0.y, aa.y);
+        aa.x = fmaf(ca.w[2 * j + 1], v1.x, aa.x); aa.y = fmaf(ca.w[2 * j + 1], v1.y, aa.y);
+        ab.x = fmaf(cb.w[2 * j], u0.x, ab.x); ab.y = fmaf(cb.w[2 * j], u0.y, ab.y);
+        ab.x = fmaf(cb.w[2 * j + 1], u1.x, ab.x); ab.y = fmaf(cb.w[2 * j + 1], u1.y, ab.y);
+    }
+    ea = va ? aa : make_float2(0.f, 0.f);
+    eb = vb ? ab : make_float2(0.f, 0.f);
+}
+
+// encode_rows with the centre-cell cache on the two coarse level slots (kt = 0); the fine slots (kt = 1) gather as usual.
+__device__ __forceinline__ void encode_rows_cached(uint32_t a[2][4], const WeightsSmem& s, const FieldParams& p, int lane,
+                                                   const float pa[3], bool va, const float pb[3], bool vb, CornerCache& cache, bool centre) {
+    const int t = lane & 3;
+    const bool smooth = p.interp_smoothstep != 0;
+#pragma unroll
+    for (int kt = 0; kt < 2; kt++) {
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const uint32_t level = kt * 8 + t + h * 4;
+            float2 ea = make_float2(0.f, 0.f), eb = make_float2(0.f, 0.f);
+            if (level < p.n_levels_active) {
+                const LevelSmem lv = s.lv[level];
+                if (kt == 0) encode_level_pair_cached(p.table, lv, pa, va, pb, vb, smooth, ea, eb, cache.key[h], cache.val[h], centre);
+                else encode_level_pair(p.table, lv, pa, va, pb, vb, smooth, ea, eb);
+            }
+            a[kt][h * 2 + 0] = pack_half2(ea.x, ea.y);
+            a[kt][h * 2 + 1] = pack_half2(eb.x, eb.y);
+        }
+    }
 }
 
 // The encoder of one stencil point for the two rows a lane owns, in A-fragment order:

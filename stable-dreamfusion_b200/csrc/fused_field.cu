@@ -78,6 +78,7 @@ k_field_forward(FieldParams p, const float* __restrict__ xyzs, const float* __re
         float sig0_a = 0.f, sig0_b = 0.f;
         float nda[3] = {0.f, 0.f, 0.f}, ndb[3] = {0.f, 0.f, 0.f};      // sigma(+eps) - sigma(-eps) per axis
         float alb_a[3] = {0.f, 0.f, 0.f}, alb_b[3] = {0.f, 0.f, 0.f};
+        CornerCache cache;
 #pragma unroll 1
         for (int sp = 0; sp < NP; sp++) {
             float pa[3], pb[3], ua[3], ub[3];
@@ -85,7 +86,8 @@ k_field_forward(FieldParams p, const float* __restrict__ xyzs, const float* __re
             stencil_point(pb, xb, sp, p.bound);
             const bool va = to_unit(ua, pa, p.bound) && ina, vb = to_unit(ub, pb, p.bound) && inb;
             uint32_t a0[2][4];
-            encode_rows(a0, s, p, lane, ua, va, ub, vb);
+            if (NP > 1) encode_rows_cached(a0, s, p, lane, ua, va, ub, vb, cache, sp == 0);
+            else encode_rows(a0, s, p, lane, ua, va, ub, vb);
             float h[4];
             mlp_forward<false>(h, a0, s, lane, nullptr, nullptr);
             // lanes t==0: h[0],h[1] = logits 0,1 of row g ; h[2],h[3] = of row g+8.  lanes t==1: logits 2,3.

@@ -260,6 +260,7 @@ k_field_backward(FieldParams p, const float* __restrict__ xyzs, const float* __r
         // software pipeline over the stencil points: the 32 fine-level gathers of point sp+1 are issued before the CTA barrier and the
         // weight-gradient products of point sp, so their latency is hidden behind tensor-core work instead of being exposed
         __half2 raw[2][16];
+        CornerCache cache;       // centre-cell corner values of the two coarse level slots, reused by the +-eps stencil points
         if (PREFETCH && warp_active) {
             float pa[3], pb[3], ua[3], ub[3];
             stencil_point(pa, xa, 0, p.bound);
@@ -299,6 +300,7 @@ k_field_backward(FieldParams p, const float* __restrict__ xyzs, const float* __r
             const bool va = to_unit(ua, pa, p.bound) && ina, vb = to_unit(ub, pb, p.bound) && inb;
             uint32_t a0[2][4], a1[4][4], a2[4][4];
             if (PREFETCH) gather_finish(a0, raw, s.w, p, lane, ua, va, ub, vb);
+            else if (NP > 1) encode_rows_cached(a0, s.w, p, lane, ua, va, ub, vb, cache, sp == 0);
             else encode_rows(a0, s.w, p, lane, ua, va, ub, vb);
             float hdummy[4];
             mlp_forward<true>(hdummy, a0, s.w, lane, a1, a2);
