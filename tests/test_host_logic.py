@@ -1,0 +1,65 @@
+"""CPU: host-side decisions that never touch the GPU — GEMM tile / split-K selection, the GEGLU row interleave, the bench's host
+core detection, the reference-facing option defaults."""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "stable-dreamfusion_b200")]
+
+
+def test_gemm_config_choice_is_valid_and_sane():
+    from sdf_b200.gemm import choose_config, estimate_us
+    shapes = [(8192, 320, 45), (8192, 2560, 5), (2048, 640, 270), (512, 1280, 180), (128, 1280, 360), (262144, 128, 18), (65536, 256, 36),
+              (16384, 512, 72), (2, 1280, 5), (154, 640, 12), (4096, 4, 72), (4096, 8, 72)]
+    for M, N, kb in shapes:
+        bn, pair, sk = choose_config(M, N, kb)
+        assert (bn, pair) in ((64, 0), (128, 0), (160, 0), (128, 1), (160, 1), (256, 1))
+        assert sk >= 1 and kb // sk >= 1
+        if pair:
+            assert M > 128 and N % 256 == 0                      # the pair tile is only chosen where it was measured to win
+        if sk > 1:
+            assert kb // sk >= 8                                 # never split below 8 k-blocks per CTA
+        assert estimate_us(M, N, kb, bn, pair, sk) <= estimate_us(M, N, kb, 128 if N > 64 else 64, 0, 1) + 1e-6
+    # batched products (attention) never split K and never pair
+    bn, pair, sk = choose_config(4096, 4096, 8, batched=True)
+    assert pair == 0 and sk == 1
+    # the wide VAE convolutions get the 2-CTA tile, the single-wave UNet convolutions do not split
+    assert choose_config(65536, 256, 36)[:2] == (256, 1)
+    assert choose_config(8192, 320, 45) == (160, 0, 1)
+
+
+def test_geglu_row_permutation_interleaves_value_and_gate():
+    from sdf_b200.sd_engine import geglu_row_permutation
+    inner = 64
+    perm = geglu_row_permutation(inner, torch.device("cpu"))
+    assert sorted(perm.tolist()) == list(range(2 * inner))
+    for c in range(2 * inner // 32):
+        chunk = perm[32 * c:32 * c + 32]
+        assert chunk[:16].tolist() == list(range(16 * c, 16 * c + 16))                      # 16 value rows ...
+        assert chunk[16:].tolist() == list(range(inner + 16 * c, inner + 16 * c + 16))      # ... then their 16 gates
+    # the fused epilogue's arithmetic on the permuted projection equals GEGLU on the original one
+    w, b, x = torch.randn(2 * inner, 24), torch.randn(2 * inner), torch.randn(5, 24)
+    y = x @ w.t() + b
+    ref = y[:, :inner] * torch.nn.functional.gelu(y[:, inner:])
+    yp = (x @ w[perm].t() + b[perm]).view(5, -1, 32)
+    fused = (yp[..., :16] * torch.nn.functional.gelu(yp[..., 16:])).reshape(5, inner)
+    assert torch.allclose(fused, ref, rtol=1e-5, atol=1e-5)
+
+
+def test_host_core_detection_is_bounded():
+    import bench
+    n = bench.host_core_limit()
+    assert 1 <= n <= (os.cpu_count() or 1)
+
+
+def test_default_options_match_the_reference_preset():
+    from sdf_b200.options import default_opt
+    o = default_opt(h=64, w=64)
+    # main.py:58-132 defaults + the -O preset (main.py:155-160)
+    assert (o.iters, o.lr, o.bound, o.dt_gamma, o.max_steps, o.update_extra_interval) == (10000, 1e-3, 1, 0, 1024, 16)
+    assert (o.latent_iter_ratio, o.albedo_iter_ratio, o.min_ambient_ratio, o.textureless_ratio) == (0.2, 0, 0.1, 0.2)
+    assert (o.lambda_entropy, o.lambda_opacity, o.lambda_orient) == (1e-3, 0, 1e-2)
+    assert (o.blob_density, o.blob_radius, o.bg_radius, o.density_activation) == (5, 0.2, 1.4, 'exp')
+    assert tuple(o.radius_range) == (3.0, 3.5) and tuple(o.fovy_range) == (10, 30) and tuple(o.theta_range) == (45, 105)
