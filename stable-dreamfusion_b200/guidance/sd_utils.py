@@ -136,9 +136,10 @@ class _SDSLoss(torch.autograd.Function):
             d = eng.grad * 2.0
             if tuple(d.shape[-2:]) != ctx.resize_from:
                 # adjoint of the bilinear resize through autograd on a tiny tensor (latent mode with h != 64 only)
-                x = torch.zeros(d.shape[0], d.shape[1], *ctx.resize_from, device=d.device, requires_grad=True)
-                y = F.interpolate(x, d.shape[-2:], mode='bilinear', align_corners=False)
-                (d,) = torch.autograd.grad(y, x, d)
+                with torch.enable_grad():            # backward() runs with grad mode off
+                    x = torch.zeros(d.shape[0], d.shape[1], *ctx.resize_from, device=d.device, requires_grad=True)
+                    y = F.interpolate(x, d.shape[-2:], mode='bilinear', align_corners=False)
+                    (d,) = torch.autograd.grad(y, x, d)
         else:
             d = eng.d_pred_rgb
         return (d * g).to(ctx.in_dtype), None, None, None, None

@@ -18,14 +18,14 @@ SMALL_VAE = dict(ch=32, ch_mult=(1, 2, 4, 4), num_res_blocks=1, in_channels=3, z
 class SmallGuidance(torch.nn.Module):
     """guidance.sd_utils.StableDiffusion with a reduced architecture (same code path, fewer channels)"""
 
-    def __init__(self, device):
+    def __init__(self, device, render_hw=64):
         super().__init__()
         from guidance import sd_utils as S
         self.S = S
         self.device = device
         usd = E.random_state(S.unet_param_shapes(SMALL_UNET), device, seed=0)
         vsd = E.random_state(S.vae_param_shapes(SMALL_VAE), device, seed=1)
-        self.engine = E.SDSEngine(usd, vsd, device, SMALL_UNET, SMALL_VAE, n_views=1, render_hw=64, ctx_len=77, vae_res=512, capture=True)
+        self.engine = E.SDSEngine(usd, vsd, device, SMALL_UNET, SMALL_VAE, n_views=1, render_hw=render_hw, ctx_len=77, vae_res=512, capture=True)
         self.min_step, self.max_step = 20, 980
 
     def get_text_embeds(self, prompt):
@@ -63,3 +63,14 @@ def test_schedule_default_path_and_occupancy_refresh(device):
         assert l == l
     assert tr.model.mean_density > 0
     assert int(tr.model.density_bitfield.sum()) > 0
+
+
+def test_config_c3_render_size(device):
+    """BASELINE.json config C3 renders 128x128 per view: same step at the larger render size (bilinear 128 -> 512 into the VAE)"""
+    opt = default_opt(h=128, w=128)
+    guidance = SmallGuidance(device, render_hw=128)
+    tr = SDSTrainer(opt, device, guidance, seed=2)
+    l1 = tr.train_step(shading="lambertian", read_loss=True)
+    l2 = tr.train_step(shading="latent", read_loss=True)
+    assert l1 == l1 and l2 == l2 and tr.last_M > 4000
+    assert all(torch.isfinite(p).all() for p in tr.model.parameters())
