@@ -186,3 +186,18 @@ class StableDiffusion(nn.Module):
 
     def encode_imgs(self, imgs):
         raise NotImplementedError('use train_step; the encoder runs inside the fused SDS step')
+
+    # ---- reference methods outside the SDS training path (guidance/sd_utils.py:166-300): they fail loudly instead of silently
+    #      falling back to anything else
+    def train_step_perpneg(self, *args, **kwargs):
+        raise NotImplementedError('Perp-Neg guidance (--perpneg) batches 1 + K prompts per view; the tcgen05 engine is built for the '
+                                  'CFG pair of the default path (SURVEY.md §8 scopes train_step)')
+
+    def produce_latents(self, *args, **kwargs):
+        raise NotImplementedError('text-to-image sampling needs the DDIM loop and the VAE decoder: outside the SDS hot path')
+
+    def decode_latents(self, latents):
+        raise NotImplementedError('the VAE decoder is outside the SDS hot path')
+
+    def prompt_to_img(self, *args, **kwargs):
+        raise NotImplementedError('text-to-image sampling is outside the SDS hot path')
