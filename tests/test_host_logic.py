@@ -63,3 +63,38 @@ def test_default_options_match_the_reference_preset():
     assert (o.lambda_entropy, o.lambda_opacity, o.lambda_orient) == (1e-3, 0, 1e-2)
     assert (o.blob_density, o.blob_radius, o.bg_radius, o.density_activation) == (5, 0.2, 1.4, 'exp')
     assert tuple(o.radius_range) == (3.0, 3.5) and tuple(o.fovy_range) == (10, 30) and tuple(o.theta_range) == (45, 105)
+
+
+def test_x_neighbour_corner_pairs_share_an_aligned_entry_pair():
+    """The fused field kernels fetch / reduce the two x-neighbours of a corner pair with ONE 8-byte load / 16-byte reduction when
+    (i0 ^ i1) == 1 (csrc/field_common.cuh: pair_issue, fused_field_bwd.cu: scatter_level).  Restate the level index rule of the
+    reference (gridencoder/src/gridencoder.cu:46-79) and check the algebra the kernels rely on:
+      * (i0 ^ i1) == 1  =>  the two entries are {2m, 2m+1}: adjacent and 8-byte aligned (level offsets are multiples of 8 entries);
+      * hashed levels with even x0 ALWAYS satisfy it (x1 = x0 ^ 1 flips only bit 0 of the hash, the level size is a power of two);
+      * dense levels satisfy it exactly when the linear index of the x0 corner is even."""
+    import numpy as np
+    from oracle import oracle as O
+    offsets, pls = O.grid_offsets(desired_resolution=2048)
+    assert all(int(o) % 8 == 0 for o in offsets)
+    rng = np.random.default_rng(0)
+    S = np.log2(pls)
+    for level in range(16):
+        size = int(offsets[level + 1] - offsets[level])
+        res = int(np.ceil(np.exp2(level * S) * 16))          # gridencoder.cu:109 (align_corners = False)
+        hashed = res ** 3 > size
+        p = rng.integers(0, res - 1, size=(20000, 3)).astype(np.uint64)
+        x0, y, z = p[:, 0], p[:, 1], p[:, 2]
+        x1 = np.minimum(x0 + 1, res - 1)
+        if hashed:
+            assert size & (size - 1) == 0                    # every hashed level of the -O backbone is a power of two
+            h = lambda x: ((x ^ (y * np.uint64(2654435761)) ^ (z * np.uint64(805459861))) & np.uint64(0xFFFFFFFF)) % np.uint64(size)
+        else:
+            h = lambda x: (x + y * np.uint64(res) + z * np.uint64(res * res)) % np.uint64(size)
+        i0, i1 = h(x0), h(x1)
+        merged = (i0 ^ i1) == 1
+        assert np.all(np.minimum(i0, i1)[merged] % 2 == 0) and np.all(np.abs(i0.astype(np.int64) - i1.astype(np.int64))[merged] == 1)
+        if hashed:
+            assert np.all(merged[x0 % 2 == 0])               # even x0: always one load
+        else:
+            assert np.array_equal(merged, i0 % 2 == 0)       # dense: exactly the even linear indices
+        assert 0.35 < merged.mean() < 0.65                   # ~half of all corner pairs merge -> ~25 % fewer scattered lanes
