@@ -2,7 +2,8 @@
 of BASELINE.json config C1 (32x32 render, 1 view/step).
 
 TEST INFRASTRUCTURE ONLY (oracle, kind "port"): used by bench.py's cpu_baseline / `--impl reference` arm; never imported by the
-product package.  Restates:
+product package.  Pinned: tests/golden/nerf_o2.npz holds outputs of the reference's own nerf/network.py + nerf/renderer.py:run on
+the same weights / rays / seeds (generator tests/golden/make_golden_o2.py, max |diff| 0.0); tests/test_oracle_o2_golden.py replays it.  Restates:
   nerf/network.py:11-116   ResBlock / BasicBlock / MLP / NeRFNetwork (frequency_torch(12) -> 5-layer ResBlock MLP(64) -> 4;
                            background frequency_torch(4) -> MLP 27->32->3), normals by autograd (:181-186)
   encoding.py:5-52         FreqEncoder_torch (log-sampled sin/cos, input included)

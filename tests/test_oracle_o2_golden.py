@@ -1,0 +1,33 @@
+"""CPU: oracle/nerf_o2.py (the port timed by bench.py's CPU reference arm) replayed against tests/golden/nerf_o2.npz — outputs of the
+reference's own `-O2` modules (nerf/network.py, nerf/renderer.py:run) on the same weights, rays and seeds, written by
+tests/golden/make_golden_o2.py in the container that has /root/reference."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import nerf_o2
+
+PATH = os.path.join(os.path.dirname(__file__), "golden", "nerf_o2.npz")
+pytestmark = pytest.mark.skipif(not os.path.exists(PATH), reason="tests/golden/nerf_o2.npz not generated")
+
+
+@pytest.mark.parametrize("shading", ["albedo", "lambertian", "textureless", "normal"])
+def test_o2_port_matches_reference_outputs(shading):
+    g = np.load(PATH)
+    port = nerf_o2.VanillaNeRF()
+    sd = {k[2:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("w.")}
+    missing, unexpected = port.load_state_dict(sd, strict=False)
+    assert not unexpected
+    ro, rd = torch.from_numpy(g["rays_o"])[None], torch.from_numpy(g["rays_d"])[None]
+    torch.manual_seed(123)                       # the generator seeds the reference the same way before each run()
+    out = port.render(ro, rd, 0.4, shading, None, perturb=True)
+    # same PyTorch CPU kernels, same operation order: agreement to float rounding of the library version
+    np.testing.assert_allclose(out["image"].detach().numpy(), g[f"{shading}.image"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(out["weights_sum"].detach().numpy(), g[f"{shading}.weights_sum"], rtol=1e-5, atol=1e-6)
+    if f"{shading}.loss_orient" in g.files:
+        assert abs(float(out["loss_orient"]) - float(g[f"{shading}.loss_orient"])) <= 1e-6 + 1e-4 * abs(float(g[f"{shading}.loss_orient"]))
+    gw = torch.autograd.grad(out["image"].sum() + out["weights_sum"].sum(), port.sigma_net.net[0].dense.weight)[0]
+    ref = g[f"{shading}.grad_w0"]
+    assert np.abs(gw.numpy() - ref).max() <= 1e-4 * np.abs(ref).max()
