@@ -31,8 +31,11 @@ class _Stub(types.ModuleType):
 
 def load_reference():
     sys.path.insert(0, REF)
+    # the reference's extension packages JIT-compile at import: never let them load here (the -O2 path does not use them)
+    for name in ["gridencoder", "freqencoder", "shencoder", "torch.utils.cpp_extension"]:
+        sys.modules.setdefault(name, _Stub(name))
     for name in ["mcubes", "trimesh", "nvdiffrast", "nvdiffrast.torch", "raymarching", "cubvh", "xatlas", "pymeshlab", "tensorboardX", "imageio",
-                 "torch_ema", "torchmetrics", "matplotlib", "matplotlib.pyplot", "lpips", "rich", "rich.console", "packaging"]:
+                 "torch_ema", "torchmetrics", "matplotlib", "matplotlib.pyplot", "lpips", "rich", "rich.console"]:
         sys.modules.setdefault(name, _Stub(name))
     import nerf.network as N
     return N
@@ -87,6 +90,17 @@ def main():
         print(f"  rel grad diff {err_g:.3e}")
         assert err_g < 1e-4
         out[f"{shading}.grad_w0"] = g_r.numpy()
+    # camera rays: nerf/utils.py:113-176 get_rays (N = -1, pixel centres) for two poses / intrinsics
+    from nerf.utils import get_rays as ref_get_rays
+    rng = np.random.default_rng(5)
+    for i, (hh, ww, fov) in enumerate([(16, 16, 20.0), (8, 24, 37.5)]):
+        pose_i, _ = synth.rand_pose(rng)
+        focal = hh / (2 * np.tan(np.deg2rad(fov) / 2))
+        rr = ref_get_rays(torch.from_numpy(pose_i)[None].float(), np.array([focal, focal, ww / 2, hh / 2]), hh, ww, -1)
+        out[f"cam{i}.pose"] = pose_i.astype(np.float32)
+        out[f"cam{i}.hwf"] = np.array([hh, ww, focal], np.float64)
+        out[f"cam{i}.rays_o"] = rr["rays_o"][0].numpy()
+        out[f"cam{i}.rays_d"] = rr["rays_d"][0].numpy()
     path = os.path.join(ROOT, "tests", "golden", "nerf_o2.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path) // 1024, "KiB")

@@ -31,3 +31,20 @@ def test_o2_port_matches_reference_outputs(shading):
     gw = torch.autograd.grad(out["image"].sum() + out["weights_sum"].sum(), port.sigma_net.net[0].dense.weight)[0]
     ref = g[f"{shading}.grad_w0"]
     assert np.abs(gw.numpy() - ref).max() <= 1e-4 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("cam", [0, 1])
+def test_camera_rays_match_reference_get_rays(cam):
+    """sdf_b200.trainer.get_rays_torch and sdf_b200.synth.get_rays against nerf/utils.py:113-176 (pixel centres, unnormalised
+    directions, camera-to-world rotation applied as d @ R^T) — square and non-square images"""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "stable-dreamfusion_b200"))
+    from sdf_b200.trainer import get_rays_torch
+    g = np.load(PATH)
+    if f"cam{cam}.pose" not in g.files:
+        pytest.skip("fixture predates the camera vectors")
+    H, W, focal = g[f"cam{cam}.hwf"]
+    H, W = int(H), int(W)
+    ro, rd = get_rays_torch(torch.from_numpy(g[f"cam{cam}.pose"])[None], float(focal), W / 2, H / 2, H, W)
+    assert np.array_equal(ro[0].numpy(), g[f"cam{cam}.rays_o"])
+    np.testing.assert_allclose(rd[0].numpy(), g[f"cam{cam}.rays_d"], rtol=0, atol=2e-7)      # three FMAs instead of a 3x3 matmul
