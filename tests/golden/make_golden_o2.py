@@ -101,6 +101,16 @@ def main():
         out[f"cam{i}.hwf"] = np.array([hh, ww, focal], np.float64)
         out[f"cam{i}.rays_o"] = rr["rays_o"][0].numpy()
         out[f"cam{i}.rays_d"] = rr["rays_d"][0].numpy()
+    # orbit camera poses: nerf/provider.py:151-197 circle_poses (the deterministic core of rand_poses with the default
+    # uniform_sphere_rate = 0, jitter_pose = False of main.py:72-76)
+    import nerf.provider as P
+    orbit = np.array([(3.2, 90.0, 0.0), (3.0, 60.0, 45.0), (3.5, 105.0, -170.0), (3.2, 45.0, 200.0), (3.33, 75.0, 90.0)], np.float32)
+    ref_poses = []
+    for r_, th_, ph_ in orbit:
+        res = P.circle_poses("cpu", radius=torch.tensor([r_]), theta=torch.tensor([th_]), phi=torch.tensor([ph_]))
+        ref_poses.append((res[0] if isinstance(res, tuple) else res)[0].numpy())
+    out["orbit.params"] = orbit
+    out["orbit.poses"] = np.stack(ref_poses)
     path = os.path.join(ROOT, "tests", "golden", "nerf_o2.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path) // 1024, "KiB")

@@ -48,3 +48,15 @@ def test_camera_rays_match_reference_get_rays(cam):
     ro, rd = get_rays_torch(torch.from_numpy(g[f"cam{cam}.pose"])[None], float(focal), W / 2, H / 2, H, W)
     assert np.array_equal(ro[0].numpy(), g[f"cam{cam}.rays_o"])
     np.testing.assert_allclose(rd[0].numpy(), g[f"cam{cam}.rays_d"], rtol=0, atol=2e-7)      # three FMAs instead of a 3x3 matmul
+
+
+def test_orbit_poses_match_reference_circle_poses():
+    """sdf_b200.synth.circle_pose (look-at orbit camera of the benchmark / trainer) against nerf/provider.py:151-197"""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "stable-dreamfusion_b200"))
+    from sdf_b200 import synth
+    g = np.load(PATH)
+    if "orbit.params" not in g.files:
+        pytest.skip("fixture predates the orbit poses")
+    for (r, th, ph), ref in zip(g["orbit.params"], g["orbit.poses"]):
+        np.testing.assert_allclose(synth.circle_pose(float(r), float(th), float(ph)), ref, rtol=0, atol=2e-6)
