@@ -98,3 +98,21 @@ def test_x_neighbour_corner_pairs_share_an_aligned_entry_pair():
         else:
             assert np.array_equal(merged, i0 % 2 == 0)       # dense: exactly the even linear indices
         assert 0.35 < merged.mean() < 0.65                   # ~half of all corner pairs merge -> ~25 % fewer scattered lanes
+
+
+def test_default_options_equal_the_reference_parser_output():
+    """every option the host mirror uses, against what main.py's own argparse block produces for `--text x -O`
+    (tests/golden/options_O.json, written by tests/golden/make_golden_opts.py from the reference source)"""
+    import json
+    from sdf_b200.options import default_opt
+    path = os.path.join(ROOT, "tests", "golden", "options_O.json")
+    ref = json.load(open(path))
+    ours = vars(default_opt(h=ref["h"], w=ref["w"]))
+    shared = [k for k in ours if k in ref]
+    assert len(shared) >= 30
+    for k in shared:
+        a, b = ours[k], ref[k]
+        if isinstance(a, (list, tuple)):
+            assert list(a) == list(b), k
+        else:
+            assert a == b, (k, a, b)
