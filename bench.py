@@ -126,7 +126,8 @@ def run_reference(args):
     vae = sd_ref.VaeEncoder(**sd_ref.VAE_SD15).eval()
     for p in list(unet.parameters()) + list(vae.parameters()):
         p.requires_grad_(False)
-    opt_ = torch.optim.Adam(model.parameters(), lr=1e-3)
+    from oracle.ref_cuda_path import TorchAdan                  # the reference's optimizer (main.py:368: Adan, foreach=False), restated in PyTorch
+    opt_ = TorchAdan([{'params': list(model.parameters()), 'lr': 5e-3}], eps=1e-8, weight_decay=2e-5, max_grad_norm=5.0)
     acp = sd_ref.alphas_cumprod()
     text = torch.randn(2, 77, 768)
     rng = __import__("numpy").random.default_rng(0)
@@ -148,7 +149,7 @@ def run_reference(args):
         opt_.zero_grad()
         loss.backward()
         opt_.step()
-        return float(loss)
+        return float(loss.detach())
 
     # bounded sample: the CPU path takes ~10-20 s per step; measure as many of the K requested steps as fit the time budget
     budget_s = float(os.environ.get("SDF_CPU_BASELINE_BUDGET_S", "150"))
