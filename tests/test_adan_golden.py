@@ -44,3 +44,18 @@ def test_fused_kernel_matches_reference_optimizer(device):
             ref = g[f"p{s + 1}.{i}"]
             err = np.abs(p.detach().cpu().numpy() - ref).max()
             assert err <= 2e-5 * max(1.0, np.abs(ref).max()), (s, i, err)
+
+
+def test_reference_arm_optimizer_matches_reference_optimizer():
+    """oracle/ref_cuda_path.TorchAdan (the optimizer of both reference arms of bench.py) against the same golden trajectory"""
+    from oracle.ref_cuda_path import TorchAdan
+    g, n, steps = _load()
+    params = [torch.nn.Parameter(torch.from_numpy(g[f"p0.{i}"]).clone()) for i in range(n)]
+    opt = TorchAdan([{"params": [p], "lr": float(lr)} for p, lr in zip(params, g["lrs"])], eps=1e-8, weight_decay=2e-5, max_grad_norm=5.0)
+    for s in range(steps):
+        for i, p in enumerate(params):
+            p.grad = torch.from_numpy(g[f"g{s}.{i}"]).clone()
+        opt.step()
+        for i, p in enumerate(params):
+            ref = g[f"p{s + 1}.{i}"]
+            assert np.abs(p.detach().numpy() - ref).max() <= 2e-6 * max(1.0, np.abs(ref).max()), (s, i)
