@@ -12,9 +12,14 @@
 //     128B-swizzled shared memory and feed tcgen05.mma (cta_group::1, M=128, N=BLOCK_N, K=16) through UMMA descriptors;
 //   * accumulators live in TMEM (double-buffered, 2 x BLOCK_N columns) so the epilogue of tile i overlaps the
 //     MMAs of tile i+1; epilogue = tcgen05.ld -> (+bias) (+per-image embedding) (+residual) (SiLU/GELU) -> fp16 store;
-//   * warp roles: warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 epilogue; 5-stage mbarrier pipeline;
-//   * split-K for the low-resolution UNet levels (M = 128..512): partials are reduced with fp32 red.global.add into a
-//     workspace and finished by a tiny epilogue kernel.
+//   * warp roles: warp 0 TMA producer, warp 1 MMA issuer, warps 2-9 epilogue (two per TMEM lane quarter, 32-column chunks with
+//     tcgen05.ld x32, 16-byte addend loads, 32-byte stores, optional GEGLU); 6-8-stage mbarrier pipeline sized to the smem budget;
+//   * PAIR = true: 2-CTA clusters issue tcgen05.mma.cta_group::2 (M = 256 per MMA); each CTA stages its own 128 rows of A and
+//     HALF of the weight tile, both CTAs' TMA loads complete on the leader's barrier, the leader's commits are multicast;
+//   * split-K for the low-resolution UNet levels (M = 128..512): partials are reduced with red.global.add.v4.f32 into a
+//     workspace and finished by a tiny epilogue kernel;
+//   * programmatic dependent launch: the prologue (barrier init, TMEM allocation, tensor-map prefetch) runs before
+//     griddepcontrol.wait, i.e. under the previous kernel's tail.
 //
 // Roofline: tensor pipe.  FLOPs per launch = 2 * M * N * taps * Cin.
 #include "common.cuh"
