@@ -9,7 +9,9 @@
 // the 32-64-64-4 MLP runs on tensor cores (m16n8k16, fp16 in / fp32 accumulate) with the
 // activations chained through registers; the 7 stencil densities of a sample end up in the
 // same lane, which finishes normal + shading.  Nothing but xyz in and (sigma, rgb, normal)
-// out touches HBM; the 24 MB fp16 table is served from L2.
+// out touches HBM; the 24 MB fp16 table is served from L2.  One hashed/dense branch per level and branch-free
+// corner arithmetic keep all 16 gathers of a level pair in flight; aligned x-neighbour corner pairs come in one
+// 8-byte load; the stencil loop is rolled and the +-eps points re-use the centre cell's coarse-level corners.
 //
 // Algorithmic bytes: forward 540 B per point-eval (12 B xyz + 128 half2
 // corner reads + 16 B out).  Roofline: HBM.

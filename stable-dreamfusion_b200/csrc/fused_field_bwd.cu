@@ -5,13 +5,16 @@
 // zero-fill and cast-back), nerf/network_grid.py:68-130 and gridencoder/grid.py:72-96.
 //
 // One CTA (16 warps) owns 256 point-evals per round: each warp re-gathers the hash-grid features of its
-// 16 rows (recompute instead of saving 3 M x 160 activations), re-runs the MLP keeping the two hidden
-// activations in registers, back-propagates through the MLP on tensor cores (weights transposed in
-// shared memory), scatters d(enc) into the fp32 table gradient with vector float2 reductions, and
-// stages activations / deltas transposed in shared memory so the CTA can form the weight gradients
-// as [features x 256 rows] x [256 rows x features] tensor-core products whose accumulators live in
-// registers for the whole kernel (flushed once with atomics).  Bias gradients ride along as an extra
-// all-ones activation row.
+// 16 rows (recompute instead of saving 3 M x 160 activations; aligned x-neighbour corner pairs come in one
+// 8-byte load, the centre cell's coarse-level corners are re-used by the +-eps stencil points), re-runs the
+// MLP keeping the two hidden activations in registers, back-propagates through the MLP on tensor cores
+// (the forward-orientation weights in shared memory are read through ldmatrix.trans: no transposed copies),
+// scatters d(enc) into the fp32 table gradient with float2 reductions (one float4 reduction for an aligned
+// x-neighbour pair), and stages activations / deltas transposed (movmatrix) in shared memory so the CTA can
+// form the weight gradients as [features x 256 rows] x [256 rows x features] tensor-core products (64 tile
+// pairs, 4 per warp) whose accumulators live in registers for the whole kernel (flushed once with atomics).
+// Bias gradients ride along as an extra all-ones activation row (layer 3's is summed per lane instead).
+// Warps whose 16 samples carry no upstream gradient skip everything but the barriers.
 //
 // Algorithmic bytes: 1 052 B per point-eval (12 B xyz + 16 B upstream + 128 float2/half2
 // RMWs counted 8 B each).  Roofline: HBM (L2 atomics in practice).
