@@ -1,9 +1,10 @@
 """SD-1.5-shaped UNet (forward) and VAE encoder (forward + data-gradient) as a static list of native launches.
 
 Every dense contraction is a tcgen05 plan (csrc/sd_gemm.cu) — 3x3 / 1x1 convolutions as implicit GEMM over NHWC fp16
-activations, linear layers, and the attention products as batched plans straight on the [tokens, heads*d] projections —
+activations and linear layers (q|k|v / k|v projections fused into one plan, GEGLU fused into its projection's epilogue) — the
+UNet attention is the fused flash kernel of csrc/flash_attn.cu straight on the [tokens, heads*d] projections, everything is
 glued by the memory-bound kernels of csrc/sd_ops.cu.  Shapes are fixed at construction, so the whole step is a flat
-list of ~1000 launches with no Python tensor ops in between; `capture()` records it into a CUDA graph.
+list of ~500 launches with no Python tensor ops in between; `capture()` records it into a CUDA graph.
 
 Structure follows the modules the reference executes (vendored CompVis code; see oracle/sd_ref.py for the citations):
 ResBlock / SpatialTransformer / BasicTransformerBlock / CrossAttention / GEGLU / Downsample / Upsample / UNetModel,
@@ -13,9 +14,9 @@ Layout conventions
   activations   NHWC fp16, a `View` = (tensor [Nimg,H,W,ld], channel offset, channels); skip connections are written
                 by their producer directly into the consumer's concat buffer (no torch.cat kernels)
   conv weights  [Cout, tap, Cin_iter] fp16, K index = tap*Cin_iter + c (Cin_iter = Cin rounded up to 64)
-  attention     S = Q K^T and O = P V are batched plans over (batch, head); the K tail (d_head = 40/80/160) is
-                zero-filled by the TMA unit, V is produced transposed ([C, tokens]) by swapping the operands of its
-                projection GEMM
+  attention     UNet: sdf_flash_attention on q / k / v views of the fused projection buffers (no score matrix in HBM).
+                VAE mid block (one head, d = 512, forward + backward): S = Q K^T and O = P V as batched tcgen05 plans with a
+                row-softmax kernel in between
 """
 import math
 
