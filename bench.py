@@ -1,9 +1,13 @@
 #!/usr/bin/env python
 """SDS steps/s of the -O preset (64x64 render, SD-1.5-shaped UNet guidance) on N B200s — BASELINE.json's metric on config C2.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W]            ours (sm_100a kernels through the C ABI)
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--config C2|C3]   ours (sm_100a kernels through the C ABI)
   python bench.py --impl reference ...                           the reference's CPU path (-O2 vanilla NeRF + PyTorch UNet/VAE on the
                                                                  host cores; oracle port, see oracle/nerf_o2.py, oracle/sd_ref.py)
+  python bench.py --impl reference-cuda ...                      the reference's own -O training loop on this GPU: its unmodified Trainer /
+                                                                 renderer / network Python on its own CUDA extensions + PyTorch fp16 SD
+                                                                 (oracle/ref_harness.py); at N = 1 the main line runs it too and reports
+                                                                 vs_baseline = ours / that (the north star's target: >= 1.5)
 Under torchrun (N > 1) every rank renders its own view and the NeRF gradients are all-reduced once per step (weak scaling:
 value = views processed by all ranks / s).  One JSON line is printed by rank 0.
 
@@ -28,7 +32,14 @@ for _p in (ROOT, PKG):
         sys.path.insert(0, _p)
 
 METRIC = "SDS steps/sec (64x64 render, SD-1.5 UNet)"
+CONFIGS = {"C2": dict(hw=64, note="BASELINE.json configs[1]: -O backbone, 64x64 render, 1 view/step/GPU"),
+           "C3": dict(hw=128, note="BASELINE.json configs[2]: -O backbone, 128x128 render, 1 view/step/GPU (4 views over 4 GPUs)")}
 CYCLE = ["latent"] * 5 + (["lambertian"] * 4 + ["textureless"]) * 4        # 20 % / 64 % / 16 %
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the two field kernels, from the ncu --set full capture summarised in
+# profiles/ (the fp16 table is L2-resident: DRAM traffic is a fraction of a percent of the algorithmic bytes)
+FIELD_DRAM_TRAFFIC = {"fwd_dram_bytes": 47.5e6, "bwd_dram_bytes": 138.7e6, "at_samples": 777269, "source": "profiles/r01_kernels.md (ncu --set full)"}
 
 
 def peaks():
@@ -162,7 +173,8 @@ def run_reference(args):
         step(1 + i)
     dt = time.perf_counter() - t0
     v = measured / dt
-    line = {"metric": METRIC, "value": v, "unit": "steps/s", "impl": "reference", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+    line = {"metric": METRIC, "value": v, "unit": "steps/s", "impl": "reference", "n_gpus": args.gpus, "steps": measured, "steps_requested": args.steps,
+            "warmup": 1,
             "ms_per_step": 1e3 * dt / measured, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "reference -O2 CPU path: vanilla NeRF 32x32 (64+32 samples/ray) + SD-1.5-shaped UNet/VAE in PyTorch fp32, 1 view/step"},
             "cpu_baseline": {"value": v, "unit": "steps/s", "cores": cores, "kind": "port",
@@ -172,31 +184,39 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------ reference, CUDA path (SURVEY §8d arm A)
+def time_reference_cuda(hw=64, steps=30, warmup=10):
+    """The reference's own training loop on this GPU, unmodified: nerf/utils.py Trainer.train_one_epoch (GradScaler, reference Adan, tqdm,
+    loss.item() per step) + nerf/renderer.py + nerf/network_grid.py on the reference's CUDA extensions, SD-1.5-shaped UNet/VAE in PyTorch
+    fp16 (cuDNN / cuBLAS / SDPA), in a fresh interpreter (oracle/ref_harness.py `time`).  Two windows, one per phase of the reference
+    schedule (latent: the first 20 % of the iterations; shaded: lambertian / textureless mix), each `warmup` untimed + `steps` timed steps with
+    cudnn.benchmark OFF (with it on, the first ~30 steps are autotuning: round 1 measured 1.35 steps/s over 13 such steps against 3.19
+    once settled); combined with the 20/80 weights of the schedule the main line cycles through."""
+    import tempfile
+    from oracle import ref_harness as RH
+    tmp = tempfile.mkdtemp(prefix="sdf_refcuda_")
+    res = {}
+    specs = []
+    for phase, gstep in (("latent", 0), ("shaded", 2096)):
+        specs.append(dict(cmd="time", workspace=os.path.join(tmp, "ws_" + phase), steps=steps, warmup=warmup, global_step=gstep, seed=0,
+                          opt=dict(h=hw, w=hw), out=os.path.join(tmp, phase + ".json")))
+    RH.run_subprocess(dict(cmd="multi", ops="reference", specs=specs), timeout=3000)
+    for phase in ("latent", "shaded"):
+        res[phase] = json.load(open(os.path.join(tmp, phase + ".json")))
+    ms = 0.2 * res["latent"]["ms_per_step"] + 0.8 * res["shaded"]["ms_per_step"]
+    return {"value": 1e3 / ms, "unit": "steps/s", "ms_per_step": ms, "ms_per_step_latent": res["latent"]["ms_per_step"],
+            "ms_per_step_shaded": res["shaded"]["ms_per_step"], "steps": 2 * steps, "warmup": 2 * warmup,
+            "what": "reference Trainer.train_one_epoch, unmodified, on its own CUDA extensions + PyTorch fp16 UNet/VAE; 0.2 x latent-phase + 0.8 x "
+                    "shaded-phase step time; cudnn.benchmark off"}
+
+
 def run_reference_cuda(args):
-    import torch
     if int(os.environ.get("RANK", "0")) != 0:
         return
-    dev = torch.device("cuda", 0)
-    torch.cuda.set_device(dev)
-    from oracle import ref_cuda_path
-    from sdf_b200.options import default_opt
-    tr = ref_cuda_path.build_reference_trainer(default_opt(h=64, w=64, batch_size=1), dev, seed=0)
-    for i in range(max(3, args.warmup)):
-        tr.train_step(shading=CYCLE[i % len(CYCLE)], read_loss=False)
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(args.steps):
-        tr.train_step(shading=CYCLE[(args.warmup + i) % len(CYCLE)], read_loss=False)
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
-    v = args.steps / (ms * 1e-3)
-    print(json.dumps({"metric": METRIC, "value": v, "unit": "steps/s", "impl": "reference-cuda", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
-                      "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
-                      "config": {"workload": "reference -O path on this GPU: its own CUDA extensions (oracle/_ref, unmodified sources) + PyTorch fp16 "
-                                             "UNet/VAE (cuDNN/cuBLAS/SDPA) + per-tensor PyTorch Adan; same schedule mix, 64x64, 1 view/step; no GradScaler/EMA/logging",
-                                 "samples_last_step": tr.last_M}}), flush=True)
+    hw = CONFIGS[args.config]["hw"]
+    r = time_reference_cuda(hw, steps=max(args.steps // 2, 10), warmup=max(args.warmup, 10))
+    print(json.dumps({"metric": METRIC, "value": r["value"], "unit": "steps/s", "impl": "reference-cuda", "n_gpus": 1, "steps": r["steps"], "warmup": r["warmup"],
+                      "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+                      "config": {"workload": f"reference -O path on this GPU ({hw}x{hw}, 1 view/step): " + r["what"]}, "detail": r}), flush=True)
 
 
 # ------------------------------------------------------------------------------------------------ ours
@@ -214,8 +234,9 @@ def run_ours(args):
     from sdf_b200.trainer import SDSTrainer
     from guidance.sd_utils import StableDiffusion
 
-    opt = default_opt(h=64, w=64, batch_size=1)
-    guidance = StableDiffusion(dev, weights="random", n_views=1, render_hw=64, seed=0, capture=True)
+    hw = CONFIGS[args.config]["hw"]
+    opt = default_opt(h=hw, w=hw, batch_size=1)
+    guidance = StableDiffusion(dev, weights="random", n_views=1, render_hw=hw, seed=0, capture=True)
     trainer = SDSTrainer(opt, dev, guidance, seed=0, rank=rank, world_size=world)
     eng = guidance.engine
     launches = {"n": 0}
@@ -225,9 +246,6 @@ def run_ours(args):
         launches["n"] += 1
         return orig_call(name, *a)
     _lib.call = counting_call
-    for mod in list(sys.modules.values()):
-        if getattr(mod, "_lib", None) is _lib:
-            pass
     graph_ops = {"unet": len(eng.unet.runlist.ops), "vae_fwd": len(eng.vae.fwd.ops), "vae_bwd": len(eng.vae.bwd.ops)}
 
     def barrier():
@@ -284,38 +302,60 @@ def run_ours(args):
     torch.cuda.synchronize()
     gemm_ms = e0.elapsed_time(e1) / reps
     achieved = flops / (gemm_ms * 1e-3) / 1e12
-    roof = {"bound": "tensor", "kernel": "k_gemm (tcgen05 implicit GEMM: all conv/linear/attention products of one SDS step)", "achieved": achieved,
+    roof_gemm = {"bound": "tensor", "kernel": "k_gemm (tcgen05 implicit GEMM: all conv/linear/attention products of one SDS step)", "achieved": achieved,
             "peak": tf_sus, "peak_kind": f"bf16_tflops_sustained ({peak_kind})", "unit": "TFLOP/s", "frac": achieved / tf_sus,
             "launches_per_step": len(gemm_plans), "flops_per_step": flops, "ms_per_step_alone": gemm_ms, "traffic": None}
 
-    # --- fused hashgrid+MLP field kernels: algorithmic bytes / CUDA-event time on a typical sample set
-    from sdf_b200 import synth
+    # --- fused hashgrid+MLP field kernels (the kernel BASELINE.json's metric names): algorithmic bytes (540 B forward /
+    # 1052 B backward per point-eval, 7 point-evals per lambertian sample) / CUDA-event time of the bare C-ABI launches on a typical sample
+    # set; L2 is flushed (256 MB write) before every timed launch, so the 24 MB fp16 table starts in HBM as it does inside a step
     fld = {}
     try:
-        xyz = (torch.rand(432000, 3, device=dev) * 2 - 1) * 0.5
-        l = torch.nn.functional.normalize(torch.randn(432000, 3, device=dev), dim=-1)
+        M = 432000
+        g = torch.Generator(device=dev).manual_seed(1)
+        xyz = ((torch.rand(M, 3, device=dev, generator=g) * 2 - 1) * 0.5).contiguous()
+        l = torch.nn.functional.normalize(torch.randn(M, 3, device=dev, generator=g), dim=-1).contiguous()
         m = trainer.model
-        for _ in range(2):
-            s, c, n = m(xyz, None, l, ratio=0.5, shading="lambertian")
-            (s.sum() + c.sum()).backward()
-        torch.cuda.synchronize()
-        ef = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
-        ef[0].record()
-        s, c, n = m(xyz, None, l, ratio=0.5, shading="lambertian")
-        ef[1].record()
-        (s.sum() + c.sum()).backward()
-        ef[2].record()
-        torch.cuda.synchronize()
-        M = xyz.shape[0]
+        c = m.field_cfg()
+        sn = m.sigma_net.net
+        P = _lib.ptr
+        table = m.table_half()
+        sig, col, nrm, aux = (torch.empty(M, device=dev), torch.empty(M, 3, device=dev), torch.empty(M, 3, device=dev), torch.empty(M, 10, device=dev))
+        gs, gc = torch.full((M,), 1e-3, device=dev), torch.randn(M, 3, device=dev, generator=g)
+        gt = torch.zeros_like(m.encoder.embeddings)
+        gw = [torch.zeros_like(t) for t in (sn[0].weight, sn[0].bias, sn[1].weight, sn[1].bias, sn[2].weight, sn[2].bias)]
+        wts = [P(t) for t in (sn[0].weight, sn[0].bias, sn[1].weight, sn[1].bias, sn[2].weight, sn[2].bias)]
+        fargs = (P(xyz), M, None, P(table), P(c["offsets"]), c["L"], c["levels_active"], c["S"], int(c["H"]), int(c["smoothstep"]), *wts, m.bound,
+                 c["blob_density"], c["blob_radius"], 1, P(l), 1, 0.5)
+        flush = torch.empty(64 * 1024 * 1024, device=dev, dtype=torch.float32)
+        st = _lib.stream()
+        tf_, tb_ = [], []
+        for rep in range(7):
+            flush.fill_(float(rep))
+            e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            e[0].record()
+            orig_call("sdf_field_forward", *fargs, P(sig), P(col), P(nrm), P(aux), st)
+            e[1].record()
+            flush.fill_(float(rep) + 0.5)
+            e[2].record()
+            orig_call("sdf_field_backward", *fargs, P(aux), P(gs), P(gc), None, P(gt), *[P(t) for t in gw], st)
+            e[3].record()
+            torch.cuda.synchronize()
+            if rep >= 2:
+                tf_.append(e[0].elapsed_time(e[1]) * 1e-3)
+                tb_.append(e[2].elapsed_time(e[3]) * 1e-3)
+        tfw, tbw = sum(tf_) / len(tf_), sum(tb_) / len(tb_)
         bf, bb = M * (7 * 540.0), M * (7 * 1052.0)
-        tfw, tbw = ef[0].elapsed_time(ef[1]) * 1e-3, ef[1].elapsed_time(ef[2]) * 1e-3
-        fld = {"bound": "hbm", "samples": M, "shading": "lambertian", "fwd_ms": tfw * 1e3, "bwd_ms": tbw * 1e3,
-               "fwd_GBps": bf / tfw / 1e9, "bwd_GBps": bb / tbw / 1e9, "peak": hbm, "fwd_frac": bf / tfw / 1e9 / hbm, "bwd_frac": bb / tbw / 1e9 / hbm,
-               "note": "algorithmic bytes 540 B fwd / 1052 B bwd per point-eval, 7 point-evals per sample; timings include the autograd wrapper",
-               "traffic": {"fwd_dram_bytes": 47.5e6, "bwd_dram_bytes": 138.7e6, "at_samples": 777269,
-                           "source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, profiles/r01_kernels.md (the fp16 table is L2-resident: "
-                                     "DRAM traffic is ~0.3 % of the algorithmic bytes)"}}
-        trainer.optimizer.zero_grad(set_to_none=False)
+        fld = {"bound": "hbm", "kernel": "k_field_forward + k_field_backward (fused hashgrid gather + 32-64-64-4 MLP + 7-point finite-difference normal + "
+                                          "shading; lambertian), bare C-ABI launches",
+               "achieved": (bf + bb) / (tfw + tbw) / 1e9, "peak": hbm, "peak_kind": f"hbm_gbs ({peak_kind})", "unit": "GB/s",
+               "frac": (bf + bb) / (tfw + tbw) / 1e9 / hbm, "samples": M, "launches_timed": len(tf_),
+               "algorithmic_bytes_per_launch": {"fwd": bf, "bwd": bb, "rule": "SURVEY.md 8d: 540 B fwd / 1052 B bwd per point-eval x 7 point-evals per sample"},
+               "fwd": {"ms": tfw * 1e3, "GBps": bf / tfw / 1e9, "frac": bf / tfw / 1e9 / hbm},
+               "bwd": {"ms": tbw * 1e3, "GBps": bb / tbw / 1e9, "frac": bb / tbw / 1e9 / hbm},
+               "l2": "flushed before every timed launch",
+               "traffic": FIELD_DRAM_TRAFFIC}
+        del flush, gt, aux
     except Exception as e:      # never let the auxiliary measurement kill the bench line
         fld = {"error": repr(e)}
 
@@ -344,28 +384,41 @@ def run_ours(args):
         cpu = None
         if not args.no_cpu_baseline and world == 1:          # the CPU leg is reported at N = 1 only
             try:
-                out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1", "--warmup", "0"],
-                                     capture_output=True, text=True, timeout=600, env={k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")})
+                out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "3", "--warmup", "1"],
+                                     capture_output=True, text=True, timeout=900, env={k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")})
                 cpu = json.loads(out.stdout.strip().splitlines()[-1])["cpu_baseline"]
             except Exception as e:
                 cpu = {"value": None, "unit": "steps/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e!r}"}
+        # --- the north star's comparison: the reference's own -O loop on this same GPU (N = 1 only; skipped with --no-ref-cuda)
+        refc, vs = None, None
+        if world == 1 and not args.no_ref_cuda:
+            try:
+                torch.cuda.empty_cache()
+                refc = time_reference_cuda(hw, steps=max(args.steps, 25), warmup=max(args.warmup, 10))
+            except Exception as e:
+                refc = {"value": None, "error": repr(e)[-400:]}
         value = world * args.steps / (ms_res * 1e-3)
+        if refc and refc.get("value"):
+            vs = value / refc["value"]
         e2e_v = world * args.steps / (ms_e2e * 1e-3)
         per_step_calls = n_calls / args.steps
         # graph replays stand for all captured launches
         frac = {s: CYCLE.count(s) / len(CYCLE) for s in set(CYCLE)}
         launches_per_step = per_step_calls + graph_ops["unet"] + (1 - frac["latent"]) * (graph_ops["vae_fwd"] + graph_ops["vae_bwd"])
         line = {"metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
-                "config": {"workload": "-O instant-NGP backbone, 64x64 render, 1 view/step/GPU, SD-1.5-shaped UNet (B=2 CFG) + VAE encoder 512x512, "
+                "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": vs,
+                "vs_baseline_kind": "value / steps-per-second of the reference's own -O CUDA-extension training loop measured on this same GPU in this run "
+                                    "(`reference_cuda` below; BASELINE.md publishes no number, its 3.1 defines this arm A)",
+                "dtype": "f16", "data": "synthetic",
+                "config": {"workload": f"{args.config}: -O instant-NGP backbone, {hw}x{hw} render, 1 view/step/GPU, SD-1.5-shaped UNet (B=2 CFG) + VAE encoder 512x512, "
                                        "reference shading schedule mix (20% latent, 64% lambertian, 16% textureless), Adan step, grid refresh every 16 steps",
-                           "rays_per_view": 4096, "samples_last_step": trainer.last_M, "l2": "per-step working set (UNet weights 1.7 GB + activations) exceeds the 126 MB L2",
+                           "rays_per_view": hw * hw, "samples_last_step": trainer.last_M, "l2": "per-step working set (UNet weights 1.7 GB + activations) exceeds the 126 MB L2",
                            "parallelism": f"dp{world}" + (" (one view per GPU for the UNet/VAE; every GPU renders 1/N of the rays of every view, pixels and pixel "
                                                          "gradients exchanged by all-to-all; one gradient all-reduce)" if world > 1 else "")},
                 "e2e": {"value": e2e_v, "unit": "steps/s", "h2d_bytes_per_step": 64 * (world if trainer.ray_parallel else 1), "d2h_bytes_per_step": 4,
                         "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": int(round(launches_per_step * args.steps)),
-                "roofline": roof, "roofline_field": fld, "cpu_baseline": cpu, "clocks": sampler.summary()}
+                "roofline": fld, "roofline_gemm": roof_gemm, "reference_cuda": refc, "cpu_baseline": cpu, "clocks": sampler.summary()}
         if stages is not None:
             line["stages"] = stages
         print(json.dumps(line), flush=True)
@@ -380,8 +433,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-cuda"],
                     help="reference = the reference's CPU path (driver contract); reference-cuda = arm (A) of SURVEY.md §8d: the reference's own "
-                         "CUDA extensions + PyTorch fp16 UNet/VAE on this GPU (oracle/ref_cuda_path.py)")
+                         "unmodified Python + CUDA extensions + PyTorch fp16 UNet/VAE on this GPU (oracle/ref_harness.py)")
+    ap.add_argument("--config", default="C2", choices=sorted(CONFIGS), help="BASELINE.json config: C2 = 64x64 (the metric's), C3 = 128x128")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ref-cuda", action="store_true", help="skip the same-GPU reference arm (vs_baseline stays null)")
     ap.add_argument("--breakdown", action="store_true", help="add per-stage CUDA-event times of one step per shading mode ('stages')")
     args = ap.parse_args()
     if args.impl == "reference":

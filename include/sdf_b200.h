@@ -83,6 +83,19 @@ int sdf_composite_rays(uint32_t n_alive, uint32_t n_step, float T_thresh, int bi
                        const float* sigmas, const float* rgbs, const float* ts, float* weights_sum, float* depth, float* image,
                        void* stream);
 
+/* The same loop (nerf/renderer.py:759-794) with its bookkeeping on the device: `state` is 32 bytes of device memory holding
+ * (n_alive, n_step = clamp(N / n_alive, 1, 8), M = n_alive * n_step, step, ...); every call is launched with capacity N and reads the
+ * counts itself; &state[2] (int32 M) is the m_dev of sdf_field_forward.  sdf_infer_compact replaces `rays_alive[rays_alive >= 0]`
+ * (a host sync + three PyTorch kernels) and advances the state; host_alive (optional, pinned int32) mirrors n_alive for polling. */
+int sdf_infer_begin(void* state, uint32_t N, uint32_t max_steps, int* rays_alive, float* rays_t, const float* nears,
+                    float* weights_sum, float* depth, float* image, int* host_alive, void* stream);
+int sdf_infer_march(const void* state, uint32_t N, const int* rays_alive, const float* rays_t, const float* rays_o, const float* rays_d,
+                    float bound, int contract, float dt_gamma, uint32_t max_steps, uint32_t C, uint32_t H, const uint8_t* grid,
+                    const float* fars, float* xyzs, float* dirs, float* ts, const float* noises /* may be NULL */, void* stream);
+int sdf_infer_composite(const void* state, uint32_t N, float T_thresh, int binarize, int* rays_alive, float* rays_t, const float* sigmas,
+                        const float* rgbs, const float* ts, float* weights_sum, float* depth, float* image, void* stream);
+int sdf_infer_compact(void* state, uint32_t N, const int* rays_in, int* rays_out, int* host_alive, void* stream);
+
 /* ------------------------------------------------------------------ gridencoder
  * replaces gridencoder/src/gridencoder.h:12-16 (pybind: gridencoder/src/bindings.cpp:5-10).
  * dtype: 0 = fp32 table/outputs/grads, 1 = fp16.  inputs are fp32 in [0,1].
@@ -202,13 +215,57 @@ int sdf_sds_grad(const void* eps, int lde, const float* noise, const int* t, con
 
 /* ------------------------------------------------------------------ fused Adan + GradScaler protocol
  * replaces optimizer.py:102-258 (Adan.step, _single_tensor_adan) and the unscale / inf-check / skip of nerf/utils.py:1063-1067.
- * Per optimiser step: sdf_adan_begin(acc) ; sdf_adan_grad_norm(grad_i, ...) for every tensor ; sdf_adan_step(...) for every tensor.
+ * Per optimiser step: sdf_adan_begin(acc) ; sdf_adan_grad_norm(grad_i, ...) for every tensor ; sdf_adan_advance ; sdf_adan_step(...) for every tensor.
  * acc: device float[2] = (sum of squared unscaled gradients, non-finite flag).  Nothing is read back to the host. */
 int sdf_adan_begin(float* acc, void* stream);
 int sdf_adan_grad_norm(const float* grad, long long n, float inv_scale, float* acc, void* stream);
+/* steps[0..n_groups) += 1 unless acc flags non-finite gradients: a skipped step advances neither the bias corrections nor the
+ * first-step initialisation of neg_pre_grad (GradScaler.step does not call optimizer.step, nerf/utils.py:1066) */
+int sdf_adan_advance(const float* acc, int* steps, int n_groups, void* stream);
+/* step: 1-based executed-step count, read from the device word step_dev when that is not NULL.  param_half (optional): fp16 mirror of
+ * the updated parameter.  ema (optional): shadow -= ema_one_minus_decay * (shadow - param_new) (torch_ema, nerf/utils.py:282-283).
+ * zero_grad: clear grad after use — also on a skipped (non-finite) step, as optimizer.zero_grad() runs every iteration (nerf/utils.py:1043). */
 int sdf_adan_step(float* param, float* grad, float* exp_avg, float* exp_avg_diff, float* exp_avg_sq, float* neg_pre_grad, long long n,
-                  float beta1, float beta2, float beta3, int step, float lr, float weight_decay, float eps, float max_grad_norm,
-                  int no_prox, float inv_scale, const float* acc, void* param_half /* may be NULL */, int zero_grad, void* stream);
+                  float beta1, float beta2, float beta3, int step, const int* step_dev, float lr, float weight_decay, float eps,
+                  float max_grad_norm, int no_prox, float inv_scale, const float* acc, void* param_half /* may be NULL */,
+                  float* ema /* may be NULL */, float ema_one_minus_decay, int zero_grad, void* stream);
+/* torch_ema.ExponentialMovingAverage.update for one tensor (nerf/utils.py:1090-1091, once per epoch) */
+int sdf_ema_update(float* shadow, const float* param, long long n, float one_minus_decay, void* stream);
+
+/* ------------------------------------------------------------------ training-render glue (csrc/render_aux.cu)
+ * The host-side arithmetic of nerf/renderer.py:run_cuda / nerf/utils.py:train_step that is neither an extension op nor the field:
+ * replaces eager PyTorch launches of the reference, so that one SDS step has no host synchronisation (see sdf_b200/render.py). */
+
+/* background colour + mix + layout: bg = sigmoid(bg_net(freq_encode(rays_d, 6))) (nerf/network_grid.py:141-147) or the constant bg_const[3]
+ * when w1 == NULL; image = image_c + (1 - weights_sum) * bg (nerf/renderer.py:796-808); pred (optional) = [B, C, HW] planar copy, channel 3
+ * = weights_sum (latent mode, nerf/utils.py:545-549).  half_round: round where fp16 autocast rounds.  bg [N,3] is kept for the backward. */
+int sdf_background_forward(const float* rays_d, uint32_t N, const float* w1, const float* b1, const float* w2, const float* b2,
+                           const float* bg_const, int half_round, const float* image_c, const float* weights_sum,
+                           float* bg /* may be NULL */, float* image /* may be NULL */, float* pred /* may be NULL */, uint32_t HW, uint32_t C, void* stream);
+/* g_image [N,3] and/or g_pred [B,C,HW] -> g_image_c [N,3], g_weights_sum [N]; bg_net gradients ACCUMULATED into gw1 [32,39] gb1 [32] gw2 [3,32] gb2 [3] */
+int sdf_background_backward(const float* g_image /* may be NULL */, const float* g_pred /* may be NULL */, uint32_t HW, uint32_t C,
+                            const float* rays_d, uint32_t N, const float* w1, const float* b1, const float* w2, const float* b2,
+                            const float* bg_const, int half_round, const float* weights_sum, float* g_image_c, float* g_weights_sum,
+                            float* gw1, float* gb1, float* gw2, float* gb2, void* stream);
+/* out[0] = mean_m entropy(clamp(weights, 1e-5, 1 - 1e-5)) (nerf/utils.py:690-694); out[1] = mean_m weights * max(normal . normalize(dir), 0)^2
+ * (nerf/renderer.py:741-743; 0 when normals == NULL); the mean runs over the live sample count *m_dev (<= M_cap).  scratch: 3 words. */
+int sdf_render_regularizers_forward(const float* weights, const float* normals /* may be NULL */, const float* dirs, const int* m_dev,
+                                    uint32_t M_cap, float* scratch, float* out, void* stream);
+/* g_out: device float[2] = d loss / d out[0], d loss / d out[1] (each further scaled by its lambda); writes g_weights [M], g_normals [M,3] (weights detached there) */
+int sdf_render_regularizers_backward(const float* g_out, float lambda_entropy, float lambda_orient, const float* weights,
+                                     const float* normals /* may be NULL */, const float* dirs, const int* m_dev, uint32_t M_cap,
+                                     float* g_weights, float* g_normals /* may be NULL */, void* stream);
+/* occupancy refresh (nerf/renderer.py:1103-1149) without host round trips: jittered cell points in Morton order (noise uniform [0,1) [n,3]),
+ * decayed max-update with running (sum, count) of valid cells in acc[2], bit packing against min(acc[0]/acc[1], density_thresh) read on the device */
+int sdf_occupancy_points(const float* noise, uint32_t n, uint32_t grid_size, float bound_cas, float* xyzs, void* stream);
+int sdf_occupancy_update(float* grid, const float* sigmas, uint32_t n, float decay, float* acc, void* stream);
+int sdf_packbits_mean(const float* grid, uint32_t N, const float* acc, float density_thresh, uint8_t* bitfield, float* mean_out /* may be NULL */,
+                      void* stream);
+/* per-ray 3-vectors -> per-sample rows through rays[N,2] = (offset, count): what `light_d[flatten_rays]` does in nerf/renderer.py:735-737 */
+int sdf_expand_ray_vec3(const float* values, const int* rays, uint32_t N, uint32_t cap, float* out, void* stream);
+/* pinhole rays (nerf/utils.py:113-176, N = -1) of pixels first, first + stride, ... of each of the B poses [B,4,4] */
+int sdf_get_rays(const float* poses, uint32_t B, uint32_t H, uint32_t W, float focal, float cx, float cy, uint32_t first, uint32_t stride,
+                 float* rays_o, float* rays_d, void* stream);
 
 #ifdef __cplusplus
 }

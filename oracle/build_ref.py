@@ -15,7 +15,14 @@ Flags follow the reference's own backend.py (raymarching/backend.py:6-12) with
 one forced change: -std=c++14 -> -std=c++17 (torch 2.11 headers do not compile
 as c++14).  Arch: compute_100a/sm_100a.
 
-Usage:  python oracle/build_ref.py [name ...]      (default: all four)
+The reference's own Python for the path (nerf/renderer.py, nerf/network_grid.py, nerf/utils.py Trainer, nerf/provider.py,
+encoding.py, activation.py, optimizer.py, main.py and the four operator wrapper packages) is byte-compiled — again from the
+unmodified sources where they lie — into sourceless .pyc trees:
+  oracle/_ref/refpy/      nerf/, encoding, activation, optimizer, main       (the host code that must run UNCHANGED on the drop-in ops)
+  oracle/_ref/refpy_ops/  raymarching/, gridencoder/, freqencoder/, shencoder/ wrappers (bind to oracle/_ref/_*.so: the all-reference arm)
+No reference source text enters the repository; the .pyc files are build outputs like the .so files.
+
+Usage:  python oracle/build_ref.py [name ...]      (default: all four + the .pyc trees)
 The outputs are git-ignored but travel to the GPU box with gpurun.
 """
 import os
@@ -61,12 +68,36 @@ def build_one(name):
     print("built", os.path.join(OUT, name + ".so"), flush=True)
 
 
+PY_CORE = ["activation.py", "encoding.py", "optimizer.py", "main.py", "nerf/utils.py", "nerf/renderer.py", "nerf/network_grid.py",
+           "nerf/provider.py"]
+PY_OPS = ["raymarching/__init__.py", "raymarching/raymarching.py", "gridencoder/__init__.py", "gridencoder/grid.py",
+          "freqencoder/__init__.py", "freqencoder/freq.py", "shencoder/__init__.py", "shencoder/sphere_harmonics.py"]
+
+
+def build_refpy():
+    """byte-compile the reference's host Python (unmodified, in place) into sourceless .pyc trees under oracle/_ref/"""
+    import py_compile
+    n = 0
+    for sub, files in (("refpy", PY_CORE), ("refpy_ops", PY_OPS)):
+        for rel in files:
+            src = os.path.join(REF, rel)
+            dst = os.path.join(OUT, sub, rel + "c")
+            if os.path.exists(dst) and os.path.getmtime(dst) >= os.path.getmtime(src) and not os.environ.get("SDF_REF_REBUILD"):
+                continue
+            os.makedirs(os.path.dirname(dst), exist_ok=True)
+            py_compile.compile(src, cfile=dst, dfile=rel, doraise=True, invalidation_mode=py_compile.PycInvalidationMode.UNCHECKED_HASH)
+            n += 1
+    print("reference python: %d file(s) byte-compiled into %s/{refpy,refpy_ops}" % (n, OUT), flush=True)
+
+
 def main(argv):
     if not os.path.isdir(REF):
         print("reference tree not present (%s): using prebuilt oracle/_ref if any" % REF)
         return 0
     os.makedirs(OUT, exist_ok=True)
     names = argv or list(EXTS)
+    if not argv:
+        build_refpy()
     for n in names:
         if os.path.exists(os.path.join(OUT, n + ".so")) and not os.environ.get("SDF_REF_REBUILD"):
             print("up to date:", n)

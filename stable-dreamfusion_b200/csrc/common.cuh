@@ -29,7 +29,8 @@ void sdf_set_error(const char* fmt, ...);
 static inline uint32_t cdiv(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
 static inline uint64_t cdiv64(uint64_t a, uint64_t b) { return (a + b - 1) / b; }
 
-constexpr int kNumSMs = 148;   // B200
+// SM count of the current device (148 on B200), queried once: grids are sized in multiples of it
+int sdf_num_sms();
 
 // ---- programmatic dependent launch (PDL).  The SD launch lists are ~950 small dependent kernels per step; with PDL the next
 // kernel's CTAs are scheduled as soon as the previous grid's CTAs have all STARTED (every kernel triggers at its first

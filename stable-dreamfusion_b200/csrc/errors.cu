@@ -13,7 +13,16 @@ void sdf_set_error(const char* fmt, ...) {
 
 SDF_API const char* sdf_last_error(void) { return g_err; }
 
-SDF_API int sdf_abi_version(void) { return 1; }
+SDF_API int sdf_abi_version(void) { return 2; }
+
+int sdf_num_sms() {
+    static const int n = [] {
+        int dev = 0, v = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+        return v;
+    }();
+    return n;
+}
 
 #include <cstdlib>
 bool sdf_pdl_enabled() {

@@ -266,7 +266,7 @@ SDF_API int sdf_flash_attention(const void* q, const void* k, const void* v, voi
 #define FLASH(DD, MM) rc = launch_flash<DD, MM>((const __half*)q, (const __half*)k, (const __half*)v, (__half*)o, B, heads, n, nkv, ldq, ldk, ldo, scale, st)
     // two query tiles per warp where the grid stays large enough to fill the GPU (the 64x64 / 32x32 self-attention layers)
     static const bool allow_mt2 = [] { const char* e = getenv("SDF_FLASH_MT2"); return !(e && e[0] == '0'); }();
-    const bool mt2 = allow_mt2 && (long long)B * heads * ((n + 127) / 128) >= 2 * kNumSMs;
+    const bool mt2 = allow_mt2 && (long long)B * heads * ((n + 127) / 128) >= 2 * sdf_num_sms();
     switch (d) {
         case 40: if (mt2) FLASH(40, 2); else FLASH(40, 1); break;
         case 80: FLASH(80, 1); break;                      // two query tiles need 255 registers at d = 80: not worth it

@@ -183,7 +183,7 @@ SDF_API int sdf_field_forward(const float* xyzs, uint32_t M, const int* m_dev, c
     const uint32_t groups = (M + 15) / 16;
     // resident CTAs per SM: 2 (128 registers; measured 1.18 ms at 432k shaded samples) or 3 (80 registers; 1.34 ms); SDF_FIELD_OCC=3 selects the latter
     static const int occ = [] { const char* e = getenv("SDF_FIELD_OCC"); return (e && e[0] == '3') ? 3 : 2; }();
-    const uint32_t blocks = min((uint32_t)(kNumSMs * occ), (groups + 7) / 8);
+    const uint32_t blocks = min((uint32_t)(sdf_num_sms() * occ), (groups + 7) / 8);
 #define LAUNCH(SH)                                                                                                   \
     do {                                                                                                             \
         if (occ == 2) k_field_forward<SH, 2><<<blocks, 256, smem, st>>>(p, xyzs, light_d, light_per_sample, ambient_ratio, M, m_dev, sigmas, colors, normals, aux); \

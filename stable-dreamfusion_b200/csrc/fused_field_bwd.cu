@@ -493,7 +493,7 @@ SDF_API int sdf_field_backward(const float* xyzs, uint32_t M, const int* m_dev, 
     do {                                                                                                                  \
         const int smem = (int)sizeof(BwdSmemT<WP>);                                                                       \
         const uint32_t n_super = (n_groups + WP - 1) / WP;                                                                \
-        const uint32_t blocks = min((uint32_t)(kNumSMs * (WP == 16 ? 1 : 2)), n_super);                                   \
+        const uint32_t blocks = min((uint32_t)(sdf_num_sms() * (WP == 16 ? 1 : 2)), n_super);                                   \
         static bool attr_set[64] = {false};                                                                               \
         int dev = 0; cudaGetDevice(&dev);                                                                                 \
         if (dev < 64 && !attr_set[dev]) {                                                                                 \

@@ -487,6 +487,131 @@ __global__ void k_composite_infer(uint32_t n_alive, uint32_t n_step, float T_thr
     image[index*3] = r; image[index*3+1] = g; image[index*3+2] = b;
 }
 
+
+// ---------------------------------------------------------------- inference loop with its bookkeeping on the device
+// nerf/renderer.py:759-794 re-reads the alive count on the host every iteration (boolean indexing = a sync + a compaction through
+// three PyTorch kernels).  Here the loop state lives in device memory: every kernel of an iteration is launched with capacity N and
+// reads (n_alive, n_step) itself; compaction is a warp-aggregated scatter whose last block advances the state.  The host only
+// enqueues and polls a pinned mirror of n_alive (never blocks on it) to stop enqueueing once the frame is done.
+struct InferState {
+    int n_alive;        // rays still marching
+    int n_step;         // samples per ray this iteration = clamp(N / n_alive, 1, 8)   (renderer.py:771)
+    int M;              // n_alive * n_step: live rows of xyzs / sigmas this iteration (the fused field's m_dev)
+    int step;           // sum of n_step so far; the loop ends at max_steps (renderer.py:763)
+    int next_alive;     // compaction cursor
+    unsigned ticket;    // blocks done in the compaction kernel
+    int N, max_steps;
+};
+
+__device__ __forceinline__ void infer_set_counts(InferState* s, int n_alive) {
+    if (s->step >= s->max_steps) n_alive = 0;
+    s->n_alive = n_alive;
+    const int n_step = n_alive > 0 ? max(min(s->N / n_alive, 8), 1) : 0;
+    s->n_step = n_step;
+    s->M = n_alive * n_step;
+}
+
+__global__ void k_infer_begin(InferState* __restrict__ st, uint32_t N, uint32_t max_steps, int* __restrict__ rays_alive,
+                              float* __restrict__ rays_t, const float* __restrict__ nears, float* __restrict__ weights_sum,
+                              float* __restrict__ depth, float* __restrict__ image, volatile int* host_alive) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n == 0) {
+        st->N = (int)N; st->max_steps = (int)max_steps; st->step = 0; st->next_alive = 0; st->ticket = 0;
+        infer_set_counts(st, (int)N);
+        if (host_alive) *host_alive = (int)N;
+    }
+    if (n >= N) return;
+    rays_alive[n] = (int)n;
+    rays_t[n] = nears[n];
+    weights_sum[n] = 0.f; depth[n] = 0.f;
+    image[n*3] = 0.f; image[n*3+1] = 0.f; image[n*3+2] = 0.f;
+}
+
+__global__ void __launch_bounds__(256) k_march_infer_dev(const InferState* __restrict__ st, const int* __restrict__ rays_alive,
+                                                         const float* __restrict__ rays_t, const float* __restrict__ rays_o,
+                                                         const float* __restrict__ rays_d, MarchParams p, const uint8_t* __restrict__ grid,
+                                                         const float* __restrict__ fars, float* __restrict__ xyzs, float* __restrict__ dirs,
+                                                         float* __restrict__ ts, const float* __restrict__ noises) {
+    const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const uint32_t n_alive = (uint32_t)st->n_alive, n_step = (uint32_t)st->n_step;
+    if (n >= n_alive) return;
+    const int index = rays_alive[n];
+    const float ox = rays_o[index*3], oy = rays_o[index*3+1], oz = rays_o[index*3+2];
+    const float dx = rays_d[index*3], dy = rays_d[index*3+1], dz = rays_d[index*3+2];
+    const float noise = noises ? noises[n] : 0.f;
+    float t = rays_t[index];
+    t = __fmaf_rn(clampf(__fmul_rn(t, p.dt_gamma), p.dt_min, p.dt_max), noise, t);
+    float* tsr = ts + (size_t)n*n_step*2;
+    const uint32_t c = march_ray_warp<true>(p, grid, ox, oy, oz, dx, dy, dz, t, fars[index], n_step,
+                                            xyzs + (size_t)n*n_step*3, dirs + (size_t)n*n_step*3, tsr);
+    // unwritten tail slots: ts[0] == 0 is the compositor's end-of-ray sentinel (the reference relies on zero-initialised buffers);
+    // their xyz must be finite for the field kernel
+    for (uint32_t s = c + lane; s < n_step; s += 32) {
+        tsr[s*2] = 0.f; tsr[s*2+1] = 0.f;
+        float* x = xyzs + ((size_t)n*n_step + s)*3;
+        x[0] = 0.f; x[1] = 0.f; x[2] = 0.f;
+    }
+}
+
+__global__ void k_composite_infer_dev(const InferState* __restrict__ st, float T_thresh, int binarize,
+                                      int* __restrict__ rays_alive, float* __restrict__ rays_t,
+                                      const float* __restrict__ sigmas, const float* __restrict__ rgbs, const float* __restrict__ ts,
+                                      float* __restrict__ weights_sum, float* __restrict__ depth, float* __restrict__ image) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t n_alive = (uint32_t)st->n_alive, n_step = (uint32_t)st->n_step;
+    if (n >= n_alive) return;
+    const int index = rays_alive[n];
+    sigmas += (size_t)n*n_step; rgbs += (size_t)n*n_step*3; ts += (size_t)n*n_step*2;
+    float t = 0.f, d = depth[index], r = image[index*3], g = image[index*3+1], b = image[index*3+2], wsum = weights_sum[index];
+    uint32_t step = 0;
+    while (step < n_step) {
+        if (ts[0] == 0.f) break;
+        const float real_alpha = 1.0f - __expf(-sigmas[0] * ts[1]);
+        const float alpha = binarize ? (real_alpha > 0.5f ? 1.0f : 0.0f) : real_alpha;
+        const float T = 1.0f - wsum;
+        const float w = alpha * T;
+        wsum += w;
+        t = ts[0];
+        d = fmaf(w, t, d); r = fmaf(w, rgbs[0], r); g = fmaf(w, rgbs[1], g); b = fmaf(w, rgbs[2], b);
+        if (T < T_thresh) break;
+        sigmas++; rgbs += 3; ts += 2; step++;
+    }
+    if (step < n_step) rays_alive[n] = -1; else rays_t[index] = t;
+    weights_sum[index] = wsum; depth[index] = d;
+    image[index*3] = r; image[index*3+1] = g; image[index*3+2] = b;
+}
+
+// rays_out <- the entries of rays_in[0 .. n_alive) that are >= 0 (order within a warp kept, warps in arrival order); the last block
+// to finish advances the loop state and mirrors the new count to pinned host memory
+__global__ void __launch_bounds__(256) k_compact_alive(InferState* __restrict__ st, const int* __restrict__ rays_in, int* __restrict__ rays_out,
+                                                       volatile int* host_alive) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
+    const uint32_t n_alive = (uint32_t)st->n_alive;
+    const int idx = n < n_alive ? rays_in[n] : -1;
+    const bool keep = idx >= 0;
+    const uint32_t m = __ballot_sync(0xffffffffu, keep);
+    if (m) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&st->next_alive, __popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (keep) rays_out[base + __popc(m & ((1u << lane) - 1u))] = idx;
+    }
+    __shared__ bool last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        last = atomicAdd(&st->ticket, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (last && threadIdx.x == 0) {
+        const int alive = atomicAdd(&st->next_alive, 0);
+        st->step += st->n_step;
+        st->next_alive = 0; st->ticket = 0;
+        infer_set_counts(st, alive);
+        if (host_alive) *host_alive = st->n_alive;
+    }
+}
+
 }  // namespace
 
 // ================================================================= C ABI
@@ -630,5 +755,46 @@ SDF_API int sdf_composite_rays(uint32_t n_alive, uint32_t n_step, float T_thresh
     k_composite_infer<<<cdiv(n_alive, 128), 128, 0, (cudaStream_t)stream>>>(n_alive, n_step, T_thresh, binarize, rays_alive, rays_t,
                                                                             sigmas, rgbs, ts, weights_sum, depth, image);
     SDF_CHECK_LAUNCH("composite_rays");
+    return SDF_OK;
+}
+
+// ---- inference loop with device-side bookkeeping (state: 8 ints of device memory; host_alive: optional pinned int32 mirror)
+SDF_API int sdf_infer_begin(void* state, uint32_t N, uint32_t max_steps, int* rays_alive, float* rays_t, const float* nears,
+                            float* weights_sum, float* depth, float* image, int* host_alive, void* stream) {
+    SDF_CHECK_ARG(state && rays_alive && rays_t && nears && weights_sum && depth && image, "infer_begin: null pointer");
+    k_infer_begin<<<cdiv(N > 0 ? N : 1, 256), 256, 0, (cudaStream_t)stream>>>((InferState*)state, N, max_steps, rays_alive, rays_t, nears, weights_sum,
+                                                                             depth, image, host_alive);
+    SDF_CHECK_LAUNCH("infer_begin");
+    return SDF_OK;
+}
+
+SDF_API int sdf_infer_march(const void* state, uint32_t N, const int* rays_alive, const float* rays_t, const float* rays_o, const float* rays_d,
+                            float bound, int contract, float dt_gamma, uint32_t max_steps, uint32_t C, uint32_t H, const uint8_t* grid,
+                            const float* fars, float* xyzs, float* dirs, float* ts, const float* noises, void* stream) {
+    if (N == 0) return SDF_OK;
+    SDF_CHECK_ARG(state && rays_alive && rays_t && rays_o && rays_d && grid && fars && xyzs && dirs && ts, "infer_march: null pointer");
+    SDF_CHECK_ARG(max_steps > 0 && H > 0 && C > 0 && (uint64_t)C * H * H * H <= (1ull << 24), "infer_march: bad max_steps/H/C");
+    const MarchParams p = make_march_params(bound, contract, dt_gamma, max_steps, C, H);
+    k_march_infer_dev<<<cdiv(N, 8), 256, 0, (cudaStream_t)stream>>>((const InferState*)state, rays_alive, rays_t, rays_o, rays_d, p, grid, fars, xyzs,
+                                                                    dirs, ts, noises);
+    SDF_CHECK_LAUNCH("infer_march");
+    return SDF_OK;
+}
+
+SDF_API int sdf_infer_composite(const void* state, uint32_t N, float T_thresh, int binarize, int* rays_alive, float* rays_t, const float* sigmas,
+                                const float* rgbs, const float* ts, float* weights_sum, float* depth, float* image, void* stream) {
+    if (N == 0) return SDF_OK;
+    SDF_CHECK_ARG(state && rays_alive && rays_t && sigmas && rgbs && ts && weights_sum && depth && image, "infer_composite: null pointer");
+    k_composite_infer_dev<<<cdiv(N, 128), 128, 0, (cudaStream_t)stream>>>((const InferState*)state, T_thresh, binarize, rays_alive, rays_t, sigmas, rgbs,
+                                                                          ts, weights_sum, depth, image);
+    SDF_CHECK_LAUNCH("infer_composite");
+    return SDF_OK;
+}
+
+SDF_API int sdf_infer_compact(void* state, uint32_t N, const int* rays_in, int* rays_out, int* host_alive, void* stream) {
+    if (N == 0) return SDF_OK;
+    SDF_CHECK_ARG(state && rays_in && rays_out && rays_in != rays_out, "infer_compact: bad arguments");
+    k_compact_alive<<<cdiv(N, 256), 256, 0, (cudaStream_t)stream>>>((InferState*)state, rays_in, rays_out, host_alive);
+    SDF_CHECK_LAUNCH("infer_compact");
     return SDF_OK;
 }

@@ -624,8 +624,8 @@ SDF_API int sdf_gemm_plan_create(const void* a, long long a_sx, long long a_sy, 
     const int tiles_x = (W + g.tw - 1) / g.tw, tiles_y = (H + g.th - 1) / g.th, tiles_i = (Nimg + g.tn - 1) / g.tn;
     const long long m_tiles = (long long)tiles_x * tiles_y * tiles_i;
     const long long work = (cta_pair ? (m_tiles + 1) / 2 : m_tiles) * ((N + block_n - 1) / block_n) * splitk;
-    if (cta_pair) p->grid = 2 * (int)std::min<long long>(work, kNumSMs / 2);
-    else p->grid = work < kNumSMs ? (int)work : kNumSMs;
+    if (cta_pair) p->grid = 2 * (int)std::min<long long>(work, sdf_num_sms() / 2);
+    else p->grid = work < sdf_num_sms() ? (int)work : sdf_num_sms();
     std::lock_guard<std::mutex> lk(g_plan_mu);
     g_plans.push_back(p);
     return (int)g_plans.size() - 1;

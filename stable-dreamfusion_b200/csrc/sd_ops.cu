@@ -640,7 +640,8 @@ __global__ void k_sds_prepare(const __half* __restrict__ moments, int ldm, const
 }
 
 // grad = grad_scale * (1 - acp_t) * (eps_u + s (eps_c - eps_u) - noise), nan_to_num; loss = 0.5 * sum(grad^2) / B;
-// d_moments (for the VAE backward): d mean = grad * vae_scale, d logvar = grad * vae_scale * eps_post * 0.5 * std (inside the clamp)
+// d_moments (for the VAE backward) = d loss / d moments with d loss / d latents = grad / B: d mean = (grad / B) * vae_scale,
+// d logvar = (grad / B) * vae_scale * eps_post * 0.5 * std (inside the clamp).  `grad` itself stays the reference's unnormalised variable.
 __global__ void k_sds_grad(const __half* __restrict__ eps, int lde, const float* __restrict__ noise, const int* __restrict__ t,
                            const float* __restrict__ acp, int Bimg, int HW, float guidance_scale, float grad_scale,
                            const __half* __restrict__ moments, int ldm, const float* __restrict__ eps_post, float vae_scale,
@@ -663,8 +664,10 @@ __global__ void k_sds_grad(const __half* __restrict__ eps, int lde, const float*
             const float lv = __half2float(moments[mi + 4 + c]);
             const bool inside = lv > -30.f && lv < 20.f;
             const float std = __expf(0.5f * fminf(fmaxf(lv, -30.f), 20.f));
-            d_moments[mi + c] = __float2half_rn(g * vae_scale);
-            d_moments[mi + 4 + c] = __float2half_rn(inside ? g * vae_scale * eps_post[nchw] * 0.5f * std : 0.f);
+            // loss = 0.5 * sum((latents - target)^2) / B  =>  d loss / d latents = grad / B  (guidance/sd_utils.py:160-161)
+            const float gb = g / (float)Bimg;
+            d_moments[mi + c] = __float2half_rn(gb * vae_scale);
+            d_moments[mi + 4 + c] = __float2half_rn(inside ? gb * vae_scale * eps_post[nchw] * 0.5f * std : 0.f);
         }
     }
     float s = warp_sum(g * g);
@@ -689,7 +692,7 @@ SDF_API int sdf_groupnorm_forward(const void* x, int ldx, void* y, int ldy, int 
     const int vpp = C / 8;
     // two passes: ~16 vectors per thread for large tensors, at least ~4 blocks per SM for small ones
     int ppb = max(1, min(HW, (256 * 16 * 8) / C));
-    const int want_blocks = 4 * kNumSMs;
+    const int want_blocks = 4 * sdf_num_sms();
     const int ppb_small = max(max(1, 256 / max(1, vpp)), (int)(((long long)HW * Nimg + want_blocks - 1) / want_blocks));
     if (ppb_small < ppb) ppb = ppb_small;
     dim3 grid((HW + ppb - 1) / ppb, Nimg);
@@ -710,7 +713,7 @@ SDF_API int sdf_groupnorm_backward(const void* x, int ldx, const void* dy, int l
     SDF_CHECK_CUDA(cudaMemsetAsync(bstats, 0, sizeof(float) * 2 * G * Nimg, st));
     int ppb = max(1, min(HW, (256 * 16 * 8) / C));
     {
-        const int vpp = C / 8, want_blocks = 4 * kNumSMs;
+        const int vpp = C / 8, want_blocks = 4 * sdf_num_sms();
         const int ppb_small = max(max(1, 256 / max(1, vpp)), (int)(((long long)HW * Nimg + want_blocks - 1) / want_blocks));
         if (ppb_small < ppb) ppb = ppb_small;
     }

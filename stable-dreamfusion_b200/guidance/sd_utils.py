@@ -133,7 +133,7 @@ class _SDSLoss(torch.autograd.Function):
     def backward(ctx, g):
         eng = ctx.sd.engine
         if ctx.as_latent:
-            d = eng.grad * 2.0
+            d = eng.grad * (2.0 / eng.grad.shape[0])          # d loss / d latents = grad / B; latents = 2 x - 1
             if tuple(d.shape[-2:]) != ctx.resize_from:
                 # adjoint of the bilinear resize through autograd on a tiny tensor (latent mode with h != 64 only)
                 with torch.enable_grad():            # backward() runs with grad mode off
@@ -147,7 +147,7 @@ class _SDSLoss(torch.autograd.Function):
 
 class StableDiffusion(nn.Module):
     def __init__(self, device, fp16=True, vram_O=False, sd_version='1.5', hf_key=None, t_range=[0.02, 0.98], weights='random',
-                 n_views=1, render_hw=64, seed=0, capture=True):
+                 n_views=1, render_hw=64, seed=0, capture=True, synthetic_text=None):
         super().__init__()
         self.device = device
         self.sd_version = sd_version
@@ -166,11 +166,19 @@ class StableDiffusion(nn.Module):
         self.max_step = int(self.num_train_timesteps * t_range[1])
         self.alphas = self.engine.acp
         self._text = None
+        self._synthetic_text = (weights == 'random') if synthetic_text is None else bool(synthetic_text)
+        self.text_encoder = None          # callable prompt list -> [n, 77, 768]; assign a CLIP text encoder when real weights are used
 
     @torch.no_grad()
     def get_text_embeds(self, prompt):
         """The CLIP text encoder is outside the SDS hot path (and its weights are not available offline): prompts map to
         deterministic pseudo-embeddings [len(prompt), 77, 768] so that the front/side/back interpolation of nerf/utils.py:597-626 works."""
+        if self.text_encoder is not None:
+            return self.text_encoder(prompt).to(self.device)
+        if not self._synthetic_text:
+            raise RuntimeError('StableDiffusion was built with real UNet/VAE weights but no text encoder: set `.text_encoder` to a callable '
+                               '(prompt list -> [n, 77, 768] CLIP embeddings) or pass precomputed embeddings to train_step; the hash-seeded '
+                               'pseudo-embeddings exist only for the synthetic-weights benchmark')
         out = []
         for p in prompt:
             h = int.from_bytes(hashlib.sha256(p.encode()).digest()[:4], 'little')

@@ -13,33 +13,38 @@ import torch.distributed as dist
 
 
 class GradBucket:
+    """Every requires_grad parameter's .grad re-homed inside ONE flat fp32 buffer, built up front over ALL parameters (zeros for
+    those that have no gradient yet): membership never depends on which parameters a particular step touched, so every rank's
+    bucket has the same layout and size whatever its schedule drew (a background net that first receives a gradient at step 40 is
+    already in it).  A gradient that something re-allocated outside the bucket is copied back in before the exchange."""
+
     def __init__(self, params):
         self.params = [p for p in params if p.requires_grad]
-        self.flat = None
-
-    def _build(self):
-        ps = [p for p in self.params if p.grad is not None]
-        dev = ps[0].device
-        self.flat = torch.zeros(sum(p.numel() for p in ps), device=dev, dtype=torch.float32)
+        dev = self.params[0].device
+        self.flat = torch.zeros(sum(p.numel() for p in self.params), device=dev, dtype=torch.float32)
+        self.views = []
         off = 0
-        for p in ps:
+        for p in self.params:
             n = p.numel()
-            view = self.flat[off:off + n].view_as(p)
-            view.copy_(p.grad)
-            p.grad = view
+            v = self.flat[off:off + n].view_as(p)
+            if p.grad is not None:
+                v.copy_(p.grad)
+            p.grad = v
+            self.views.append(v)
             off += n
-        self.members = ps
+
+    def rehome(self):
+        for p, v in zip(self.params, self.views):
+            if p.grad is None:
+                v.zero_()
+                p.grad = v
+            elif p.grad.data_ptr() != v.data_ptr():
+                v.copy_(p.grad)
+                p.grad = v
 
     def all_reduce(self):
-        """SUM over ranks, in place in every parameter's .grad (which lives inside the bucket after the first call)."""
-        if self.flat is None:
-            self._build()
-        else:
-            for p in self.members:      # a gradient that autograd re-allocated must be brought back into the bucket
-                if p.grad is not None and (p.grad.data_ptr() < self.flat.data_ptr() or p.grad.data_ptr() >= self.flat.data_ptr() + self.flat.numel() * 4):
-                    self.flat = None
-                    self._build()
-                    break
+        """SUM over ranks, in place in every parameter's .grad"""
+        self.rehome()
         dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
         return self.flat
 

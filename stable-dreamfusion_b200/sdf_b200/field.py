@@ -37,7 +37,9 @@ class _FusedField(Function):
         xyzs = _f32c(xyzs)
         M = xyzs.shape[0]
         dev = xyzs.device
-        table = half_table(embeddings) if embeddings.dtype == torch.float32 else embeddings.detach()
+        table = cfg.get('table_half')
+        if table is None:
+            table = half_table(embeddings) if embeddings.dtype == torch.float32 else embeddings.detach()
         ws = [_f32c(t) for t in (w1, b1, w2, b2, w3, b3)]
         shading = SHADING_ID[cfg['shading']]
         if light_d is None:
@@ -60,7 +62,7 @@ class _FusedField(Function):
         _lib.call('sdf_field_forward', *args, _lib.ptr(sig), _lib.ptr(col), _lib.ptr(nrm), _lib.ptr(aux), _lib.stream())
         if need_grad:
             ctx.save_for_backward(xyzs, embeddings, table, offsets, light, aux, *ws)
-            ctx.cfg = dict(cfg)
+            ctx.cfg = {k: v for k, v in cfg.items() if k != 'table_half'}
             ctx.per_sample = per_sample
             ps = (embeddings, w1, b1, w2, b2, w3, b3)
             ctx.direct_params = ps if all(isinstance(p, torch.nn.Parameter) and p.dtype == torch.float32 for p in ps) else None
@@ -98,11 +100,11 @@ class _FusedField(Function):
 
 def fused_field(xyzs, embeddings, w1, b1, w2, b2, w3, b3, offsets, light_d, *, shading='albedo', ratio=1.0, bound=1.0,
                 per_level_scale=2.0, base_resolution=16, smoothstep=True, levels_active=None, blob_density=5.0, blob_radius=0.2,
-                want_color=True):
+                want_color=True, table_half=None):
     """-> (sigma [M], color [M,3] | None, normal [M,3] | None); differentiable wrt embeddings and the six MLP tensors."""
     L = offsets.shape[0] - 1
     train = torch.is_grad_enabled() and any(t.requires_grad for t in (embeddings, w1, b1, w2, b2, w3, b3))
     cfg = dict(shading=shading, ratio=ratio, bound=bound, S=float(np.log2(per_level_scale)), H=base_resolution, smoothstep=bool(smoothstep),
                levels_active=L if levels_active is None else levels_active, blob_density=blob_density, blob_radius=blob_radius,
-               want_color=want_color, train=train)
+               want_color=want_color, train=train, table_half=table_half)
     return _FusedField.apply(xyzs, embeddings, w1, b1, w2, b2, w3, b3, offsets, light_d, cfg)

@@ -23,17 +23,23 @@ def _worker(rank, world, port, out):
     torch.manual_seed(0)
     model = torch.nn.Sequential(torch.nn.Linear(7, 5), torch.nn.ReLU(), torch.nn.Linear(5, 3))
     table = torch.nn.Parameter(torch.randn(101, 2))
-    params = [table] + list(model.parameters())
+    late = torch.nn.Parameter(torch.randn(4))          # receives its first gradient at step 1, on rank 1 only (a bg_net that a
+    params = [table] + list(model.parameters()) + [late]   # schedule draw switches on later, and not on every rank)
     bucket = GradBucket(params)
+    assert late.grad is not None and bucket.flat.numel() == sum(p.numel() for p in params)
     results = []
     for step in range(3):
         g = torch.Generator().manual_seed(100 * step + rank)          # each rank sees its own "view"
         x = torch.randn(11, 7, generator=g)
         idx = torch.randint(0, 101, (11,), generator=g)
         loss = (model(x) ** 2).sum() + (table[idx] ** 2).sum() * (rank + 1)
+        if step >= 1 and rank == 1:
+            loss = loss + (late * late).sum() * step
         for p in params:
             if p.grad is not None:
                 p.grad.zero_()
+        if step == 2:
+            model[0].weight.grad = None                                # something dropped a gradient: it must be re-homed, not lost
         loss.backward()
         flat = bucket.all_reduce()
         assert all(p.grad.data_ptr() >= flat.data_ptr() and p.grad.data_ptr() < flat.data_ptr() + flat.numel() * 4 for p in params)
@@ -56,15 +62,19 @@ def test_bucket_allreduce_equals_single_process_sum(tmp_path):
     torch.manual_seed(0)
     model = torch.nn.Sequential(torch.nn.Linear(7, 5), torch.nn.ReLU(), torch.nn.Linear(5, 3))
     table = torch.nn.Parameter(torch.randn(101, 2))
-    params = [table] + list(model.parameters())
+    late = torch.nn.Parameter(torch.randn(4))
+    params = [table] + list(model.parameters()) + [late]
     for step in range(3):
         for p in params:
-            p.grad = None
+            p.grad = torch.zeros_like(p)
         for rank in range(2):
             g = torch.Generator().manual_seed(100 * step + rank)
             x = torch.randn(11, 7, generator=g)
             idx = torch.randint(0, 101, (11,), generator=g)
-            ((model(x) ** 2).sum() + (table[idx] ** 2).sum() * (rank + 1)).backward()
+            loss = (model(x) ** 2).sum() + (table[idx] ** 2).sum() * (rank + 1)
+            if step >= 1 and rank == 1:
+                loss = loss + (late * late).sum() * step
+            loss.backward()
         for a, p in zip(got[step], params):
             assert torch.allclose(a, p.grad, atol=1e-5), (step, (a - p.grad).abs().max())
 

@@ -29,7 +29,7 @@ def test_empty_encoders_and_field(device):
     import freqencoder
     import gridencoder
     import shencoder
-    from sdf_b200.network_grid import NeRFNetwork
+    from sdf_b200.ngp import InstantNGP
     from sdf_b200.options import default_opt
     enc = gridencoder.GridEncoder(input_dim=3, num_levels=16, level_dim=2, base_resolution=16, log2_hashmap_size=19, desired_resolution=2048,
                                   gridtype='hash', align_corners=False, interpolation='smoothstep').to(device)
@@ -38,7 +38,7 @@ def test_empty_encoders_and_field(device):
         assert enc(x0, bound=1).shape == (0, 32)
     assert freqencoder.FreqEncoder(input_dim=3, degree=6).to(device)(x0).shape == (0, 39)
     assert shencoder.SHEncoder(input_dim=3, degree=4).to(device)(x0).shape == (0, 16)
-    net = NeRFNetwork(default_opt(h=8, w=8), fused=True).to(device)
+    net = InstantNGP(default_opt(h=8, w=8)).to(device)
     s, c, n = net(x0, None, torch.zeros(0, 3, device=device), ratio=0.5, shading="lambertian")
     assert s.shape == (0,) and c.shape == (0, 3)
     (s.sum() + c.sum()).backward()                      # empty backward: gradients stay zero / None, no launch error

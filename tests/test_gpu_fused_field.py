@@ -1,142 +1,130 @@
-"""GPU: the fused radiance-field kernels (csrc/fused_field{,_bwd}.cu) against the operator-by-operator graph of the
-reference's NeRFNetwork (nerf/network_grid.py:68-130) executed on the already-validated drop-in ops, under fp16 autocast
-(the -O preset) and in fp32.
+"""GPU: the fused radiance-field kernels (csrc/fused_field{,_bwd}.cu) through sdf_b200.ngp.InstantNGP — self-consistency checks that need
+no reference: (i) the analytic table / MLP gradients of the fused backward against central finite differences of the fused forward in
+float64-accumulated losses, (ii) forward invariants (albedo mode returns no normal, normals are unit or zero, colours in [0,1], outside-box
+clamping), (iii) the fp16 table mirror path equals the cast-per-call path.
 
-Tolerances (floating point; stated by the north star as 'stated fp tolerance for rendered RGB'):
-  sigma: rtol 1e-2 (fp16 logits enter an exp); colour/normal: atol 2e-2; parameter gradients: 3e-2 of the max-norm."""
+The comparisons against the reference's own NeRFNetwork (its unmodified nerf/network_grid.py on its own CUDA extensions and on the
+drop-in ops, points over the whole box, all four shading modes, forward and gradients) live in tests/test_gpu_dropin_reference.py."""
 import numpy as np
 import pytest
 import torch
 
-from sdf_b200.network_grid import NeRFNetwork
+from sdf_b200.ngp import InstantNGP
 from sdf_b200.options import default_opt
 
 pytestmark = pytest.mark.gpu
 
 
-def make_models(device, seed=0, emb_scale=0.1):
+def make_model(device, seed=0, emb_scale=0.1):
     torch.manual_seed(seed)
-    opt = default_opt()
-    fused = NeRFNetwork(opt, fused=True).to(device)
-    fused.encoder.embeddings.data.uniform_(-emb_scale, emb_scale)
-    plain = NeRFNetwork(opt, fused=False).to(device)
-    plain.load_state_dict(fused.state_dict())
-    return fused, plain
+    m = InstantNGP(default_opt()).to(device)
+    m.encoder.embeddings.data.uniform_(-emb_scale, emb_scale)
+    m.invalidate_mirror()
+    return m
 
 
-def sample_points(device, M, seed=0):
+def sample_points(device, M, seed=0, box=False):
     g = torch.Generator(device="cpu").manual_seed(seed)
-    # inside the density blob (|x| < 0.35): there the finite-difference signal dwarfs fp16 rounding of the logits,
-    # so normals are well defined in every arithmetic
-    v = torch.randn(M, 3, generator=g)
-    x = v / v.norm(dim=-1, keepdim=True) * (0.05 + 0.30 * torch.rand(M, 1, generator=g))
-    d = torch.nn.functional.normalize(torch.randn(M, 3, generator=g), dim=-1)
+    if box:
+        x = torch.rand(M, 3, generator=g) * 2 - 1
+    else:
+        v = torch.randn(M, 3, generator=g)
+        x = v / v.norm(dim=-1, keepdim=True) * (0.05 + 0.30 * torch.rand(M, 1, generator=g))
     l = torch.nn.functional.normalize(torch.randn(M, 3, generator=g), dim=-1)
-    return x.to(device), d.to(device), l.to(device)
+    return x.to(device), l.to(device)
 
 
 @pytest.mark.parametrize("shading", ["albedo", "lambertian", "textureless", "normal"])
-def test_forward_matches_operator_graph(device, shading):
-    fused, plain = make_models(device)
+def test_forward_invariants(device, shading):
+    m = make_model(device)
     M = 5000 + 7
-    x, d, l = sample_points(device, M)
+    x, l = sample_points(device, M, box=True)
+    x[-8:] = 1.0
     with torch.no_grad():
-        with torch.autocast("cuda", dtype=torch.float16):
-            s_p, c_p, n_p = plain(x, d, l, ratio=0.3, shading=shading)
-        s_f, c_f, n_f = fused(x, d, l, ratio=0.3, shading=shading)
-        s_32, c_32, n_32 = plain(x, d, l, ratio=0.3, shading=shading)       # fp32 graph
-    assert s_f.shape == (M,) and c_f.shape == (M, 3)
-    for ref_s, ref_c, ref_n, tol in ((s_p, c_p, n_p, 1.0), (s_32, c_32, n_32, 1.5)):
-        rel = ((s_f - ref_s.float()).abs() / (ref_s.float().abs() + 1e-6)).max().item()
-        assert rel < 1e-2 * tol, rel
-        assert (c_f - ref_c.float()).abs().max().item() < 2e-2 * tol
-        if shading != "albedo":
-            assert (n_f - ref_n.float()).abs().max().item() < 2e-2 * tol
+        s, c, n = m(x, None, l, ratio=0.3, shading=shading)
+    assert s.shape == (M,) and c.shape == (M, 3) and torch.isfinite(s).all() and torch.isfinite(c).all() and (s >= 0).all()
+    assert c.min().item() >= 0.0 and c.max().item() <= 1.0 + 1e-3
     if shading == "albedo":
-        assert n_f is None
+        assert n is None
+    else:
+        nn_ = n.norm(dim=-1)
+        assert ((nn_ - 1).abs() < 1e-3).logical_or(nn_ < 1e-6).all()
+        if shading == "normal":
+            assert torch.allclose(c, (n + 1) / 2, atol=1e-6)
 
 
-def test_density_and_partial_levels(device):
-    fused, plain = make_models(device, seed=1)
-    x, d, l = sample_points(device, 3000, seed=1)
-    g = torch.Generator(device="cpu").manual_seed(11)
-    x = torch.cat([x, (torch.rand(1000, 3, generator=g) * 2 - 1).to(device)])       # whole box, faces included
-    x[-16:-8] = 1.0; x[-8:] = -1.0                                                     # corners
-    for ml in (None, 0.5, 0.26):
-        fused.max_level = ml; plain.max_level = ml
-        with torch.no_grad():
-            a = fused.density(x)["sigma"]
-            with torch.autocast("cuda", dtype=torch.float16):
-                b = plain.density(x)["sigma"]
-        assert ((a - b.float()).abs() / (b.float().abs() + 1e-6)).max().item() < 1e-2
+def test_mirror_path_equals_cast_path(device):
+    m = make_model(device, seed=4)
+    x, l = sample_points(device, 3000, seed=4)
+    with torch.no_grad():
+        a = m(x, None, l, ratio=0.5, shading="lambertian")
+        from sdf_b200.optimizer import Adan
+        opt = Adan(m.get_params(1e-3))
+        m.attach_half_mirror(opt)
+        b = m(x, None, l, ratio=0.5, shading="lambertian")
+    for u, v in zip(a, b):
+        assert torch.equal(u, v)
 
 
-@pytest.mark.parametrize("shading", ["albedo", "lambertian", "textureless", "normal"])
-def test_backward_matches_operator_graph(device, shading):
-    fused, plain = make_models(device, seed=2)
-    M = 4096 + 5
-    x, d, l = sample_points(device, M, seed=2)
+@pytest.mark.parametrize("shading", ["albedo", "lambertian"])
+def test_backward_against_finite_differences_of_the_forward(device, shading):
+    """directional derivative of L = <g_sigma, sigma> + <g_color, color> along a random direction in (table, MLP) space: analytic gradient
+    of the fused backward vs a central difference of the fused forward.  The forward rounds features / logits to fp16 (it mirrors the -O
+    autocast graph), so the difference quotient uses a step large enough to dominate that rounding; agreement 5 % (albedo) / 15 % (7-point stencil)."""
+    m = make_model(device, seed=2, emb_scale=0.2)
+    M = 4096
+    x, l = sample_points(device, M, seed=2)
     g = torch.Generator(device="cpu").manual_seed(5)
     gs = (torch.randn(M, generator=g) * 0.01).to(device)
     gc = torch.randn(M, 3, generator=g).to(device)
-    gn = (torch.randn(M, 3, generator=g) * 0.1).to(device)
 
-    def run(model, autocast):
-        model.zero_grad(set_to_none=True)
-        with torch.autocast("cuda", dtype=torch.float16, enabled=autocast):
-            s, c, n = model(x, d, l, ratio=0.3, shading=shading)
-        loss = (s.float() * gs).sum() + (c.float() * gc).sum()
-        if n is not None:
-            loss = loss + (n.float() * gn).sum()
-        loss.backward()
-        out = {k: v.grad.detach().double().clone() for k, v in model.named_parameters() if v.grad is not None}
-        return out
+    def loss_of():
+        s, c, _ = m(x, None, l, ratio=0.3, shading=shading)
+        return (s.double() * gs.double()).sum() + (c.double() * gc.double()).sum()
 
-    gf = run(fused, False)
-    gp = run(plain, False)       # fp32 operator graph = the exact gradient of the same function
-    gh = run(plain, True)        # the reference's own arithmetic (fp16 autocast): defines the noise floor
-    keys = ["encoder.embeddings"] + [f"sigma_net.net.{i}.{w}" for i in range(3) for w in ("weight", "bias")]
-    for k in keys:
-        a, b, h = gf[k], gp[k], gh[k]
-        scale = b.abs().max().item() + 1e-12
-        err = (a - b).abs().max().item() / scale
-        err_ref = (h - b).abs().max().item() / scale
-        l2 = ((a - b).norm() / (b.norm() + 1e-30)).item()
-        l2_ref = ((h - b).norm() / (b.norm() + 1e-30)).item()
-        print(f"{shading:12s} {k:28s} max-err fused {err:.3e} (fp16 graph {err_ref:.3e})   rel-L2 fused {l2:.3e} (fp16 graph {l2_ref:.3e})")
-        # shaded modes difference +-eps stencil terms of magnitude 0.5/eps: the fp16 rounding of either path is amplified the same way
-        assert err < max(3e-2, 2.0 * err_ref), (k, err, err_ref)
-        assert l2 < max(3e-2, 2.0 * l2_ref), (k, l2, l2_ref)
-        assert a.abs().max().item() > 0
-    a, b = gf["encoder.embeddings"].flatten(), gp["encoder.embeddings"].flatten()
-    cos = (a @ b) / (a.norm() * b.norm())
-    assert cos.item() > 0.995, cos.item()
+    for p in m.parameters():
+        p.grad = None
+    loss_of().backward()
+    names = ["encoder.embeddings"] + [f"sigma_net.net.{i}.weight" for i in range(3)]
+    named = dict(m.named_parameters())
+    for nm in names:
+        p = named[nm]
+        assert p.grad is not None and torch.isfinite(p.grad).all() and p.grad.abs().max().item() > 0
+        torch.manual_seed(11)
+        d = torch.randn_like(p) * (p.grad != 0)              # perturb only entries the points touch
+        d = d / (d.norm() + 1e-12)
+        ana = (p.grad.double() * d.double()).sum().item()
+        eps = 2e-2 * max(p.detach().abs().max().item(), 1e-3) / d.abs().max().item()       # largest component moves by 2 % of the parameter scale
+        with torch.no_grad():
+            p.add_(eps * d)
+            m.invalidate_mirror()
+            lp = loss_of().item()
+            p.sub_(2 * eps * d)
+            lm = loss_of().item()
+            p.add_(eps * d)
+        num = (lp - lm) / (2 * eps)
+        tol = 0.05 if shading == "albedo" else 0.15
+        print(f"{shading:10s} {nm:24s} analytic {ana:+.5e} numeric {num:+.5e}")
+        assert abs(ana - num) <= tol * max(abs(ana), abs(num)) + 1e-4, (nm, ana, num)
 
 
-def test_render_step_through_renderer(device):
-    """run_cuda (training branch) end to end with the fused field: image + gradients flow into table and MLPs."""
-    from sdf_b200 import synth
-    fused, plain = make_models(device, seed=3)
-    bf = torch.from_numpy(synth.occupancy_bitfield("blob", 128, 1, 1.0, seed=0)).to(device)
-    for m in (fused, plain):
-        m.density_bitfield.copy_(bf)
-        m.train()
-    pose = synth.circle_pose(3.2, 80.0, 20.0)
-    ro, rd = synth.get_rays(pose, 32, 32, 20.0)
-    ro = torch.from_numpy(ro).to(device)[None]; rd = torch.from_numpy(rd).to(device)[None]
-    outs = []
-    for m, ac in ((fused, False), (plain, True)):
-        torch.manual_seed(0)
-        m.zero_grad(set_to_none=True)
-        with torch.autocast("cuda", dtype=torch.float16, enabled=ac):
-            res = m.render(rays_o=ro, rays_d=rd, ambient_ratio=0.4, shading="lambertian", perturb=False, bg_color=None)
-        img = res["image"]
-        (img.float() ** 2).sum().backward()
-        outs.append((img.detach().float(), res["loss_orient"].detach().float(), m.encoder.embeddings.grad.detach().clone(),
-                     m.bg_net.net[0].weight.grad.detach().clone()))
-    (i0, o0, g0, b0), (i1, o1, g1, b1) = outs
-    assert (i0 - i1).abs().max().item() < 2e-2
-    assert abs(o0.item() - o1.item()) < 2e-2 * max(1e-3, abs(o1.item())) + 1e-4
-    cos = (g0.flatten().double() @ g1.flatten().double()) / (g0.norm().double() * g1.norm().double() + 1e-30)
-    assert cos.item() > 0.99, cos.item()
-    assert (b0 - b1).abs().max().item() < 2e-2 * (b1.abs().max().item() + 1e-6) + 1e-5
+def test_density_partial_levels_zero_fill(device):
+    """max_level < 1 computes only the first ceil(max_level * L) levels (gridencoder/grid.py:42,53): evaluating with max_level must equal
+    evaluating a table whose remaining levels are zero"""
+    m = make_model(device, seed=1)
+    x, _ = sample_points(device, 4000, seed=1, box=True)
+    off = m.encoder.offsets.tolist()
+    for ml in (0.5, 0.26):
+        L = 16
+        active = max(min(int(np.ceil(ml * L)), L), 1)
+        m.max_level = ml
+        with torch.no_grad():
+            a = m.density(x)["sigma"]
+            m.max_level = None
+            saved = m.encoder.embeddings.detach().clone()
+            m.encoder.embeddings.data[off[active]:] = 0
+            m.invalidate_mirror()
+            b = m.density(x)["sigma"]
+            m.encoder.embeddings.data.copy_(saved)
+            m.invalidate_mirror()
+        assert torch.allclose(a, b, rtol=1e-6, atol=0), (ml, (a - b).abs().max().item())

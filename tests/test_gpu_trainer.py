@@ -27,6 +27,7 @@ class SmallGuidance(torch.nn.Module):
         vsd = E.random_state(S.vae_param_shapes(SMALL_VAE), device, seed=1)
         self.engine = E.SDSEngine(usd, vsd, device, SMALL_UNET, SMALL_VAE, n_views=1, render_hw=render_hw, ctx_len=77, vae_res=512, capture=True)
         self.min_step, self.max_step = 20, 980
+        self.text_encoder, self._synthetic_text = None, True
 
     def get_text_embeds(self, prompt):
         return self.S.StableDiffusion.get_text_embeds(self, prompt)
@@ -63,6 +64,43 @@ def test_schedule_default_path_and_occupancy_refresh(device):
         assert l == l
     assert tr.model.mean_density > 0
     assert int(tr.model.density_bitfield.sum()) > 0
+    # the fp16 working copy of the table is maintained by the fused Adan step
+    assert torch.equal(tr.model.table_half(), tr.model.encoder.embeddings.detach().half())
+    # EMA shadow exists and follows torch_ema's per-epoch schedule (steps_per_epoch = 100 by default: untouched after 4 steps)
+    emb = tr.model.encoder.embeddings
+    assert id(emb) in tr.optimizer.ema_shadow and tr.optimizer.ema_num_updates == 0
+
+
+def test_ema_rides_in_the_adan_pass_on_epoch_boundaries(device):
+    opt = default_opt(h=64, w=64)
+    guidance = SmallGuidance(device)
+    tr = SDSTrainer(opt, device, guidance, seed=4, steps_per_epoch=2)
+    emb = tr.model.encoder.embeddings
+    s0 = tr.optimizer.ema_shadow[id(emb)].clone()
+    tr.train_step(shading="albedo")
+    assert torch.equal(tr.optimizer.ema_shadow[id(emb)], s0)
+    tr.train_step(shading="albedo")                         # step 2 = end of epoch 1: shadow -= (1 - min(.95, 2/11)) (shadow - p)
+    d = min(0.95, 2 / 11)
+    exp = s0.double() - (1 - d) * (s0.double() - emb.detach().double())
+    assert (tr.optimizer.ema_shadow[id(emb)].double() - exp).abs().max().item() < 1e-6
+    assert tr.optimizer.ema_num_updates == 1
+
+
+def test_no_host_synchronisation_inside_a_step(device):
+    """the training step enqueues without blocking: with the GPU held busy by a long-running kernel, train_step() returns before that
+    kernel has finished (a .item() / cudaStreamSynchronize anywhere in the step would wait for it)"""
+    opt = default_opt(h=64, w=64)
+    guidance = SmallGuidance(device)
+    tr = SDSTrainer(opt, device, guidance, seed=5)
+    for _ in range(3):
+        tr.train_step(shading="lambertian")                # warm-up: allocations, graph capture, first occupancy refresh
+    torch.cuda.synchronize()
+    done = torch.cuda.Event()
+    torch.cuda._sleep(int(2e9))                             # ~1 s of GPU time ahead of the step
+    done.record()
+    tr.train_step(shading="lambertian")
+    assert not done.query(), "train_step blocked on the device"
+    torch.cuda.synchronize()
 
 
 def test_config_c3_render_size(device):

@@ -1,6 +1,6 @@
 """Inference render rate of the instant-NGP backbone (the reference's only published number is
-"~10 FPS at 800x800", readme.md:28, V100): march_rays / composite_rays loop of nerf/renderer.py:759-794 through the drop-in
-ops and the fused field kernel, random camera on the unit-sphere blob scene after a few occupancy refreshes."""
+"~10 FPS at 800x800", readme.md:28, V100): march / field / composite loop of nerf/renderer.py:759-794 with device-side bookkeeping
+(sdf_b200/render_eval.py: no host sync per iteration, on-device alive-ray compaction), random camera on the unit-sphere blob scene after a few occupancy refreshes."""
 import os
 import sys
 import time
@@ -9,16 +9,17 @@ sys.path[:0] = [ROOT, os.path.join(ROOT, "stable-dreamfusion_b200")]
 import numpy as np
 import torch
 from sdf_b200 import synth
-from sdf_b200.network_grid import NeRFNetwork
+from sdf_b200.ngp import InstantNGP
 from sdf_b200.options import default_opt
 
 H = W = int(sys.argv[1]) if len(sys.argv) > 1 else 800
 dev = torch.device("cuda:0")
 torch.manual_seed(0)
 opt = default_opt(h=64, w=64)
-m = NeRFNetwork(opt, fused=True).to(dev)
+m = InstantNGP(opt).to(dev)
 with torch.no_grad():
     m.encoder.embeddings.uniform_(-0.5, 0.5)          # "trained-like" table so that all levels matter
+m.invalidate_mirror()
 m.train()
 for _ in range(3):
     m.update_extra_state()

@@ -6,14 +6,13 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "stable-dreamfusion_b200")]
 import torch
 from sdf_b200 import field
-from sdf_b200.network_grid import NeRFNetwork
+from sdf_b200.ngp import InstantNGP
 from sdf_b200.options import default_opt
 
 M = int(sys.argv[1]) if len(sys.argv) > 1 else 432000
 dev = torch.device("cuda:0")
 torch.manual_seed(0)
-m = NeRFNetwork(default_opt(h=64, w=64), fused=True).to(dev)
-field.DIRECT_GRAD_ACCUM = True
+m = InstantNGP(default_opt(h=64, w=64)).to(dev)
 xyz = (torch.rand(M, 3, device=dev) * 2 - 1) * 0.5
 l = torch.nn.functional.normalize(torch.randn(M, 3, device=dev), dim=-1)
 for shading in (sys.argv[2:] or ["albedo", "lambertian", "normal"]):
