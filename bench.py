@@ -327,6 +327,7 @@ def run_ours(args):
         wts = [P(t) for t in (sn[0].weight, sn[0].bias, sn[1].weight, sn[1].bias, sn[2].weight, sn[2].bias)]
         fargs = (P(xyz), M, None, P(table), P(c["offsets"]), c["L"], c["levels_active"], c["S"], int(c["H"]), int(c["smoothstep"]), *wts, m.bound,
                  c["blob_density"], c["blob_radius"], 1, P(l), 1, 0.5)
+        feat = torch.empty(_lib.query("sdf_field_feat_bytes", M, 1) // 4, device=dev, dtype=torch.int32)      # forward -> backward feature stash (as in a step)
         flush = torch.empty(64 * 1024 * 1024, device=dev, dtype=torch.float32)
         st = _lib.stream()
         tf_, tb_ = [], []
@@ -334,11 +335,11 @@ def run_ours(args):
             flush.fill_(float(rep))
             e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
             e[0].record()
-            orig_call("sdf_field_forward", *fargs, P(sig), P(col), P(nrm), P(aux), st)
+            orig_call("sdf_field_forward", *fargs, P(sig), P(col), P(nrm), P(aux), P(feat), st)
             e[1].record()
             flush.fill_(float(rep) + 0.5)
             e[2].record()
-            orig_call("sdf_field_backward", *fargs, P(aux), P(gs), P(gc), None, P(gt), *[P(t) for t in gw], st)
+            orig_call("sdf_field_backward", *fargs, P(aux), P(gs), P(gc), None, P(gt), *[P(t) for t in gw], P(feat), st)
             e[3].record()
             torch.cuda.synchronize()
             if rep >= 2:

@@ -141,7 +141,9 @@ int sdf_field_forward(const float* xyzs, uint32_t M, const int* m_dev, const voi
                       const float* w3, const float* b3, float bound, float blob_density, float blob_radius,
                       int shading, const float* light_d, int light_per_sample, float ambient_ratio,
                       float* sigmas, float* colors /* may be NULL */, float* normals /* may be NULL */, float* aux /* may be NULL */,
-                      void* stream);
+                      void* feat /* may be NULL: feature stash, sdf_field_feat_bytes(M, shading) bytes */, void* stream);
+/* size of the optional feature stash (interpolated features of every stencil point, so the backward need not gather again) */
+long long sdf_field_feat_bytes(uint32_t M, int shading);
 /* backward: gradients are ACCUMULATED into grad_table [n_entries,2] fp32 and gw1 [64,32] gb1 [64] gw2 [64,64] gb2 [64] gw3 [4,64] gb3 [4]
  * (replaces 7 x {MLP autograd, gridencoder.cu:253 kernel_grid_backward} of the reference). */
 int sdf_field_backward(const float* xyzs, uint32_t M, const int* m_dev, const void* table_fp16, const int* offsets,
@@ -150,7 +152,8 @@ int sdf_field_backward(const float* xyzs, uint32_t M, const int* m_dev, const vo
                        const float* w3, const float* b3, float bound, float blob_density, float blob_radius,
                        int shading, const float* light_d, int light_per_sample, float ambient_ratio, const float* aux,
                        const float* g_sigmas /* may be NULL */, const float* g_colors /* may be NULL */, const float* g_normals /* may be NULL */,
-                       float* grad_table, float* gw1, float* gb1, float* gw2, float* gb2, float* gw3, float* gb3, void* stream);
+                       float* grad_table, float* gw1, float* gb1, float* gw2, float* gb2, float* gw3, float* gb3,
+                       const void* feat /* may be NULL: re-gather */, void* stream);
 
 /* ------------------------------------------------------------------ SD-1.5-shaped UNet / VAE encoder building blocks
  * replace the cuDNN / cuBLAS calls underneath guidance/sd_utils.py:95-108 (diffusers UNet2DConditionModel / AutoencoderKL;

@@ -474,6 +474,8 @@ def run_subprocess(spec, timeout=1800):
 COMMANDS = {"render": cmd_render, "points": cmd_points, "steps": cmd_steps, "time": cmd_time}
 
 if __name__ == "__main__":
+    if HERE in sys.path:
+        sys.path.remove(HERE)             # the script directory would make `import oracle` resolve to oracle/oracle.py instead of the package
     _spec = json.loads(sys.argv[1])
     if _spec["cmd"] == "multi":                 # several commands of ONE arm in one interpreter (torch import + CUDA init paid once)
         for _s in _spec["specs"]:

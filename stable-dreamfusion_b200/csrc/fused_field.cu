@@ -56,7 +56,8 @@ template <int SHADING, int OCC>
 __global__ void __launch_bounds__(256, OCC)
 k_field_forward(FieldParams p, const float* __restrict__ xyzs, const float* __restrict__ light_d, int light_per_sample,
                 float ratio, uint32_t M_cap, const int* __restrict__ m_dev,
-                float* __restrict__ sigmas, float* __restrict__ colors, float* __restrict__ normals, float* __restrict__ aux) {
+                float* __restrict__ sigmas, float* __restrict__ colors, float* __restrict__ normals, float* __restrict__ aux,
+                uint4* __restrict__ feat) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     WeightsSmem& s = *reinterpret_cast<WeightsSmem*>(smem_raw);
     load_weights(s, p);
@@ -90,6 +91,14 @@ k_field_forward(FieldParams p, const float* __restrict__ xyzs, const float* __re
             uint32_t a0[2][4];
             if (NP > 1) encode_rows_cached(a0, s, p, lane, ua, va, ub, vb, cache, sp == 0);
             else encode_rows(a0, s, p, lane, ua, va, ub, vb);
+            if (feat) {
+                // feature stash for the backward: the lane's A fragments (2 rows x 4 levels x 2 features, fp16) as two 16-byte stores;
+                // a warp writes 1 KB contiguous per stencil point.  Re-gathering them in the backward costs ~1 ms of scattered L1/L2
+                // traffic at 432 k samples; streaming them through HBM costs ~0.03 ms each way.
+                uint4* f = feat + ((size_t)grp * NP + sp) * 64 + lane * 2;
+                f[0] = make_uint4(a0[0][0], a0[0][1], a0[0][2], a0[0][3]);
+                f[1] = make_uint4(a0[1][0], a0[1][1], a0[1][2], a0[1][3]);
+            }
             float h[4];
             mlp_forward<false>(h, a0, s, lane, nullptr, nullptr);
             // lanes t==0: h[0],h[1] = logits 0,1 of row g ; h[2],h[3] = of row g+8.  lanes t==1: logits 2,3.
@@ -156,13 +165,14 @@ k_field_forward(FieldParams p, const float* __restrict__ xyzs, const float* __re
 // shading: 0 albedo, 1 lambertian, 2 textureless, 3 normal.  light_d: [3] (light_per_sample=0) or [M,3].
 // m_dev (optional): device int32 holding the live sample count (<= M); lets a caller that never learned M on the host
 // launch with M = capacity.  colors / normals may be NULL (density-only query).  aux (optional, [M,10] fp32) receives the
-// per-sample stash sdf_field_backward needs.
+// per-sample stash sdf_field_backward needs.  feat (optional, sdf_field_feat_bytes(M, shading) bytes, 16-byte aligned) receives the
+// interpolated hash-grid features of every stencil point so that the backward does not have to gather them again.
 SDF_API int sdf_field_forward(const float* xyzs, uint32_t M, const int* m_dev, const void* table_fp16, const int* offsets,
                               uint32_t n_levels, uint32_t n_levels_active, float per_level_scale_log2, uint32_t base_resolution,
                               int interp_smoothstep, const float* w1, const float* b1, const float* w2, const float* b2,
                               const float* w3, const float* b3, float bound, float blob_density, float blob_radius,
                               int shading, const float* light_d, int light_per_sample, float ambient_ratio,
-                              float* sigmas, float* colors, float* normals, float* aux, void* stream) {
+                              float* sigmas, float* colors, float* normals, float* aux, void* feat, void* stream) {
     if (M == 0) return SDF_OK;
     SDF_CHECK_ARG(xyzs && table_fp16 && offsets && w1 && b1 && w2 && b2 && w3 && b3 && sigmas, "field_forward: null pointer");
     SDF_CHECK_ARG(n_levels == (uint32_t)kLevels, "field_forward: this build fuses the 16-level / 2-feature grid of the -O backbone");
@@ -186,8 +196,8 @@ SDF_API int sdf_field_forward(const float* xyzs, uint32_t M, const int* m_dev, c
     const uint32_t blocks = min((uint32_t)(sdf_num_sms() * occ), (groups + 7) / 8);
 #define LAUNCH(SH)                                                                                                   \
     do {                                                                                                             \
-        if (occ == 2) k_field_forward<SH, 2><<<blocks, 256, smem, st>>>(p, xyzs, light_d, light_per_sample, ambient_ratio, M, m_dev, sigmas, colors, normals, aux); \
-        else k_field_forward<SH, 3><<<blocks, 256, smem, st>>>(p, xyzs, light_d, light_per_sample, ambient_ratio, M, m_dev, sigmas, colors, normals, aux); \
+        if (occ == 2) k_field_forward<SH, 2><<<blocks, 256, smem, st>>>(p, xyzs, light_d, light_per_sample, ambient_ratio, M, m_dev, sigmas, colors, normals, aux, (uint4*)feat); \
+        else k_field_forward<SH, 3><<<blocks, 256, smem, st>>>(p, xyzs, light_d, light_per_sample, ambient_ratio, M, m_dev, sigmas, colors, normals, aux, (uint4*)feat); \
     } while (0)
     switch (shading) {
         case 0: LAUNCH(kAlbedo); break;
@@ -198,4 +208,9 @@ SDF_API int sdf_field_forward(const float* xyzs, uint32_t M, const int* m_dev, c
 #undef LAUNCH
     SDF_CHECK_LAUNCH("field_forward");
     return SDF_OK;
+}
+
+// bytes of the optional feature stash: ceil(M / 16) groups x (1 | 7) stencil points x 1 KB
+SDF_API long long sdf_field_feat_bytes(uint32_t M, int shading) {
+    return (long long)((M + 15) / 16) * (shading == 0 ? 1 : 7) * 1024;
 }

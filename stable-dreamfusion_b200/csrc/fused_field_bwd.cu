@@ -182,7 +182,7 @@ k_field_backward(FieldParams p, const float* __restrict__ xyzs, const float* __r
                  float ratio, uint32_t M_cap, const int* __restrict__ m_dev, const float* __restrict__ aux,
                  const float* __restrict__ g_sigmas, const float* __restrict__ g_colors, const float* __restrict__ g_normals,
                  float* __restrict__ grad_table, float* __restrict__ gw1, float* __restrict__ gb1, float* __restrict__ gw2,
-                 float* __restrict__ gb2, float* __restrict__ gw3, float* __restrict__ gb3) {
+                 float* __restrict__ gb2, float* __restrict__ gw3, float* __restrict__ gb3, const uint4* __restrict__ feat) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     using Smem = BwdSmemT<WARPS>;
     constexpr int kWarps = WARPS, kRows = Smem::kRows, kTStride = Smem::kTStride;
@@ -264,7 +264,7 @@ k_field_backward(FieldParams p, const float* __restrict__ xyzs, const float* __r
         // weight-gradient products of point sp, so their latency is hidden behind tensor-core work instead of being exposed
         __half2 raw[2][16];
         CornerCache cache;       // centre-cell corner values of the two coarse level slots, reused by the +-eps stencil points
-        if (PREFETCH && warp_active) {
+        if (PREFETCH && !feat && warp_active) {
             float pa[3], pb[3], ua[3], ub[3];
             stencil_point(pa, xa, 0, p.bound);
             stencil_point(pb, xb, 0, p.bound);
@@ -302,7 +302,13 @@ k_field_backward(FieldParams p, const float* __restrict__ xyzs, const float* __r
             stencil_point(pb, xb, sp, p.bound);
             const bool va = to_unit(ua, pa, p.bound) && ina, vb = to_unit(ub, pb, p.bound) && inb;
             uint32_t a0[2][4], a1[4][4], a2[4][4];
-            if (PREFETCH) gather_finish(a0, raw, s.w, p, lane, ua, va, ub, vb);
+            if (feat) {
+                // features stashed by the forward (coalesced 2 x 16 B per lane) instead of 64 scattered gathers per lane
+                const uint4* f = feat + ((size_t)grp * NP + sp) * 64 + lane * 2;
+                const uint4 f0 = __ldg(f), f1 = __ldg(f + 1);
+                a0[0][0] = f0.x; a0[0][1] = f0.y; a0[0][2] = f0.z; a0[0][3] = f0.w;
+                a0[1][0] = f1.x; a0[1][1] = f1.y; a0[1][2] = f1.z; a0[1][3] = f1.w;
+            } else if (PREFETCH) gather_finish(a0, raw, s.w, p, lane, ua, va, ub, vb);
             else if (NP > 1) encode_rows_cached(a0, s.w, p, lane, ua, va, ub, vb, cache, sp == 0);
             else encode_rows(a0, s.w, p, lane, ua, va, ub, vb);
             float hdummy[4];
@@ -386,7 +392,7 @@ k_field_backward(FieldParams p, const float* __restrict__ xyzs, const float* __r
                     }
                 }
             }
-            if (PREFETCH && sp + 1 < NP) {      // next stencil point's gathers fly during the barrier + weight-gradient phase
+            if (PREFETCH && !feat && sp + 1 < NP) {      // next stencil point's gathers fly during the barrier + weight-gradient phase
                 float qa[3], qb[3], wa[3], wb[3];
                 stencil_point(qa, xa, sp + 1, p.bound);
                 stencil_point(qb, xb, sp + 1, p.bound);
@@ -461,6 +467,7 @@ k_field_backward(FieldParams p, const float* __restrict__ xyzs, const float* __r
 // Backward of sdf_field_forward.  Upstream gradients: g_sigmas [M] (may be NULL), g_colors [M,3] (may be NULL),
 // g_normals [M,3] (may be NULL).  aux: the [M,10] stash written by the forward.  All outputs are ACCUMULATED into
 // (caller zero-fills): grad_table fp32 [n_entries,2]; gw1 [64,32], gb1 [64], gw2 [64,64], gb2 [64], gw3 [4,64], gb3 [4].
+// feat (optional): the feature stash the forward wrote for the SAME (xyzs, M, shading); NULL = re-gather from the table.
 SDF_API int sdf_field_backward(const float* xyzs, uint32_t M, const int* m_dev, const void* table_fp16, const int* offsets,
                                uint32_t n_levels, uint32_t n_levels_active, float per_level_scale_log2, uint32_t base_resolution,
                                int interp_smoothstep, const float* w1, const float* b1, const float* w2, const float* b2,
@@ -468,7 +475,7 @@ SDF_API int sdf_field_backward(const float* xyzs, uint32_t M, const int* m_dev, 
                                int shading, const float* light_d, int light_per_sample, float ambient_ratio, const float* aux,
                                const float* g_sigmas, const float* g_colors, const float* g_normals,
                                float* grad_table, float* gw1, float* gb1, float* gw2, float* gb2, float* gw3, float* gb3,
-                               void* stream) {
+                               const void* feat, void* stream) {
     if (M == 0) return SDF_OK;
     SDF_CHECK_ARG(xyzs && table_fp16 && offsets && w1 && b1 && w2 && b2 && w3 && b3 && aux, "field_backward: null pointer");
     SDF_CHECK_ARG(grad_table && gw1 && gb1 && gw2 && gb2 && gw3 && gb3, "field_backward: null gradient output");
@@ -501,7 +508,7 @@ SDF_API int sdf_field_backward(const float* xyzs, uint32_t M, const int* m_dev, 
             attr_set[dev] = true;                                                                                         \
         }                                                                                                                 \
         k_field_backward<SH, PF, WP><<<blocks, WP * 32, smem, st>>>(p, xyzs, light_d, light_per_sample, ambient_ratio, M, m_dev, aux, \
-                                                                   g_sigmas, g_colors, g_normals, grad_table, gw1, gb1, gw2, gb2, gw3, gb3); \
+                                                                   g_sigmas, g_colors, g_normals, grad_table, gw1, gb1, gw2, gb2, gw3, gb3, (const uint4*)feat); \
     } while (0)
 #define LAUNCH(SH)                                                                           \
     do {                                                                                     \

@@ -28,9 +28,9 @@ def parse_header(path=HEADER_PATH):
     src = re.sub(r"/\*.*?\*/", " ", src, flags=re.S)
     src = re.sub(r"//[^\n]*", " ", src)
     protos = {}
-    for m in re.finditer(r"(const\s+char\s*\*|int)\s+(sdf_\w+)\s*\(([^;{]*?)\)\s*;", src, flags=re.S):
+    for m in re.finditer(r"(const\s+char\s*\*|long\s+long|int)\s+(sdf_\w+)\s*\(([^;{]*?)\)\s*;", src, flags=re.S):
         ret, name, args = m.group(1), m.group(2), m.group(3)
-        restype = C.c_char_p if "char" in ret else C.c_int
+        restype = C.c_char_p if "char" in ret else (C.c_longlong if "long" in ret else C.c_int)
         argl = []
         args = args.strip()
         if args and args != "void":
@@ -69,6 +69,10 @@ class _Lib:
         if rc != 0:
             raise RuntimeError(f"{name} failed (rc={rc}): {self.last_error()}")
 
+    def query(self, name, *args):
+        """value-returning entry points (sizes): no error protocol"""
+        return getattr(self.cdll, name)(*args)
+
 
 _LIB = None
 
@@ -82,6 +86,15 @@ def lib():
 
 def call(name, *args):
     lib().call(name, *args)
+
+
+def query(name, *args):
+    return lib().query(name, *args)
+
+
+def feat_stash_budget_bytes():
+    """largest feature stash (fused field forward -> backward) a caller may allocate; beyond it the backward re-gathers"""
+    return int(float(os.environ.get("SDF_FEAT_STASH_GB", "12")) * (1 << 30))
 
 
 def ptr(t):

@@ -59,8 +59,14 @@ class _FusedField(Function):
         args = (_lib.ptr(xyzs), M, None, _lib.ptr(table), _lib.ptr(offsets), L, int(cfg['levels_active']), float(cfg['S']), int(cfg['H']),
                 int(cfg['smoothstep']), *[_lib.ptr(t) for t in ws], float(cfg['bound']), float(cfg['blob_density']),
                 float(cfg['blob_radius']), shading, _lib.ptr(light), per_sample, float(cfg['ratio']))
-        _lib.call('sdf_field_forward', *args, _lib.ptr(sig), _lib.ptr(col), _lib.ptr(nrm), _lib.ptr(aux), _lib.stream())
+        feat = None
+        if need_grad and M > 0:
+            nbytes = _lib.query('sdf_field_feat_bytes', M, shading)
+            if nbytes <= _lib.feat_stash_budget_bytes():
+                feat = torch.empty(nbytes // 4, device=dev, dtype=torch.int32)
+        _lib.call('sdf_field_forward', *args, _lib.ptr(sig), _lib.ptr(col), _lib.ptr(nrm), _lib.ptr(aux), _lib.ptr(feat), _lib.stream())
         if need_grad:
+            ctx.feat = feat
             ctx.save_for_backward(xyzs, embeddings, table, offsets, light, aux, *ws)
             ctx.cfg = {k: v for k, v in cfg.items() if k != 'table_half'}
             ctx.per_sample = per_sample
@@ -90,7 +96,7 @@ class _FusedField(Function):
                   float(cfg['S']), int(cfg['H']), int(cfg['smoothstep']), *[_lib.ptr(t) for t in (w1, b1, w2, b2, w3, b3)],
                   float(cfg['bound']), float(cfg['blob_density']), float(cfg['blob_radius']), shading, _lib.ptr(light), ctx.per_sample,
                   float(cfg['ratio']), _lib.ptr(aux), _lib.ptr(g_sig), _lib.ptr(g_col), _lib.ptr(g_nrm), _lib.ptr(g_table),
-                  *[_lib.ptr(t) for t in gws], _lib.stream())
+                  *[_lib.ptr(t) for t in gws], _lib.ptr(ctx.feat), _lib.stream())
         if direct:
             return (None,) * 11
         if embeddings.dtype != torch.float32:

@@ -156,7 +156,7 @@ class InstantNGP(nn.Module):
             _lib.call('sdf_occupancy_points', _lib.ptr(noise), n, G, float(b), _lib.ptr(xyz), st)
             _lib.call('sdf_field_forward', _lib.ptr(xyz), n, None, _lib.ptr(table), _lib.ptr(c['offsets']), c['L'], c['levels_active'], c['S'], int(c['H']),
                       int(c['smoothstep']), *[_lib.ptr(t) for t in (sn[0].weight, sn[0].bias, sn[1].weight, sn[1].bias, sn[2].weight, sn[2].bias)],
-                      self.bound, c['blob_density'], c['blob_radius'], 0, None, 0, 1.0, _lib.ptr(sig), None, None, None, st)
+                      self.bound, c['blob_density'], c['blob_radius'], 0, None, 0, 1.0, _lib.ptr(sig), None, None, None, None, st)
             _lib.call('sdf_occupancy_update', _lib.ptr(self.density_grid[cas]), _lib.ptr(sig), n, float(decay), _lib.ptr(self._occ_acc), st)
         _lib.call('sdf_packbits_mean', _lib.ptr(self.density_grid), self.cascade * n // 8, _lib.ptr(self._occ_acc), float(self.opt.density_thresh),
                   _lib.ptr(self.density_bitfield), _lib.ptr(self._occ_acc[2:]), st)

@@ -36,6 +36,9 @@ class RenderWorkspace:
         self.xyzs, self.dirs, self.ts = f(cap, 3), f(cap, 3), f(cap, 2)
         self.sigmas, self.colors, self.normals, self.aux = f(cap), f(cap, 3), f(cap, 3), f(cap, AUX_STRIDE)
         self.weights = f(cap)
+        # feature stash of the fused field (7 x 64 B per sample): the backward streams it back instead of re-gathering the hash grid
+        nbytes = _lib.query('sdf_field_feat_bytes', cap, 1)
+        self.feat = torch.empty(nbytes // 4, device=device, dtype=torch.int32) if nbytes <= _lib.feat_stash_budget_bytes() else None
         self.weights_sum, self.depth, self.image_c, self.bg = f(N), f(N), f(N, 3), f(N, 3)
         self.light = None                      # [cap, 3], allocated on first per-sample-light use
         self.reg_scratch, self.reg_out = torch.zeros(3, device=device), torch.zeros(2, device=device)
@@ -90,7 +93,7 @@ class _RenderTrain(Function):
                  int(f['H']), int(f['smoothstep']), *[_p(t) for t in ws_list], float(m['bound']), float(f['blob_density']), float(f['blob_radius']),
                  shading, _p(light), per_sample, float(cfg['ratio']))
         need_n = shading != 0
-        _lib.call('sdf_field_forward', *fargs, _p(ws.sigmas), _p(ws.colors), _p(ws.normals) if need_n else None, _p(ws.aux), st)
+        _lib.call('sdf_field_forward', *fargs, _p(ws.sigmas), _p(ws.colors), _p(ws.normals) if need_n else None, _p(ws.aux), _p(ws.feat), st)
         _lib.call('sdf_composite_rays_train_forward', _p(ws.sigmas), _p(ws.colors), _p(ws.ts), _p(ws.rays), cap, N, float(cfg['T_thresh']), 0,
                   _p(ws.weights), _p(ws.weights_sum), _p(ws.depth), _p(ws.image_c), st)
         B, HW, C = cfg['B'], N // cfg['B'], cfg['C']
@@ -155,7 +158,7 @@ class _RenderTrain(Function):
                   _p(ws.g_sigmas), _p(ws.g_colors), st)
         gf = [grad_buf(p) for p in (table, w1, b1, w2, b2, w3, b3)]
         _lib.call('sdf_field_backward', *ctx.fargs, _p(ws.aux), _p(ws.g_sigmas), _p(ws.g_colors),
-                  _p(ws.g_normals) if (have_reg and ctx.want_orient) else None, *[_p(t) for t in gf], st)
+                  _p(ws.g_normals) if (have_reg and ctx.want_orient) else None, *[_p(t) for t in gf], _p(ws.feat), st)
         if direct:
             return (None,) * 16
         return (None, None, None, None, *gf, *gb, None)

@@ -69,7 +69,7 @@ def render_eval(model, rays_o, rays_d, *, light_d=None, ambient_ratio=1.0, shadi
                       p(ws.ts), p(noises) if it == 0 else None, st)
             _lib.call('sdf_field_forward', p(ws.xyzs), N, m_dev, p(table), p(c['offsets']), c['L'], c['levels_active'], c['S'], int(c['H']),
                       int(c['smoothstep']), *wts, model.bound, c['blob_density'], c['blob_radius'], sid, p(light), 0, float(ambient_ratio),
-                      p(ws.sigmas), p(ws.colors), None, None, st)
+                      p(ws.sigmas), p(ws.colors), None, None, None, st)
             _lib.call('sdf_infer_composite', p(ws.state), N, float(T_thresh), 0, p(ws.alive[cur]), p(ws.rays_t), p(ws.sigmas), p(ws.colors), p(ws.ts),
                       p(weights_sum), p(depth), p(image_c), st)
             _lib.call('sdf_infer_compact', p(ws.state), N, p(ws.alive[cur]), p(ws.alive[1 - cur]), ws.host_alive.data_ptr(), st)

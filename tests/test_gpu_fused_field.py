@@ -68,7 +68,7 @@ def test_mirror_path_equals_cast_path(device):
 
 @pytest.mark.parametrize("shading", ["albedo", "lambertian"])
 def test_backward_against_finite_differences_of_the_forward(device, shading):
-    """directional derivative of L = <g_sigma, sigma> + <g_color, color> along a random direction in (table, MLP) space: analytic gradient
+    """directional derivative of L = <g_sigma, sigma> + <g_color, color> along the gradient direction in (table, MLP) space: analytic gradient
     of the fused backward vs a central difference of the fused forward.  The forward rounds features / logits to fp16 (it mirrors the -O
     autocast graph), so the difference quotient uses a step large enough to dominate that rounding; agreement 5 % (albedo) / 15 % (7-point stencil)."""
     m = make_model(device, seed=2, emb_scale=0.2)
