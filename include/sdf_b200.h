@@ -213,7 +213,8 @@ int sdf_bilinear_backward(const void* ddst, int ldd, int H, int W, float* dsrc, 
 int sdf_sds_prepare(const void* moments, int ldm, const float* latents_in, const float* eps_post, const float* noise, const int* t,
                     const float* alphas_cumprod, int Bimg, int HW, float* latents, void* x_in, int ldx, float vae_scale, void* stream);
 int sdf_sds_grad(const void* eps, int lde, const float* noise, const int* t, const float* alphas_cumprod, int Bimg, int HW,
-                 float guidance_scale, float grad_scale, const void* moments, int ldm, const float* eps_post, float vae_scale,
+                 float guidance_scale, float grad_scale, const float* view_scale /* may be NULL: per-image factor (Zero123 angle scaling,
+                 guidance/zero123_utils.py:124-126) */, const void* moments, int ldm, const float* eps_post, float vae_scale,
                  float* grad, void* d_moments, float* loss, void* stream);
 
 /* ------------------------------------------------------------------ fused Adan + GradScaler protocol

@@ -128,6 +128,15 @@ def make_opt(**over):
     """the option namespace `main.py --text <prompt> -O` produces (tests/golden/options_O.json was written by its own argparse block)"""
     d = json.load(open(os.path.join(ROOT, "tests", "golden", "options_O.json")))
     d = d.get("opt", d)
+    # what main.py:186-254 derives from the parsed arguments for a text-only run (no --image / --image_config / --dmtet)
+    d.setdefault("images", None)
+    for k in ("ref_radii", "ref_polars", "ref_azimuths", "zero123_ws"):
+        d.setdefault(k, [])
+    d.setdefault("default_zero123_w", 1)
+    d["exp_start_iter"] = d.get("exp_start_iter") or 0
+    d["exp_end_iter"] = d.get("exp_end_iter") or d["iters"]
+    if d.get("text") is None:
+        d["text"] = "a hamburger"
     d.update(over)
     return types.SimpleNamespace(**d)
 

@@ -385,3 +385,85 @@ def sds_train_step(unet, vae, acp, text_embeddings, pred_rgb, t, noise, post_eps
     targets = (latents - grad).detach()
     loss = 0.5 * F.mse_loss(latents.float(), targets.float(), reduction="sum") / latents.shape[0]
     return loss, latents, grad
+
+
+# ----------------------------------------------------------------------------- Zero-1-to-3 SDS step (guidance/zero123_utils.py:113-231)
+UNET_ZERO123 = dict(in_channels=8, model_channels=320, out_channels=4, num_res_blocks=2, attention_resolutions=(4, 2, 1),
+                    channel_mult=(1, 2, 4, 4), num_heads=8, context_dim=768)       # zero123 config sd-objaverse-finetune-c_concat-256.yaml
+
+
+def zero123_angles(polar, azimuth, radius, ref_polars, ref_azimuths, ref_radii):
+    """zero123_utils.py:93-109,118-123: angle (degrees) between the novel view and every reference view; [B, R]"""
+    def cart(r, th, ph):
+        return torch.stack([r * torch.sin(th) * torch.cos(ph), r * torch.sin(th) * torch.sin(ph), r * torch.cos(th)], -1)
+    v1 = cart(radius + ref_radii[0], torch.deg2rad(polar + ref_polars[0]), torch.deg2rad(azimuth + ref_azimuths[0]))        # [B, 3]
+    v2 = cart(torch.tensor(ref_radii, dtype=torch.float32), torch.deg2rad(torch.tensor(ref_polars, dtype=torch.float32)),
+              torch.deg2rad(torch.tensor(ref_azimuths, dtype=torch.float32)))                                                # [R, 3]
+    v1 = v1 / v1.norm(dim=-1, keepdim=True)
+    v2 = v2 / v2.norm(dim=-1, keepdim=True)
+    return torch.rad2deg(torch.arccos(torch.clip(v1 @ v2.T, -1.0, 1.0)))
+
+
+def zero123_weights(angles, user_ws):
+    """zero123_utils.py:140-152: closeness weights per reference image; [B, R]"""
+    R = angles.shape[1]
+    if R > 1:
+        inv = 1 / angles
+        inv[inv > 100] = 100
+        inv = inv / inv.max(dim=-1, keepdim=True)[0]
+        inv[inv < 0.1] = 0
+    else:
+        inv = torch.ones(1)
+    ws = torch.tensor(user_ws, dtype=torch.float32)[None, :] * inv
+    ws = ws / ws.max(dim=-1, keepdim=True)[0]
+    ws[ws < 0.1] = 0
+    return ws
+
+
+def zero123_train_step(unet, vae, cc_w, cc_b, acp, emb, pred_rgb, polar, azimuth, radius, t, noise, post_eps, guidance_scale=3.0,
+                       as_latent=False, grad_scale=1.0, grad_scale_mode="angle"):
+    """guidance/zero123_utils.py:113-231 with the random draws passed in.  emb: dict(c_crossattn [R x [1,1,768]], c_concat [R x [1,4,h,h]],
+    ref_polars, ref_azimuths, ref_radii, zero123_ws).  polar / azimuth / radius: [B] CPU float tensors (deltas wrt the default view).
+    The LatentDiffusion wrapper (ldm/models/diffusion/ddpm.py, needs pytorch_lightning: absent) is restated: apply_model = UNet on
+    cat([x, c_concat], 1) with context c_crossattn; cc_projection = Linear(772, 768).  Returns (loss, latents, grad)."""
+    dev = pred_rgb.device
+    angles = zero123_angles(polar, azimuth, radius, emb["ref_polars"], emb["ref_azimuths"], emb["ref_radii"])
+    R = len(emb["ref_azimuths"])
+    if grad_scale_mode == "angle":
+        gs = (angles.min(dim=1)[0] / (180 / R)) * grad_scale
+    else:
+        gs = torch.ones(angles.shape[0])
+    gs = gs.to(dev)
+    lat_hw = emb["c_concat"][0].shape[-1]
+    if as_latent:
+        latents = F.interpolate(pred_rgb, (lat_hw, lat_hw), mode="bilinear", align_corners=False) * 2 - 1
+    else:
+        rgb = F.interpolate(pred_rgb, (lat_hw * 8, lat_hw * 8), mode="bilinear", align_corners=False)
+        latents = posterior_sample(vae(2 * rgb - 1), post_eps) * VAE_SCALING
+    ws = zero123_weights(angles, emb["zero123_ws"]).to(dev)
+    with torch.no_grad():
+        a = acp.to(dev)[t].view(-1, 1, 1, 1).to(latents.dtype)
+        noisy = a.sqrt() * latents + (1 - a).sqrt() * noise
+        x_in = torch.cat([noisy] * 2)
+        tt = torch.cat([t] * 2)
+        preds = []
+        for r in range(R):
+            p = polar + emb["ref_polars"][0] - emb["ref_polars"][r]
+            az = azimuth + emb["ref_azimuths"][0] - emb["ref_azimuths"][r]
+            az = torch.where(az > 180, az - 360, az)
+            rr = radius + emb["ref_radii"][0] - emb["ref_radii"][r]
+            T = torch.stack([torch.deg2rad(p), torch.sin(torch.deg2rad(-az)), torch.cos(torch.deg2rad(az)), rr], dim=-1)[:, None, :].to(dev)
+            cc = emb["c_crossattn"][r].to(dev)
+            clip_emb = F.linear(torch.cat([cc.repeat(len(T), 1, 1), T.to(cc.dtype)], dim=-1), cc_w.to(cc.dtype), cc_b.to(cc.dtype))
+            ctx = torch.cat([torch.zeros_like(clip_emb), clip_emb], dim=0)
+            c_cat = emb["c_concat"][r].to(dev)
+            cat = torch.cat([torch.zeros_like(c_cat).repeat(len(T), 1, 1, 1), c_cat.repeat(len(T), 1, 1, 1)], dim=0)
+            eps = unet(torch.cat([x_in, cat.to(x_in.dtype)], dim=1), tt, ctx.to(x_in.dtype))
+            e_u, e_c = eps.chunk(2)
+            preds.append(ws[:, r][:, None, None, None] * (e_u + guidance_scale * (e_c - e_u)))
+        noise_pred = torch.stack(preds).sum(dim=0) / ws.sum(dim=-1)[:, None, None, None]
+        w = 1 - a
+        grad = torch.nan_to_num(gs.view(-1, 1, 1, 1) * w * (noise_pred - noise))
+    targets = (latents - grad).detach()
+    loss = 0.5 * F.mse_loss(latents.float(), targets.float(), reduction="sum") / latents.shape[0]
+    return loss, latents, grad

@@ -644,7 +644,8 @@ __global__ void k_sds_prepare(const __half* __restrict__ moments, int ldm, const
 // d logvar = (grad / B) * vae_scale * eps_post * 0.5 * std (inside the clamp).  `grad` itself stays the reference's unnormalised variable.
 __global__ void k_sds_grad(const __half* __restrict__ eps, int lde, const float* __restrict__ noise, const int* __restrict__ t,
                            const float* __restrict__ acp, int Bimg, int HW, float guidance_scale, float grad_scale,
-                           const __half* __restrict__ moments, int ldm, const float* __restrict__ eps_post, float vae_scale,
+                           const float* __restrict__ view_scale, const __half* __restrict__ moments, int ldm,
+                           const float* __restrict__ eps_post, float vae_scale,
                            float* __restrict__ grad, __half* __restrict__ d_moments, float* __restrict__ loss) {
     pdl_prologue();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -655,7 +656,7 @@ __global__ void k_sds_grad(const __half* __restrict__ eps, int lde, const float*
         const float eu = __half2float(eps[((long long)img * HW + pix) * lde + c]);
         const float ec = __half2float(eps[((long long)(img + Bimg) * HW + pix) * lde + c]);
         const float e = eu + guidance_scale * (ec - eu);
-        g = grad_scale * (1.f - acp[t[img]]) * (e - noise[nchw]);
+        g = grad_scale * (view_scale ? view_scale[img] : 1.f) * (1.f - acp[t[img]]) * (e - noise[nchw]);
         if (isnan(g)) g = 0.f;
         else if (isinf(g)) g = g > 0 ? 3.4028234663852886e38f : -3.4028234663852886e38f;
         grad[nchw] = g;
@@ -855,15 +856,15 @@ SDF_API int sdf_sds_prepare(const void* moments, int ldm, const float* latents_i
 }
 // classifier-free guidance + w(t) (eps_hat - eps) + loss value + gradient wrt the VAE moments (sd_utils.py:110-131,160-161)
 SDF_API int sdf_sds_grad(const void* eps, int lde, const float* noise, const int* t, const float* alphas_cumprod, int Bimg, int HW,
-                         float guidance_scale, float grad_scale, const void* moments, int ldm, const float* eps_post, float vae_scale,
-                         float* grad, void* d_moments, float* loss, void* stream) {
+                         float guidance_scale, float grad_scale, const float* view_scale, const void* moments, int ldm, const float* eps_post,
+                         float vae_scale, float* grad, void* d_moments, float* loss, void* stream) {
     SDF_CHECK_ARG(eps && noise && t && alphas_cumprod && grad && loss, "sds_grad: null pointer");
     SDF_CHECK_ARG(!d_moments || (moments && eps_post), "sds_grad: moments / posterior noise required for d_moments");
     cudaStream_t st = (cudaStream_t)stream;
     SDF_CHECK_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), st));
     const int total = Bimg * HW * 4;
     k_sds_grad<<<(total + 255) / 256, 256, 0, st>>>((const __half*)eps, lde, noise, t, alphas_cumprod, Bimg, HW, guidance_scale, grad_scale,
-                                                    (const __half*)moments, ldm, eps_post, vae_scale, grad, (__half*)d_moments, loss);
+                                                    view_scale, (const __half*)moments, ldm, eps_post, vae_scale, grad, (__half*)d_moments, loss);
     SDF_CHECK_LAUNCH("sds_grad");
     return SDF_OK;
 }

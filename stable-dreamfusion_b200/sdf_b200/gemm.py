@@ -14,7 +14,8 @@ def pick_block_n(N):
     return 128
 
 
-NUM_SMS = 148
+import torch as _torch
+NUM_SMS = _torch.cuda.get_device_properties(0).multi_processor_count if _torch.cuda.is_available() else 148      # B200: 148
 
 # Cost model of one plan launch, fitted to tools/gemm_sweep.py on a B200 (profiles/r01_gemm_sweep.txt): the persistent kernel
 # retires one 64-deep k-block per CTA every ~0.32 us whatever the tile width (0.44 us for the 256-wide CTA-pair tile), a tile's

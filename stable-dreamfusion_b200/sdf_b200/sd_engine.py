@@ -27,7 +27,7 @@ import os
 
 from .gemm import GemmPlan, choose_config, conv_plan, linear_plan, pack_conv_weight, pick_block_n
 
-NUM_SMS = 148
+NUM_SMS = torch.cuda.get_device_properties(0).multi_processor_count if torch.cuda.is_available() else 148      # B200: 148
 USE_CTA_PAIRS = os.environ.get('SDF_GEMM_CTA_PAIRS', '1') != '0'
 FUSE_GEGLU = os.environ.get('SDF_FUSE_GEGLU', '1') != '0'                 # A/B switch: GEGLU in the projection GEMM's epilogue      # A/B switch for the cta_group::2 GEMM variant
 
@@ -840,6 +840,12 @@ class SDSEngine:
 
     def step(self, as_latent=False):
         """Consumes self.pred_rgb / self.latents_in, self.t, self.noise, self.eps_post; fills self.loss, self.grad, self.d_pred_rgb."""
+        self.encode(as_latent)
+        self.unet.runlist.run()
+        self.finish(as_latent)
+
+    def encode(self, as_latent=False):
+        """pred_rgb -> (resize, VAE encoder, posterior sample | latent resize) -> latents -> add_noise into both CFG halves of the UNet input"""
         st = _lib.stream()
         B, hw = self.nv, self.lat_hw
         u = self.unet
@@ -854,15 +860,21 @@ class SDSEngine:
             v.fwd.run()
             _lib.call('sdf_sds_prepare', _lib.ptr(v.moments), 8, None, _lib.ptr(self.eps_post), _lib.ptr(self.noise), _lib.ptr(self.t), _lib.ptr(self.acp), B,
                       hw * hw, _lib.ptr(self.latents), _lib.ptr(u.x_in), 8, VAE_SCALING, st)
-        u.runlist.run()
+
+    def finish(self, as_latent=False, view_scale=None):
+        """CFG + w(t)(eps_hat - eps) + loss on self.unet.eps, then the VAE data-gradient and the resize adjoint; view_scale: optional
+        device float [n_views] multiplying the gradient per image"""
+        st = _lib.stream()
+        B, hw = self.nv, self.lat_hw
+        u = self.unet
         if as_latent:
             _lib.call('sdf_sds_grad', _lib.ptr(u.eps), 8, _lib.ptr(self.noise), _lib.ptr(self.t), _lib.ptr(self.acp), B, hw * hw, float(self.guidance_scale),
-                      float(self.grad_scale), None, 0, None, VAE_SCALING, _lib.ptr(self.grad), None, _lib.ptr(self.loss), st)
+                      float(self.grad_scale), _lib.ptr(view_scale), None, 0, None, VAE_SCALING, _lib.ptr(self.grad), None, _lib.ptr(self.loss), st)
         else:
             v = self.vae
             _lib.call('sdf_sds_grad', _lib.ptr(u.eps), 8, _lib.ptr(self.noise), _lib.ptr(self.t), _lib.ptr(self.acp), B, hw * hw, float(self.guidance_scale),
-                      float(self.grad_scale), _lib.ptr(v.moments), 8, _lib.ptr(self.eps_post), VAE_SCALING, _lib.ptr(self.grad), _lib.ptr(v.d_moments),
-                      _lib.ptr(self.loss), st)
+                      float(self.grad_scale), _lib.ptr(view_scale), _lib.ptr(v.moments), 8, _lib.ptr(self.eps_post), VAE_SCALING, _lib.ptr(self.grad),
+                      _lib.ptr(v.d_moments), _lib.ptr(self.loss), st)
             v.bwd.run()
             _lib.call('sdf_bilinear_backward', _lib.ptr(v.d_img), 8, self.vae_res, self.vae_res, _lib.ptr(self.d_pred_rgb), B, 3, self.rhw, self.rhw, 2.0, st)
 
