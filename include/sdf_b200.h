@@ -178,6 +178,10 @@ int sdf_gemm_plan_create(const void* a, long long a_sx, long long a_sy, long lon
                          const float* bias, const void* temb, int temb_ld,
                          const void* residual, long long r_sx, long long r_sy, long long r_simg,
                          int act, float alpha, int splitk, float* workspace, int block_n, int cta_pair);
+/* let the plan's epilogue accumulate the GroupNorm(32, C) statistics of a consumer of its output (two consumers per plan): stats fp32
+ * [Nimg, 32, 2] zeroed by the caller; channel_offset = consumer channel of this product's column 0 (concatenated inputs).  Returns
+ * SDF_ERR_UNSUPPORTED for split-K / ragged-N / GEGLU plans: the caller then keeps sdf_groupnorm_forward's own statistics pass. */
+int sdf_gemm_plan_set_gn_stats(int plan, int slot, float* stats, int channels_per_group, int channel_offset);
 int sdf_gemm_run(int plan, void* stream);
 int sdf_gemm_plan_destroy(int plan);
 
@@ -186,6 +190,9 @@ int sdf_gemm_plan_destroy(int plan);
  * kept for sdf_groupnorm_backward). */
 int sdf_groupnorm_forward(const void* x, int ldx, void* y, int ldy, int Nimg, int HW, int C, int G, const float* gamma, const float* beta,
                           float eps, int silu_act, float* stats, void* stream);
+/* the normalise(+SiLU) pass alone, for statistics produced by sdf_gemm_plan_set_gn_stats */
+int sdf_groupnorm_apply(const void* x, int ldx, void* y, int ldy, int Nimg, int HW, int C, int G, const float* gamma, const float* beta,
+                        float eps, int silu_act, const float* stats, void* stream);
 int sdf_groupnorm_backward(const void* x, int ldx, const void* dy, int ldd, void* dx, int ldo, int Nimg, int HW, int C, int G,
                            const float* gamma, const float* beta, float eps, int silu_act, const float* stats, float* bstats,
                            int accumulate, void* stream);

@@ -436,6 +436,10 @@ def cmd_steps(spec):
 
     model.render = render
     trainer.train_step = train_step
+    # building the two arms consumes the global generators differently (PyTorch module initialisers vs the engine's own generator):
+    # both arms start the epoch from the same state, so the loader draws the same cameras and the Trainer the same schedule
+    from nerf.utils import seed_everything
+    seed_everything(int(spec.get("seed", 0)) + 17)
     trainer.train_one_epoch(loader, 1)
     torch.cuda.synchronize()
     for n, p in model.named_parameters():

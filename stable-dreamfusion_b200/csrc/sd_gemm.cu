@@ -52,6 +52,11 @@ struct GemmArgs {
     float* workspace;                // [M, N] fp32 when splitk > 1
     int act;
     float alpha;                     // scale applied to the accumulator before bias
+    // GroupNorm statistics of up to two CONSUMERS of this output, accumulated by the epilogue (sum and sum of squares per (image, group),
+    // fp32 atomics into [Nimg, 32, 2]): the consumer's separate statistics pass (a full re-read of the tensor) disappears
+    float* gn_stats[2];
+    int gn_cpg[2];                   // channels per group of the consumer's GroupNorm
+    int gn_coff[2];                  // channel of the consumer's tensor that this product's column 0 lands on
 };
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -160,7 +165,7 @@ struct SmemLayout {
     static_assert(kTotal <= 227 * 1024, "shared memory budget");
 };
 
-template <int BLOCK_N, bool PAIR>
+template <int BLOCK_N, bool PAIR, bool STATS>
 __global__ void __launch_bounds__(kNumThreads, 1)      // 10 warps -> 3 on one SM sub-partition -> 168 registers per thread at most
 k_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const GemmArgs g) {
     using L = SmemLayout<BLOCK_N, PAIR>;
@@ -322,10 +327,12 @@ k_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtens
             if (half < kChunks) { tmem_ld32_nowait(taddr + half * 32, va); tmem_ld_wait(); }
             auto process_chunk = [&](const uint32_t (&cur)[32], int ch) {
                 const int nbase = n0 + ch * 32;
+                float f[32];
+                bool have = false;
                 if (row_ok && nbase < g.N) {
                     if (vec_ok && nbase + 32 <= g.N) {
                         // ---- fast path: whole chunk, 16-byte aligned operands
-                        float f[32];
+                        have = true;
 #pragma unroll
                         for (int j = 0; j < 32; j++) f[j] = __uint_as_float(cur[j]) * g.alpha;
                         if (g.bias) {
@@ -378,7 +385,14 @@ k_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtens
                         }
                         uint32_t pk[16];
 #pragma unroll
-                        for (int j = 0; j < 16; j++) { const __half2 h2 = __floats2half2_rn(f[2 * j], f[2 * j + 1]); pk[j] = *reinterpret_cast<const uint32_t*>(&h2); }
+                        for (int j = 0; j < 16; j++) {
+                            const __half2 h2 = __floats2half2_rn(f[2 * j], f[2 * j + 1]);
+                            pk[j] = *reinterpret_cast<const uint32_t*>(&h2);
+                            if (STATS) {            // what the consumer will read (GroupNorm statistics below)
+                                const float2 r2 = __half22float2(h2);
+                                f[2 * j] = r2.x; f[2 * j + 1] = r2.y;
+                            }
+                        }
                         __half* o = out_row + nbase;
                         if (st32_ok) {       // two full 32-byte sectors per thread
                             asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(o), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]),
@@ -391,6 +405,7 @@ k_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtens
                         }
                         if (ch + 2 < kChunks) fetch_addends(n0 + (ch + 2) * 32);      // next chunk's addends fly during the TMEM wait
                     } else {
+                        have = false;
                         // ---- general path: split-K partial sums, ragged N, unaligned rows
 #pragma unroll
                         for (int hh = 0; hh < 2; hh++) {
@@ -418,6 +433,34 @@ k_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtens
                                     if (res_row) f[j] += __half2float(res_row[n + j]);
                                     out_row[n + j] = __float2half_rn(act_apply(f[j], g.act));
                                 }
+                            }
+                        }
+                    }
+                }
+                // ---- GroupNorm statistics for the consumer(s) of this output (plans that request it are direct, N % 32 == 0, and their
+                //      32-row quarters never straddle an image): warp-uniform control flow, rows that stored nothing contribute zeros
+                if (STATS && (g.gn_stats[0] || g.gn_stats[1]) && nbase + 32 <= g.N) {
+                    if (!have) {
+#pragma unroll
+                        for (int j = 0; j < 32; j++) f[j] = 0.f;
+                    }
+                    const uint32_t vm = __ballot_sync(0xffffffffu, have);
+                    if (vm) {
+                        const int img0 = __shfl_sync(0xffffffffu, img, __ffs(vm) - 1);
+#pragma unroll
+                        for (int slot = 0; slot < 2; slot++) {
+                            float* stp = g.gn_stats[slot];
+                            if (!stp) continue;
+                            const int cpg = g.gn_cpg[slot], c0 = g.gn_coff[slot] + nbase;
+                            int grp = c0 / cpg, lo = 0, left = (grp + 1) * cpg - c0;
+                            while (lo < 32) {
+                                const int hi = min(32, lo + left);
+                                float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+                                for (int j = 0; j < 32; j++) { const float v = (j >= lo && j < hi) ? f[j] : 0.f; s1 += v; s2 = fmaf(v, v, s2); }
+                                s1 = warp_sum(s1); s2 = warp_sum(s2);
+                                if (lane == 0) { atomicAdd(stp + ((size_t)img0 * 32 + grp) * 2, s1); atomicAdd(stp + ((size_t)img0 * 32 + grp) * 2 + 1, s2); }
+                                grp++; lo = hi; left = cpg;
                             }
                         }
                     }
@@ -498,14 +541,14 @@ struct GemmPlan {
 std::mutex g_plan_mu;
 std::vector<GemmPlan*> g_plans;
 
-template <int BN, bool PAIR>
-int launch_gemm(const GemmPlan& p, cudaStream_t st) {
+template <int BN, bool PAIR, bool STATS>
+int launch_gemm_v(const GemmPlan& p, cudaStream_t st) {
     using L = SmemLayout<BN, PAIR>;
     static bool attr_set[64] = {false};
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 64 && !attr_set[dev]) {
-        SDF_CHECK_CUDA(cudaFuncSetAttribute(k_gemm<BN, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+        SDF_CHECK_CUDA(cudaFuncSetAttribute(k_gemm<BN, PAIR, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
         attr_set[dev] = true;
     }
     // split-K plans follow their workspace memset: programmatic launch needs a kernel as stream predecessor
@@ -525,8 +568,15 @@ int launch_gemm(const GemmPlan& p, cudaStream_t st) {
         na++;
     }
     cfg.attrs = attr; cfg.numAttrs = na;
-    SDF_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k_gemm<BN, PAIR>, p.map_a, p.map_b, p.args));
+    SDF_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k_gemm<BN, PAIR, STATS>, p.map_a, p.map_b, p.args));
     return SDF_OK;
+}
+
+// the statistics-carrying epilogue is a separate instantiation: plans without a GroupNorm consumer keep the leaner one
+template <int BN, bool PAIR>
+int launch_gemm(const GemmPlan& p, cudaStream_t st) {
+    if (p.args.gn_stats[0] || p.args.gn_stats[1]) return launch_gemm_v<BN, PAIR, true>(p, st);
+    return launch_gemm_v<BN, PAIR, false>(p, st);
 }
 
 }  // namespace
@@ -595,6 +645,7 @@ SDF_API int sdf_gemm_plan_create(const void* a, long long a_sx, long long a_sy, 
     g.residual = (const __half*)residual; g.r_sx = r_sx; g.r_sy = r_sy; g.r_simg = r_simg;
     g.out = (__half*)out; g.o_sx = o_sx; g.o_sy = o_sy; g.o_simg = o_simg; g.workspace = workspace;
     g.act = act; g.alpha = alpha;
+    g.gn_stats[0] = g.gn_stats[1] = nullptr; g.gn_cpg[0] = g.gn_cpg[1] = 1; g.gn_coff[0] = g.gn_coff[1] = 0;
     p->block_n = block_n;
     p->pair = cta_pair ? 1 : 0;
 
@@ -629,6 +680,23 @@ SDF_API int sdf_gemm_plan_create(const void* a, long long a_sx, long long a_sy, 
     std::lock_guard<std::mutex> lk(g_plan_mu);
     g_plans.push_back(p);
     return (int)g_plans.size() - 1;
+}
+
+// Ask a plan's epilogue to accumulate the GroupNorm statistics of a consumer of its output: stats fp32 [Nimg, 32, 2] (sum, sum of squares;
+// zeroed by the caller before the plan runs), `channels_per_group` of the consumer's GroupNorm(32, C), `channel_offset` = the consumer's
+// channel that column 0 of this product lands on (non-zero when the output is one part of a concatenation).  Two consumers per plan.
+// Requirements (else SDF_ERR_UNSUPPORTED and the caller keeps its separate statistics pass): no split-K, N % 32 == 0, no GEGLU, 16-byte
+// aligned output rows, tiles whose 32-row quarters stay inside one image.
+SDF_API int sdf_gemm_plan_set_gn_stats(int plan, int slot, float* stats, int channels_per_group, int channel_offset) {
+    std::lock_guard<std::mutex> lk(g_plan_mu);
+    SDF_CHECK_ARG(plan >= 0 && plan < (int)g_plans.size() && g_plans[plan], "gemm_plan_set_gn_stats: bad plan handle");
+    SDF_CHECK_ARG(slot >= 0 && slot < 2 && stats && channels_per_group > 0 && channel_offset >= 0, "gemm_plan_set_gn_stats: bad arguments");
+    GemmArgs& g = g_plans[plan]->args;
+    const bool ok = g.splitk == 1 && (g.N % 32) == 0 && g.act != kActGeglu && ((g.tw * g.th) % 32) == 0 && (g.o_sx % 8) == 0 &&
+                    ((reinterpret_cast<uintptr_t>(g.out) & 15) == 0);
+    if (!ok) { sdf_set_error("gemm_plan_set_gn_stats: plan shape cannot carry statistics (split-K / ragged N / GEGLU / tile geometry)"); return SDF_ERR_UNSUPPORTED; }
+    g.gn_stats[slot] = stats; g.gn_cpg[slot] = channels_per_group; g.gn_coff[slot] = channel_offset;
+    return SDF_OK;
 }
 
 SDF_API int sdf_gemm_run(int plan, void* stream) {

@@ -680,6 +680,24 @@ __global__ void k_sds_grad(const __half* __restrict__ eps, int lde, const float*
 #define LAUNCH_1D(kernel, total, st, ...)                                                       \
     do { const long long t_ = (total); if (t_ > 0) sdf_launch_pdl(kernel, dim3((unsigned)((t_ + 255) / 256)), dim3(256), (size_t)0, st, __VA_ARGS__); } while (0)
 
+// GroupNorm(+SiLU) whose statistics were accumulated by the producing GEMM's epilogue (sdf_gemm_plan_set_gn_stats): the apply pass only
+SDF_API int sdf_groupnorm_apply(const void* x, int ldx, void* y, int ldy, int Nimg, int HW, int C, int G, const float* gamma, const float* beta,
+                                float eps, int silu_act, const float* stats, void* stream) {
+    SDF_CHECK_ARG(x && y && gamma && beta && stats, "groupnorm_apply: null pointer");
+    SDF_CHECK_ARG(C % 8 == 0 && C % G == 0 && ldx % 8 == 0 && ldy % 8 == 0, "groupnorm_apply: C %% 8, C %% G, ld %% 8 must be 0");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int vpp = C / 8;
+    int ppb = max(1, min(HW, (256 * 16 * 8) / C));
+    const int want_blocks = 4 * sdf_num_sms();
+    const int ppb_small = max(max(1, 256 / max(1, vpp)), (int)(((long long)HW * Nimg + want_blocks - 1) / want_blocks));
+    if (ppb_small < ppb) ppb = ppb_small;
+    dim3 grid((HW + ppb - 1) / ppb, Nimg);
+    if (silu_act) sdf_launch_pdl(k_gn_apply<true>, dim3(grid), dim3(256), (size_t)(0), st, (const __half*)x, ldx, (__half*)y, ldy, HW, C, G, ppb, stats, gamma, beta, eps);
+    else sdf_launch_pdl(k_gn_apply<false>, dim3(grid), dim3(256), (size_t)(0), st, (const __half*)x, ldx, (__half*)y, ldy, HW, C, G, ppb, stats, gamma, beta, eps);
+    SDF_CHECK_LAUNCH("groupnorm_apply");
+    return SDF_OK;
+}
+
 // stats: fp32 scratch [Nimg, G, 2] (sum, sum of squares), kept for the backward.
 // (A single-pass variant — rows held in registers, grid-wide arrival counter between the statistics and the normalisation —
 // was measured 2-4x SLOWER than these two passes on B200: 60 us vs 14 us at 2x4096x320; the spin on a contended L2 line costs

@@ -91,6 +91,19 @@ class GemmPlan:
         if h < 0:
             raise RuntimeError(f"sdf_gemm_plan_create failed ({h}): {_lib.lib().last_error()}")
         self.handle = h
+        self.gn_slots = 0
+        self._stats_ok = (splitk == 1 and N % 32 == 0 and act != 'geglu' and all(int(v) % 8 == 0 for v in o_strides))
+
+    def can_carry_stats(self):
+        """may this plan's epilogue accumulate one more consumer's GroupNorm statistics? (csrc/sd_gemm.cu: sdf_gemm_plan_set_gn_stats)"""
+        return self._stats_ok and self.gn_slots < 2
+
+    def add_gn_stats(self, stats, channels_per_group, channel_offset):
+        rc = _lib.lib().cdll.sdf_gemm_plan_set_gn_stats(self.handle, self.gn_slots, _lib.ptr(stats), int(channels_per_group), int(channel_offset))
+        if rc != 0:
+            raise RuntimeError(f"sdf_gemm_plan_set_gn_stats failed ({rc}): {_lib.lib().last_error()}")
+        self.keep = self.keep + (stats,)
+        self.gn_slots += 1
 
     def run(self):
         _lib.call('sdf_gemm_run', self.handle, _lib.stream())

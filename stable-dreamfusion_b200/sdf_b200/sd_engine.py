@@ -29,6 +29,7 @@ from .gemm import GemmPlan, choose_config, conv_plan, linear_plan, pack_conv_wei
 
 NUM_SMS = torch.cuda.get_device_properties(0).multi_processor_count if torch.cuda.is_available() else 148      # B200: 148
 USE_CTA_PAIRS = os.environ.get('SDF_GEMM_CTA_PAIRS', '1') != '0'
+FUSE_GN_STATS = os.environ.get('SDF_FUSE_GN_STATS', '1') != '0'           # A/B switch: GroupNorm statistics in the producing GEMM's epilogue
 FUSE_GEGLU = os.environ.get('SDF_FUSE_GEGLU', '1') != '0'                 # A/B switch: GEGLU in the projection GEMM's epilogue      # A/B switch for the cta_group::2 GEMM variant
 
 
@@ -111,6 +112,48 @@ class Builder:
         self.flops = 0.0
         self.flops_attn = 0.0
         self.bytes_act = 0
+        # which GEMM plan last wrote which channel range of which tensor (GroupNorm statistics ride in that plan's epilogue)
+        self.producers = {}
+        self.gn_arena = None             # fp32 arena of all epilogue-accumulated statistics, zeroed by the first op of the list
+        self.gn_used = 0
+        self.gn_fused = 0
+
+    # ---- producer tracking for the GroupNorm-statistics fusion
+    def _touch(self, view, plan=None, N=None, geom=None):
+        """record `plan` as the writer of channels [off, off+N) of view.t (or forget the range when a non-GEMM kernel writes it)"""
+        key = view.t.data_ptr()
+        lo, hi = view.off, view.off + (view.C if N is None else N)
+        ent = [e for e in self.producers.get(key, []) if e['hi'] <= lo or e['lo'] >= hi]
+        if plan is not None:
+            ent.append(dict(lo=lo, hi=hi, plan=plan, geom=geom))
+        self.producers[key] = ent
+
+    def _gn_stats_from_producers(self, x):
+        """-> stats tensor filled by the epilogues of the plans that wrote x, or None when x is not completely covered by such plans"""
+        if not FUSE_GN_STATS:
+            return None
+        ent = sorted([e for e in self.producers.get(x.t.data_ptr(), []) if e['lo'] >= x.off and e['hi'] <= x.off + x.C], key=lambda e: e['lo'])
+        pos = x.off
+        for e in ent:
+            if e['lo'] != pos or e['geom'] != (x.Nimg, x.H, x.W) or not e['plan'].can_carry_stats():
+                return None
+            pos = e['hi']
+        if pos != x.off + x.C or not ent:
+            return None
+        n = x.Nimg * 32 * 2
+        if self.gn_arena is None:
+            self.gn_arena = torch.zeros(64 * 1024, device=self.device, dtype=torch.float32)
+            arena = self.gn_arena
+            self.ops.insert(0, ('zero_gn_stats', lambda a=arena: a.zero_()))
+        if self.gn_used + n > self.gn_arena.numel():
+            return None
+        stats = self.gn_arena[self.gn_used:self.gn_used + n].view(x.Nimg, 32, 2)
+        self.gn_used += n
+        cpg = x.C // 32
+        for e in ent:
+            e['plan'].add_gn_stats(stats, cpg, e['lo'] - x.off)
+        self.gn_fused += 1
+        return stats
 
     def buf(self, Nimg, H, W, C, zero=False):
         f = torch.zeros if zero else torch.empty
@@ -158,14 +201,21 @@ class Builder:
                         r_strides=r_str, act=act, alpha=alpha, splitk=sk, block_n=bn, cta_pair=pair)
         self.flops += 2.0 * M * N * taps * c_valid
         self.add(name, plan.run)
+        if isinstance(out, View):
+            n_out = N // 2 if act == 'geglu' else N
+            self._touch(out, plan if (o_strides is None and geom is None and act != 'geglu') else None, n_out, (Nimg, H, W))
         return plan
 
     # ---- memory-bound
     def groupnorm(self, name, x, y, gamma, beta, eps, silu, stats=None):
-        stats = self.f32(x.Nimg, 32, 2) if stats is None else stats
+        fused = self._gn_stats_from_producers(x) if stats is None else None
+        stats = (self.f32(x.Nimg, 32, 2) if stats is None else stats) if fused is None else fused
         args = (x.ptr, x.ld, y.ptr, y.ld, x.Nimg, x.H * x.W, x.C, 32, _lib.ptr(gamma), _lib.ptr(beta), float(eps), int(silu), _lib.ptr(stats))
         keep = (x, y, gamma, beta, stats)
-        self.add(name, lambda a=args, k=keep: _lib.call('sdf_groupnorm_forward', *a, _lib.stream()))
+        # statistics accumulated by the producing GEMMs' epilogues: only the normalise(+SiLU) pass is left
+        fn = 'sdf_groupnorm_apply' if fused is not None else 'sdf_groupnorm_forward'
+        self.add(name + ('(apply)' if fused is not None else ''), lambda a=args, k=keep, f=fn: _lib.call(f, *a, _lib.stream()))
+        self._touch(y)
         return stats
 
     def groupnorm_bwd(self, name, x, dy, dx, gamma, beta, eps, silu, stats, accumulate):
@@ -179,6 +229,7 @@ class Builder:
         args = (x.ptr, x.ld, y.ptr, y.ld, x.rows, x.C, _lib.ptr(gamma), _lib.ptr(beta), float(eps))
         keep = (x, y, gamma, beta)
         self.add(name, lambda a=args, k=keep: _lib.call('sdf_layernorm_forward', *a, _lib.stream()))
+        self._touch(y)
 
     def softmax(self, name, s, rows, cols, ld, scale=1.0):
         args = (s.data_ptr(), s.data_ptr(), rows, cols, ld, float(scale))
@@ -189,6 +240,7 @@ class Builder:
         assert k.ld == v.ld
         self.flops_attn += 4.0 * B * heads * n * nkv * d
         self.add(name, lambda a=args, keep=(q, k, v, o): _lib.call('sdf_flash_attention', *a, _lib.stream()))
+        self._touch(o)
 
     def softmax_bwd(self, name, p, dp, ds, rows, cols, ld, scale):
         args = (p.data_ptr(), dp.data_ptr(), ds.data_ptr(), rows, cols, ld, float(scale))
@@ -197,10 +249,12 @@ class Builder:
     def geglu(self, name, x, y, inner):
         args = (x.ptr, x.ld, y.ptr, y.ld, x.rows, inner)
         self.add(name, lambda a=args, k=(x, y): _lib.call('sdf_geglu', *a, _lib.stream()))
+        self._touch(y)
 
     def upsample2(self, name, x, y):
         args = (x.ptr, x.ld, y.ptr, y.ld, x.Nimg, x.H, x.W, x.C)
         self.add(name, lambda a=args, k=(x, y): _lib.call('sdf_upsample_nearest2', *a, _lib.stream()))
+        self._touch(y)
 
     def im2col_s2(self, name, x, col, pt, pl):
         args = (x.ptr, x.ld, col.data_ptr(), x.Nimg, x.H, x.W, x.C, col.shape[1], col.shape[2], pt, pl)
@@ -209,14 +263,17 @@ class Builder:
     def col2im_s2(self, name, dcol, dx, pt, pl):
         args = (dcol.data_ptr(), dx.ptr, dx.ld, dx.Nimg, dx.H, dx.W, dx.C, dcol.shape[1], dcol.shape[2], pt, pl)
         self.add(name, lambda a=args, k=(dcol, dx): _lib.call('sdf_col2im_s2', *a, _lib.stream()))
+        self._touch(dx)
 
     def copy(self, name, x, y):
         args = (x.ptr, x.ld, y.ptr, y.ld, x.rows, x.C)
         self.add(name, lambda a=args, k=(x, y): _lib.call('sdf_copy2d', *a, _lib.stream()))
+        self._touch(y)
 
     def add2(self, name, a_, b_, y):
         args = (a_.ptr, a_.ld, b_.ptr, b_.ld, y.ptr, y.ld, y.rows, y.C)
         self.add(name, lambda a=args, k=(a_, b_, y): _lib.call('sdf_add2d', *a, _lib.stream()))
+        self._touch(y)
 
     def transpose(self, name, x_t, ldx, y_t, ldy, batch, rows, C):
         args = (x_t.data_ptr(), ldx, y_t.data_ptr(), ldy, batch, rows, C)
@@ -376,6 +433,25 @@ class UNetEngine:
             self.temb_off[p] = off
             off += c
 
+        # ---- every cross-attention's k|v projection of the (layer-independent) context as ONE product: 16 launches of M = B*ctx_len rows
+        #      (154: two row tiles each) become one with a few hundred column tiles
+        attn_prefixes = []
+        for i, layers in enumerate(inp):
+            attn_prefixes += [(f'input_blocks.{i}.{j}', l[1]) for j, l in enumerate(layers) if l[0] == 'attn']
+        attn_prefixes += [(f'middle_block.{j}', l[1]) for j, l in enumerate(mid) if l[0] == 'attn']
+        for i, (layers, _) in enumerate(out):
+            attn_prefixes += [(f'output_blocks.{i}.{j}', l[1]) for j, l in enumerate(layers) if l[0] == 'attn']
+        self.kv_off = {}
+        if attn_prefixes and os.environ.get('SDF_HOIST_CTX_KV', '1') != '0':
+            ws_, off = [], 0
+            for p_, c_ in attn_prefixes:
+                a2 = p_ + '.transformer_blocks.0.attn2'
+                ws_ += [self._lin(a2 + '.to_k.weight'), self._lin(a2 + '.to_v.weight')]
+                self.kv_off[a2] = off
+                off += 2 * c_
+            self.kv_all = View(b.buf(1, 1, B * ctx_len, off))
+            b.gemm('attn2.to_kv(all)', View(self.ctx), cfg['context_dim'], torch.cat(ws_, 0).contiguous(), off, self.kv_all)
+
         # ---- buffers for the skip concatenations: output block k reads cat_k = [h (ch) | skip (ich)]
         # spatial size of every input block's output
         sizes = []
@@ -454,6 +530,7 @@ class UNetEngine:
         b.gemm('out.2', tfin, final.C, pack_conv_weight(sd['out.2.weight'].to(device)), cfg['out_channels'], View(self.eps), taps=9,
                bias=self._f32('out.2.bias'))
         self.runlist = RunList(b.ops)
+        self.gn_fused = b.gn_fused          # GroupNorms whose statistics ride in their producers' epilogues
         self.flops = b.flops + b.flops_attn
         self.flops_gemm, self.flops_attn = b.flops, b.flops_attn
         self.sd = None          # fp32 originals are no longer needed
@@ -507,12 +584,15 @@ class UNetEngine:
             b.gemm(p + '.to_qkv', lnf, C, self._lin_cat([p + '.to_q.weight', p + '.to_k.weight', p + '.to_v.weight']), 3 * C, qkv)
             q, k, v = qkv.sub(0, C), qkv.sub(C, C), qkv.sub(2 * C, C)
         else:
-            kvf = View(kv_src.t.view(1, 1, B * nkv, kv_src.ld), kv_src.off, kv_src.C)
             q = View(b.buf(1, 1, B * n, C))
-            kv = View(b.buf(1, 1, B * nkv, 2 * C))
             b.gemm(p + '.to_q', lnf, C, self._lin(p + '.to_q.weight'), C, q)
-            b.gemm(p + '.to_kv', kvf, kv_dim, self._lin_cat([p + '.to_k.weight', p + '.to_v.weight']), 2 * C, kv)
-            k, v = kv.sub(0, C), kv.sub(C, C)
+            if p in self.kv_off:         # projected once for all layers at the top of the list
+                k, v = self.kv_all.sub(self.kv_off[p], C), self.kv_all.sub(self.kv_off[p] + C, C)
+            else:
+                kvf = View(kv_src.t.view(1, 1, B * nkv, kv_src.ld), kv_src.off, kv_src.C)
+                kv = View(b.buf(1, 1, B * nkv, 2 * C))
+                b.gemm(p + '.to_kv', kvf, kv_dim, self._lin_cat([p + '.to_k.weight', p + '.to_v.weight']), 2 * C, kv)
+                k, v = kv.sub(0, C), kv.sub(C, C)
         o = View(b.buf(1, 1, B * n, C))
         b.flash_attention(p + '.attention', q, k, v, o, B, heads, n, nkv, d)
         uf = View(u.t.view(1, 1, B * n, u.ld), u.off, u.C)
@@ -649,6 +729,7 @@ class VaeEncoderEngine:
         wq = sd['quant_conv.weight'].reshape(zc, zc)
         fb.gemm('quant_conv', co, zc, _pack_linear(wq, device), zc, View(self.moments), bias=self._f32('quant_conv.bias'))
         self.fwd = RunList(fb.ops)
+        self.gn_fused = fb.gn_fused
 
         # ---------------- backward list
         self.d_moments = bb.buf(B, x.H, x.W, 8, zero=True)

@@ -325,7 +325,7 @@ def test_product_step_matches_reference_trainer_step(steps, device, phase):
     vsd = E.random_state(vae_param_shapes(), device, seed=1)
     guidance = StableDiffusion(device, True, False, "1.5", None, [0.02, 0.98], weights={"unet": usd, "vae": vsd}, n_views=1, render_hw=64, synthetic_text=True)
     del usd, vsd
-    tr = SDSTrainer(opt, device, guidance, seed=0, ema_decay=None)
+    tr = SDSTrainer(opt, device, guidance, seed=0, ema_decay=None, prompt="x")        # options_O.json: --text x, negative ''
     z = np.load(steps["state"])
     sd = tr.model.state_dict()
     for kk in sd:
