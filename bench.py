@@ -219,6 +219,48 @@ def run_reference_cuda(args):
                       "config": {"workload": f"reference -O path on this GPU ({hw}x{hw}, 1 view/step): " + r["what"]}, "detail": r}), flush=True)
 
 
+# ------------------------------------------------------------------------------------------------ multi-GPU equivalence
+def ray_parallel_selfcheck(opt, dev, rank, world):
+    """SURVEY.md 8e: N GPUs x 1 view == 1 GPU x N views.  One ray-parallel step (every rank renders pixels rank::N of every view, all-to-all of
+    pixels / pixel gradients, ONE all-reduce of the flat gradient bucket) against a single-process render of the same N whole views on this
+    rank, same cameras / lights / weights, march jitter off, with a linear per-view loss <pred_rgb, G_view> so that the comparison isolates the
+    distributed plumbing.  Returns the relative L2 distance of the summed parameter gradients (every rank computes it)."""
+    import copy
+    import torch
+    from sdf_b200.render import render_train
+    from sdf_b200.trainer import SDSTrainer
+    o = copy.copy(opt)
+    o.lambda_entropy, o.lambda_orient, o.lambda_opacity = 0.0, 0.0, 0.0      # their means run over per-rank sample sets
+    H, W, Bv = o.h, o.w, o.batch_size
+    gen = torch.Generator(device="cpu").manual_seed(4242)
+    G_all = torch.randn(world * Bv, 3, H, W, generator=gen).to(dev)
+
+    class LinearGuidance:
+        def get_text_embeds(self, prompt):
+            return torch.zeros(len(prompt), 1, 1, device=dev)
+
+        def train_step(self, text_z, pred_rgb, as_latent=False, **kw):
+            return (pred_rgb * G_all[rank * Bv:(rank + 1) * Bv, :pred_rgb.shape[1]]).sum()
+
+    tr = SDSTrainer(o, dev, LinearGuidance(), seed=123, rank=rank, world_size=world, ema_decay=None)
+    tr.perturb = False
+    tr.optimizer.step = lambda **k: None                                      # keep the reduced gradients for inspection
+    tr.train_step(shading="lambertian")
+    dist_grad = tr.bucket.flat.clone()
+    tr.bucket.flat.zero_()
+    L = tr._last_shared
+    rays_o, rays_d = tr._rays(L["poses"], L["fov"])
+    light = L["light"].repeat_interleave(H * W, dim=0)
+    out = render_train(tr.model, rays_o, rays_d, light_d=light, ambient_ratio=L["ambient"], shading=L["mode"], bg_color=L["bg_color"], perturb=False,
+                       as_latent=False, B=world * Bv, H=H, W=W, direct_grads=True)
+    (out["pred_rgb"] * G_all).sum().backward()
+    single = tr.bucket.flat
+    rel = float(((dist_grad - single).norm() / (single.norm() + 1e-30)).item())
+    cos = float((dist_grad @ single / (dist_grad.norm() * single.norm() + 1e-30)).item())
+    return {"table_and_mlp_grad_rel_l2": rel, "cosine": cos, "grad_norm": float(single.norm().item()),
+            "what": f"{world}-rank ray-parallel step (all-to-all pixels + one bucket all-reduce) vs one rank rendering the same {world * Bv} whole views"}
+
+
 # ------------------------------------------------------------------------------------------------ ours
 def run_ours(args):
     import numpy as np
@@ -360,6 +402,13 @@ def run_ours(args):
     except Exception as e:      # never let the auxiliary measurement kill the bench line
         fld = {"error": repr(e)}
 
+    mg_check = None
+    if world > 1:
+        try:
+            mg_check = ray_parallel_selfcheck(opt, dev, rank, world)
+        except Exception as e:
+            mg_check = {"error": repr(e)[-300:]}
+
     stages = None
     if args.breakdown:
         stages = {}
@@ -422,6 +471,8 @@ def run_ours(args):
                 "roofline": fld, "roofline_gemm": roof_gemm, "reference_cuda": refc, "cpu_baseline": cpu, "clocks": sampler.summary()}
         if stages is not None:
             line["stages"] = stages
+        if mg_check is not None:
+            line["multi_gpu_check"] = mg_check
         print(json.dumps(line), flush=True)
     if world > 1:
         torch.distributed.destroy_process_group()

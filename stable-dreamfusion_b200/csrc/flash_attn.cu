@@ -254,6 +254,9 @@ int launch_flash(const __half* q, const __half* k, const __half* v, __half* o, i
 
 }  // namespace
 
+int sdf_flash_attention_tc(const void* q, const void* k, const void* v, void* o, int B, int heads, int n, int nkv, int d, int ldq, int ldk, int ldo,
+                           float scale, cudaStream_t st);      // flash_attn_tc.cu
+
 // o[b, i, h*d + :] = softmax_j(scale * q[b,i,h] . k[b,j,h]) v[b,j,h]     (fp16, token-major; d in {40, 80, 160})
 SDF_API int sdf_flash_attention(const void* q, const void* k, const void* v, void* o, int B, int heads, int n, int nkv, int d,
                                 int ldq, int ldk, int ldo, float scale, void* stream) {
@@ -263,6 +266,14 @@ SDF_API int sdf_flash_attention(const void* q, const void* k, const void* v, voi
                   "flash_attention: q/k/v must be 16-byte aligned with row strides multiple of 8");
     cudaStream_t st = (cudaStream_t)stream;
     int rc;
+    // long self-attention (the 64x64-latent layers: 4096 x 4096 scores per head) runs on tcgen05 / TMEM / TMA (flash_attn_tc.cu); short
+    // sequences, cross-attention and d > 64 stay on the mma.sync kernel below.  SDF_FLASH_TC=0 disables the tcgen05 path.
+    static const bool allow_tc = [] { const char* e = getenv("SDF_FLASH_TC"); return !(e && e[0] == '0'); }();
+    if (allow_tc && d <= 64 && n >= 512 && nkv >= 512) {
+        rc = sdf_flash_attention_tc(q, k, v, o, B, heads, n, nkv, d, ldq, ldk, ldo, scale, st);
+        if (rc == SDF_OK) { SDF_CHECK_LAUNCH("flash_attention(tcgen05)"); return SDF_OK; }
+        if (rc != SDF_ERR_UNSUPPORTED) return rc;
+    }
 #define FLASH(DD, MM) rc = launch_flash<DD, MM>((const __half*)q, (const __half*)k, (const __half*)v, (__half*)o, B, heads, n, nkv, ldq, ldk, ldo, scale, st)
     // two query tiles per warp where the grid stays large enough to fill the GPU (the 64x64 / 32x32 self-attention layers)
     static const bool allow_mt2 = [] { const char* e = getenv("SDF_FLASH_MT2"); return !(e && e[0] == '0'); }();

@@ -83,6 +83,7 @@ class SDSTrainer:
         self.pin_ring = [torch.zeros(n_pose, 4, 4).pin_memory() for _ in range(4)]
         self.pin_events = [None] * len(self.pin_ring)
         self.comm_stream = torch.cuda.Stream(device=device) if (world_size > 1 and device.type == 'cuda') else None
+        self.perturb = True              # march jitter (nerf/utils.py:537 perturb=True); the multi-GPU self-check turns it off
         self.stage_events = None         # set to [] to record (name, cuda event) marks of the next step (bench.py --breakdown)
 
     @property
@@ -197,6 +198,7 @@ class SDSTrainer:
             l = poses[:, :3, 3] + light_off                                             # per-view light (nerf/renderer.py:726-727)
             l = l / torch.sqrt(torch.clamp((l * l).sum(-1, keepdim=True), min=1e-20))
             light = l.repeat_interleave((H * W) // WS, dim=0)
+            self._last_shared = dict(poses=poses, fov=fov, light=l, mode=mode, ambient=ambient, as_latent=as_latent, bg_color=bg_color)
         else:
             rays_o, rays_d = self._rays(poses, fov)
             light = None
@@ -210,7 +212,7 @@ class SDSTrainer:
         H, W, WS, Bv = opt.h, opt.w, self.world_size, opt.batch_size
         if ray_par:
             P = (H * W) // WS
-            out = render_train(self.model, rays_o, rays_d, light_d=light_d, ambient_ratio=ambient, shading=mode, bg_color=bg_color, perturb=True,
+            out = render_train(self.model, rays_o, rays_d, light_d=light_d, ambient_ratio=ambient, shading=mode, bg_color=bg_color, perturb=self.perturb,
                                as_latent=as_latent, B=WS * Bv, H=1, W=P, direct_grads=True)
             from .dist import exchange_pixels
             C = out['pred_rgb'].shape[1]
@@ -219,7 +221,7 @@ class SDSTrainer:
             pred_rgb = full.reshape(Bv, H, W, C).permute(0, 3, 1, 2).contiguous()
         else:
             B = rays_o.reshape(-1, 3).shape[0] // (H * W)
-            out = render_train(self.model, rays_o, rays_d, light_d=light_d, ambient_ratio=ambient, shading=mode, bg_color=bg_color, perturb=True,
+            out = render_train(self.model, rays_o, rays_d, light_d=light_d, ambient_ratio=ambient, shading=mode, bg_color=bg_color, perturb=self.perturb,
                                as_latent=as_latent, B=B, H=H, W=W, direct_grads=True)
             pred_rgb = out['pred_rgb']
         self._last_ws = self.model.workspace(rays_o.reshape(-1, 3).shape[0])

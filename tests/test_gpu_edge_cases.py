@@ -79,3 +79,23 @@ def test_adan_without_gradients_and_zero_size(device):
     p[0].grad = torch.ones_like(p[0]); p[1].grad = torch.zeros_like(p[1])
     opt.step()
     assert torch.isfinite(p[0]).all() and not torch.equal(p[0].detach(), before)
+
+
+@pytest.mark.parametrize("n,d,heads", [(4096, 40, 8), (1024, 40, 2), (600, 40, 3), (1000, 64, 2), (512, 32, 2), (777, 48, 1)])
+def test_flash_attention_tcgen05_path(device, n, d, heads):
+    """long self-attention takes the tcgen05 / TMEM / TMA kernel (csrc/flash_attn_tc.cu: n, nkv >= 512, d <= 64), including query / key
+    counts that are not multiples of its 128-wide tiles, read in place from a fused q|k|v projection buffer (row stride 3 * heads * d);
+    same bar as the mma.sync kernel: |err| <= 4e-3 + 4e-3 |ref| against fp32 softmax(q k^T / sqrt(d)) v on the same fp16 inputs"""
+    B = 2
+    C = heads * d
+    g = torch.Generator(device="cpu").manual_seed(n + d)
+    qkv = (torch.randn(B, n, 3 * C, generator=g) * 1.5).to(device).half()
+    q, k, v = qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:]
+    o = torch.full((B, n, C), float("nan"), device=device, dtype=torch.float16)
+    _lib.call("sdf_flash_attention", q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), B, heads, n, n, d, 3 * C, 3 * C, C, d ** -0.5, _lib.stream())
+    torch.cuda.synchronize()
+    qf, kf, vf = (t.float().reshape(B, n, heads, d).permute(0, 2, 1, 3) for t in (q, k, v))
+    ref = (torch.softmax(qf @ kf.transpose(-1, -2) * d ** -0.5, -1) @ vf).permute(0, 2, 1, 3).reshape(B, n, C)
+    assert torch.isfinite(o.float()).all()
+    err = (o.float() - ref).abs()
+    assert (err <= 4e-3 + 4e-3 * ref.abs()).all(), (err.max().item(), ref.abs().max().item())

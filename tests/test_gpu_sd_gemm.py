@@ -198,3 +198,43 @@ def test_geglu_epilogue(device, M, K, inner, bn, pair):
     y = a.float().view(M, K) @ w.float().t() + bias
     ref = y[:, :inner] * F.gelu(y[:, inner:])
     check(out.view(M, inner), ref, K)
+
+
+@pytest.mark.parametrize("Cout,H,block_n,pair,coff,Ctot", [(320, 64, 160, 0, 0, 320), (320, 32, 128, 0, 640, 960), (128, 64, 128, 0, 0, 128),
+                                                          (256, 64, 256, 1, 0, 256), (640, 8, 128, 0, 0, 640)])
+def test_epilogue_groupnorm_statistics(device, Cout, H, block_n, pair, coff, Ctot):
+    """sdf_gemm_plan_set_gn_stats: per-(image, group) sum / sum of squares of the fp16 outputs, accumulated by the GEMM epilogue for a
+    consumer GroupNorm(32, Ctot) whose input holds this product at channel offset `coff` (concatenated skip inputs), against torch sums of
+    the stored tensor; and the apply-only GroupNorm on those statistics against F.group_norm."""
+    from sdf_b200 import _lib
+    Nimg, Cin = 2, 64
+    g = torch.Generator(device="cpu").manual_seed(Cout + H)
+    a = (torch.randn(Nimg, H, H, Cin, generator=g) * 0.5).to(device).half()
+    w = (torch.randn(Cout, Cin, 3, 3, generator=g) * 0.05).to(device).half()
+    bias = torch.randn(Cout, generator=g).to(device)
+    cat = torch.zeros(Nimg, H, H, Ctot, device=device, dtype=torch.float16)
+    out_view = cat[..., coff:coff + Cout]
+    wt = gemm.pack_conv_weight(w)
+    ldc = Ctot
+    plan = gemm.GemmPlan(a, (Cin, H * Cin, H * H * Cin), Cin, wt, (wt.shape[1], 0, 0), wt.shape[1], wt.shape[0], Nimg, H, H, 64, 9, Cout,
+                         type("P", (), {"data_ptr": lambda self: cat.data_ptr() + 2 * coff, "device": device})(), (ldc, H * ldc, H * H * ldc),
+                         bias=bias, act="silu", splitk=1, block_n=block_n, cta_pair=pair)
+    assert plan.can_carry_stats()
+    stats = torch.zeros(Nimg, 32, 2, device=device)
+    plan.add_gn_stats(stats, Ctot // 32, coff)
+    plan.run()
+    torch.cuda.synchronize()
+    check(out_view, ref_conv(a, w, bias=bias, act="silu"), 9 * Cin)
+    cpg = Ctot // 32
+    x = cat.float()                                                  # channels outside [coff, coff + Cout) are zero: they add nothing
+    ref_sum = x.view(Nimg, H * H, 32, cpg).sum(dim=(1, 3))
+    ref_sq = (x * x).view(Nimg, H * H, 32, cpg).sum(dim=(1, 3))
+    assert torch.allclose(stats[..., 0], ref_sum, rtol=2e-4, atol=2e-2), (stats[..., 0] - ref_sum).abs().max()
+    assert torch.allclose(stats[..., 1], ref_sq, rtol=2e-4, atol=2e-2), (stats[..., 1] - ref_sq).abs().max()
+    if coff == 0 and Ctot == Cout:
+        gamma, beta = torch.randn(Cout, generator=g).to(device), torch.randn(Cout, generator=g).to(device)
+        y = torch.empty_like(cat)
+        _lib.call("sdf_groupnorm_apply", cat.data_ptr(), Ctot, y.data_ptr(), Ctot, Nimg, H * H, Ctot, 32, gamma.data_ptr(), beta.data_ptr(), 1e-5, 1,
+                  stats.data_ptr(), _lib.stream())
+        ref = F.silu(F.group_norm(x.permute(0, 3, 1, 2), 32, gamma, beta, 1e-5)).permute(0, 2, 3, 1)
+        assert (y.float() - ref).abs().max().item() < 2e-2 * max(1.0, ref.abs().max().item())
