@@ -405,6 +405,10 @@ def cmd_steps(spec):
         np.savez(spec["state"], **sd)
     if spec.get("global_step"):
         trainer.global_step = int(spec["global_step"])       # e.g. past the latent phase
+    if spec.get("init_scale"):
+        # GradScaler's default 65536 overflows the fp16 backward of the first steps in BOTH arms (the reference skips those steps and halves
+        # the scale); a smaller initial scale makes the very first steps comparable instead of skipped
+        trainer.scaler = torch.cuda.amp.GradScaler(init_scale=float(spec["init_scale"]), enabled=trainer.fp16)
     out, rec = {}, {"i": 0}
     real_render = model.render
     real_train_step = trainer.train_step

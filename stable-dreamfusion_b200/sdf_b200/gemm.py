@@ -92,7 +92,9 @@ class GemmPlan:
             raise RuntimeError(f"sdf_gemm_plan_create failed ({h}): {_lib.lib().last_error()}")
         self.handle = h
         self.gn_slots = 0
-        self._stats_ok = (splitk == 1 and N % 32 == 0 and act != 'geglu' and all(int(v) % 8 == 0 for v in o_strides))
+        tw = 128 if W >= 128 else W
+        th = 1 if (W >= 128 or w_strides[1] != 0 or w_strides[2] != 0) else max(1, min(H, 128 // tw))
+        self._stats_ok = (splitk == 1 and N % 32 == 0 and act != 'geglu' and all(int(v) % 8 == 0 for v in o_strides) and (tw * th) % 32 == 0)
 
     def can_carry_stats(self):
         """may this plan's epilogue accumulate one more consumer's GroupNorm statistics? (csrc/sd_gemm.cu: sdf_gemm_plan_set_gn_stats)"""

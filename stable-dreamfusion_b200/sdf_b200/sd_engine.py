@@ -29,7 +29,10 @@ from .gemm import GemmPlan, choose_config, conv_plan, linear_plan, pack_conv_wei
 
 NUM_SMS = torch.cuda.get_device_properties(0).multi_processor_count if torch.cuda.is_available() else 148      # B200: 148
 USE_CTA_PAIRS = os.environ.get('SDF_GEMM_CTA_PAIRS', '1') != '0'
-FUSE_GN_STATS = os.environ.get('SDF_FUSE_GN_STATS', '1') != '0'           # A/B switch: GroupNorm statistics in the producing GEMM's epilogue
+# GroupNorm statistics in the producing GEMM's epilogue.  OFF by default: measured on B200 (gpurun_out/r2_bench4*.log, launches_r02.csv) the
+# statistics-carrying epilogue costs more than the separate statistics pass it removes (k_gemm<128> 107 us vs 26 us: the per-chunk group
+# reduction runs on the critical path of single-tile CTAs and spills); kept behind the switch with its parity tests.
+FUSE_GN_STATS = os.environ.get('SDF_FUSE_GN_STATS', '0') != '0'
 FUSE_GEGLU = os.environ.get('SDF_FUSE_GEGLU', '1') != '0'                 # A/B switch: GEGLU in the projection GEMM's epilogue      # A/B switch for the cta_group::2 GEMM variant
 
 

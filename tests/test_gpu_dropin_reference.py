@@ -271,7 +271,7 @@ def steps(tmp_path_factory, device):
     for ops in ("reference", "dropin"):
         specs = []
         for phase, gstep, n in (("latent", 0, 2), ("shaded", 2096, 3)):
-            specs.append(dict(cmd="steps", workspace=str(tmp / f"ws_{ops}_{phase}"), state=state, n_steps=n, global_step=gstep, seed=3,
+            specs.append(dict(cmd="steps", workspace=str(tmp / f"ws_{ops}_{phase}"), state=state, n_steps=n, global_step=gstep, seed=3, init_scale=128.0,
                               out=str(tmp / f"steps_{ops}_{phase}.npz")))
         RH.run_subprocess(dict(cmd="multi", ops=ops, specs=specs), timeout=2400)
         for phase in ("latent", "shaded"):
@@ -305,6 +305,10 @@ def test_reference_trainer_runs_unchanged_on_dropin_packages(steps, phase, n):
             assert abs(la - lb) <= 0.25 * abs(la), (la, lb)
     da = A["final.encoder.embeddings"].astype(np.float64) - np.load(steps["state"])["encoder.embeddings"]
     db = B["final.encoder.embeddings"].astype(np.float64) - np.load(steps["state"])["encoder.embeddings"]
+    if np.linalg.norm(da) == 0:
+        assert np.linalg.norm(db) == 0, "the reference skipped every step (GradScaler overflow) but the drop-in run moved the table"
+        print(f"{phase}: every step skipped by the GradScaler in both arms")
+        return
     cos = float((da * db).sum() / (np.linalg.norm(da) * np.linalg.norm(db) + 1e-300))
     print(f"{phase}: table update over {n} steps, cosine A vs B {cos:.4f}")
     assert cos > 0.80, cos       # Adan's first steps are sign-like (m / sqrt(n)): near-zero gradient entries flip on fp16 noise

@@ -70,7 +70,7 @@ def test_mirror_path_equals_cast_path(device):
 def test_backward_against_finite_differences_of_the_forward(device, shading):
     """directional derivative of L = <g_sigma, sigma> + <g_color, color> along the gradient direction in (table, MLP) space: analytic gradient
     of the fused backward vs a central difference of the fused forward.  The forward rounds features / logits to fp16 (it mirrors the -O
-    autocast graph), so the difference quotient uses a step large enough to dominate that rounding; agreement 10 % (albedo) / 15 % (7-point stencil)."""
+    autocast graph), so the difference quotient uses a step large enough to dominate that rounding; agreement 15 %."""
     m = make_model(device, seed=2, emb_scale=0.2)
     M = 4096
     x, l = sample_points(device, M, seed=2)
@@ -104,7 +104,7 @@ def test_backward_against_finite_differences_of_the_forward(device, shading):
             lm = loss_of().item()
             p.add_(eps * d)
         num = (lp - lm) / (2 * eps)
-        tol = 0.10 if shading == "albedo" else 0.15
+        tol = 0.15
         print(f"{shading:10s} {nm:24s} analytic {ana:+.5e} numeric {num:+.5e}")
         assert abs(ana - num) <= tol * max(abs(ana), abs(num)) + 1e-4, (nm, ana, num)
 

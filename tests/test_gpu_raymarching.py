@@ -9,7 +9,7 @@ import torch
 
 from helpers import ref, scenes
 from oracle import oracle as O
-from sdf_b200 import synth
+from sdf_b200 import _lib, synth
 
 pytestmark = pytest.mark.gpu
 
@@ -182,9 +182,13 @@ def test_composite_train_fwd_bwd(device, binarize):
         assert np.abs(gso - gs2.cpu().numpy()).max() / scale < 2e-4
 
 
-def test_inference_loop(device):
-    """march_rays + composite_rays driven like nerf/renderer.py:759-794, ours vs oracle step by step."""
+@pytest.mark.parametrize("perturb", [False, True])
+def test_inference_loop(device, perturb):
+    """march_rays + composite_rays driven like nerf/renderer.py:759-794: ours, the CPU oracle AND the reference's own extension
+    (oracle/_ref/_raymarching.so: raymarching.cu:714-829, :843-925) step by step on identical state — sample positions / ts bit-exact,
+    alive lists equal, accumulated image / weights_sum / depth within 2e-4."""
     import raymarching
+    rm = ref.load("_raymarching")
     bf = synth.occupancy_bitfield("blob", 128, 1, 1.0, seed=1)
     ro, rd, aabb, nears, fars, _ = scenes.make_rays(24, 24, 1.0, 20.0, seed=9)
     N = ro.shape[0]
@@ -192,8 +196,10 @@ def test_inference_loop(device):
     rng = np.random.default_rng(2)
     t_ro, t_rd, t_bf, t_n, t_f = d(ro), d(rd), d(bf), d(nears), d(fars)
     ws = torch.zeros(N, device=device); dep = torch.zeros(N, device=device); img = torch.zeros(N, 3, device=device)
+    ws_r = torch.zeros(N, device=device); dep_r = torch.zeros(N, device=device); img_r = torch.zeros(N, 3, device=device)
     ws_o = np.zeros(N, np.float32); dep_o = np.zeros(N, np.float32); img_o = np.zeros((N, 3), np.float32)
     alive = torch.arange(N, dtype=torch.int32, device=device); rt = t_n.clone()
+    alive_r = alive.clone(); rt_r = t_n.clone()
     alive_o = np.arange(N, dtype=np.int32); rt_o = nears.copy()
     step = 0
     while step < 1024:
@@ -202,15 +208,86 @@ def test_inference_loop(device):
         if n_alive <= 0:
             break
         n_step = max(min(N // n_alive, 8), 1)
-        x, dd, t = raymarching.march_rays(n_alive, n_step, alive, rt, t_ro, t_rd, 1.0, t_bf, 1, 128, t_n, t_f, False, 0, 1024)
-        xo, do, to = O.march_rays(n_alive, n_step, alive_o, rt_o, ro, rd, 1.0, bf, 1, 128, nears, fars, None, 0.0, 1024)
+        noises = rng.random(n_alive, dtype=np.float32) if (perturb and step == 0) else None
+        M = n_alive * n_step
+        x = torch.zeros(M, 3, device=device); dd = torch.zeros(M, 3, device=device); t = torch.zeros(M, 2, device=device)
+        _lib.call("sdf_march_rays", n_alive, n_step, alive.data_ptr(), rt.data_ptr(), t_ro.data_ptr(), t_rd.data_ptr(), 1.0, 0, 0.0, 1024, 1, 128,
+                  t_bf.data_ptr(), t_n.data_ptr(), t_f.data_ptr(), x.data_ptr(), dd.data_ptr(), t.data_ptr(), None if noises is None else d(noises).data_ptr(),
+                  _lib.stream())
+        xo, do, to = O.march_rays(n_alive, n_step, alive_o, rt_o, ro, rd, 1.0, bf, 1, 128, nears, fars, noises, 0.0, 1024)
         assert np.array_equal(x.cpu().numpy(), xo) and np.array_equal(t.cpu().numpy(), to)
-        sig = np.exp(rng.normal(1.0, 2.0, n_alive * n_step)).astype(np.float32)
-        rgb = rng.random((n_alive * n_step, 3), dtype=np.float32)
+        if rm is not None:
+            xr = torch.zeros(M, 3, device=device); dr = torch.zeros(M, 3, device=device); tr = torch.zeros(M, 2, device=device)
+            nz = d(noises) if noises is not None else torch.zeros(n_alive, device=device)
+            rm.march_rays(n_alive, n_step, alive_r, rt_r, t_ro, t_rd, 1.0, False, 0.0, 1024, 1, 128, t_bf, t_n, t_f, xr, dr, tr, nz)
+            assert torch.equal(xr, x) and torch.equal(tr, t) and torch.equal(dr, dd), "march_rays differs from the reference extension"
+        sig = np.exp(rng.normal(1.0, 2.0, M)).astype(np.float32)
+        rgb = rng.random((M, 3), dtype=np.float32)
         raymarching.composite_rays(n_alive, n_step, alive, rt, d(sig), d(rgb), t, ws, dep, img, 1e-2)
         O.composite_rays(n_alive, n_step, alive_o, rt_o, sig, rgb, to, ws_o, dep_o, img_o, 1e-2)
         assert np.array_equal(alive.cpu().numpy(), alive_o)
+        if rm is not None:
+            rm.composite_rays(n_alive, n_step, 1e-2, False, alive_r, rt_r, d(sig), d(rgb), tr, ws_r, dep_r, img_r)
+            assert torch.equal(alive_r, alive), "composite_rays kills a different set of rays than the reference extension"
+            np.testing.assert_allclose(rt.cpu().numpy(), rt_r.cpu().numpy(), rtol=0, atol=0)
+            alive_r = alive_r[alive_r >= 0]
         alive = alive[alive >= 0]; alive_o = alive_o[alive_o >= 0]
         step += n_step
     np.testing.assert_allclose(img.cpu().numpy(), img_o, rtol=2e-4, atol=2e-5)
     np.testing.assert_allclose(ws.cpu().numpy(), ws_o, rtol=2e-4, atol=2e-5)
+    if rm is not None:
+        np.testing.assert_allclose(img.cpu().numpy(), img_r.cpu().numpy(), rtol=2e-4, atol=2e-5)
+        np.testing.assert_allclose(ws.cpu().numpy(), ws_r.cpu().numpy(), rtol=2e-4, atol=2e-5)
+        np.testing.assert_allclose(dep.cpu().numpy(), dep_r.cpu().numpy(), rtol=2e-4, atol=2e-5)
+
+
+def test_device_side_inference_loop_matches_host_driven_loop(device):
+    """sdf_infer_begin / _march / _composite / _compact (loop state and alive-ray compaction on the device, no host sync) against the
+    host-driven reference protocol above on the same synthetic densities: same image, weights_sum, depth (rays are independent of their slot)."""
+    bf = synth.occupancy_bitfield("blob", 128, 1, 1.0, seed=1)
+    ro, rd, aabb, nears, fars, _ = scenes.make_rays(32, 32, 1.0, 20.0, seed=10)
+    N = ro.shape[0]
+    d = lambda a: T(a, device)
+    t_ro, t_rd, t_bf, t_n, t_f = d(ro), d(rd), d(bf), d(nears), d(fars)
+    P = lambda t: t.data_ptr()
+
+    def field(x):           # a smooth synthetic density / colour of the sample position, evaluated identically in both loops
+        r2 = (x * x).sum(-1)
+        return (40.0 * torch.exp(-r2 / 0.08)).contiguous(), (0.5 + 0.5 * torch.sin(7.0 * x)).contiguous()
+
+    # host-driven loop (reference protocol)
+    import raymarching
+    ws = torch.zeros(N, device=device); dep = torch.zeros(N, device=device); img = torch.zeros(N, 3, device=device)
+    alive = torch.arange(N, dtype=torch.int32, device=device); rt = t_n.clone()
+    step = 0
+    while step < 1024 and alive.shape[0] > 0:
+        n_alive = alive.shape[0]
+        n_step = max(min(N // n_alive, 8), 1)
+        x, dd, t = raymarching.march_rays(n_alive, n_step, alive, rt, t_ro, t_rd, 1.0, t_bf, 1, 128, t_n, t_f, False, 0, 1024)
+        s, c = field(x)
+        raymarching.composite_rays(n_alive, n_step, alive, rt, s, c, t, ws, dep, img, 1e-4)
+        alive = alive[alive >= 0]
+        step += n_step
+    # device-driven loop
+    state = torch.zeros(8, dtype=torch.int32, device=device)
+    al = [torch.empty(N, dtype=torch.int32, device=device) for _ in range(2)]
+    rt2 = torch.empty(N, device=device)
+    ws2 = torch.empty(N, device=device); dep2 = torch.empty(N, device=device); img2 = torch.empty(N, 3, device=device)
+    xs = torch.empty(N, 3, device=device); ds = torch.empty(N, 3, device=device); ts = torch.empty(N, 2, device=device)
+    st = _lib.stream()
+    _lib.call("sdf_infer_begin", P(state), N, 1024, P(al[0]), P(rt2), P(t_n), P(ws2), P(dep2), P(img2), None, st)
+    cur, iters = 0, 0
+    for it in range(1024):
+        _lib.call("sdf_infer_march", P(state), N, P(al[cur]), P(rt2), P(t_ro), P(t_rd), 1.0, 0, 0.0, 1024, 1, 128, P(t_bf), P(t_f), P(xs), P(ds), P(ts), None, st)
+        s, c = field(xs)                    # capacity-sized: rows >= M are ignored by the compositor
+        _lib.call("sdf_infer_composite", P(state), N, 1e-4, 0, P(al[cur]), P(rt2), P(s), P(c), P(ts), P(ws2), P(dep2), P(img2), st)
+        _lib.call("sdf_infer_compact", P(state), N, P(al[cur]), P(al[1 - cur]), None, st)
+        cur = 1 - cur
+        iters += 1
+        if it % 16 == 15 and int(state[0].item()) == 0:
+            break
+    stt = state.cpu().numpy()
+    assert stt[0] == 0, f"rays still alive after {iters} iterations: {stt}"
+    np.testing.assert_allclose(img2.cpu().numpy(), img.cpu().numpy(), rtol=2e-5, atol=2e-6)
+    np.testing.assert_allclose(ws2.cpu().numpy(), ws.cpu().numpy(), rtol=2e-5, atol=2e-6)
+    np.testing.assert_allclose(dep2.cpu().numpy(), dep.cpu().numpy(), rtol=2e-5, atol=2e-6)
