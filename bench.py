@@ -33,7 +33,9 @@ for _p in (ROOT, PKG):
 
 METRIC = "SDS steps/sec (64x64 render, SD-1.5 UNet)"
 CONFIGS = {"C2": dict(hw=64, note="BASELINE.json configs[1]: -O backbone, 64x64 render, 1 view/step/GPU"),
-           "C3": dict(hw=128, note="BASELINE.json configs[2]: -O backbone, 128x128 render, 1 view/step/GPU (4 views over 4 GPUs)")}
+           "C3": dict(hw=128, note="BASELINE.json configs[2]: -O backbone, 128x128 render, 1 view/step/GPU (4 views over 4 GPUs)"),
+           "C4": dict(hw=64, zero123=True, note="BASELINE.json configs[3]: Zero-1-to-3-shaped UNet guidance (8-channel input, 1-token context, 32x32 "
+                                               "latents, VAE 256x256), 64x64 render, 1 view/step/GPU")}
 CYCLE = ["latent"] * 5 + (["lambertian"] * 4 + ["textureless"]) * 4        # 20 % / 64 % / 16 %
 
 
@@ -278,8 +280,19 @@ def run_ours(args):
 
     hw = CONFIGS[args.config]["hw"]
     opt = default_opt(h=hw, w=hw, batch_size=1)
-    guidance = StableDiffusion(dev, weights="random", n_views=1, render_hw=hw, seed=0, capture=True)
-    trainer = SDSTrainer(opt, dev, guidance, seed=0, rank=rank, world_size=world)
+    if CONFIGS[args.config].get("zero123"):
+        from guidance.zero123_utils import Zero123
+        opt.guidance_scale, opt.latent_iter_ratio = 5.0, 0.0            # main.py:196-219 defaults of an image-only run
+        opt.zero123_grad_scale = "angle"
+        guidance = Zero123(dev, opt=opt, weights="random", n_views=1, render_hw=hw, seed=0, capture=True)
+        ref_img = torch.rand(1, 3, 256, 256, generator=torch.Generator().manual_seed(0)).to(dev)
+        c, v = guidance.get_img_embeds(ref_img)
+        emb = {"c_crossattn": c, "c_concat": v, "ref_polars": [90.0], "ref_azimuths": [0.0], "ref_radii": [3.2], "zero123_ws": [1.0]}
+        trainer = SDSTrainer(opt, dev, guidance, seed=0, rank=rank, world_size=world, image_embeddings=emb)
+    else:
+        guidance = StableDiffusion(dev, weights="random", n_views=1, render_hw=hw, seed=0, capture=True)
+        trainer = SDSTrainer(opt, dev, guidance, seed=0, rank=rank, world_size=world)
+    cycle = [c for c in CYCLE if c != "latent"] if CONFIGS[args.config].get("zero123") else CYCLE
     eng = guidance.engine
     launches = {"n": 0}
     orig_call = _lib.call
@@ -300,7 +313,7 @@ def run_ours(args):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for i in range(n_steps):
-            trainer.train_step(shading=CYCLE[(first_index + i) % len(CYCLE)], read_loss=read_loss)
+            trainer.train_step(shading=cycle[(first_index + i) % len(cycle)], read_loss=read_loss)
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -311,7 +324,7 @@ def run_ours(args):
         return ms
 
     for i in range(max(3, args.warmup)):
-        trainer.train_step(shading=CYCLE[i % len(CYCLE)], read_loss=False)
+        trainer.train_step(shading=cycle[i % len(cycle)], read_loss=False)
     sampler = ClockSampler(local)
     sampler.start()
     launches["n"] = 0
@@ -402,6 +415,33 @@ def run_ours(args):
     except Exception as e:      # never let the auxiliary measurement kill the bench line
         fld = {"error": repr(e)}
 
+    # --- secondary figure: inference render rate at 800x800 with the device-side loop (no host sync per iteration,
+    #     on-device alive-ray compaction); the reference's only published number is "~10 FPS at 800x800" on a V100 (readme.md:28)
+    eval_fps = None
+    if world == 1 and not args.no_eval:
+        try:
+            from sdf_b200 import synth as _synth
+            m = trainer.model
+            m.eval()
+            ro, rd = _synth.get_rays(_synth.circle_pose(3.2, 80.0, 30.0), 800, 800, 20.0)
+            ro_t, rd_t = torch.from_numpy(ro).to(dev)[None], torch.from_numpy(rd).to(dev)[None]
+            light = torch.nn.functional.normalize(torch.tensor([[0.3, 0.8, 0.5]], device=dev), dim=-1)
+            eval_fps = {}
+            for sh in ("albedo", "lambertian"):
+                for rep in range(4):
+                    if rep == 1:
+                        torch.cuda.synchronize()
+                        t0 = time.perf_counter()
+                    out_e = m.render(ro_t, rd_t, None, 800, 800, staged=False, perturb=False, bg_color=None, ambient_ratio=0.5, shading=sh, light_d=light)
+                torch.cuda.synchronize()
+                eval_fps[sh] = 3.0 / (time.perf_counter() - t0)
+            eval_fps["coverage"] = float((out_e["weights_sum"] > 0.5).float().mean())
+            eval_fps["what"] = "800x800 frames/s, default view, scene as trained so far (blob); wall clock over 3 frames after 1 warm-up"
+            m.train()
+        except Exception as e:
+            eval_fps = {"error": repr(e)[-300:]}
+            trainer.model.train()
+
     mg_check = None
     if world > 1:
         try:
@@ -441,7 +481,7 @@ def run_ours(args):
                 cpu = {"value": None, "unit": "steps/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e!r}"}
         # --- the north star's comparison: the reference's own -O loop on this same GPU (N = 1 only; skipped with --no-ref-cuda)
         refc, vs = None, None
-        if world == 1 and not args.no_ref_cuda:
+        if world == 1 and not args.no_ref_cuda and args.config != "C4":        # the reference's Zero123 needs ldm + a checkpoint: no same-GPU arm
             try:
                 torch.cuda.empty_cache()
                 refc = time_reference_cuda(hw, steps=max(args.steps, 25), warmup=max(args.warmup, 10))
@@ -453,15 +493,18 @@ def run_ours(args):
         e2e_v = world * args.steps / (ms_e2e * 1e-3)
         per_step_calls = n_calls / args.steps
         # graph replays stand for all captured launches
-        frac = {s: CYCLE.count(s) / len(CYCLE) for s in set(CYCLE)}
-        launches_per_step = per_step_calls + graph_ops["unet"] + (1 - frac["latent"]) * (graph_ops["vae_fwd"] + graph_ops["vae_bwd"])
+        frac_latent = cycle.count("latent") / len(cycle)
+        launches_per_step = per_step_calls + graph_ops["unet"] + (1 - frac_latent) * (graph_ops["vae_fwd"] + graph_ops["vae_bwd"])
         line = {"metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": vs,
                 "vs_baseline_kind": "value / steps-per-second of the reference's own -O CUDA-extension training loop measured on this same GPU in this run "
                                     "(`reference_cuda` below; BASELINE.md publishes no number, its 3.1 defines this arm A)",
                 "dtype": "f16", "data": "synthetic",
-                "config": {"workload": f"{args.config}: -O instant-NGP backbone, {hw}x{hw} render, 1 view/step/GPU, SD-1.5-shaped UNet (B=2 CFG) + VAE encoder 512x512, "
-                                       "reference shading schedule mix (20% latent, 64% lambertian, 16% textureless), Adan step, grid refresh every 16 steps",
+                "config": {"workload": f"{args.config}: -O instant-NGP backbone, {hw}x{hw} render, 1 view/step/GPU, " +
+                                       ("Zero-1-to-3-shaped UNet (8-ch input, 1-token context, 32x32 latents, B=2 CFG) + VAE encoder 256x256, " if CONFIGS[args.config].get("zero123")
+                                        else "SD-1.5-shaped UNet (B=2 CFG) + VAE encoder 512x512, ") +
+                                       ("shading mix 80% lambertian / 20% textureless (no latent phase with image guidance), " if CONFIGS[args.config].get("zero123")
+                                        else "reference shading schedule mix (20% latent, 64% lambertian, 16% textureless), ") + "Adan step, grid refresh every 16 steps",
                            "rays_per_view": hw * hw, "samples_last_step": trainer.last_M, "l2": "per-step working set (UNet weights 1.7 GB + activations) exceeds the 126 MB L2",
                            "parallelism": f"dp{world}" + (" (one view per GPU for the UNet/VAE; every GPU renders 1/N of the rays of every view, pixels and pixel "
                                                          "gradients exchanged by all-to-all; one gradient all-reduce)" if world > 1 else "")},
@@ -473,6 +516,8 @@ def run_ours(args):
             line["stages"] = stages
         if mg_check is not None:
             line["multi_gpu_check"] = mg_check
+        if eval_fps is not None:
+            line["eval_render"] = eval_fps
         print(json.dumps(line), flush=True)
     if world > 1:
         torch.distributed.destroy_process_group()
@@ -488,6 +533,7 @@ def main():
                          "unmodified Python + CUDA extensions + PyTorch fp16 UNet/VAE on this GPU (oracle/ref_harness.py)")
     ap.add_argument("--config", default="C2", choices=sorted(CONFIGS), help="BASELINE.json config: C2 = 64x64 (the metric's), C3 = 128x128")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-eval", action="store_true", help="skip the 800x800 inference-render figure")
     ap.add_argument("--no-ref-cuda", action="store_true", help="skip the same-GPU reference arm (vs_baseline stays null)")
     ap.add_argument("--breakdown", action="store_true", help="add per-stage CUDA-event times of one step per shading mode ('stages')")
     args = ap.parse_args()

@@ -190,6 +190,9 @@ int sdf_gemm_plan_destroy(int plan);
  * kept for sdf_groupnorm_backward). */
 int sdf_groupnorm_forward(const void* x, int ldx, void* y, int ldy, int Nimg, int HW, int C, int G, const float* gamma, const float* beta,
                           float eps, int silu_act, float* stats, void* stream);
+/* sdf_groupnorm_forward without its own memset: `stats` was zeroed by the caller (one memset for all norms of a launch list) */
+int sdf_groupnorm_forward_prezeroed(const void* x, int ldx, void* y, int ldy, int Nimg, int HW, int C, int G, const float* gamma, const float* beta,
+                                    float eps, int silu_act, float* stats, void* stream);
 /* the normalise(+SiLU) pass alone, for statistics produced by sdf_gemm_plan_set_gn_stats */
 int sdf_groupnorm_apply(const void* x, int ldx, void* y, int ldy, int Nimg, int HW, int C, int G, const float* gamma, const float* beta,
                         float eps, int silu_act, const float* stats, void* stream);

@@ -702,12 +702,12 @@ SDF_API int sdf_groupnorm_apply(const void* x, int ldx, void* y, int ldy, int Ni
 // (A single-pass variant — rows held in registers, grid-wide arrival counter between the statistics and the normalisation —
 // was measured 2-4x SLOWER than these two passes on B200: 60 us vs 14 us at 2x4096x320; the spin on a contended L2 line costs
 // more than re-reading 5 MB.  Not kept.)
-SDF_API int sdf_groupnorm_forward(const void* x, int ldx, void* y, int ldy, int Nimg, int HW, int C, int G, const float* gamma, const float* beta,
-                                  float eps, int silu_act, float* stats, void* stream) {
+static int groupnorm_forward_impl(const void* x, int ldx, void* y, int ldy, int Nimg, int HW, int C, int G, const float* gamma, const float* beta,
+                                  float eps, int silu_act, float* stats, void* stream, bool zero_stats) {
     SDF_CHECK_ARG(x && y && gamma && beta && stats, "groupnorm_forward: null pointer");
     SDF_CHECK_ARG(C % 8 == 0 && C % G == 0 && ldx % 8 == 0 && ldy % 8 == 0, "groupnorm_forward: C %% 8, C %% G, ld %% 8 must be 0");
     cudaStream_t st = (cudaStream_t)stream;
-    SDF_CHECK_CUDA(cudaMemsetAsync(stats, 0, sizeof(float) * 2 * G * Nimg, st));
+    if (zero_stats) SDF_CHECK_CUDA(cudaMemsetAsync(stats, 0, sizeof(float) * 2 * G * Nimg, st));
     const int vpp = C / 8;
     // two passes: ~16 vectors per thread for large tensors, at least ~4 blocks per SM for small ones
     int ppb = max(1, min(HW, (256 * 16 * 8) / C));
@@ -721,6 +721,17 @@ SDF_API int sdf_groupnorm_forward(const void* x, int ldx, void* y, int ldy, int 
     else sdf_launch_pdl(k_gn_apply<false>, dim3(grid), dim3(256), (size_t)(0), st, (const __half*)x, ldx, (__half*)y, ldy, HW, C, G, ppb, stats, gamma, beta, eps);
     SDF_CHECK_LAUNCH("groupnorm(apply)");
     return SDF_OK;
+}
+
+SDF_API int sdf_groupnorm_forward(const void* x, int ldx, void* y, int ldy, int Nimg, int HW, int C, int G, const float* gamma, const float* beta,
+                                  float eps, int silu_act, float* stats, void* stream) {
+    return groupnorm_forward_impl(x, ldx, y, ldy, Nimg, HW, C, G, gamma, beta, eps, silu_act, stats, stream, true);
+}
+
+// the same with `stats` already zeroed by the caller (one memset for a whole launch list's statistics instead of one per norm)
+SDF_API int sdf_groupnorm_forward_prezeroed(const void* x, int ldx, void* y, int ldy, int Nimg, int HW, int C, int G, const float* gamma, const float* beta,
+                                            float eps, int silu_act, float* stats, void* stream) {
+    return groupnorm_forward_impl(x, ldx, y, ldy, Nimg, HW, C, G, gamma, beta, eps, silu_act, stats, stream, false);
 }
 
 SDF_API int sdf_groupnorm_backward(const void* x, int ldx, const void* dy, int ldd, void* dx, int ldo, int Nimg, int HW, int C, int G,

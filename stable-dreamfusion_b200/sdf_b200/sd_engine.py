@@ -131,6 +131,19 @@ class Builder:
             ent.append(dict(lo=lo, hi=hi, plan=plan, geom=geom))
         self.producers[key] = ent
 
+    def _arena_stats(self, Nimg):
+        """[Nimg, 32, 2] fp32 statistics slot inside ONE arena that the first op of the list zeroes (instead of a memset node per norm)"""
+        n = Nimg * 32 * 2
+        if self.gn_arena is None:
+            self.gn_arena = torch.zeros(64 * 1024, device=self.device, dtype=torch.float32)
+            arena = self.gn_arena
+            self.ops.insert(0, ('zero_gn_stats', lambda a=arena: a.zero_()))
+        if self.gn_used + n > self.gn_arena.numel():
+            return None
+        stats = self.gn_arena[self.gn_used:self.gn_used + n].view(Nimg, 32, 2)
+        self.gn_used += n
+        return stats
+
     def _gn_stats_from_producers(self, x):
         """-> stats tensor filled by the epilogues of the plans that wrote x, or None when x is not completely covered by such plans"""
         if not FUSE_GN_STATS:
@@ -143,15 +156,9 @@ class Builder:
             pos = e['hi']
         if pos != x.off + x.C or not ent:
             return None
-        n = x.Nimg * 32 * 2
-        if self.gn_arena is None:
-            self.gn_arena = torch.zeros(64 * 1024, device=self.device, dtype=torch.float32)
-            arena = self.gn_arena
-            self.ops.insert(0, ('zero_gn_stats', lambda a=arena: a.zero_()))
-        if self.gn_used + n > self.gn_arena.numel():
+        stats = self._arena_stats(x.Nimg)
+        if stats is None:
             return None
-        stats = self.gn_arena[self.gn_used:self.gn_used + n].view(x.Nimg, 32, 2)
-        self.gn_used += n
         cpg = x.C // 32
         for e in ent:
             e['plan'].add_gn_stats(stats, cpg, e['lo'] - x.off)
@@ -212,11 +219,17 @@ class Builder:
     # ---- memory-bound
     def groupnorm(self, name, x, y, gamma, beta, eps, silu, stats=None):
         fused = self._gn_stats_from_producers(x) if stats is None else None
-        stats = (self.f32(x.Nimg, 32, 2) if stats is None else stats) if fused is None else fused
+        fn = 'sdf_groupnorm_forward'
+        if fused is not None:
+            stats, fn = fused, 'sdf_groupnorm_apply'      # statistics accumulated by the producing GEMMs' epilogues: normalise(+SiLU) only
+        elif stats is None:
+            stats = self._arena_stats(x.Nimg)             # zeroed once per list run together with every other norm's statistics
+            if stats is not None:
+                fn = 'sdf_groupnorm_forward_prezeroed'
+            else:
+                stats = self.f32(x.Nimg, 32, 2)
         args = (x.ptr, x.ld, y.ptr, y.ld, x.Nimg, x.H * x.W, x.C, 32, _lib.ptr(gamma), _lib.ptr(beta), float(eps), int(silu), _lib.ptr(stats))
         keep = (x, y, gamma, beta, stats)
-        # statistics accumulated by the producing GEMMs' epilogues: only the normalise(+SiLU) pass is left
-        fn = 'sdf_groupnorm_apply' if fused is not None else 'sdf_groupnorm_forward'
         self.add(name + ('(apply)' if fused is not None else ''), lambda a=args, k=keep, f=fn: _lib.call(f, *a, _lib.stream()))
         self._touch(y)
         return stats

@@ -45,8 +45,12 @@ def get_rays_torch(poses, focal, cx, cy, H, W):
 
 
 class SDSTrainer:
-    def __init__(self, opt, device, guidance, seed=0, rank=0, world_size=1, prompt='a hamburger', ema_decay=0.95, steps_per_epoch=None):
+    def __init__(self, opt, device, guidance, seed=0, rank=0, world_size=1, prompt='a hamburger', ema_decay=0.95, steps_per_epoch=None,
+                 image_embeddings=None):
+        """image_embeddings: for Zero123 guidance, the dict nerf/utils.py:414-425 builds (c_crossattn, c_concat, ref_polars, ref_azimuths,
+        ref_radii, zero123_ws); text prompts are then unused."""
         self.opt, self.device, self.guidance = opt, device, guidance
+        self.image_embeddings = image_embeddings
         self.rank, self.world_size = rank, world_size
         torch.manual_seed(seed)                       # identical initial parameters on every rank
         self.model = InstantNGP(opt).to(device)
@@ -71,10 +75,11 @@ class SDSTrainer:
         torch.manual_seed(seed * 1000 + rank + 1)
         torch.cuda.manual_seed(seed * 1000 + rank + 1)
         # text embeddings (nerf/utils.py:352-377): uncond + front/side/back
-        te = guidance.get_text_embeds
-        self.embeddings = {'uncond': te(['']), 'default': te([prompt])}
-        for d in ('front', 'side', 'back'):
-            self.embeddings[d] = te([f'{prompt}, {d} view'])
+        if image_embeddings is None:
+            te = guidance.get_text_embeds
+            self.embeddings = {'uncond': te(['']), 'default': te([prompt])}
+            for d in ('front', 'side', 'back'):
+                self.embeddings[d] = te([f'{prompt}, {d} view'])
         self.ray_parallel = world_size > 1 and (opt.h * opt.w) % world_size == 0
         self.rng_shared = np.random.default_rng(seed * 1000 + 999)
         # pinned staging ring for the poses: the host may run several steps ahead of the GPU, so a slot is only rewritten after
@@ -106,11 +111,12 @@ class SDSTrainer:
         opt = self.opt
         B = opt.batch_size if n is None else n
         rng = self.rng if rng is None else rng
-        poses, az = [], []
+        poses, az, self._cam = [], [], []
         for _ in range(B):
-            pose, (_, _, ph) = synth.rand_pose(rng, tuple(opt.radius_range), tuple(opt.theta_range), tuple(opt.phi_range))
+            pose, (r, th, ph) = synth.rand_pose(rng, tuple(opt.radius_range), tuple(opt.theta_range), tuple(opt.phi_range))
             poses.append(pose)
             az.append(ph - 360 if ph > 180 else ph)
+            self._cam.append((r, th, az[-1]))            # radius, polar, azimuth: the image-conditioned guidance needs them (nerf/provider.py:295-300)
         return np.stack(poses), np.array(az, np.float32), float(rng.uniform(*opt.fovy_range))
 
     def text_z(self, azimuth):
@@ -228,8 +234,17 @@ class SDSTrainer:
         self.last_pred_rgb = pred_rgb
         self._mark('render (rays, march, field forward, composite, background, regularisers)')
 
-        loss = self.guidance.train_step(self.text_z(azimuth), pred_rgb, as_latent=as_latent, guidance_scale=opt.guidance_scale,
-                                        grad_scale=opt.lambda_guidance)
+        if self.image_embeddings is not None:
+            # Zero-1-to-3 guidance (nerf/utils.py:668-676): camera deltas wrt the default view instead of a text embedding
+            cam = self._cam[self.rank * Bv:(self.rank + 1) * Bv] if ray_par else self._cam
+            polar = [c[1] - getattr(opt, 'default_polar', 90.0) for c in cam]
+            azim = [c[2] - getattr(opt, 'default_azimuth', 0.0) for c in cam]
+            rad = [c[0] - getattr(opt, 'default_radius', 3.2) for c in cam]
+            loss = self.guidance.train_step(self.image_embeddings, pred_rgb, polar, azim, rad, guidance_scale=opt.guidance_scale,
+                                            as_latent=as_latent, grad_scale=opt.lambda_guidance)
+        else:
+            loss = self.guidance.train_step(self.text_z(azimuth), pred_rgb, as_latent=as_latent, guidance_scale=opt.guidance_scale,
+                                            grad_scale=opt.lambda_guidance)
         self._mark('guidance (VAE encode, UNet, SDS gradient, VAE data-gradient)')
         loss = loss + out['reg']                                    # entropy + orientation (nerf/utils.py:690-704), lambdas folded in
         if opt.lambda_opacity > 0:

@@ -1,0 +1,77 @@
+"""The round's headline kernels once each between cudaProfilerStart/Stop, for one `ncu --set full` capture:
+    ncu --set full --clock-control none --import-source on --profile-from-start off -o gpurun_out/r02_kernels python tools/profile_kernels.py
+  1. k_field_forward  (lambertian, 432 k samples, feature stash on)      2. k_field_backward (same samples, features streamed back)
+  3. flash attention at the 64x64-latent self-attention shape (tcgen05 path unless SDF_FLASH_TC=0)
+  4. one UNet 3x3 convolution (2 x 64 x 64 x 320 -> 320) as tcgen05 implicit GEMM     5. the fused Adan step over the 12.2 M-entry table"""
+import os
+import sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "stable-dreamfusion_b200")]
+import torch
+from sdf_b200 import _lib, gemm
+from sdf_b200.ngp import InstantNGP
+from sdf_b200.optimizer import Adan
+from sdf_b200.options import default_opt
+
+dev = torch.device("cuda:0")
+torch.manual_seed(0)
+m = InstantNGP(default_opt()).to(dev)
+opt = Adan(m.get_params(5e-3), eps=1e-8, weight_decay=2e-5, max_grad_norm=5.0)
+m.attach_half_mirror(opt)
+M = 432000
+g = torch.Generator(device=dev).manual_seed(1)
+xyz = ((torch.rand(M, 3, device=dev, generator=g) * 2 - 1) * 0.5).contiguous()
+l = torch.nn.functional.normalize(torch.randn(M, 3, device=dev, generator=g), dim=-1).contiguous()
+c = m.field_cfg()
+sn = m.sigma_net.net
+P = _lib.ptr
+table = m.table_half()
+sig, col, nrm, aux = torch.empty(M, device=dev), torch.empty(M, 3, device=dev), torch.empty(M, 3, device=dev), torch.empty(M, 10, device=dev)
+feat = torch.empty(_lib.query("sdf_field_feat_bytes", M, 1) // 4, device=dev, dtype=torch.int32)
+gs, gc = torch.full((M,), 1e-3, device=dev), torch.randn(M, 3, device=dev, generator=g)
+gt = torch.zeros_like(m.encoder.embeddings)
+gw = [torch.zeros_like(t) for t in (sn[0].weight, sn[0].bias, sn[1].weight, sn[1].bias, sn[2].weight, sn[2].bias)]
+wts = [P(t) for t in (sn[0].weight, sn[0].bias, sn[1].weight, sn[1].bias, sn[2].weight, sn[2].bias)]
+fargs = (P(xyz), M, None, P(table), P(c["offsets"]), c["L"], c["levels_active"], c["S"], int(c["H"]), int(c["smoothstep"]), *wts, m.bound, c["blob_density"],
+         c["blob_radius"], 1, P(l), 1, 0.5)
+st = _lib.stream()
+
+
+def field():
+    _lib.call("sdf_field_forward", *fargs, P(sig), P(col), P(nrm), P(aux), P(feat), st)
+    _lib.call("sdf_field_backward", *fargs, P(aux), P(gs), P(gc), None, P(gt), *[P(t) for t in gw], P(feat), st)
+
+
+B, heads, n, d = 2, 8, 4096, 40
+C = heads * d
+qkv = torch.randn(B, n, 3 * C, device=dev, generator=g).half()
+o = torch.empty(B, n, C, device=dev, dtype=torch.float16)
+
+
+def attn():
+    _lib.call("sdf_flash_attention", qkv.data_ptr(), qkv.data_ptr() + 2 * C, qkv.data_ptr() + 4 * C, o.data_ptr(), B, heads, n, n, d, 3 * C, 3 * C, C, d ** -0.5, st)
+
+
+a = torch.randn(2, 64, 64, 320, device=dev, generator=g).half()
+w = gemm.pack_conv_weight((torch.randn(320, 320, 3, 3, device=dev, generator=g) * 0.02))
+out = torch.empty(2, 64, 64, 320, device=dev, dtype=torch.float16)
+bn, pair, sk = gemm.choose_config(2 * 64 * 64, 320, 9 * 320 // 64, False)
+plan = gemm.conv_plan(a, 320, w, 320, out, taps=9, bias=torch.zeros(320, device=dev), act="silu", splitk=sk, block_n=bn, cta_pair=pair)
+
+
+def adan():
+    m.encoder.embeddings.grad = gt
+    for p_, g_ in zip(m.sigma_net.parameters(), gw):
+        p_.grad = g_
+    opt.step(zero_grad=False)
+
+
+for fn in (field, attn, plan.run, adan):
+    fn(); fn()
+torch.cuda.synchronize()
+torch.cuda.cudart().cudaProfilerStart()
+for fn in (field, attn, plan.run, adan):
+    fn()
+torch.cuda.synchronize()
+torch.cuda.cudart().cudaProfilerStop()
+print("profiled: field fwd/bwd, attention, conv GEMM", (bn, pair, sk), ", Adan")
