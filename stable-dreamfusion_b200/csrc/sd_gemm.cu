@@ -151,6 +151,25 @@ __device__ __forceinline__ float act_apply(float v, int act) {
     return v;
 }
 
+constexpr int kGnMaxImg = 4;          // images a statistics-carrying plan may span (UNet: 2 CFG halves x views, VAE: views)
+
+// v[c] = value of column c in this lane's row.  After the call v[0] of lane l holds the sum of column l over the 32 lanes: each step
+// trades half of the remaining columns with the partner lane and adds the half it keeps (16 + 8 + 4 + 2 + 1 shuffles).
+template <int HALF>
+__device__ __forceinline__ void column_sums_step(float (&v)[32], int lane) {
+    const bool up = (lane & HALF) != 0;
+#pragma unroll
+    for (int i = 0; i < HALF; i++) {
+        const float send = up ? v[i] : v[i + HALF];
+        const float keep = up ? v[i + HALF] : v[i];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, HALF);
+    }
+}
+__device__ __forceinline__ void column_sums(float (&v)[32], int lane) {
+    column_sums_step<16>(v, lane); column_sums_step<8>(v, lane); column_sums_step<4>(v, lane);
+    column_sums_step<2>(v, lane); column_sums_step<1>(v, lane);
+}
+
 template <int BLOCK_N, bool PAIR>
 struct SmemLayout {
     static constexpr int kABytes = kBlockM * kBlockK * 2;
@@ -159,7 +178,7 @@ struct SmemLayout {
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kMaxStages = (220 * 1024) / kStageBytes;
     static constexpr int kStages = kMaxStages > 8 ? 8 : kMaxStages;
-    static constexpr int kBarrierBytes = (2 * kStages + 4) * 8 + 16;
+    static constexpr int kBarrierBytes = (2 * kStages + 4) * 8 + 16 + 2 * kGnMaxImg * 32 * 2 * 4;      // + the GroupNorm accumulators (STATS)
     static constexpr int kTotal = kStages * kStageBytes + kBarrierBytes + 1024;   // + alignment slack
     static_assert(kStageBytes % 1024 == 0, "stages must keep the 1024-byte swizzle-atom alignment");
     static_assert(kTotal <= 227 * 1024, "shared memory budget");
@@ -177,6 +196,10 @@ k_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtens
     uint64_t* tmem_full = empty_bar + kStages;
     uint64_t* tmem_empty = tmem_full + 2;
     uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    float* gn_acc = reinterpret_cast<float*>(tmem_base_smem + 4);        // [2 consumers][kGnMaxImg][32 groups][sum, sum of squares]
+    if (STATS) {
+        for (int i = threadIdx.x; i < 2 * kGnMaxImg * 32 * 2; i += blockDim.x) gn_acc[i] = 0.f;
+    }
 
     pdl_trigger();        // the next kernel of the stream may be scheduled (it blocks in its own griddepcontrol.wait)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -438,30 +461,25 @@ k_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtens
                     }
                 }
                 // ---- GroupNorm statistics for the consumer(s) of this output (plans that request it are direct, N % 32 == 0, and their
-                //      32-row quarters never straddle an image): warp-uniform control flow, rows that stored nothing contribute zeros
-                if (STATS && (g.gn_stats[0] || g.gn_stats[1]) && nbase + 32 <= g.N) {
-                    if (!have) {
+                //      32-row quarters never straddle an image).  Column sums over the warp's 32 rows by a halving butterfly (31 shuffles
+                //      for 32 columns: after the 5 steps lane l holds column l), then one shared-memory add per lane into the CTA's
+                //      (image, group) accumulators; the CTA flushes them with global atomics once, after its last tile.
+                if (STATS && nbase + 32 <= g.N) {
+                    float sq[32];
 #pragma unroll
-                        for (int j = 0; j < 32; j++) f[j] = 0.f;
-                    }
+                    for (int j = 0; j < 32; j++) { f[j] = have ? f[j] : 0.f; sq[j] = f[j] * f[j]; }
+                    column_sums(f, lane);
+                    column_sums(sq, lane);
                     const uint32_t vm = __ballot_sync(0xffffffffu, have);
                     if (vm) {
                         const int img0 = __shfl_sync(0xffffffffu, img, __ffs(vm) - 1);
 #pragma unroll
                         for (int slot = 0; slot < 2; slot++) {
-                            float* stp = g.gn_stats[slot];
-                            if (!stp) continue;
-                            const int cpg = g.gn_cpg[slot], c0 = g.gn_coff[slot] + nbase;
-                            int grp = c0 / cpg, lo = 0, left = (grp + 1) * cpg - c0;
-                            while (lo < 32) {
-                                const int hi = min(32, lo + left);
-                                float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-                                for (int j = 0; j < 32; j++) { const float v = (j >= lo && j < hi) ? f[j] : 0.f; s1 += v; s2 = fmaf(v, v, s2); }
-                                s1 = warp_sum(s1); s2 = warp_sum(s2);
-                                if (lane == 0) { atomicAdd(stp + ((size_t)img0 * 32 + grp) * 2, s1); atomicAdd(stp + ((size_t)img0 * 32 + grp) * 2 + 1, s2); }
-                                grp++; lo = hi; left = cpg;
-                            }
+                            if (!g.gn_stats[slot]) continue;
+                            const int grp = (g.gn_coff[slot] + nbase + lane) / g.gn_cpg[slot];
+                            float* acc_p = gn_acc + ((slot * kGnMaxImg + img0) * 32 + grp) * 2;
+                            atomicAdd(acc_p, f[0]);
+                            atomicAdd(acc_p + 1, sq[0]);
                         }
                     }
                 }
@@ -486,6 +504,16 @@ k_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtens
                 else mbar_arrive(&tmem_empty[acc]);
             }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+        if (STATS) {
+            // all 8 epilogue warps have added their last tile: flush the CTA's (image, group) partial sums, one global atomic each
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            const int et = threadIdx.x - 64;
+            for (int i = et; i < 2 * kGnMaxImg * 32 * 2; i += 256) {
+                const float v = gn_acc[i];
+                const int slot = i / (kGnMaxImg * 64), rem = i - slot * (kGnMaxImg * 64), im = rem >> 6, k = rem & 63;
+                if (v != 0.f && g.gn_stats[slot]) atomicAdd(g.gn_stats[slot] + (size_t)im * 64 + k, v);
+            }
         }
     }
 
@@ -692,7 +720,7 @@ SDF_API int sdf_gemm_plan_set_gn_stats(int plan, int slot, float* stats, int cha
     SDF_CHECK_ARG(plan >= 0 && plan < (int)g_plans.size() && g_plans[plan], "gemm_plan_set_gn_stats: bad plan handle");
     SDF_CHECK_ARG(slot >= 0 && slot < 2 && stats && channels_per_group > 0 && channel_offset >= 0, "gemm_plan_set_gn_stats: bad arguments");
     GemmArgs& g = g_plans[plan]->args;
-    const bool ok = g.splitk == 1 && (g.N % 32) == 0 && g.act != kActGeglu && ((g.tw * g.th) % 32) == 0 && (g.o_sx % 8) == 0 &&
+    const bool ok = g.splitk == 1 && (g.N % 32) == 0 && g.act != kActGeglu && ((g.tw * g.th) % 32) == 0 && (g.o_sx % 8) == 0 && g.Nimg <= kGnMaxImg &&
                     ((reinterpret_cast<uintptr_t>(g.out) & 15) == 0);
     if (!ok) { sdf_set_error("gemm_plan_set_gn_stats: plan shape cannot carry statistics (split-K / ragged N / GEGLU / tile geometry)"); return SDF_ERR_UNSUPPORTED; }
     g.gn_stats[slot] = stats; g.gn_cpg[slot] = channels_per_group; g.gn_coff[slot] = channel_offset;
