@@ -134,3 +134,38 @@ def test_sds_step_small(device):
     eng.latents_in.copy_(lat.detach())
     eng.step(as_latent=True)
     assert rell2(eng.grad, grad) < 5e-2
+
+
+def test_sds_step_two_views_gradient_scale(device):
+    """loss = 0.5 * sum((latents - target)^2) / B, so d loss / d latents = grad / B (guidance/sd_utils.py:160-161).  With two views
+    per call the back-propagated gradient must carry that 1/B — checked against autograd through oracle/sd_ref.sds_train_step."""
+    unet = make_unet(SMALL_UNET, device, seed=8)
+    vae_cfg = dict(SMALL_VAE, ch_mult=(1, 2, 2, 2))
+    vae = make_vae(vae_cfg, device, seed=9)
+    eng = E.SDSEngine(unet.state_dict(), vae.state_dict(), device, SMALL_UNET, vae_cfg, n_views=2, render_hw=16, ctx_len=7, vae_res=128)
+    g = torch.Generator(device="cpu").manual_seed(10)
+    rgb = torch.rand(2, 3, 16, 16, generator=g).to(device)
+    text = torch.randn(4, 7, 64, generator=g).to(device)
+    t = torch.tensor([300, 720], device=device)
+    noise = torch.randn(2, 4, 16, 16, generator=g).to(device)
+    post = torch.randn(2, 4, 16, 16, generator=g).to(device)
+    eng.set_text(text); eng.pred_rgb.copy_(rgb); eng.t.copy_(t.int()); eng.noise.copy_(noise); eng.eps_post.copy_(post)
+    eng.guidance_scale = 7.5
+    eng.step(as_latent=False)
+    rgb_r = rgb.clone().requires_grad_(True)
+    acp = sd_ref.alphas_cumprod().to(device)
+    import torch.nn.functional as F
+    # sd_ref.sds_train_step resizes to 512: restate with this test's 128-pixel VAE input
+    rgb128 = F.interpolate(rgb_r, (128, 128), mode="bilinear", align_corners=False)
+    lat = sd_ref.posterior_sample(vae(2 * rgb128 - 1), post) * sd_ref.VAE_SCALING
+    with torch.no_grad():
+        a = acp[t].view(-1, 1, 1, 1)
+        noisy = a.sqrt() * lat + (1 - a).sqrt() * noise
+        eps = unet(torch.cat([noisy] * 2).half().float(), torch.cat([t] * 2), text.half().float())
+        e_u, e_c = eps.chunk(2)
+        grad = (1 - a) * (e_u + 7.5 * (e_c - e_u) - noise)
+    loss = 0.5 * F.mse_loss(lat, (lat - grad).detach(), reduction="sum") / lat.shape[0]
+    (g_rgb,) = torch.autograd.grad(loss, rgb_r)
+    assert rell2(eng.grad, grad) < 5e-2
+    assert abs(eng.loss.item() - loss.item()) < 0.1 * abs(loss.item())
+    assert rell2(eng.d_pred_rgb, g_rgb) < 6e-2, rell2(eng.d_pred_rgb, g_rgb)            # off by a factor B without the 1/B
