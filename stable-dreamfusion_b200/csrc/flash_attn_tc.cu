@@ -205,44 +205,56 @@ k_flash_attn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant
             tc_fence_after();
             const int key0 = j * kBN;
             const bool ragged = key0 + kBN > a.nkv;
-            // pass 1: row maximum
+            // pass 1: row maximum.  The next chunk's TMEM read is issued before the current one is consumed (tcgen05.wait::ld waits for
+            // every outstanding load, so the order is wait -> issue next -> use current).
             float mx = -INFINITY;
-#pragma unroll 1
-            for (int c = 0; c < 4; c++) {
-                uint32_t v[32];
-                tmem_ld32(t_row + c * 32, v);
-                tmem_ld_wait();
+            uint32_t va[32], vb[32];
+            tmem_ld32(t_row, va);
 #pragma unroll
-                for (int i = 0; i < 32; i++) {
-                    float s = __uint_as_float(v[i]);
-                    if (ragged && key0 + c * 32 + i >= a.nkv) s = -INFINITY;
-                    mx = fmaxf(mx, s);
+            for (int c = 0; c < 4; c++) {
+                tmem_ld_wait();
+                uint32_t (&cur)[32] = (c & 1) ? vb : va;
+                uint32_t (&nxt)[32] = (c & 1) ? va : vb;
+                tmem_ld32(t_row + ((c + 1) & 3) * 32, nxt);         // chunk c + 1; after the last chunk: chunk 0 again, for pass 2
+                if (ragged) {
+#pragma unroll
+                    for (int i = 0; i < 32; i++) mx = fmaxf(mx, key0 + c * 32 + i < a.nkv ? __uint_as_float(cur[i]) : -INFINITY);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; i += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(cur[i]), __uint_as_float(cur[i + 1])));
                 }
             }
             const float m_new = fmaxf(m, mx);                 // in units of raw scores; exponent = (s - m_new) * scale_log2
             const float alpha = ex2((m - m_new) * a.scale_log2);     // 0 on the first tile (m = -inf)
             const float mb = m_new * a.scale_log2;
             float rs = 0.f;
-            // pass 2: p = exp2(s * scale_log2 - mb), row sum, fp16 P into the swizzled A-operand layout
-#pragma unroll 1
+            // pass 2: p = exp2(s * scale_log2 - mb) evaluated two at a time in fp16 (P is fp16 for the MMA anyway: one cvt.f16x2 + one
+            // MUFU.EX2.f16x2 per pair instead of two fp32 exponentials and a pack), row sum through short fp16x2 chains folded into fp32,
+            // P into the swizzled A-operand layout.  va holds chunk 0 again (issued at the end of pass 1).
+#pragma unroll
             for (int c = 0; c < 4; c++) {
-                uint32_t v[32];
-                tmem_ld32(t_row + c * 32, v);
                 tmem_ld_wait();
+                uint32_t (&cur)[32] = (c & 1) ? vb : va;
+                uint32_t (&nxt)[32] = (c & 1) ? va : vb;
+                if (c < 3) tmem_ld32(t_row + (c + 1) * 32, nxt);
                 uint32_t pk[16];
+                __half2 acc2[4] = {__float2half2_rn(0.f), __float2half2_rn(0.f), __float2half2_rn(0.f), __float2half2_rn(0.f)};
 #pragma unroll
                 for (int i = 0; i < 16; i++) {
-                    float p0 = ex2(fmaf(__uint_as_float(v[2 * i]), a.scale_log2, -mb));
-                    float p1 = ex2(fmaf(__uint_as_float(v[2 * i + 1]), a.scale_log2, -mb));
+                    float x0 = fmaf(__uint_as_float(cur[2 * i]), a.scale_log2, -mb);
+                    float x1 = fmaf(__uint_as_float(cur[2 * i + 1]), a.scale_log2, -mb);
                     if (ragged) {
-                        if (key0 + c * 32 + 2 * i >= a.nkv) p0 = 0.f;
-                        if (key0 + c * 32 + 2 * i + 1 >= a.nkv) p1 = 0.f;
+                        if (key0 + c * 32 + 2 * i >= a.nkv) x0 = -INFINITY;
+                        if (key0 + c * 32 + 2 * i + 1 >= a.nkv) x1 = -INFINITY;
                     }
-                    const __half2 h2 = __floats2half2_rn(p0, p1);
-                    const float2 back = __half22float2(h2);         // the row sum uses what the MMA will see
-                    rs += back.x + back.y;
-                    pk[i] = *reinterpret_cast<const uint32_t*>(&h2);
+                    uint32_t h2, p2;
+                    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h2) : "f"(x1), "f"(x0));          // hi = x1, lo = x0
+                    asm("ex2.approx.f16x2 %0, %1;" : "=r"(p2) : "r"(h2));
+                    pk[i] = p2;
+                    acc2[i & 3] = __hadd2(acc2[i & 3], *reinterpret_cast<const __half2*>(&p2));
                 }
+#pragma unroll
+                for (int q = 0; q < 4; q++) { const float2 f2 = __half22float2(acc2[q]); rs += f2.x + f2.y; }
                 // columns c*32 .. c*32+31 of row r: chunk (c >> 1), 16-byte units u = (c & 1) * 4 .. +3, physical unit = u ^ (r & 7)
                 unsigned char* base = p_row + (c >> 1) * kTileBytes;
 #pragma unroll
