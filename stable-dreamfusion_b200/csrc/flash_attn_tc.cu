@@ -197,7 +197,7 @@ k_flash_attn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         float o_acc[D16];
 #pragma unroll
         for (int i = 0; i < D16; i++) o_acc[i] = 0.f;
-        float m = -INFINITY, l = 0.f;
+        float m = -INFINITY, l = 0.f, alpha_prev = 0.f;
         unsigned char* p_row = sP + r * 128;
         const int sw = r & 7;
         for (int j = 0; j < n_tiles; j++) {
@@ -228,6 +228,21 @@ k_flash_attn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant
             const float alpha = ex2((m - m_new) * a.scale_log2);     // 0 on the first tile (m = -inf)
             const float mb = m_new * a.scale_log2;
             float rs = 0.f;
+            // fold the PREVIOUS tile's T = P V into the output row now: its MMA ran while pass 1 above was reading S, so the wait is short;
+            // it also guarantees that the MMA has finished reading P before pass 2 overwrites it
+            if (j > 0) {
+                mbar_wait(t_full, (j - 1) & 1);
+                tc_fence_after();
+#pragma unroll
+                for (int c0 = 0; c0 < D16; c0 += 16) {
+                    uint32_t v[16];
+                    tmem_ld16(t_row + 128 + c0, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 16; i++) o_acc[c0 + i] = fmaf(o_acc[c0 + i], alpha_prev, __uint_as_float(v[i]));
+                }
+            }
+            alpha_prev = alpha;
             // pass 2: p = exp2(s * scale_log2 - mb) evaluated two at a time in fp16 (P is fp16 for the MMA anyway: one cvt.f16x2 + one
             // MUFU.EX2.f16x2 per pair instead of two fp32 exponentials and a pack), row sum through short fp16x2 chains folded into fp32,
             // P into the swizzled A-operand layout.  va holds chunk 0 again (issued at the end of pass 1).
@@ -269,19 +284,19 @@ k_flash_attn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             tc_fence_before();
             mbar_arrive(p_full);
-            // O_row = alpha * O_row + T_row
-            mbar_wait(t_full, j & 1);
-            tc_fence_after();
-#pragma unroll
-            for (int c0 = 0; c0 < D16; c0 += 16) {
-                uint32_t v[16];
-                tmem_ld16(t_row + 128 + c0, v);
-                tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 16; i++) o_acc[c0 + i] = fmaf(o_acc[c0 + i], alpha, __uint_as_float(v[i]));
-            }
-            tc_fence_before();
         }
+        // the last tile's T
+        mbar_wait(t_full, (n_tiles - 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int c0 = 0; c0 < D16; c0 += 16) {
+            uint32_t v[16];
+            tmem_ld16(t_row + 128 + c0, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; i++) o_acc[c0 + i] = fmaf(o_acc[c0 + i], alpha_prev, __uint_as_float(v[i]));
+        }
+        tc_fence_before();
         // ---- normalise and store
         const int qi = q0 + r;
         if (qi < a.n) {

@@ -9,7 +9,10 @@ KEYS = [("gpu__time_duration.sum", "time"), ("launch__grid_size", "grid"), ("lau
         ("dram__bytes_read.sum", "dram rd"), ("dram__bytes_write.sum", "dram wr"), ("lts__t_sector_hit_rate.pct", "L2 hit %"),
         ("l1tex__t_sector_hit_rate.pct", "L1 hit %"), ("sm__warps_active.avg.pct_of_peak_sustained_active", "warps act %"),
         ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue %"), ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor %"),
-        ("lts__throughput.avg.pct_of_peak_sustained_elapsed", "L2 thr %"), ("dram__throughput.avg.pct_of_peak_sustained_elapsed", "dram thr %")]
+        ("lts__throughput.avg.pct_of_peak_sustained_elapsed", "L2 thr %"), ("dram__throughput.avg.pct_of_peak_sustained_elapsed", "dram thr %"),
+        ("l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "L1/TEX thr %"), ("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "LSU wavefronts % of peak"),
+        ("lts__t_sectors.sum", "L2 sectors"), ("sm__cycles_elapsed.max", "cycles")]
+SKIP = ("k_level_params", "k_grad_norm", "k_advance")
 STALLS = ["long_scoreboard", "short_scoreboard", "mio_throttle", "lg_throttle", "barrier", "wait", "no_instructions", "math_pipe_throttle", "not_selected"]
 
 
@@ -26,6 +29,8 @@ for rep in sys.argv[1:]:
     ix = {h: i for i, h in enumerate(hdr)}
     for d in data:
         name = d[ix["Kernel Name"]].replace("void ", "").replace("<unnamed>::", "").split("(")[0]
+        if any(k in name for k in SKIP) or (ix.get("launch__grid_size") is not None and d[ix["launch__grid_size"]] in ("1", "2", "4")):
+            continue
         cells = []
         for k, _ in KEYS:
             if k in ix and d[ix[k]] not in ("", "n/a"):
