@@ -4,16 +4,15 @@
 //
 // for the long self-attention layers of the UNet (64x64 latents: 4096 x 4096 scores per head, d = 40; 32x32: d = 80), where the
 // mma.sync kernel of flash_attn.cu sits at its legacy-pipe issue limit.  One CTA owns 128 queries of one (batch, head):
-//   warp 8    TMA producer: the Q tile once, then K / V tiles of 128 keys through a 2-stage ring.  The tensor maps view q / k / v as
+//   warp 4    TMA producer: the Q tile once, then K / V tiles of 128 keys through a 2-stage ring.  The tensor maps view q / k / v as
 //             (d, heads, tokens, batch) so that a 64-wide box at (0, h, token0, b) is ONE head's slice, zero-filled beyond d (and beyond
 //             the last token): no padding or transposition of the projection buffers
-//   warp 9    MMA issuer: S = Q K^T (M128 x N128, K = d rounded up to 16) into TMEM columns [0,128); then, when the softmax warps have
+//   warp 5    MMA issuer: S = Q K^T (M128 x N128, K = d rounded up to 16) into TMEM columns [0,128); then, when the softmax warps have
 //             published P, T = P V (M128 x N = d rounded up to 16, K = 128 keys; V is the MN-major B operand straight from its token-major
 //             tile) into TMEM columns [128, 128 + d)
-//   warps 0-7 softmax: two threads per query row (TMEM lane = row; each thread owns one 64-key half of every tile and half of the output
-//             columns): two passes over its S columns from TMEM (maximum — the only value the two threads exchange per tile —, then
-//             exp2 in fp16x2 / partial row sum / fp16 P written to shared memory in the 128B-swizzled K-major layout the MMA reads), then
-//             O = alpha * O + T with O in registers; finally O / l -> fp16 -> global
+//   warps 0-3 softmax: thread r owns query row r (TMEM lane r) — no cross-thread reductions at all: two passes over S from TMEM (row
+//             maximum, then exp2 / row sum / fp16 P written to shared memory in the 128B-swizzled K-major layout the MMA reads), then
+//             O_row = alpha * O_row + T_row with O in registers; finally O / l -> fp16 -> global
 // Shared memory 112 KB and 256 TMEM columns per CTA: two CTAs per SM, so one CTA's exponentials overlap the other's MMAs.
 #include "common.cuh"
 #include <cuda.h>
@@ -21,7 +20,7 @@
 
 namespace {
 
-constexpr int kBM = 128, kBN = 128, kThreads = 320;      // warps 0-7 softmax, warp 8 TMA producer, warp 9 MMA issuer
+constexpr int kBM = 128, kBN = 128, kThreads = 192;
 constexpr int kTileBytes = 128 * 64 * 2;          // one [128 rows x 64 fp16] swizzled tile
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -75,10 +74,6 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t v[16]) {
                    "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
                  : "r"(taddr));
 }
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t v[8]) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "r"(taddr));
-}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ float ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
@@ -120,23 +115,22 @@ k_flash_attn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     uint64_t* p_full = bars + 6;          // P in smem, S consumed (128 arrivals)
     uint64_t* t_full = bars + 7;          // T ready in TMEM (P and the V stage are free again)
     uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(bars + 8);
-    float* mxbuf = reinterpret_cast<float*>(bars + 10);      // [2 tiles in flight][2 key halves][128 rows] partial row maxima (and the final partial row sums)
-    if (threadIdx.x == 0 && reinterpret_cast<unsigned char*>(bars) + 128 + 2048 > smem_raw + (7 * kTileBytes + 128 + 2048 + 512)) __trap();   // alignment slack exhausted
+    if (threadIdx.x == 0 && reinterpret_cast<unsigned char*>(bars) + 128 > smem_raw + (7 * kTileBytes + 128 + 896)) __trap();   // alignment slack exhausted
 
     pdl_trigger();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q0 = blockIdx.x * kBM, bh = blockIdx.y, b = bh / a.heads, h = bh - b * a.heads;
     const int n_tiles = (a.nkv + kBN - 1) / kBN;
 
-    if (warp == 8 && lane == 0) {
+    if (warp == 4 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_q) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_k) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_v) : "memory");
     }
-    if (warp == 9 && lane == 0) {
+    if (warp == 5 && lane == 0) {
         mbar_init(q_full, 1);
         for (int i = 0; i < 2; i++) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
-        mbar_init(s_full, 1); mbar_init(p_full, 256); mbar_init(t_full, 1);
+        mbar_init(s_full, 1); mbar_init(p_full, 128); mbar_init(t_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -149,7 +143,7 @@ k_flash_attn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     const uint32_t tmem_base = *tmem_base_smem;
     pdl_wait();
 
-    if (warp == 8) {
+    if (warp == 4) {
         // ===================== TMA producer =====================
         if (lane == 0) {
             mbar_expect_tx(q_full, kTileBytes);
@@ -162,7 +156,7 @@ k_flash_attn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant
                 tma_load_4d(&map_v, &kv_full[st], sV + st * kTileBytes, 0, h, j * kBN, b);
             }
         }
-    } else if (warp == 9) {
+    } else if (warp == 5) {
         // ===================== MMA issuer =====================
         constexpr uint32_t idesc_s = (1u << 4) | ((uint32_t)(kBN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);                     // K-major A and B
         // B (= V) MN-major; N = the whole 64-wide swizzle atom (columns >= d are zero-filled by the TMA and never read back)
@@ -197,42 +191,31 @@ k_flash_attn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant
             __syncwarp();
         }
     } else {
-        // ===================== softmax + output =====================
-        // 8 warps: warp w reads TMEM lanes 32 (w % 4) .. +31 (the hardware's lane-quarter rule), i.e. query rows 32 (w % 4) + lane, and owns
-        // the key half (w / 4) of every tile: 64 score columns, P chunk (w / 4), and half of the output columns.  The two threads of a row
-        // exchange only their partial row maximum per tile (shared memory + a 64-thread named barrier); row sums stay partial until the end.
-        const int q = warp & 3, half = warp >> 2;
-        const int r = q * 32 + lane;
-        const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
-        constexpr int OC = D16 / 2;                       // output columns per thread: 8, 16, 24 or 32
-        float o_acc[OC];
+        // ===================== softmax + output: thread r <-> query row r <-> TMEM lane r =====================
+        const int r = warp * 32 + lane;
+        const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16);
+        float o_acc[D16];
 #pragma unroll
-        for (int i = 0; i < OC; i++) o_acc[i] = 0.f;
+        for (int i = 0; i < D16; i++) o_acc[i] = 0.f;
         float m = -INFINITY, l = 0.f, alpha_prev = 0.f;
-        unsigned char* p_row = sP + half * kTileBytes + r * 128;
+        unsigned char* p_row = sP + r * 128;
         const int sw = r & 7;
-        auto fold_T = [&](float scale) {
-#pragma unroll
-            for (int c0 = 0; c0 < OC; c0 += 8) {
-                uint32_t v[8];
-                tmem_ld8(t_row + 128 + half * OC + c0, v);
-                tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 8; i++) o_acc[c0 + i] = fmaf(o_acc[c0 + i], scale, __uint_as_float(v[i]));
-            }
-        };
         for (int j = 0; j < n_tiles; j++) {
             mbar_wait(s_full, j & 1);
             tc_fence_after();
-            const int key0 = j * kBN + half * 64;
-            const bool ragged = key0 + 64 > a.nkv;
-            // pass 1: maximum of this thread's 64 columns (four warps per scheduler hide the TMEM read latency: no register double buffer)
+            const int key0 = j * kBN;
+            const bool ragged = key0 + kBN > a.nkv;
+            // pass 1: row maximum.  The next chunk's TMEM read is issued before the current one is consumed (tcgen05.wait::ld waits for
+            // every outstanding load, so the order is wait -> issue next -> use current).
             float mx = -INFINITY;
-            uint32_t cur[32];
+            uint32_t va[32], vb[32];
+            tmem_ld32(t_row, va);
 #pragma unroll
-            for (int c = 0; c < 2; c++) {
-                tmem_ld32(t_row + half * 64 + c * 32, cur);
+            for (int c = 0; c < 4; c++) {
                 tmem_ld_wait();
+                uint32_t (&cur)[32] = (c & 1) ? vb : va;
+                uint32_t (&nxt)[32] = (c & 1) ? va : vb;
+                tmem_ld32(t_row + ((c + 1) & 3) * 32, nxt);         // chunk c + 1; after the last chunk: chunk 0 again, for pass 2
                 if (ragged) {
 #pragma unroll
                     for (int i = 0; i < 32; i++) mx = fmaxf(mx, key0 + c * 32 + i < a.nkv ? __uint_as_float(cur[i]) : -INFINITY);
@@ -241,28 +224,34 @@ k_flash_attn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant
                     for (int i = 0; i < 32; i += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(cur[i]), __uint_as_float(cur[i + 1])));
                 }
             }
-            // row maximum over both key halves
-            mxbuf[(j & 1) * 256 + half * 128 + r] = mx;
-            asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
-            mx = fmaxf(mx, mxbuf[(j & 1) * 256 + (1 - half) * 128 + r]);
             const float m_new = fmaxf(m, mx);                 // in units of raw scores; exponent = (s - m_new) * scale_log2
             const float alpha = ex2((m - m_new) * a.scale_log2);     // 0 on the first tile (m = -inf)
             const float mb = m_new * a.scale_log2;
             float rs = 0.f;
-            // fold the PREVIOUS tile's T = P V into the output columns now: its MMA ran while pass 1 above was reading S; it also guarantees
-            // that the MMA has finished reading P before pass 2 overwrites it
+            // fold the PREVIOUS tile's T = P V into the output row now: its MMA ran while pass 1 above was reading S, so the wait is short;
+            // it also guarantees that the MMA has finished reading P before pass 2 overwrites it
             if (j > 0) {
                 mbar_wait(t_full, (j - 1) & 1);
                 tc_fence_after();
-                fold_T(alpha_prev);
+#pragma unroll
+                for (int c0 = 0; c0 < D16; c0 += 16) {
+                    uint32_t v[16];
+                    tmem_ld16(t_row + 128 + c0, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 16; i++) o_acc[c0 + i] = fmaf(o_acc[c0 + i], alpha_prev, __uint_as_float(v[i]));
+                }
             }
             alpha_prev = alpha;
-            // pass 2: p = exp2(s * scale_log2 - mb) two at a time in fp16 (P is fp16 for the MMA anyway), partial row sum through short fp16x2
-            // chains folded into fp32, P into the swizzled A-operand layout.
+            // pass 2: p = exp2(s * scale_log2 - mb) evaluated two at a time in fp16 (P is fp16 for the MMA anyway: one cvt.f16x2 + one
+            // MUFU.EX2.f16x2 per pair instead of two fp32 exponentials and a pack), row sum through short fp16x2 chains folded into fp32,
+            // P into the swizzled A-operand layout.  va holds chunk 0 again (issued at the end of pass 1).
 #pragma unroll
-            for (int c = 0; c < 2; c++) {
-                tmem_ld32(t_row + half * 64 + c * 32, cur);
+            for (int c = 0; c < 4; c++) {
                 tmem_ld_wait();
+                uint32_t (&cur)[32] = (c & 1) ? vb : va;
+                uint32_t (&nxt)[32] = (c & 1) ? va : vb;
+                if (c < 3) tmem_ld32(t_row + (c + 1) * 32, nxt);
                 uint32_t pk[16];
                 __half2 acc2[4] = {__float2half2_rn(0.f), __float2half2_rn(0.f), __float2half2_rn(0.f), __float2half2_rn(0.f)};
 #pragma unroll
@@ -280,12 +269,13 @@ k_flash_attn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant
                     acc2[i & 3] = __hadd2(acc2[i & 3], *reinterpret_cast<const __half2*>(&p2));
                 }
 #pragma unroll
-                for (int qq = 0; qq < 4; qq++) { const float2 f2 = __half22float2(acc2[qq]); rs += f2.x + f2.y; }
-                // columns c*32 .. c*32+31 of this thread's P chunk: 16-byte units u = c * 4 .. +3, physical unit = u ^ (r & 7)
+                for (int q = 0; q < 4; q++) { const float2 f2 = __half22float2(acc2[q]); rs += f2.x + f2.y; }
+                // columns c*32 .. c*32+31 of row r: chunk (c >> 1), 16-byte units u = (c & 1) * 4 .. +3, physical unit = u ^ (r & 7)
+                unsigned char* base = p_row + (c >> 1) * kTileBytes;
 #pragma unroll
                 for (int u = 0; u < 4; u++) {
-                    const int unit = (c * 4 + u) ^ sw;
-                    *reinterpret_cast<uint4*>(p_row + unit * 16) = make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+                    const int unit = ((c & 1) * 4 + u) ^ sw;
+                    *reinterpret_cast<uint4*>(base + unit * 16) = make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
                 }
             }
             l = l * alpha + rs;
@@ -298,19 +288,23 @@ k_flash_attn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         // the last tile's T
         mbar_wait(t_full, (n_tiles - 1) & 1);
         tc_fence_after();
-        fold_T(alpha_prev);
+#pragma unroll
+        for (int c0 = 0; c0 < D16; c0 += 16) {
+            uint32_t v[16];
+            tmem_ld16(t_row + 128 + c0, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; i++) o_acc[c0 + i] = fmaf(o_acc[c0 + i], alpha_prev, __uint_as_float(v[i]));
+        }
         tc_fence_before();
-        // ---- row sum over both key halves, normalise, store this thread's output columns
-        mxbuf[half * 128 + r] = l;
-        asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
-        l += mxbuf[(1 - half) * 128 + r];
+        // ---- normalise and store
         const int qi = q0 + r;
         if (qi < a.n) {
             const float inv = 1.f / l;
-            __half* op = a.o + ((size_t)b * a.n + qi) * a.ldo + h * a.d + half * OC;
+            __half* op = a.o + ((size_t)b * a.n + qi) * a.ldo + h * a.d;
 #pragma unroll
-            for (int i = 0; i < OC; i += 2) {
-                if (half * OC + i < a.d) *reinterpret_cast<__half2*>(op + i) = __floats2half2_rn(o_acc[i] * inv, o_acc[i + 1] * inv);
+            for (int i = 0; i < D16; i += 2) {
+                if (i < a.d) *reinterpret_cast<__half2*>(op + i) = __floats2half2_rn(o_acc[i] * inv, o_acc[i + 1] * inv);
             }
         }
     }
@@ -352,7 +346,7 @@ int make_head_map(CUtensorMap* map, const void* base, int d, int heads, int toke
 
 template <int D16>
 int launch_tc(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const FaArgs& a, int B, cudaStream_t st) {
-    constexpr int kSmem = 7 * kTileBytes + 128 + 2048 + 512;       // tiles + barriers + row-maximum exchange + alignment slack
+    constexpr int kSmem = 7 * kTileBytes + 128 + 896;       // tiles + barriers + alignment slack: two CTAs per SM
     static bool attr_set[64] = {false};
     int dev = 0;
     cudaGetDevice(&dev);
