@@ -476,10 +476,23 @@ k_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtens
 #pragma unroll
                         for (int slot = 0; slot < 2; slot++) {
                             if (!g.gn_stats[slot]) continue;
+                            // lane l holds column l: sum the lanes of one group first (segmented reduction towards the group's first lane), so
+                            // that each (image, group) accumulator receives ONE shared-memory add per warp — fp32 shared atomics are CAS loops,
+                            // and several lanes on one address serialise them
                             const int grp = (g.gn_coff[slot] + nbase + lane) / g.gn_cpg[slot];
-                            float* acc_p = gn_acc + ((slot * kGnMaxImg + img0) * 32 + grp) * 2;
-                            atomicAdd(acc_p, f[0]);
-                            atomicAdd(acc_p + 1, sq[0]);
+                            float s1 = f[0], s2 = sq[0];
+#pragma unroll
+                            for (int dlt = 1; dlt < 32; dlt <<= 1) {
+                                const int og = __shfl_down_sync(0xffffffffu, grp, dlt);
+                                const float o1 = __shfl_down_sync(0xffffffffu, s1, dlt), o2 = __shfl_down_sync(0xffffffffu, s2, dlt);
+                                if (lane + dlt < 32 && og == grp) { s1 += o1; s2 += o2; }
+                            }
+                            const int pg = __shfl_up_sync(0xffffffffu, grp, 1);
+                            if (lane == 0 || pg != grp) {
+                                float* acc_p = gn_acc + ((slot * kGnMaxImg + img0) * 32 + grp) * 2;
+                                atomicAdd(acc_p, s1);
+                                atomicAdd(acc_p + 1, s2);
+                            }
                         }
                     }
                 }
