@@ -182,6 +182,10 @@ int sdf_gemm_plan_create(const void* a, long long a_sx, long long a_sy, long lon
  * [Nimg, 32, 2] zeroed by the caller; channel_offset = consumer channel of this product's column 0 (concatenated inputs).  Returns
  * SDF_ERR_UNSUPPORTED for split-K / ragged-N / GEGLU plans: the caller then keeps sdf_groupnorm_forward's own statistics pass. */
 int sdf_gemm_plan_set_gn_stats(int plan, int slot, float* stats, int channels_per_group, int channel_offset);
+/* split-K finished by the CTA that adds a tile's last partial sum (no workspace memset, no reduction launch): `counters` = one zeroed uint32 per
+ * output tile (sdf_gemm_plan_num_tiles), workspace zeroed once by the caller; both are left zero after every run. */
+int sdf_gemm_plan_fold_splitk(int plan, void* counters);
+int sdf_gemm_plan_num_tiles(int plan);
 int sdf_gemm_run(int plan, void* stream);
 int sdf_gemm_plan_destroy(int plan);
 
