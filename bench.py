@@ -40,8 +40,10 @@ CYCLE = ["latent"] * 5 + (["lambertian"] * 4 + ["textureless"]) * 4        # 20 
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the two field kernels, from the ncu --set full capture summarised in
-# profiles/ (the fp16 table is L2-resident: DRAM traffic is a fraction of a percent of the algorithmic bytes)
-FIELD_DRAM_TRAFFIC = {"fwd_dram_bytes": 47.5e6, "bwd_dram_bytes": 138.7e6, "at_samples": 777269, "source": "profiles/r01_kernels.md (ncu --set full)"}
+# profiles/ (the fp16 table is L2-resident: DRAM traffic is ~11 % of the 4.8 GB of algorithmic bytes, most of it the feature stash)
+FIELD_DRAM_TRAFFIC = {"fwd_dram_bytes": 212.0e6, "bwd_dram_bytes": 318.6e6, "at_samples": 432000,
+                      "source": "profiles/r02_kernels.md (ncu --set full, same 432 k-sample launches; 180 MB of the forward's writes and 193 MB of the "
+                                "backward's reads are the feature stash)"}
 
 
 def peaks():
@@ -410,7 +412,7 @@ def run_ours(args):
                "fwd": {"ms": tfw * 1e3, "GBps": bf / tfw / 1e9, "frac": bf / tfw / 1e9 / hbm},
                "bwd": {"ms": tbw * 1e3, "GBps": bb / tbw / 1e9, "frac": bb / tbw / 1e9 / hbm},
                "l2": "flushed before every timed launch",
-               "traffic": FIELD_DRAM_TRAFFIC}
+               "traffic": FIELD_DRAM_TRAFFIC["fwd_dram_bytes"] + FIELD_DRAM_TRAFFIC["bwd_dram_bytes"], "traffic_detail": FIELD_DRAM_TRAFFIC}
         del flush, gt, aux
     except Exception as e:      # never let the auxiliary measurement kill the bench line
         fld = {"error": repr(e)}
