@@ -212,6 +212,11 @@ int sdf_flash_attention(const void* q, const void* k, const void* v, void* o, in
                         int ldq, int ldk, int ldo, float scale, void* stream);
 int sdf_softmax_rows_backward(const void* p, const void* dp, void* ds, long long rows, int cols, int ld, float scale, void* stream);
 int sdf_geglu(const void* x, int ldx, void* y, int ldy, long long rows, int inner, void* stream);
+/* direct 3x3 convolution (stride 1, zero pad 1) with <= 4 real channels on its image side, and its data-gradient: the VAE encoder's conv_in
+ * (ldm/modules/diffusionmodules/model.py:387) without the zero-padded k-blocks of the implicit GEMM.  w fp32 [Cout, Cin, 3, 3]. */
+int sdf_conv3x3_small_cin_forward(const void* x, int ldx, const float* w, const float* bias /* may be NULL */, void* y, int ldy, int Nimg, int H, int W,
+                                  int Cin, int Cout, void* stream);
+int sdf_conv3x3_small_cin_dgrad(const void* dy, int ldd, const float* w, void* dx, int ldx, int Nimg, int H, int W, int Cin, int C, void* stream);
 int sdf_upsample_nearest2(const void* x, int ldx, void* y, int ldy, int Nimg, int H, int W, int C, void* stream);
 int sdf_im2col_s2(const void* x, int ldx, void* col, int Nimg, int H, int W, int C, int Ho, int Wo, int pad_top, int pad_left, void* stream);
 int sdf_col2im_s2(const void* dcol, void* dx, int ldx, int Nimg, int H, int W, int C, int Ho, int Wo, int pad_top, int pad_left, void* stream);

@@ -675,6 +675,90 @@ __global__ void k_sds_grad(const __half* __restrict__ eps, int lde, const float*
     if ((threadIdx.x & 31) == 0 && s != 0.f) atomicAdd(loss, 0.5f * s / (float)Bimg);
 }
 
+
+// ---------------------------------------------------------------- 3x3 convolutions with <= 4 channels on one side (the VAE's image end)
+// conv_in 3 -> 128 at 512x512 and its data-gradient 128 -> 3 as implicit GEMMs pad the 3-channel side to a 64-deep k-block per tap: 97 + 123 us
+// of mostly zero operands.  Direct kernels on the FMA pipe are bound by the 67 MB activation they write / read instead.
+constexpr int kSmallC = 4;
+
+// y[n, y, x, co] = bias[co] + sum_{ky,kx,ci} x[n, y+ky-1, x+kx-1, ci] * w[co, ci, ky, kx]; thread = (pixel, 8 output channels); x rows are
+// 8-channel (16-byte) pixels of which the first Cin are real
+__global__ void __launch_bounds__(256) k_conv3x3_cin_small(const __half* __restrict__ x, int ldx, const float* __restrict__ w, const float* __restrict__ bias,
+                                                           __half* __restrict__ y, int ldy, int Nimg, int H, int W, int Cin, int Cout) {
+    extern __shared__ float s_w[];                 // [tap][ci][co]
+    pdl_prologue();
+    for (int i = threadIdx.x; i < 9 * Cin * Cout; i += blockDim.x) {
+        const int co = i % Cout, ci = (i / Cout) % Cin, tap = i / (Cout * Cin);
+        s_w[i] = w[((size_t)co * Cin + ci) * 9 + tap];
+    }
+    __syncthreads();
+    const int groups = Cout / 8;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)Nimg * H * W * groups) return;
+    const int gidx = (int)(t % groups);
+    const long long pix = t / groups;
+    const int px = (int)(pix % W), py = (int)((pix / W) % H), n = (int)(pix / ((long long)W * H));
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) acc[j] = bias ? bias[gidx * 8 + j] : 0.f;
+#pragma unroll
+    for (int tap = 0; tap < 9; tap++) {
+        const int yy = py + tap / 3 - 1, xx = px + tap % 3 - 1;
+        if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+        const uint2 raw = *reinterpret_cast<const uint2*>(x + (((size_t)n * H + yy) * W + xx) * ldx);       // 4 channels
+        const float2 a01 = __half22float2(*reinterpret_cast<const __half2*>(&raw.x)), a23 = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
+        const float in[4] = {a01.x, a01.y, a23.x, a23.y};
+        for (int ci = 0; ci < Cin; ci++) {
+            const float* wp = s_w + (tap * Cin + ci) * Cout + gidx * 8;
+#pragma unroll
+            for (int j = 0; j < 8; j++) acc[j] = fmaf(in[ci], wp[j], acc[j]);
+        }
+    }
+    uint32_t pk[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) { const __half2 h2 = __floats2half2_rn(acc[2 * j], acc[2 * j + 1]); pk[j] = *reinterpret_cast<const uint32_t*>(&h2); }
+    *reinterpret_cast<uint4*>(y + (size_t)pix * ldy + gidx * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+}
+
+// data-gradient of the same convolution: dx[n, y, x, ci] = sum_{ky,kx,co} dy[n, y-ky+1, x-kx+1, co] * w[co, ci, ky, kx]; warp = pixel, lane = C/32 channels
+__global__ void __launch_bounds__(256) k_conv3x3_cin_small_dgrad(const __half* __restrict__ dy, int ldd, const float* __restrict__ w, __half* __restrict__ dx,
+                                                                 int ldx, int Nimg, int H, int W, int Cin, int C) {
+    extern __shared__ float s_w[];                 // [tap][ci][co]
+    pdl_prologue();
+    for (int i = threadIdx.x; i < 9 * Cin * C; i += blockDim.x) {
+        const int co = i % C, ci = (i / C) % Cin, tap = i / (C * Cin);
+        s_w[i] = w[((size_t)co * Cin + ci) * 9 + tap];
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, cpl = C / 32;           // channels per lane: 4 (C = 128) or 8 (C = 256)
+    const long long pix = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (pix >= (long long)Nimg * H * W) return;
+    const int px = (int)(pix % W), py = (int)((pix / W) % H), n = (int)(pix / ((long long)W * H));
+    float acc[kSmallC] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int tap = 0; tap < 9; tap++) {
+        const int yy = py - (tap / 3) + 1, xx = px - (tap % 3) + 1;
+        if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+        const __half* dp = dy + (((size_t)n * H + yy) * W + xx) * ldd + lane * cpl;
+        for (int c0 = 0; c0 < cpl; c0 += 4) {
+            const uint2 raw = *reinterpret_cast<const uint2*>(dp + c0);
+            const float2 d01 = __half22float2(*reinterpret_cast<const __half2*>(&raw.x)), d23 = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
+            const float d[4] = {d01.x, d01.y, d23.x, d23.y};
+            for (int ci = 0; ci < Cin; ci++) {
+                const float* wp = s_w + (tap * Cin + ci) * C + lane * cpl + c0;
+                acc[ci] = fmaf(d[0], wp[0], fmaf(d[1], wp[1], fmaf(d[2], wp[2], fmaf(d[3], wp[3], acc[ci]))));
+            }
+        }
+    }
+#pragma unroll
+    for (int ci = 0; ci < kSmallC; ci++) acc[ci] = warp_sum(acc[ci]);
+    if (lane == 0) {
+        const __half2 h01 = __floats2half2_rn(acc[0], acc[1]), h23 = __floats2half2_rn(acc[2], acc[3]);
+        uint2 o; o.x = *reinterpret_cast<const uint32_t*>(&h01); o.y = *reinterpret_cast<const uint32_t*>(&h23);
+        *reinterpret_cast<uint2*>(dx + (size_t)pix * ldx) = o;           // channels >= Cin are written as zeros
+    }
+}
+
 }  // namespace
 
 #define LAUNCH_1D(kernel, total, st, ...)                                                       \
@@ -895,5 +979,34 @@ SDF_API int sdf_sds_grad(const void* eps, int lde, const float* noise, const int
     k_sds_grad<<<(total + 255) / 256, 256, 0, st>>>((const __half*)eps, lde, noise, t, alphas_cumprod, Bimg, HW, guidance_scale, grad_scale,
                                                     view_scale, (const __half*)moments, ldm, eps_post, vae_scale, grad, (__half*)d_moments, loss);
     SDF_CHECK_LAUNCH("sds_grad");
+    return SDF_OK;
+}
+
+// Direct 3x3 convolution (stride 1, zero pad 1) whose input has <= 4 real channels (x: NHWC fp16 rows of >= 4 channels, 8-byte aligned pixels);
+// w fp32 [Cout, Cin, 3, 3] (the nn.Conv2d layout), bias fp32 [Cout] or NULL.  Cout % 8 == 0.  Replaces the zero-padded implicit GEMM of the VAE's
+// conv_in (ldm/modules/diffusionmodules/model.py:387).
+SDF_API int sdf_conv3x3_small_cin_forward(const void* x, int ldx, const float* w, const float* bias, void* y, int ldy, int Nimg, int H, int W, int Cin,
+                                          int Cout, void* stream) {
+    SDF_CHECK_ARG(x && w && y && Cin >= 1 && Cin <= kSmallC && Cout % 8 == 0 && ldx % 4 == 0 && ldy % 8 == 0, "conv3x3_small_cin_forward: bad arguments");
+    const size_t smem = (size_t)9 * Cin * Cout * sizeof(float);
+    SDF_CHECK_ARG(smem <= 48 * 1024, "conv3x3_small_cin_forward: weights exceed 48 KB of shared memory");
+    const long long total = (long long)Nimg * H * W * (Cout / 8);
+    if (total == 0) return SDF_OK;
+    sdf_launch_pdl(k_conv3x3_cin_small, dim3((unsigned)((total + 255) / 256)), dim3(256), smem, (cudaStream_t)stream, (const __half*)x, ldx, w, bias, (__half*)y, ldy,
+                   Nimg, H, W, Cin, Cout);
+    SDF_CHECK_LAUNCH("conv3x3_small_cin_forward");
+    return SDF_OK;
+}
+
+// its data-gradient: dy NHWC fp16 [.., C] -> dx NHWC fp16 (4 channels written per pixel, channels >= Cin zero).  C in {32, 64, 128, 256}.
+SDF_API int sdf_conv3x3_small_cin_dgrad(const void* dy, int ldd, const float* w, void* dx, int ldx, int Nimg, int H, int W, int Cin, int C, void* stream) {
+    SDF_CHECK_ARG(dy && w && dx && Cin >= 1 && Cin <= kSmallC && C % 128 == 0 && C <= 256 && ldd % 4 == 0 && ldx % 4 == 0, "conv3x3_small_cin_dgrad: bad arguments");
+    const size_t smem = (size_t)9 * Cin * C * sizeof(float);
+    SDF_CHECK_ARG(smem <= 48 * 1024, "conv3x3_small_cin_dgrad: weights exceed 48 KB of shared memory");
+    const long long warps = (long long)Nimg * H * W;
+    if (warps == 0) return SDF_OK;
+    sdf_launch_pdl(k_conv3x3_cin_small_dgrad, dim3((unsigned)((warps * 32 + 255) / 256)), dim3(256), smem, (cudaStream_t)stream, (const __half*)dy, ldd, w, (__half*)dx,
+                   ldx, Nimg, H, W, Cin, C);
+    SDF_CHECK_LAUNCH("conv3x3_small_cin_dgrad");
     return SDF_OK;
 }

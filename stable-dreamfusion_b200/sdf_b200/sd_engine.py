@@ -33,6 +33,7 @@ USE_CTA_PAIRS = os.environ.get('SDF_GEMM_CTA_PAIRS', '1') != '0'
 # statistics-carrying epilogue costs more than the separate statistics pass it removes (k_gemm<128> 107 us vs 26 us: the per-chunk group
 # reduction runs on the critical path of single-tile CTAs and spills); kept behind the switch with its parity tests.
 FUSE_GN_STATS = os.environ.get('SDF_FUSE_GN_STATS', '0') != '0'
+DIRECT_CONV_IN = os.environ.get('SDF_DIRECT_CONV_IN', '1') != '0'          # A/B switch: FMA-pipe conv_in / conv_in^T instead of the padded implicit GEMM
 FUSE_GEGLU = os.environ.get('SDF_FUSE_GEGLU', '1') != '0'                 # A/B switch: GEGLU in the projection GEMM's epilogue      # A/B switch for the cta_group::2 GEMM variant
 
 
@@ -271,6 +272,19 @@ class Builder:
         args = (x.ptr, x.ld, y.ptr, y.ld, x.Nimg, x.H, x.W, x.C)
         self.add(name, lambda a=args, k=(x, y): _lib.call('sdf_upsample_nearest2', *a, _lib.stream()))
         self._touch(y)
+
+    def conv3x3_small_cin(self, name, x, cin, w, bias, y):
+        """direct 3x3 convolution whose input has <= 4 real channels (the VAE's conv_in); w fp32 [Cout, Cin, 3, 3]"""
+        args = (x.ptr, x.ld, w.data_ptr(), bias.data_ptr() if bias is not None else None, y.ptr, y.ld, x.Nimg, x.H, x.W, cin, y.C)
+        self.flops += 2.0 * x.rows * 9 * cin * y.C
+        self.add(name, lambda a=args, k=(x, w, bias, y): _lib.call('sdf_conv3x3_small_cin_forward', *a, _lib.stream()))
+        self._touch(y)
+
+    def conv3x3_small_cin_dgrad(self, name, dy, w, cin, dx):
+        args = (dy.ptr, dy.ld, w.data_ptr(), dx.ptr, dx.ld, dy.Nimg, dy.H, dy.W, cin, dy.C)
+        self.flops += 2.0 * dy.rows * 9 * cin * dy.C
+        self.add(name, lambda a=args, k=(dy, w, dx): _lib.call('sdf_conv3x3_small_cin_dgrad', *a, _lib.stream()))
+        self._touch(dx)
 
     def im2col_s2(self, name, x, col, pt, pl):
         args = (x.ptr, x.ld, col.data_ptr(), x.Nimg, x.H, x.W, x.C, col.shape[1], col.shape[2], pt, pl)
@@ -719,7 +733,11 @@ class VaeEncoderEngine:
         B, ch = batch, cfg['ch']
         self.img = fb.buf(B, res, res, 8, zero=True)
         x = View(fb.buf(B, res, res, ch))
-        fb.gemm('conv_in', View(self.img), cfg['in_channels'], pack_conv_weight(sd['conv_in.weight'].to(device)), ch, x, taps=9, bias=self._f32('conv_in.bias'))
+        self._w_in = _f32(sd['conv_in.weight'], device).contiguous() if DIRECT_CONV_IN and cfg['in_channels'] <= 4 and ch % 128 == 0 else None
+        if self._w_in is not None:
+            fb.conv3x3_small_cin('conv_in', View(self.img), cfg['in_channels'], self._w_in, self._f32('conv_in.bias'), x)
+        else:
+            fb.gemm('conv_in', View(self.img), cfg['in_channels'], pack_conv_weight(sd['conv_in.weight'].to(device)), ch, x, taps=9, bias=self._f32('conv_in.bias'))
         x0 = x
         in_mult = (1,) + tuple(cfg['ch_mult'])
         nlev = len(cfg['ch_mult'])
@@ -758,7 +776,10 @@ class VaeEncoderEngine:
         for fn in reversed(self._bwd):
             dx = fn(dx)
         self.d_img = bb.buf(B, res, res, 8, zero=True)
-        bb.gemm('conv_in^T', dx, ch, pack_conv_weight(_flip_conv_weight(sd['conv_in.weight'].to(device))), cfg['in_channels'], View(self.d_img), taps=9)
+        if self._w_in is not None:
+            bb.conv3x3_small_cin_dgrad('conv_in^T', dx, self._w_in, cfg['in_channels'], View(self.d_img))
+        else:
+            bb.gemm('conv_in^T', dx, ch, pack_conv_weight(_flip_conv_weight(sd['conv_in.weight'].to(device))), cfg['in_channels'], View(self.d_img), taps=9)
         self.bwd = RunList(bb.ops)
         self.flops_fwd, self.flops_bwd = fb.flops, bb.flops
         self.sd = None

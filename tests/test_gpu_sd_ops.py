@@ -138,3 +138,26 @@ def test_flash_attention(device, B, heads, n, nkv, d, fused):
     ref = torch.softmax(qf @ kf.transpose(-1, -2) * d ** -0.5, -1) @ vf
     ref = ref.permute(0, 2, 1, 3).reshape(B, n, C)
     close(o, ref, rtol=4e-3, atol=4e-3)
+
+
+@pytest.mark.parametrize("Nimg,H,W,Cin,C", [(1, 64, 64, 3, 128), (2, 17, 23, 3, 128), (1, 9, 8, 4, 256), (1, 1, 1, 3, 128)])
+def test_conv3x3_small_cin_and_its_data_gradient(device, Nimg, H, W, Cin, C):
+    """the VAE's conv_in (ldm/modules/diffusionmodules/model.py:387) as a direct convolution, against F.conv2d / its autograd on the same fp16 image"""
+    x = torch.zeros(Nimg, H, W, 8, device=device, dtype=torch.float16)
+    x[..., :Cin] = rnd(Nimg, H, W, Cin, device=device, seed=31)
+    g = torch.Generator(device="cpu").manual_seed(32)
+    w = (torch.randn(C, Cin, 3, 3, generator=g) * 0.2).to(device)
+    b = (torch.randn(C, generator=g) * 0.1).to(device)
+    y = torch.empty(Nimg, H, W, C, device=device, dtype=torch.float16)
+    _lib.call("sdf_conv3x3_small_cin_forward", _lib.ptr(x), 8, _lib.ptr(w), _lib.ptr(b), _lib.ptr(y), C, Nimg, H, W, Cin, C, _lib.stream())
+    xr = x[..., :Cin].float().permute(0, 3, 1, 2).requires_grad_(True)
+    yr = F.conv2d(xr, w, b, padding=1)
+    close(y, yr.permute(0, 2, 3, 1))
+    dy = rnd(Nimg, H, W, C, device=device, seed=33, scale=0.1)
+    dx = torch.full((Nimg, H, W, 8), 7.0, device=device, dtype=torch.float16)
+    _lib.call("sdf_conv3x3_small_cin_dgrad", _lib.ptr(dy), C, _lib.ptr(w), _lib.ptr(dx), 8, Nimg, H, W, Cin, C, _lib.stream())
+    yr.backward(dy.float().permute(0, 3, 1, 2))
+    close(dx[..., :Cin], xr.grad.permute(0, 2, 3, 1), atol=4e-3)
+    assert (dx[..., Cin:4] == 0).all() and (dx[..., 4:] == 7.0).all()        # writes exactly one 4-channel pixel
+    with pytest.raises(RuntimeError):
+        _lib.call("sdf_conv3x3_small_cin_forward", _lib.ptr(x), 8, _lib.ptr(w), _lib.ptr(b), _lib.ptr(y), C, Nimg, H, W, 5, C, _lib.stream())
