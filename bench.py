@@ -379,6 +379,7 @@ def run_ours(args):
         xyz = _rm.march_rays_train(_ro, _rd, trainer.model.bound, trainer.model.density_bitfield, trainer.model.cascade, trainer.model.grid_size, _n, _f,
                                    True, opt.dt_gamma, opt.max_steps)[0].contiguous()
         M = int(xyz.shape[0])
+        l = torch.nn.functional.normalize(torch.randn(M, 3, device=dev, generator=g), dim=-1).contiguous()
         m = trainer.model
         c = m.field_cfg()
         sn = m.sigma_net.net

@@ -10,6 +10,7 @@
 //   nearest x2                   openaimodel.py:110-120, bilinear 64->512: guidance/sd_utils.py:93
 //   SDS gradient                 guidance/sd_utils.py:103-131,160-161
 #include "common.cuh"
+#include <cooperative_groups.h>
 #include <cstdlib>
 
 namespace {
@@ -125,6 +126,98 @@ __global__ void __launch_bounds__(256) k_gn_apply(const __half* __restrict__ x, 
         for (int j = 0; j < 8; j++) { a[j] *= gamma[v * 8 + j]; b[j] = fmaf(-b[j], a[j], beta[v * 8 + j]); }
         const __half* xp = x + v * 8;
         __half* yp = y + v * 8;
+        int pix = p0 + pg;
+        for (; pix + 3 * ngroups < p1; pix += 4 * ngroups) {
+            float f[4][8];
+#pragma unroll
+            for (int u = 0; u < 4; u++) load8(xp + (base + pix + u * ngroups) * ldx, f[u]);
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+#pragma unroll
+                for (int j = 0; j < 8; j++) { const float o = fmaf(f[u][j], a[j], b[j]); f[u][j] = ACT ? silu(o) : o; }
+                store8(yp + (base + pix + u * ngroups) * ldy, f[u]);
+            }
+        }
+        for (; pix < p1; pix += ngroups) {
+            float f[8];
+            load8(xp + (base + pix) * ldx, f);
+#pragma unroll
+            for (int j = 0; j < 8; j++) { const float o = fmaf(f[j], a[j], b[j]); f[j] = ACT ? silu(o) : o; }
+            store8(yp + (base + pix) * ldy, f);
+        }
+    }
+}
+
+// One-launch GroupNorm(+SiLU) for L2-sized activations (every UNet norm): a thread-block cluster of 8 CTAs owns (image, slab of `gpc` groups);
+// CTA r of the cluster reduces rows [r, r+1) * HW/8 of the slab into shared memory, the 8 partial (sum, sum of squares) vectors are added
+// through distributed shared memory between two cluster barriers, and every CTA then normalises the rows it has just read (L1/L2-hot).
+// No statistics memset, no global atomics, no second launch; the totals are also written to `stats` for the backward.
+constexpr int kGnClusterSize = 8, kGnMaxGpc = 32;
+template <bool ACT>
+__global__ void __cluster_dims__(kGnClusterSize, 1, 1) __launch_bounds__(256)
+k_gn_cluster(const __half* __restrict__ x, int ldx, __half* __restrict__ y, int ldy, int HW, int C, int G, int gpc, float* __restrict__ stats,
+             const float* __restrict__ gamma, const float* __restrict__ beta, float eps) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    __shared__ float part[2 * kGnMaxGpc], tot[2 * kGnMaxGpc];
+    pdl_prologue();
+    const int rank = (int)cluster.block_rank(), slab = blockIdx.x / kGnClusterSize, img = blockIdx.y;
+    const int cpg = C / G, slab_c = gpc * cpg, c0 = slab * slab_c, vps = slab_c / 8;
+    const int rows_per = (HW + kGnClusterSize - 1) / kGnClusterSize;
+    const int p0 = min(HW, rank * rows_per), p1 = min(HW, p0 + rows_per);
+    const long long base = (long long)img * HW;
+    const int ngroups = max(1, (int)blockDim.x / vps);
+    if (threadIdx.x < 2 * gpc) part[threadIdx.x] = 0.f;
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < vps * ngroups; idx += blockDim.x) {
+        const int v = idx % vps, pg = idx / vps;
+        const __half* xp = x + c0 + v * 8;
+        float s[8], ss[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) s[j] = ss[j] = 0.f;
+        int pix = p0 + pg;
+        for (; pix + 3 * ngroups < p1; pix += 4 * ngroups) {
+            float f[4][8];
+#pragma unroll
+            for (int u = 0; u < 4; u++) load8(xp + (base + pix + u * ngroups) * ldx, f[u]);
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+#pragma unroll
+                for (int j = 0; j < 8; j++) { s[j] += f[u][j]; ss[j] = fmaf(f[u][j], f[u][j], ss[j]); }
+            }
+        }
+        for (; pix < p1; pix += ngroups) {
+            float f[8];
+            load8(xp + (base + pix) * ldx, f);
+#pragma unroll
+            for (int j = 0; j < 8; j++) { s[j] += f[j]; ss[j] = fmaf(f[j], f[j], ss[j]); }
+        }
+        gn_flush(part, v, cpg, s, ss);
+    }
+    __syncthreads();
+    cluster.sync();
+    if (threadIdx.x < 2 * gpc) {
+        float t = 0.f;
+#pragma unroll
+        for (int r = 0; r < kGnClusterSize; r++) t += cluster.map_shared_rank(part, r)[threadIdx.x];
+        tot[threadIdx.x] = t;
+        if (rank == 0 && stats) stats[((long long)img * G + (long long)slab * gpc) * 2 + threadIdx.x] = t;
+    }
+    cluster.sync();                       // peers have finished reading `part`; `tot` is visible to the CTA
+    const float inv_cnt = 1.f / ((float)HW * cpg);
+    for (int idx = threadIdx.x; idx < vps * ngroups; idx += blockDim.x) {
+        const int v = idx % vps, pg = idx / vps;
+        float a[8], b[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const int gi = (v * 8 + j) / cpg;
+            const float m = tot[gi * 2] * inv_cnt;
+            const float var = fmaxf(tot[gi * 2 + 1] * inv_cnt - m * m, 0.f);
+            a[j] = rsqrtf(var + eps) * gamma[c0 + v * 8 + j];
+            b[j] = fmaf(-m, a[j], beta[c0 + v * 8 + j]);
+        }
+        const __half* xp = x + c0 + v * 8;
+        __half* yp = y + c0 + v * 8;
         int pix = p0 + pg;
         for (; pix + 3 * ngroups < p1; pix += 4 * ngroups) {
             float f[4][8];
@@ -681,81 +774,137 @@ __global__ void k_sds_grad(const __half* __restrict__ eps, int lde, const float*
 // of mostly zero operands.  Direct kernels on the FMA pipe are bound by the 67 MB activation they write / read instead.
 constexpr int kSmallC = 4;
 
-// y[n, y, x, co] = bias[co] + sum_{ky,kx,ci} x[n, y+ky-1, x+kx-1, ci] * w[co, ci, ky, kx]; thread = (pixel, 8 output channels); x rows are
-// 8-channel (16-byte) pixels of which the first Cin are real
+// y[n, y, x, co] = bias[co] + sum_{ky,kx,ci} x[n, y+ky-1, x+kx-1, ci] * w[co, ci, ky, kx].  A warp = 32 consecutive pixels x ONE group of 16 output
+// channels: the weights of the group are broadcast shared-memory reads (one wavefront per LDS.128), every lane holds its pixel's 3x3xCIN patch in
+// registers and writes one full 32-byte sector.  x rows are >= 4-channel (8-byte) pixels of which the first CIN are real.
+template <int CIN>
 __global__ void __launch_bounds__(256) k_conv3x3_cin_small(const __half* __restrict__ x, int ldx, const float* __restrict__ w, const float* __restrict__ bias,
-                                                           __half* __restrict__ y, int ldy, int Nimg, int H, int W, int Cin, int Cout) {
-    extern __shared__ float s_w[];                 // [tap][ci][co]
+                                                           __half* __restrict__ y, int ldy, int Nimg, int H, int W, int Cout) {
+    extern __shared__ __align__(16) float s_w[];   // [tap][ci][co]
     pdl_prologue();
-    for (int i = threadIdx.x; i < 9 * Cin * Cout; i += blockDim.x) {
-        const int co = i % Cout, ci = (i / Cout) % Cin, tap = i / (Cout * Cin);
-        s_w[i] = w[((size_t)co * Cin + ci) * 9 + tap];
+    for (int i = threadIdx.x; i < 9 * CIN * Cout; i += blockDim.x) {
+        const int co = i % Cout, ci = (i / Cout) % CIN, tap = i / (Cout * CIN);
+        s_w[i] = w[((size_t)co * CIN + ci) * 9 + tap];
     }
     __syncthreads();
-    const int groups = Cout / 8;
-    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (long long)Nimg * H * W * groups) return;
-    const int gidx = (int)(t % groups);
-    const long long pix = t / groups;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, groups = Cout / 16;
+    const long long npix = (long long)Nimg * H * W;
+    const long long pix = (long long)blockIdx.x * 32 + lane;
+    const bool live = pix < npix;
     const int px = (int)(pix % W), py = (int)((pix / W) % H), n = (int)(pix / ((long long)W * H));
-    float acc[8];
-#pragma unroll
-    for (int j = 0; j < 8; j++) acc[j] = bias ? bias[gidx * 8 + j] : 0.f;
+    float in[9][CIN];
 #pragma unroll
     for (int tap = 0; tap < 9; tap++) {
         const int yy = py + tap / 3 - 1, xx = px + tap % 3 - 1;
-        if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
-        const uint2 raw = *reinterpret_cast<const uint2*>(x + (((size_t)n * H + yy) * W + xx) * ldx);       // 4 channels
+        uint2 raw = make_uint2(0u, 0u);
+        if (live && yy >= 0 && yy < H && xx >= 0 && xx < W) raw = *reinterpret_cast<const uint2*>(x + (((size_t)n * H + yy) * W + xx) * ldx);
         const float2 a01 = __half22float2(*reinterpret_cast<const __half2*>(&raw.x)), a23 = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
-        const float in[4] = {a01.x, a01.y, a23.x, a23.y};
-        for (int ci = 0; ci < Cin; ci++) {
-            const float* wp = s_w + (tap * Cin + ci) * Cout + gidx * 8;
+        const float v[4] = {a01.x, a01.y, a23.x, a23.y};
 #pragma unroll
-            for (int j = 0; j < 8; j++) acc[j] = fmaf(in[ci], wp[j], acc[j]);
+        for (int ci = 0; ci < CIN; ci++) in[tap][ci] = v[ci];
+    }
+    for (int grp = warp; grp < groups; grp += (int)(blockDim.x >> 5)) {
+        float acc[16];
+#pragma unroll
+        for (int j = 0; j < 16; j++) acc[j] = bias ? bias[grp * 16 + j] : 0.f;
+#pragma unroll
+        for (int tap = 0; tap < 9; tap++) {
+#pragma unroll
+            for (int ci = 0; ci < CIN; ci++) {
+                const float4* wp = reinterpret_cast<const float4*>(s_w + (tap * CIN + ci) * Cout + grp * 16);
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const float4 wv = wp[q];
+                    acc[4 * q + 0] = fmaf(in[tap][ci], wv.x, acc[4 * q + 0]);
+                    acc[4 * q + 1] = fmaf(in[tap][ci], wv.y, acc[4 * q + 1]);
+                    acc[4 * q + 2] = fmaf(in[tap][ci], wv.z, acc[4 * q + 2]);
+                    acc[4 * q + 3] = fmaf(in[tap][ci], wv.w, acc[4 * q + 3]);
+                }
+            }
+        }
+        if (live) {
+            store8(y + (size_t)pix * ldy + grp * 16, acc);
+            store8(y + (size_t)pix * ldy + grp * 16 + 8, acc + 8);
         }
     }
-    uint32_t pk[4];
-#pragma unroll
-    for (int j = 0; j < 4; j++) { const __half2 h2 = __floats2half2_rn(acc[2 * j], acc[2 * j + 1]); pk[j] = *reinterpret_cast<const uint32_t*>(&h2); }
-    *reinterpret_cast<uint4*>(y + (size_t)pix * ldy + gidx * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
 }
 
-// data-gradient of the same convolution: dx[n, y, x, ci] = sum_{ky,kx,co} dy[n, y-ky+1, x-kx+1, co] * w[co, ci, ky, kx]; warp = pixel, lane = C/32 channels
+// data-gradient of the same convolution: dx[n, y, x, ci] = sum_{ky,kx,co} dy[n, y-ky+1, x-kx+1, co] * w[co, ci, ky, kx].  A warp walks a run of pixels;
+// lane l owns channels [4l, 4l+4) (+128 for C = 256) and keeps their 9 x CIN x 4 weights in REGISTERS, so a pixel costs 9 coalesced 256-byte row reads,
+// 36 * CIN FMAs per lane and one butterfly reduction of the CIN sums.
+template <int CIN, int CPL>
 __global__ void __launch_bounds__(256) k_conv3x3_cin_small_dgrad(const __half* __restrict__ dy, int ldd, const float* __restrict__ w, __half* __restrict__ dx,
-                                                                 int ldx, int Nimg, int H, int W, int Cin, int C) {
-    extern __shared__ float s_w[];                 // [tap][ci][co]
+                                                                 int ldx, int Nimg, int H, int W, int pix_per_warp) {
     pdl_prologue();
-    for (int i = threadIdx.x; i < 9 * Cin * C; i += blockDim.x) {
-        const int co = i % C, ci = (i / C) % Cin, tap = i / (C * Cin);
-        s_w[i] = w[((size_t)co * Cin + ci) * 9 + tap];
-    }
-    __syncthreads();
-    const int lane = threadIdx.x & 31, cpl = C / 32;           // channels per lane: 4 (C = 128) or 8 (C = 256)
-    const long long pix = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (pix >= (long long)Nimg * H * W) return;
-    const int px = (int)(pix % W), py = (int)((pix / W) % H), n = (int)(pix / ((long long)W * H));
-    float acc[kSmallC] = {0.f, 0.f, 0.f, 0.f};
+    const int lane = threadIdx.x & 31;
+    constexpr int C = 32 * CPL;
+    float wr[9][CIN][CPL];
 #pragma unroll
     for (int tap = 0; tap < 9; tap++) {
-        const int yy = py - (tap / 3) + 1, xx = px - (tap % 3) + 1;
-        if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
-        const __half* dp = dy + (((size_t)n * H + yy) * W + xx) * ldd + lane * cpl;
-        for (int c0 = 0; c0 < cpl; c0 += 4) {
-            const uint2 raw = *reinterpret_cast<const uint2*>(dp + c0);
-            const float2 d01 = __half22float2(*reinterpret_cast<const __half2*>(&raw.x)), d23 = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
-            const float d[4] = {d01.x, d01.y, d23.x, d23.y};
-            for (int ci = 0; ci < Cin; ci++) {
-                const float* wp = s_w + (tap * Cin + ci) * C + lane * cpl + c0;
-                acc[ci] = fmaf(d[0], wp[0], fmaf(d[1], wp[1], fmaf(d[2], wp[2], fmaf(d[3], wp[3], acc[ci]))));
+#pragma unroll
+        for (int ci = 0; ci < CIN; ci++) {
+#pragma unroll
+            for (int c = 0; c < CPL; c++) {
+                const int co = (c / 4) * 128 + lane * 4 + (c % 4);
+                wr[tap][ci][c] = w[((size_t)co * CIN + ci) * 9 + tap];
             }
         }
     }
+    (void)C;
+    const long long npix = (long long)Nimg * H * W;
+    const long long first = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * pix_per_warp;
+    const long long last = min(npix, first + pix_per_warp);
+    constexpr int U = 4;                   // pixels per iteration: 36 row reads in flight per warp (the loop is latency-bound otherwise)
+    for (long long pix0 = first; pix0 < last; pix0 += U) {
+        uint2 raw[U][9][CPL / 4];
 #pragma unroll
-    for (int ci = 0; ci < kSmallC; ci++) acc[ci] = warp_sum(acc[ci]);
-    if (lane == 0) {
-        const __half2 h01 = __floats2half2_rn(acc[0], acc[1]), h23 = __floats2half2_rn(acc[2], acc[3]);
-        uint2 o; o.x = *reinterpret_cast<const uint32_t*>(&h01); o.y = *reinterpret_cast<const uint32_t*>(&h23);
-        *reinterpret_cast<uint2*>(dx + (size_t)pix * ldx) = o;           // channels >= Cin are written as zeros
+        for (int u = 0; u < U; u++) {
+            const long long pix = pix0 + u;
+            const int px = (int)(pix % W), py = (int)((pix / W) % H), n = (int)(pix / ((long long)W * H));
+#pragma unroll
+            for (int tap = 0; tap < 9; tap++) {
+                const int yy = py - (tap / 3) + 1, xx = px - (tap % 3) + 1;
+                const bool ok = pix < last && yy >= 0 && yy < H && xx >= 0 && xx < W;      // warp-uniform
+                const __half* dp = dy + (((size_t)n * H + yy) * W + xx) * ldd + lane * 4;
+#pragma unroll
+                for (int c4 = 0; c4 < CPL / 4; c4++) raw[u][tap][c4] = ok ? *reinterpret_cast<const uint2*>(dp + c4 * 128) : make_uint2(0u, 0u);
+            }
+        }
+        float acc[U][CIN];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+#pragma unroll
+            for (int ci = 0; ci < CIN; ci++) acc[u][ci] = 0.f;
+#pragma unroll
+            for (int tap = 0; tap < 9; tap++) {
+#pragma unroll
+                for (int c4 = 0; c4 < CPL / 4; c4++) {
+                    const float2 d01 = __half22float2(*reinterpret_cast<const __half2*>(&raw[u][tap][c4].x));
+                    const float2 d23 = __half22float2(*reinterpret_cast<const __half2*>(&raw[u][tap][c4].y));
+#pragma unroll
+                    for (int ci = 0; ci < CIN; ci++)
+                        acc[u][ci] = fmaf(d01.x, wr[tap][ci][4 * c4], fmaf(d01.y, wr[tap][ci][4 * c4 + 1],
+                                     fmaf(d23.x, wr[tap][ci][4 * c4 + 2], fmaf(d23.y, wr[tap][ci][4 * c4 + 3], acc[u][ci]))));
+                }
+            }
+        }
+        // reduce the U x CIN sums over the 32 lanes; lane u ends up writing pixel u
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+#pragma unroll
+            for (int ci = 0; ci < CIN; ci++) acc[u][ci] = warp_sum(acc[u][ci]);
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            if (lane == u && pix0 + u < last) {
+                float o[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int ci = 0; ci < CIN; ci++) o[ci] = acc[u][ci];
+                const __half2 h01 = __floats2half2_rn(o[0], o[1]), h23 = __floats2half2_rn(o[2], o[3]);
+                uint2 ov; ov.x = *reinterpret_cast<const uint32_t*>(&h01); ov.y = *reinterpret_cast<const uint32_t*>(&h23);
+                *reinterpret_cast<uint2*>(dx + (size_t)(pix0 + u) * ldx) = ov;       // channels >= CIN of the 4-channel pixel are written as zeros
+            }
+        }
     }
 }
 
@@ -791,6 +940,21 @@ static int groupnorm_forward_impl(const void* x, int ldx, void* y, int ldy, int 
     SDF_CHECK_ARG(x && y && gamma && beta && stats, "groupnorm_forward: null pointer");
     SDF_CHECK_ARG(C % 8 == 0 && C % G == 0 && ldx % 8 == 0 && ldy % 8 == 0, "groupnorm_forward: C %% 8, C %% G, ld %% 8 must be 0");
     cudaStream_t st = (cudaStream_t)stream;
+    // one cluster launch when the tensor is L2-sized and (images x group slabs) x 8 CTAs fill the GPU; the big VAE activations take two passes
+    static const bool use_cluster = [] { const char* e = std::getenv("SDF_GN_CLUSTER"); return !(e && e[0] == '0'); }();
+    if (use_cluster && HW >= 64 && (long long)Nimg * HW * C * 2 <= (32ll << 20)) {
+        const int cpg = C / G;
+        int gpc = 0;
+        for (int d = 1; d <= G && d <= kGnMaxGpc; d++)
+            if (G % d == 0 && (d * cpg) % 8 == 0 && d * cpg >= 32) { gpc = d; break; }
+        if (gpc && (long long)Nimg * (G / gpc) * kGnClusterSize >= 96) {
+            dim3 grid((unsigned)(G / gpc * kGnClusterSize), (unsigned)Nimg);
+            if (silu_act) sdf_launch_pdl(k_gn_cluster<true>, grid, dim3(256), (size_t)0, st, (const __half*)x, ldx, (__half*)y, ldy, HW, C, G, gpc, stats, gamma, beta, eps);
+            else sdf_launch_pdl(k_gn_cluster<false>, grid, dim3(256), (size_t)0, st, (const __half*)x, ldx, (__half*)y, ldy, HW, C, G, gpc, stats, gamma, beta, eps);
+            SDF_CHECK_LAUNCH("groupnorm(cluster)");
+            return SDF_OK;
+        }
+    }
     if (zero_stats) SDF_CHECK_CUDA(cudaMemsetAsync(stats, 0, sizeof(float) * 2 * G * Nimg, st));
     const int vpp = C / 8;
     // two passes: ~16 vectors per thread for large tensors, at least ~4 blocks per SM for small ones
@@ -983,30 +1147,39 @@ SDF_API int sdf_sds_grad(const void* eps, int lde, const float* noise, const int
 }
 
 // Direct 3x3 convolution (stride 1, zero pad 1) whose input has <= 4 real channels (x: NHWC fp16 rows of >= 4 channels, 8-byte aligned pixels);
-// w fp32 [Cout, Cin, 3, 3] (the nn.Conv2d layout), bias fp32 [Cout] or NULL.  Cout % 8 == 0.  Replaces the zero-padded implicit GEMM of the VAE's
+// w fp32 [Cout, Cin, 3, 3] (the nn.Conv2d layout), bias fp32 [Cout] or NULL.  Cout % 16 == 0.  Replaces the zero-padded implicit GEMM of the VAE's
 // conv_in (ldm/modules/diffusionmodules/model.py:387).
 SDF_API int sdf_conv3x3_small_cin_forward(const void* x, int ldx, const float* w, const float* bias, void* y, int ldy, int Nimg, int H, int W, int Cin,
                                           int Cout, void* stream) {
-    SDF_CHECK_ARG(x && w && y && Cin >= 1 && Cin <= kSmallC && Cout % 8 == 0 && ldx % 4 == 0 && ldy % 8 == 0, "conv3x3_small_cin_forward: bad arguments");
+    SDF_CHECK_ARG(x && w && y && Cin >= 1 && Cin <= kSmallC && Cout % 16 == 0 && ldx % 4 == 0 && ldy % 8 == 0, "conv3x3_small_cin_forward: bad arguments");
     const size_t smem = (size_t)9 * Cin * Cout * sizeof(float);
     SDF_CHECK_ARG(smem <= 48 * 1024, "conv3x3_small_cin_forward: weights exceed 48 KB of shared memory");
-    const long long total = (long long)Nimg * H * W * (Cout / 8);
-    if (total == 0) return SDF_OK;
-    sdf_launch_pdl(k_conv3x3_cin_small, dim3((unsigned)((total + 255) / 256)), dim3(256), smem, (cudaStream_t)stream, (const __half*)x, ldx, w, bias, (__half*)y, ldy,
-                   Nimg, H, W, Cin, Cout);
+    const long long npix = (long long)Nimg * H * W;
+    if (npix == 0) return SDF_OK;
+    const dim3 grid((unsigned)((npix + 31) / 32)), block(256);
+    cudaStream_t st = (cudaStream_t)stream;
+#define CONV_FWD(CI) sdf_launch_pdl(k_conv3x3_cin_small<CI>, grid, block, smem, st, (const __half*)x, ldx, w, bias, (__half*)y, ldy, Nimg, H, W, Cout)
+    switch (Cin) { case 1: CONV_FWD(1); break; case 2: CONV_FWD(2); break; case 3: CONV_FWD(3); break; default: CONV_FWD(4); break; }
+#undef CONV_FWD
     SDF_CHECK_LAUNCH("conv3x3_small_cin_forward");
     return SDF_OK;
 }
 
-// its data-gradient: dy NHWC fp16 [.., C] -> dx NHWC fp16 (4 channels written per pixel, channels >= Cin zero).  C in {32, 64, 128, 256}.
+// its data-gradient: dy NHWC fp16 [.., C] -> dx NHWC fp16 (4 channels written per pixel, channels >= Cin zero).  C in {128, 256}.
 SDF_API int sdf_conv3x3_small_cin_dgrad(const void* dy, int ldd, const float* w, void* dx, int ldx, int Nimg, int H, int W, int Cin, int C, void* stream) {
-    SDF_CHECK_ARG(dy && w && dx && Cin >= 1 && Cin <= kSmallC && C % 128 == 0 && C <= 256 && ldd % 4 == 0 && ldx % 4 == 0, "conv3x3_small_cin_dgrad: bad arguments");
-    const size_t smem = (size_t)9 * Cin * C * sizeof(float);
-    SDF_CHECK_ARG(smem <= 48 * 1024, "conv3x3_small_cin_dgrad: weights exceed 48 KB of shared memory");
-    const long long warps = (long long)Nimg * H * W;
-    if (warps == 0) return SDF_OK;
-    sdf_launch_pdl(k_conv3x3_cin_small_dgrad, dim3((unsigned)((warps * 32 + 255) / 256)), dim3(256), smem, (cudaStream_t)stream, (const __half*)dy, ldd, w, (__half*)dx,
-                   ldx, Nimg, H, W, Cin, C);
+    SDF_CHECK_ARG(dy && w && dx && Cin >= 1 && Cin <= kSmallC && (C == 128 || C == 256) && ldd % 4 == 0 && ldx % 4 == 0, "conv3x3_small_cin_dgrad: bad arguments");
+    const long long npix = (long long)Nimg * H * W;
+    if (npix == 0) return SDF_OK;
+    // ~4 CTAs of 8 warps per SM, at least 8 pixels per warp so that the register-resident weights are amortised
+    const long long warps_target = (long long)sdf_num_sms() * 4 * 8;
+    const int ppw = (int)max(8ll, (npix + warps_target - 1) / warps_target);
+    const long long warps = (npix + ppw - 1) / ppw;
+    const dim3 grid((unsigned)((warps + 7) / 8)), block(256);
+    cudaStream_t st = (cudaStream_t)stream;
+#define CONV_DG(CI, CPL) sdf_launch_pdl(k_conv3x3_cin_small_dgrad<CI, CPL>, grid, block, (size_t)0, st, (const __half*)dy, ldd, w, (__half*)dx, ldx, Nimg, H, W, ppw)
+    if (C == 128) { switch (Cin) { case 1: CONV_DG(1, 4); break; case 2: CONV_DG(2, 4); break; case 3: CONV_DG(3, 4); break; default: CONV_DG(4, 4); break; } }
+    else { switch (Cin) { case 1: CONV_DG(1, 8); break; case 2: CONV_DG(2, 8); break; case 3: CONV_DG(3, 8); break; default: CONV_DG(4, 8); break; } }
+#undef CONV_DG
     SDF_CHECK_LAUNCH("conv3x3_small_cin_dgrad");
     return SDF_OK;
 }
