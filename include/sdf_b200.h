@@ -182,10 +182,6 @@ int sdf_gemm_plan_create(const void* a, long long a_sx, long long a_sy, long lon
  * [Nimg, 32, 2] zeroed by the caller; channel_offset = consumer channel of this product's column 0 (concatenated inputs).  Returns
  * SDF_ERR_UNSUPPORTED for split-K / ragged-N / GEGLU plans: the caller then keeps sdf_groupnorm_forward's own statistics pass. */
 int sdf_gemm_plan_set_gn_stats(int plan, int slot, float* stats, int channels_per_group, int channel_offset);
-/* split-K finished by the CTA that adds a tile's last partial sum (no workspace memset, no reduction launch): `counters` = one zeroed uint32 per
- * output tile (sdf_gemm_plan_num_tiles), workspace zeroed once by the caller; both are left zero after every run. */
-int sdf_gemm_plan_fold_splitk(int plan, void* counters);
-int sdf_gemm_plan_num_tiles(int plan);
 int sdf_gemm_run(int plan, void* stream);
 int sdf_gemm_plan_destroy(int plan);
 
@@ -289,6 +285,31 @@ int sdf_expand_ray_vec3(const float* values, const int* rays, uint32_t N, uint32
 /* pinhole rays (nerf/utils.py:113-176, N = -1) of pixels first, first + stride, ... of each of the B poses [B,4,4] */
 int sdf_get_rays(const float* poses, uint32_t B, uint32_t H, uint32_t W, float focal, float cx, float cy, uint32_t first, uint32_t stride,
                  float* rays_o, float* rays_d, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------------------------
+ * DMTet stage (BASELINE config C5): marching tetrahedra on a fixed lattice, mesh normals, mesh regularisers, differentiable rasterisation.
+ * Replaces the eager PyTorch of nerf/renderer.py:94-174 (DMTet.__call__), :877-890 (normals), :176-254 (normal_consistency,
+ * laplacian_smooth_loss) and the nvdiffrast calls of :893-903 (rasterize, interpolate).  Every output is capacity-sized with device-side
+ * counts[4] = (vertices, faces, one-triangle tets, two-triangle tets): no host synchronisation.  Lattice topology: sdf_b200/tetgrid.py. */
+long long sdf_dmtet_scratch_ints(int E, int F);
+int sdf_dmtet_extract(const float* pos, const float* deform /* may be NULL */, float tet_grid_size, const float* sdf, const int* tets, const int* edges,
+                      const int* tet_edges, int N, int F, int E, float* verts, int* vert_edge, int* faces, int* counts, int* scratch, void* stream);
+int sdf_dmtet_extract_backward(const float* pos, const float* deform, float tet_grid_size, const float* sdf, const int* edges, const int* vert_edge,
+                               const int* counts, int E, const float* d_verts, float* d_sdf, float* d_deform, void* stream);
+int sdf_mesh_normals_forward(const float* verts, const int* faces, const int* counts, int vcap, int fcap, float* face_n, float* vert_n_raw, float* vert_n,
+                             void* stream);
+int sdf_mesh_normals_backward(const float* verts, const int* faces, const int* counts, int fcap, const float* vert_n_raw, const float* d_vert_n,
+                              const float* d_face_n, float* d_verts, void* stream);
+int sdf_mesh_halfedge_keys(const int* faces, const int* counts, int vcap, int fcap, long long* keys, int* face_of, void* stream);
+int sdf_mesh_losses_forward(const long long* sorted_keys, const int* sorted_face_of, const int* counts, int vcap, int fcap, const float* face_n,
+                            const float* verts, float* work, float* losses, void* stream);
+int sdf_mesh_losses_backward(const long long* sorted_keys, const int* sorted_face_of, const int* counts, int vcap, int fcap, const float* face_n,
+                             const float* work, const float* g /* device [2] */, float* d_face_n, float* d_verts, void* stream);
+int sdf_mesh_clip_transform(const float* verts, const int* counts, int vcap, const float* mvp, float* clip, void* stream);
+int sdf_mesh_rasterize(const float* clip, const int* faces, const int* counts, int fcap, const float* verts, const float* vert_n, int H, int W,
+                       void* zbuf, float* rast, float* xyz, float* nrm, float* mask, void* stream);
+int sdf_mesh_rasterize_backward(const float* rast, const float* clip, const int* faces, const float* verts, const float* vert_n, const float* mvp, int H,
+                                int W, const float* d_xyz, const float* d_nrm, float* d_verts, float* d_vert_n, void* stream);
 
 #ifdef __cplusplus
 }

@@ -54,8 +54,6 @@ struct GemmArgs {
     float alpha;                     // scale applied to the accumulator before bias
     // GroupNorm statistics of up to two CONSUMERS of this output, accumulated by the epilogue (sum and sum of squares per (image, group),
     // fp32 atomics into [Nimg, 32, 2]): the consumer's separate statistics pass (a full re-read of the tensor) disappears
-    unsigned* tile_counters;         // split-K: arrivals per output tile; the LAST split's CTA finishes the tile (epilogue + fp16 store) and
-                                     // leaves workspace and counter zeroed for the next run: no memset, no separate epilogue launch
     float* gn_stats[2];
     int gn_cpg[2];                   // channels per group of the consumer's GroupNorm
     int gn_coff[2];                  // channel of the consumer's tensor that this product's column 0 lands on
@@ -478,23 +476,10 @@ k_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtens
 #pragma unroll
                         for (int slot = 0; slot < 2; slot++) {
                             if (!g.gn_stats[slot]) continue;
-                            // lane l holds column l: sum the lanes of one group first (segmented reduction towards the group's first lane), so
-                            // that each (image, group) accumulator receives ONE shared-memory add per warp — fp32 shared atomics are CAS loops,
-                            // and several lanes on one address serialise them
                             const int grp = (g.gn_coff[slot] + nbase + lane) / g.gn_cpg[slot];
-                            float s1 = f[0], s2 = sq[0];
-#pragma unroll
-                            for (int dlt = 1; dlt < 32; dlt <<= 1) {
-                                const int og = __shfl_down_sync(0xffffffffu, grp, dlt);
-                                const float o1 = __shfl_down_sync(0xffffffffu, s1, dlt), o2 = __shfl_down_sync(0xffffffffu, s2, dlt);
-                                if (lane + dlt < 32 && og == grp) { s1 += o1; s2 += o2; }
-                            }
-                            const int pg = __shfl_up_sync(0xffffffffu, grp, 1);
-                            if (lane == 0 || pg != grp) {
-                                float* acc_p = gn_acc + ((slot * kGnMaxImg + img0) * 32 + grp) * 2;
-                                atomicAdd(acc_p, s1);
-                                atomicAdd(acc_p + 1, s2);
-                            }
+                            float* acc_p = gn_acc + ((slot * kGnMaxImg + img0) * 32 + grp) * 2;
+                            atomicAdd(acc_p, f[0]);
+                            atomicAdd(acc_p + 1, sq[0]);
                         }
                     }
                 }
@@ -519,67 +504,6 @@ k_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtens
                 else mbar_arrive(&tmem_empty[acc]);
             }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-            if (g.tile_counters) {
-                // ---- split-K, folded epilogue: this CTA's partial tile is in the workspace (fp32 reductions above).  Count the arrival; the CTA
-                //      that completes the tile reads the sums back (L2), applies bias / embedding / residual / activation, stores fp16 and
-                //      zeroes workspace + counter for the next run.
-                __threadfence();
-                asm volatile("bar.sync 2, 256;" ::: "memory");
-                if (threadIdx.x == 64) {
-                    const unsigned tile_id = (unsigned)(mt * n_tiles + nt);
-                    const unsigned ticket = atomicAdd(&g.tile_counters[tile_id], 1u);
-                    const bool last = ticket == (unsigned)g.splitk - 1u;
-                    if (last) g.tile_counters[tile_id] = 0u;
-                    tmem_base_smem[1] = last ? 1u : 0u;
-                }
-                asm volatile("bar.sync 2, 256;" ::: "memory");
-                if (tmem_base_smem[1]) {
-                    __threadfence();
-                    for (int ch = half; ch < kChunks; ch += 2) {
-                        const int nbase = n0 + ch * 32;
-                        if (!(row_ok && nbase + 32 <= g.N)) continue;
-                        float4* wsp = reinterpret_cast<float4*>(g.workspace + m * g.N + nbase);
-                        float f[32];
-#pragma unroll
-                        for (int j = 0; j < 8; j++) {
-                            const float4 v4 = __ldcg(wsp + j);
-                            f[4 * j] = v4.x; f[4 * j + 1] = v4.y; f[4 * j + 2] = v4.z; f[4 * j + 3] = v4.w;
-                            wsp[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        }
-                        if (g.bias) {
-#pragma unroll
-                            for (int j = 0; j < 8; j++) {
-                                const float4 b4 = __ldg(reinterpret_cast<const float4*>(g.bias + nbase) + j);
-                                f[4 * j] += b4.x; f[4 * j + 1] += b4.y; f[4 * j + 2] += b4.z; f[4 * j + 3] += b4.w;
-                            }
-                        }
-#pragma unroll
-                        for (int j = 0; j < 4; j++) {
-                            if (temb_row) {
-                                const uint4 t4 = __ldg(reinterpret_cast<const uint4*>(temb_row + nbase) + j);
-                                const __half2* hh = reinterpret_cast<const __half2*>(&t4);
-#pragma unroll
-                                for (int k = 0; k < 4; k++) { const float2 t2v = __half22float2(hh[k]); f[8 * j + 2 * k] += t2v.x; f[8 * j + 2 * k + 1] += t2v.y; }
-                            }
-                            if (res_row) {
-                                const uint4 r4 = *(reinterpret_cast<const uint4*>(res_row + nbase) + j);
-                                const __half2* hh = reinterpret_cast<const __half2*>(&r4);
-#pragma unroll
-                                for (int k = 0; k < 4; k++) { const float2 t2v = __half22float2(hh[k]); f[8 * j + 2 * k] += t2v.x; f[8 * j + 2 * k + 1] += t2v.y; }
-                            }
-                        }
-                        uint32_t pk[16];
-#pragma unroll
-                        for (int j = 0; j < 16; j++) {
-                            const __half2 h2 = __floats2half2_rn(act_apply(f[2 * j], g.act), act_apply(f[2 * j + 1], g.act));
-                            pk[j] = *reinterpret_cast<const uint32_t*>(&h2);
-                        }
-                        __half* o = out_row + nbase;
-#pragma unroll
-                        for (int j = 0; j < 4; j++) *reinterpret_cast<uint4*>(o + 8 * j) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
-                    }
-                }
-            }
         }
         if (STATS) {
             // all 8 epilogue warps have added their last tile: flush the CTA's (image, group) partial sums, one global atomic each
@@ -656,7 +580,7 @@ int launch_gemm_v(const GemmPlan& p, cudaStream_t st) {
         attr_set[dev] = true;
     }
     // split-K plans follow their workspace memset: programmatic launch needs a kernel as stream predecessor
-    const bool pdl = sdf_pdl_enabled() && (p.args.splitk == 1 || p.args.tile_counters);
+    const bool pdl = sdf_pdl_enabled() && p.args.splitk == 1;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(p.grid); cfg.blockDim = dim3(kNumThreads); cfg.dynamicSmemBytes = L::kTotal; cfg.stream = st;
     cudaLaunchAttribute attr[2];
@@ -750,7 +674,6 @@ SDF_API int sdf_gemm_plan_create(const void* a, long long a_sx, long long a_sy, 
     g.out = (__half*)out; g.o_sx = o_sx; g.o_sy = o_sy; g.o_simg = o_simg; g.workspace = workspace;
     g.act = act; g.alpha = alpha;
     g.gn_stats[0] = g.gn_stats[1] = nullptr; g.gn_cpg[0] = g.gn_cpg[1] = 1; g.gn_coff[0] = g.gn_coff[1] = 0;
-    g.tile_counters = nullptr;
     p->block_n = block_n;
     p->pair = cta_pair ? 1 : 0;
 
@@ -804,30 +727,6 @@ SDF_API int sdf_gemm_plan_set_gn_stats(int plan, int slot, float* stats, int cha
     return SDF_OK;
 }
 
-// Split-K without the separate reduction launch: `counters` (one uint32 per output tile, >= sdf_gemm_plan_num_tiles(plan)) and the plan's
-// workspace must be zero when the plan first runs; every run leaves them zero again (the CTA that adds the last partial sum of a tile applies the
-// epilogue and clears them).  Requirements: splitk > 1, N % 32 == 0, no GEGLU, 16-byte aligned output rows; else SDF_ERR_UNSUPPORTED.
-SDF_API int sdf_gemm_plan_fold_splitk(int plan, void* counters) {
-    std::lock_guard<std::mutex> lk(g_plan_mu);
-    SDF_CHECK_ARG(plan >= 0 && plan < (int)g_plans.size() && g_plans[plan] && counters, "gemm_plan_fold_splitk: bad arguments");
-    GemmArgs& g = g_plans[plan]->args;
-    const bool ok = g.splitk > 1 && (g.N % 32) == 0 && g.act != kActGeglu && (g.o_sx % 8) == 0 && ((reinterpret_cast<uintptr_t>(g.out) & 15) == 0) &&
-                    !g.gn_stats[0] && !g.gn_stats[1];
-    if (!ok) { sdf_set_error("gemm_plan_fold_splitk: plan shape cannot fold its split-K epilogue"); return SDF_ERR_UNSUPPORTED; }
-    g.tile_counters = reinterpret_cast<unsigned*>(counters);
-    return SDF_OK;
-}
-
-SDF_API int sdf_gemm_plan_num_tiles(int plan) {
-    std::lock_guard<std::mutex> lk(g_plan_mu);
-    SDF_CHECK_ARG(plan >= 0 && plan < (int)g_plans.size() && g_plans[plan], "gemm_plan_num_tiles: bad plan handle");
-    const GemmArgs& g = g_plans[plan]->args;
-    const int tiles_x = (g.W + g.tw - 1) / g.tw, tiles_y = (g.H + g.th - 1) / g.th, tiles_i = (g.Nimg + g.tn - 1) / g.tn;
-    int m_tiles = tiles_x * tiles_y * tiles_i;
-    if (g_plans[plan]->pair) m_tiles = (m_tiles + 1) / 2 * 2;
-    return m_tiles * ((g.N + g_plans[plan]->block_n - 1) / g_plans[plan]->block_n);
-}
-
 SDF_API int sdf_gemm_run(int plan, void* stream) {
     GemmPlan* p;
     {
@@ -837,8 +736,7 @@ SDF_API int sdf_gemm_run(int plan, void* stream) {
     }
     cudaStream_t st = (cudaStream_t)stream;
     const GemmArgs& g = p->args;
-    const bool fold = g.splitk > 1 && g.tile_counters;
-    if (g.splitk > 1 && !fold) SDF_CHECK_CUDA(cudaMemsetAsync(g.workspace, 0, (size_t)g.M * g.N * sizeof(float), st));
+    if (g.splitk > 1) SDF_CHECK_CUDA(cudaMemsetAsync(g.workspace, 0, (size_t)g.M * g.N * sizeof(float), st));
     int rc;
     if (p->pair) {
         if (p->block_n == 128) rc = launch_gemm<128, true>(*p, st);
@@ -851,7 +749,7 @@ SDF_API int sdf_gemm_run(int plan, void* stream) {
     }
     if (rc) return rc;
     SDF_CHECK_LAUNCH("gemm");
-    if (g.splitk > 1 && !fold) {
+    if (g.splitk > 1) {
         const long long total = (long long)g.M * g.N;
         sdf_launch_pdl(k_splitk_epilogue, dim3((unsigned)((total + 255) / 256)), dim3(256), (size_t)0, st, (const float*)g.workspace, g);
         SDF_CHECK_LAUNCH("gemm(split-K epilogue)");

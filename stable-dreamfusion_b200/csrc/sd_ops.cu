@@ -10,7 +10,6 @@
 //   nearest x2                   openaimodel.py:110-120, bilinear 64->512: guidance/sd_utils.py:93
 //   SDS gradient                 guidance/sd_utils.py:103-131,160-161
 #include "common.cuh"
-#include <cooperative_groups.h>
 #include <cstdlib>
 
 namespace {
@@ -126,98 +125,6 @@ __global__ void __launch_bounds__(256) k_gn_apply(const __half* __restrict__ x, 
         for (int j = 0; j < 8; j++) { a[j] *= gamma[v * 8 + j]; b[j] = fmaf(-b[j], a[j], beta[v * 8 + j]); }
         const __half* xp = x + v * 8;
         __half* yp = y + v * 8;
-        int pix = p0 + pg;
-        for (; pix + 3 * ngroups < p1; pix += 4 * ngroups) {
-            float f[4][8];
-#pragma unroll
-            for (int u = 0; u < 4; u++) load8(xp + (base + pix + u * ngroups) * ldx, f[u]);
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-#pragma unroll
-                for (int j = 0; j < 8; j++) { const float o = fmaf(f[u][j], a[j], b[j]); f[u][j] = ACT ? silu(o) : o; }
-                store8(yp + (base + pix + u * ngroups) * ldy, f[u]);
-            }
-        }
-        for (; pix < p1; pix += ngroups) {
-            float f[8];
-            load8(xp + (base + pix) * ldx, f);
-#pragma unroll
-            for (int j = 0; j < 8; j++) { const float o = fmaf(f[j], a[j], b[j]); f[j] = ACT ? silu(o) : o; }
-            store8(yp + (base + pix) * ldy, f);
-        }
-    }
-}
-
-// One-launch GroupNorm(+SiLU) for L2-sized activations (every UNet norm): a thread-block cluster of 8 CTAs owns (image, slab of `gpc` groups);
-// CTA r of the cluster reduces rows [r, r+1) * HW/8 of the slab into shared memory, the 8 partial (sum, sum of squares) vectors are added
-// through distributed shared memory between two cluster barriers, and every CTA then normalises the rows it has just read (L1/L2-hot).
-// No statistics memset, no global atomics, no second launch; the totals are also written to `stats` for the backward.
-constexpr int kGnClusterSize = 8, kGnMaxGpc = 32;
-template <bool ACT>
-__global__ void __cluster_dims__(kGnClusterSize, 1, 1) __launch_bounds__(256)
-k_gn_cluster(const __half* __restrict__ x, int ldx, __half* __restrict__ y, int ldy, int HW, int C, int G, int gpc, float* __restrict__ stats,
-             const float* __restrict__ gamma, const float* __restrict__ beta, float eps) {
-    namespace cg = cooperative_groups;
-    cg::cluster_group cluster = cg::this_cluster();
-    __shared__ float part[2 * kGnMaxGpc], tot[2 * kGnMaxGpc];
-    pdl_prologue();
-    const int rank = (int)cluster.block_rank(), slab = blockIdx.x / kGnClusterSize, img = blockIdx.y;
-    const int cpg = C / G, slab_c = gpc * cpg, c0 = slab * slab_c, vps = slab_c / 8;
-    const int rows_per = (HW + kGnClusterSize - 1) / kGnClusterSize;
-    const int p0 = min(HW, rank * rows_per), p1 = min(HW, p0 + rows_per);
-    const long long base = (long long)img * HW;
-    const int ngroups = max(1, (int)blockDim.x / vps);
-    if (threadIdx.x < 2 * gpc) part[threadIdx.x] = 0.f;
-    __syncthreads();
-    for (int idx = threadIdx.x; idx < vps * ngroups; idx += blockDim.x) {
-        const int v = idx % vps, pg = idx / vps;
-        const __half* xp = x + c0 + v * 8;
-        float s[8], ss[8];
-#pragma unroll
-        for (int j = 0; j < 8; j++) s[j] = ss[j] = 0.f;
-        int pix = p0 + pg;
-        for (; pix + 3 * ngroups < p1; pix += 4 * ngroups) {
-            float f[4][8];
-#pragma unroll
-            for (int u = 0; u < 4; u++) load8(xp + (base + pix + u * ngroups) * ldx, f[u]);
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-#pragma unroll
-                for (int j = 0; j < 8; j++) { s[j] += f[u][j]; ss[j] = fmaf(f[u][j], f[u][j], ss[j]); }
-            }
-        }
-        for (; pix < p1; pix += ngroups) {
-            float f[8];
-            load8(xp + (base + pix) * ldx, f);
-#pragma unroll
-            for (int j = 0; j < 8; j++) { s[j] += f[j]; ss[j] = fmaf(f[j], f[j], ss[j]); }
-        }
-        gn_flush(part, v, cpg, s, ss);
-    }
-    __syncthreads();
-    cluster.sync();
-    if (threadIdx.x < 2 * gpc) {
-        float t = 0.f;
-#pragma unroll
-        for (int r = 0; r < kGnClusterSize; r++) t += cluster.map_shared_rank(part, r)[threadIdx.x];
-        tot[threadIdx.x] = t;
-        if (rank == 0 && stats) stats[((long long)img * G + (long long)slab * gpc) * 2 + threadIdx.x] = t;
-    }
-    cluster.sync();                       // peers have finished reading `part`; `tot` is visible to the CTA
-    const float inv_cnt = 1.f / ((float)HW * cpg);
-    for (int idx = threadIdx.x; idx < vps * ngroups; idx += blockDim.x) {
-        const int v = idx % vps, pg = idx / vps;
-        float a[8], b[8];
-#pragma unroll
-        for (int j = 0; j < 8; j++) {
-            const int gi = (v * 8 + j) / cpg;
-            const float m = tot[gi * 2] * inv_cnt;
-            const float var = fmaxf(tot[gi * 2 + 1] * inv_cnt - m * m, 0.f);
-            a[j] = rsqrtf(var + eps) * gamma[c0 + v * 8 + j];
-            b[j] = fmaf(-m, a[j], beta[c0 + v * 8 + j]);
-        }
-        const __half* xp = x + c0 + v * 8;
-        __half* yp = y + c0 + v * 8;
         int pix = p0 + pg;
         for (; pix + 3 * ngroups < p1; pix += 4 * ngroups) {
             float f[4][8];
@@ -934,27 +841,14 @@ SDF_API int sdf_groupnorm_apply(const void* x, int ldx, void* y, int ldy, int Ni
 // stats: fp32 scratch [Nimg, G, 2] (sum, sum of squares), kept for the backward.
 // (A single-pass variant — rows held in registers, grid-wide arrival counter between the statistics and the normalisation —
 // was measured 2-4x SLOWER than these two passes on B200: 60 us vs 14 us at 2x4096x320; the spin on a contended L2 line costs
-// more than re-reading 5 MB.  Not kept.)
+// more than re-reading 5 MB.  A thread-block-cluster variant (8 CTAs per (image, group slab), partial sums added through distributed shared
+// memory between two cluster barriers, one launch, no atomics) measured 17 us with 256-thread CTAs and 70 us with 1024-thread CTAs against
+// 12 us for these two passes: 128 CTAs expose too little memory parallelism for a 5 MB tensor.  Not kept either.)
 static int groupnorm_forward_impl(const void* x, int ldx, void* y, int ldy, int Nimg, int HW, int C, int G, const float* gamma, const float* beta,
                                   float eps, int silu_act, float* stats, void* stream, bool zero_stats) {
     SDF_CHECK_ARG(x && y && gamma && beta && stats, "groupnorm_forward: null pointer");
     SDF_CHECK_ARG(C % 8 == 0 && C % G == 0 && ldx % 8 == 0 && ldy % 8 == 0, "groupnorm_forward: C %% 8, C %% G, ld %% 8 must be 0");
     cudaStream_t st = (cudaStream_t)stream;
-    // one cluster launch when the tensor is L2-sized and (images x group slabs) x 8 CTAs fill the GPU; the big VAE activations take two passes
-    static const bool use_cluster = [] { const char* e = std::getenv("SDF_GN_CLUSTER"); return !(e && e[0] == '0'); }();
-    if (use_cluster && HW >= 64 && (long long)Nimg * HW * C * 2 <= (32ll << 20)) {
-        const int cpg = C / G;
-        int gpc = 0;
-        for (int d = 1; d <= G && d <= kGnMaxGpc; d++)
-            if (G % d == 0 && (d * cpg) % 8 == 0 && d * cpg >= 32) { gpc = d; break; }
-        if (gpc && (long long)Nimg * (G / gpc) * kGnClusterSize >= 96) {
-            dim3 grid((unsigned)(G / gpc * kGnClusterSize), (unsigned)Nimg);
-            if (silu_act) sdf_launch_pdl(k_gn_cluster<true>, grid, dim3(256), (size_t)0, st, (const __half*)x, ldx, (__half*)y, ldy, HW, C, G, gpc, stats, gamma, beta, eps);
-            else sdf_launch_pdl(k_gn_cluster<false>, grid, dim3(256), (size_t)0, st, (const __half*)x, ldx, (__half*)y, ldy, HW, C, G, gpc, stats, gamma, beta, eps);
-            SDF_CHECK_LAUNCH("groupnorm(cluster)");
-            return SDF_OK;
-        }
-    }
     if (zero_stats) SDF_CHECK_CUDA(cudaMemsetAsync(stats, 0, sizeof(float) * 2 * G * Nimg, st));
     const int vpp = C / 8;
     // two passes: ~16 vectors per thread for large tensors, at least ~4 blocks per SM for small ones

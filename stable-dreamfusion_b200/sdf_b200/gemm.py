@@ -4,11 +4,6 @@ import torch
 from . import _lib
 
 ACT = {None: 0, 'none': 0, 'silu': 1, 'gelu': 2, 'geglu': 3}
-import os as _os
-# A/B switch: split-K finished inside the GEMM kernel by the last-arriving CTA of each tile.  Measured on B200 (bench.py, 40 steps): GEMM time per
-# step 7.46 ms folded vs 6.95 ms with the separate k_splitk_epilogue launch (the last CTA reduces its whole tile serially while the other SMs
-# idle; the separate pass spreads the same reads over every SM) -> off by default.
-FOLD_SPLITK = _os.environ.get('SDF_FOLD_SPLITK', '0') != '0'
 
 
 def pick_block_n(N):
@@ -85,7 +80,7 @@ class GemmPlan:
                  bias=None, temb=None, temb_ld=0, residual=None, r_strides=(0, 0, 0), act=None, alpha=1.0, splitk=1, block_n=None, cta_pair=0):
         self.keep = (a, wt, out, bias, temb, residual)
         block_n = pick_block_n(N) if block_n is None else block_n
-        self.workspace = torch.zeros(Nimg * H * W, N, device=out.device, dtype=torch.float32) if splitk > 1 else None
+        self.workspace = torch.empty(Nimg * H * W, N, device=out.device, dtype=torch.float32) if splitk > 1 else None
         self.flops = 2.0 * Nimg * H * W * N * taps * Cin
         self.shape = dict(M=Nimg * H * W, N=N, K=taps * Cin, taps=taps, block_n=block_n, splitk=splitk, pair=int(cta_pair))
         h = _lib.lib().cdll.sdf_gemm_plan_create(
@@ -96,13 +91,6 @@ class GemmPlan:
         if h < 0:
             raise RuntimeError(f"sdf_gemm_plan_create failed ({h}): {_lib.lib().last_error()}")
         self.handle = h
-        self.counters = None
-        if splitk > 1 and FOLD_SPLITK and N % 32 == 0 and act != 'geglu':
-            # the CTA that adds a tile's last partial sum finishes the tile: no memset node, no reduction launch (csrc/sd_gemm.cu)
-            nt = _lib.lib().cdll.sdf_gemm_plan_num_tiles(h)
-            self.counters = torch.zeros(max(int(nt), 1), device=out.device, dtype=torch.int32)
-            if _lib.lib().cdll.sdf_gemm_plan_fold_splitk(h, _lib.ptr(self.counters)) != 0:
-                self.counters = None
         self.gn_slots = 0
         tw = 128 if W >= 128 else W
         th = 1 if (W >= 128 or w_strides[1] != 0 or w_strides[2] != 0) else max(1, min(H, 128 // tw))

@@ -33,7 +33,9 @@ USE_CTA_PAIRS = os.environ.get('SDF_GEMM_CTA_PAIRS', '1') != '0'
 # statistics-carrying epilogue costs more than the separate statistics pass it removes (k_gemm<128> 107 us vs 26 us: the per-chunk group
 # reduction runs on the critical path of single-tile CTAs and spills); kept behind the switch with its parity tests.
 FUSE_GN_STATS = os.environ.get('SDF_FUSE_GN_STATS', '0') != '0'
-DIRECT_CONV_IN = os.environ.get('SDF_DIRECT_CONV_IN', '1') != '0'          # A/B switch: FMA-pipe conv_in / conv_in^T instead of the padded implicit GEMM
+# A/B switch: FMA-pipe conv_in / conv_in^T kernels instead of the zero-padded implicit GEMM.  Measured (tools/bench_conv_in.py, 512x512, L2 flushed):
+# forward 210 us direct vs 92 us GEMM, data-gradient 248 us vs 123 us -> the tcgen05 path wins even at 3/64 useful k-columns; off by default.
+DIRECT_CONV_IN = os.environ.get('SDF_DIRECT_CONV_IN', '0') != '0'
 FUSE_GEGLU = os.environ.get('SDF_FUSE_GEGLU', '1') != '0'                 # A/B switch: GEGLU in the projection GEMM's epilogue      # A/B switch for the cta_group::2 GEMM variant
 
 
