@@ -1,0 +1,209 @@
+"""GPU: the DMTet mesh stage (csrc/dmtet.cu, csrc/meshrast.cu) through the C ABI.
+
+* marching tetrahedra against OUTPUTS OF THE REFERENCE'S OWN DMTet class (tests/golden/dmtet.npz, nerf/renderer.py:94-174): face indices
+  bit-exact in the reference's order, vertices to 1 ulp; its backward against torch autograd of the same interpolation formula;
+* mesh normals / normal-consistency / Laplacian against the reference's loss values and torch autograd;
+* the rasteriser against oracle/dmtet_ref.py's restatement of nvdiffrast's published algorithm (parity unpinned: nvdiffrast is not available)
+  and its backward against torch autograd of the barycentric formulas with the winning triangles held fixed.
+Tolerances: fp32 kernels vs fp32/fp64 references: 1e-5 relative on values, 1e-3 relative L2 on gradients accumulated by float atomics."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "stable-dreamfusion_b200")]
+from oracle import dmtet_ref as O
+from sdf_b200 import dmtet
+
+pytestmark = pytest.mark.gpu
+G = np.load(os.path.join(ROOT, "tests", "golden", "dmtet.npz"))
+
+
+def lattice_and_params(tag, device, requires_grad=False):
+    n = int(G[f"{tag}_n"])
+    lat = dmtet.TetLattice(tet_grid_size=1, device=device, n_cells=n)        # tet_grid_size 1: position = pos + tanh(deform_raw)
+    sdf = torch.from_numpy(G[f"{tag}_sdf"]).to(device).requires_grad_(requires_grad)
+    raw = torch.atanh(torch.from_numpy(G[f"{tag}_deform"].astype(np.float64)).clamp(-0.999, 0.999)).float().to(device).requires_grad_(requires_grad)
+    return lat, sdf, raw
+
+
+def rel_l2(a, b):
+    return float((a - b).norm() / b.norm().clamp_min(1e-12))
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_marching_tets_match_the_reference_class(device, tag):
+    lat, sdf, raw = lattice_and_params(tag, device)
+    mesh = dmtet.extract_mesh(lat, sdf, raw)
+    nv, nf = lat.mesh_counts()
+    v_ref, f_ref = G[f"{tag}_verts"], G[f"{tag}_faces"]
+    assert (nv, nf) == (len(v_ref), len(f_ref))
+    assert np.array_equal(mesh.faces[:nf].cpu().numpy(), f_ref)                       # bit-exact indices, the reference's order
+    # the golden positions were produced from verts + deform in fp32; tanh(atanh(d)) re-rounds the deformation by <= 1 ulp
+    assert np.abs(mesh.verts[:nv].cpu().numpy() - v_ref).max() <= 2e-6
+
+
+def torch_marching_verts(lat, sdf, raw, faces_np):
+    """the reference's interpolation (nerf/renderer.py:146-153) in torch for the crossing edges the kernel reported"""
+    nv = lat.mesh_counts()[0]
+    e = lat.edges[lat.vert_edge[:nv].long()].long()
+    pos = lat.pos + torch.tanh(raw) / lat.tet_grid_size
+    pa, pb = pos[e[:, 0]], pos[e[:, 1]]
+    sa, sb = sdf[e[:, 0]], -sdf[e[:, 1]]
+    den = sa + sb
+    return pa * (sb / den)[:, None] + pb * (sa / den)[:, None]
+
+
+def test_marching_tets_backward(device):
+    lat, sdf, raw = lattice_and_params("b", device, requires_grad=True)
+    mesh = dmtet.extract_mesh(lat, sdf, raw)
+    nv, nf = lat.mesh_counts()
+    g = torch.randn(nv, 3, device=device, generator=torch.Generator(device=device).manual_seed(3))
+    full = torch.zeros_like(mesh.verts)
+    full[:nv] = g
+    mesh.verts.backward(full)
+    d_sdf, d_raw = sdf.grad.clone(), raw.grad.clone()
+    sdf.grad = raw.grad = None
+    v_t = torch_marching_verts(lat, sdf, raw, None)
+    assert (v_t.detach() - mesh.verts[:nv].detach()).abs().max() < 1e-6
+    v_t.backward(g)
+    assert rel_l2(d_sdf, sdf.grad) < 1e-4 and rel_l2(d_raw, raw.grad) < 1e-4
+
+
+def torch_normals(verts, faces):
+    v0, v1, v2 = verts[faces[:, 0]], verts[faces[:, 1]], verts[faces[:, 2]]
+    c = torch.cross(v1 - v0, v2 - v0, dim=-1)
+    fn = c / torch.sqrt(torch.clamp((c * c).sum(-1, keepdim=True), min=1e-20))
+    vn = torch.zeros_like(verts)
+    for k in range(3):
+        vn = vn.index_add(0, faces[:, k], fn)
+    vn = torch.where((vn * vn).sum(-1, keepdim=True) > 1e-20, vn, torch.tensor([0.0, 0.0, 1.0], device=verts.device))
+    return fn, vn
+
+
+def test_mesh_normals_forward_backward(device):
+    lat, sdf, raw = lattice_and_params("b", device)
+    mesh = dmtet.extract_mesh(lat, sdf, raw)
+    nv, nf = lat.mesh_counts()
+    verts = mesh.verts.detach().clone().requires_grad_(True)
+    m2 = dmtet.Mesh(lat, verts)
+    fn, vn = dmtet.mesh_normals(m2)
+    fn_o, vn_o = O.mesh_normals(G["b_verts"], G["b_faces"].astype(np.int64))
+    assert np.abs(fn[:nf].detach().cpu().numpy() - fn_o).max() < 1e-4 and np.abs(vn[:nv].detach().cpu().numpy() - vn_o).max() < 1e-4
+    gen = torch.Generator(device=device).manual_seed(5)
+    gf, gv = torch.randn(nf, 3, device=device, generator=gen), torch.randn(nv, 3, device=device, generator=gen)
+    loss = (fn[:nf] * gf).sum() + (vn[:nv] * gv).sum()
+    loss.backward()
+    got = verts.grad[:nv].clone()
+    vt = mesh.verts[:nv].detach().clone().requires_grad_(True)
+    fn_t, vn_t = torch_normals(vt, mesh.faces[:nf].long())
+    ((fn_t * gf).sum() + (vn_t * gv).sum()).backward()
+    assert rel_l2(got, vt.grad) < 1e-3
+
+
+def torch_mesh_losses(verts, faces_np):
+    """the reference's two regularisers (nerf/renderer.py:176-254) in torch, differentiable"""
+    faces = torch.from_numpy(faces_np).to(verts.device)
+    fn, _ = torch_normals(verts, faces)
+    tpe = torch.from_numpy(O.edge_to_face(faces_np)).to(verts.device)
+    term = 1.0 - torch.clamp((fn[tpe[:, 0]] * fn[tpe[:, 1]]).sum(-1), -1.0, 1.0)
+    nc = term.abs().mean()
+    ii, jj = faces[:, [1, 2, 0]].reshape(-1), faces[:, [2, 0, 1]].reshape(-1)
+    adj = torch.unique(torch.stack([torch.cat([ii, jj]), torch.cat([jj, ii])], 0), dim=1)
+    acc = torch.zeros_like(verts).index_add(0, adj[0], verts[adj[0]] - verts[adj[1]])
+    lap = acc.norm(dim=1).mean()
+    return nc, lap
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_mesh_regularisers_match_the_reference(device, tag):
+    lat, sdf, raw = lattice_and_params(tag, device)
+    mesh = dmtet.extract_mesh(lat, sdf, raw)
+    nv, nf = lat.mesh_counts()
+    verts = mesh.verts.detach().clone().requires_grad_(True)
+    m2 = dmtet.Mesh(lat, verts)
+    fn, vn = dmtet.mesh_normals(m2)
+    losses = dmtet.mesh_losses(m2, fn)
+    assert abs(float(losses[0]) - float(G[f"{tag}_normal_consistency"])) < 2e-5        # values of the reference's own functions
+    assert abs(float(losses[1]) - float(G[f"{tag}_laplacian"])) < 2e-5
+    (0.7 * losses[0] + 1.3 * losses[1]).backward()
+    got = verts.grad[:nv].clone()
+    vt = mesh.verts[:nv].detach().clone().requires_grad_(True)
+    nc, lap = torch_mesh_losses(vt, G[f"{tag}_faces"].astype(np.int64))
+    (0.7 * nc + 1.3 * lap).backward()
+    assert rel_l2(got, vt.grad) < 2e-3
+
+
+def look_at_mvp(device, radius=2.6, az=0.6, el=0.35, fovy=40.0):
+    eye = np.array([radius * np.cos(el) * np.sin(az), radius * np.sin(el), radius * np.cos(el) * np.cos(az)])
+    f = -eye / np.linalg.norm(eye)
+    r = np.cross(f, [0, 1, 0]); r /= np.linalg.norm(r)
+    u = np.cross(r, f)
+    view = np.eye(4)
+    view[0, :3], view[1, :3], view[2, :3] = r, u, -f
+    view[:3, 3] = -view[:3, :3] @ eye
+    t = np.tan(np.radians(fovy) / 2)
+    near, far = 0.1, 10.0
+    proj = np.array([[1 / t, 0, 0, 0], [0, 1 / t, 0, 0], [0, 0, -(far + near) / (far - near), -2 * far * near / (far - near)], [0, 0, -1, 0]])
+    return torch.from_numpy((proj @ view).astype(np.float32)).to(device)
+
+
+def torch_gbuffer(verts, vn, mvp, faces, rast, H, W):
+    """differentiable restatement of rasterize + interpolate for the triangles the kernel selected"""
+    tri = rast[..., 3].reshape(-1).long() - 1
+    hit = tri >= 0
+    f = faces[tri[hit]]
+    clip = torch.cat([verts, torch.ones_like(verts[:, :1])], 1) @ mvp.t()
+    p = clip[:, [0, 1, 3]]
+    p0, p1, p2 = p[f[:, 0]], p[f[:, 1]], p[f[:, 2]]
+    ys, xs = torch.meshgrid(torch.arange(H, device=verts.device), torch.arange(W, device=verts.device), indexing="ij")
+    P = torch.stack([(xs.reshape(-1) + 0.5) / W * 2 - 1, (ys.reshape(-1) + 0.5) / H * 2 - 1, torch.ones(H * W, device=verts.device)], -1)[hit]
+    b0 = (P * torch.cross(p1, p2, dim=-1)).sum(-1)
+    b1 = (P * torch.cross(p2, p0, dim=-1)).sum(-1)
+    b2 = (P * torch.cross(p0, p1, dim=-1)).sum(-1)
+    s = b0 + b1 + b2
+    u, v = (b0 / s)[:, None], (b1 / s)[:, None]
+    xyz = u * verts[f[:, 0]] + v * verts[f[:, 1]] + (1 - u - v) * verts[f[:, 2]]
+    n = u * vn[f[:, 0]] + v * vn[f[:, 1]] + (1 - u - v) * vn[f[:, 2]]
+    n = n / torch.sqrt(torch.clamp((n * n).sum(-1, keepdim=True), min=1e-20))
+    return hit, xyz, n
+
+
+def test_rasterizer_against_the_restatement_and_autograd(device):
+    lat, sdf, raw = lattice_and_params("b", device)
+    mesh = dmtet.extract_mesh(lat, sdf, raw)
+    nv, nf = lat.mesh_counts()
+    H = W = 96
+    mvp = look_at_mvp(device)
+    verts = mesh.verts.detach().clone().requires_grad_(True)
+    m2 = dmtet.Mesh(lat, verts)
+    fn, vn = dmtet.mesh_normals(m2)
+    vn_leaf = vn.detach().clone().requires_grad_(True)
+    xyz, nrm, mask, rast = dmtet.rasterize(m2, vn_leaf, mvp, H, W)
+    # forward vs the numpy restatement
+    clip = (np.concatenate([G["b_verts"], np.ones((nv, 1), np.float32)], 1) @ mvp.cpu().numpy().T).astype(np.float32)
+    r_o = O.rasterize_ref(clip, G["b_faces"], H, W)
+    tri_k, tri_o = rast[..., 3].cpu().numpy(), r_o[..., 3]
+    same = tri_k == tri_o
+    assert same.mean() > 0.995, same.mean()                       # ties on shared edges / equal depths may resolve differently
+    assert 0.05 < (tri_k > 0).mean() < 0.9
+    sel = same & (tri_o > 0)
+    assert np.abs(rast.cpu().numpy()[sel][:, :3] - r_o[sel][:, :3]).max() < 2e-4
+    xyz_o = O.interpolate_ref(G["b_verts"], r_o, G["b_faces"])
+    assert np.abs(xyz.view(H, W, 3).detach().cpu().numpy()[sel] - xyz_o[sel]).max() < 2e-4
+    assert np.array_equal(mask.view(H, W).cpu().numpy() > 0, tri_k > 0)
+    # backward vs torch autograd with the same winners
+    gen = torch.Generator(device=device).manual_seed(7)
+    gx, gn = torch.randn(H * W, 3, device=device, generator=gen), torch.randn(H * W, 3, device=device, generator=gen)
+    ((xyz * gx).sum() + (nrm * gn).sum()).backward()
+    got_v, got_n = verts.grad[:nv].clone(), vn_leaf.grad[:nv].clone()
+    vt = mesh.verts[:nv].detach().clone().requires_grad_(True)
+    nt = vn[:nv].detach().clone().requires_grad_(True)
+    hit, xyz_t, n_t = torch_gbuffer(vt, nt, mvp, mesh.faces[:nf].long(), rast, H, W)
+    assert (xyz_t.detach() - xyz[hit].detach()).abs().max() < 1e-4 and (n_t.detach() - nrm[hit].detach()).abs().max() < 1e-3
+    ((xyz_t * gx[hit]).sum() + (n_t * gn[hit]).sum()).backward()
+    assert rel_l2(got_n, nt.grad) < 1e-3
+    assert rel_l2(got_v, vt.grad) < 5e-3
