@@ -311,6 +311,22 @@ int sdf_mesh_rasterize(const float* clip, const int* faces, const int* counts, i
 int sdf_mesh_rasterize_backward(const float* rast, const float* clip, const int* faces, const float* verts, const float* vert_n, const float* mvp, int H,
                                 int W, const float* d_xyz, const float* d_nrm, float* d_verts, float* d_vert_n, void* stream);
 
+/* G-buffer shading (nerf/renderer.py:916-928; mode 0 albedo, 1 lambertian, 2 textureless, 3 normal; light = 3 device floats) into c4 [P,4] = (rgb, coverage),
+ * and clamp(c4, 0, 1) split into sdf_background_forward's inputs (nerf/renderer.py:930-947). */
+int sdf_mesh_shade_forward(const float* albedo, const float* nrm, const float* mask, const float* light, float ambient, int mode, int P, float* c4, void* stream);
+int sdf_mesh_shade_backward(const float* g_c4, const float* albedo, const float* nrm, const float* mask, const float* light, float ambient, int mode, int P,
+                            float* g_albedo, float* g_nrm, void* stream);
+int sdf_mesh_c4_split(const float* c4, int P, float* image_c, float* weights_sum, void* stream);
+int sdf_mesh_c4_split_backward(const float* g_image_c, const float* g_weights_sum, const float* c4, int P, float* g_c4, void* stream);
+
+/* dr.antialias (nerf/renderer.py:930-931) restated: silhouette-edge coverage blending of the (rgb, coverage) image over horizontally / vertically
+ * adjacent pixel pairs; face_adj [adj_faces,3] from sdf_mesh_face_adjacency (sorted half-edge keys + the sort permutation). */
+int sdf_mesh_face_adjacency(const long long* sorted_keys, const int* order, const int* counts, int fcap, int* face_adj, void* stream);
+int sdf_mesh_antialias_forward(const float* c4, const float* rast, const float* clip, const int* faces, const int* face_adj, int adj_faces, int H, int W,
+                               float* out, void* stream);
+int sdf_mesh_antialias_backward(const float* g_out, const float* c4, const float* rast, const float* clip, const int* faces, const int* face_adj,
+                                int adj_faces, const float* mvp, int H, int W, float* g_c4, float* d_verts /* may be NULL */, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -212,6 +212,212 @@ __global__ void __launch_bounds__(256) k_gbuffer_bwd(const float* __restrict__ r
     }
 }
 
+// ------------------------------------------------------------------ shading of the G-buffer (nerf/renderer.py:916-928) and the clamp before the background mix
+enum MeshShading { kMeshAlbedo = 0, kMeshLambertian = 1, kMeshTextureless = 2, kMeshNormal = 3 };
+
+// c4 = (shaded rgb, coverage).  albedo is the texture network's output at every pixel; it counts only where the mask is set (the reference
+// evaluates the network on the covered pixels and leaves zeros elsewhere, :908-912).  Uncovered pixels keep the reference's values: lambertian
+// factor = ambient (their normal is zero), so textureless / normal modes paint them ambient / 0.5 before the background is added.
+__global__ void k_mesh_shade_fwd(const float* __restrict__ albedo, const float* __restrict__ nrm, const float* __restrict__ mask, const float* __restrict__ light,
+                                 float ambient, int mode, int P, float* __restrict__ c4) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    const float m = mask[p];
+    float n[3], a[3];
+    load3(n, nrm, p); load3(a, albedo, p);
+    const float lam = ambient + (1.f - ambient) * fmaxf(n[0] * light[0] + n[1] * light[1] + n[2] * light[2], 0.f);
+    float4 o;
+    if (mode == kMeshAlbedo) o = make_float4(a[0] * m, a[1] * m, a[2] * m, m);
+    else if (mode == kMeshTextureless) o = make_float4(lam, lam, lam, m);
+    else if (mode == kMeshNormal) o = make_float4((n[0] + 1.f) * 0.5f, (n[1] + 1.f) * 0.5f, (n[2] + 1.f) * 0.5f, m);
+    else o = make_float4(a[0] * m * lam, a[1] * m * lam, a[2] * m * lam, m);
+    reinterpret_cast<float4*>(c4)[p] = o;
+}
+
+__global__ void k_mesh_shade_bwd(const float* __restrict__ g_c4, const float* __restrict__ albedo, const float* __restrict__ nrm, const float* __restrict__ mask,
+                                 const float* __restrict__ light, float ambient, int mode, int P, float* __restrict__ g_albedo, float* __restrict__ g_nrm) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    const float m = mask[p];
+    const float4 g = reinterpret_cast<const float4*>(g_c4)[p];
+    float n[3], a[3];
+    load3(n, nrm, p); load3(a, albedo, p);
+    const float dot = n[0] * light[0] + n[1] * light[1] + n[2] * light[2];
+    const float lam = ambient + (1.f - ambient) * fmaxf(dot, 0.f);
+    float ga[3] = {0.f, 0.f, 0.f}, gn[3] = {0.f, 0.f, 0.f}, glam = 0.f;
+    if (mode == kMeshAlbedo) { ga[0] = g.x * m; ga[1] = g.y * m; ga[2] = g.z * m; }
+    else if (mode == kMeshTextureless) glam = g.x + g.y + g.z;
+    else if (mode == kMeshNormal) { gn[0] = 0.5f * g.x; gn[1] = 0.5f * g.y; gn[2] = 0.5f * g.z; }
+    else { ga[0] = g.x * m * lam; ga[1] = g.y * m * lam; ga[2] = g.z * m * lam; glam = (g.x * a[0] + g.y * a[1] + g.z * a[2]) * m; }
+    if (glam != 0.f && dot > 0.f) {
+#pragma unroll
+        for (int d = 0; d < 3; d++) gn[d] += glam * (1.f - ambient) * light[d];
+    }
+#pragma unroll
+    for (int d = 0; d < 3; d++) { g_albedo[3 * (size_t)p + d] = ga[d]; g_nrm[3 * (size_t)p + d] = gn[d]; }
+}
+
+// colour / coverage clamped to [0, 1] (nerf/renderer.py:930-931) and split into the background kernel's inputs
+__global__ void k_mesh_c4_split(const float* __restrict__ c4, int P, float* __restrict__ image_c, float* __restrict__ wsum) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    const float4 c = reinterpret_cast<const float4*>(c4)[p];
+    image_c[3 * (size_t)p] = fminf(fmaxf(c.x, 0.f), 1.f); image_c[3 * (size_t)p + 1] = fminf(fmaxf(c.y, 0.f), 1.f); image_c[3 * (size_t)p + 2] = fminf(fmaxf(c.z, 0.f), 1.f);
+    wsum[p] = fminf(fmaxf(c.w, 0.f), 1.f);
+}
+
+__global__ void k_mesh_c4_split_bwd(const float* __restrict__ g_image_c, const float* __restrict__ g_wsum, const float* __restrict__ c4, int P, float* __restrict__ g_c4) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    const float4 c = reinterpret_cast<const float4*>(c4)[p];
+    float4 g;
+    g.x = (c.x >= 0.f && c.x <= 1.f) ? g_image_c[3 * (size_t)p] : 0.f;
+    g.y = (c.y >= 0.f && c.y <= 1.f) ? g_image_c[3 * (size_t)p + 1] : 0.f;
+    g.z = (c.z >= 0.f && c.z <= 1.f) ? g_image_c[3 * (size_t)p + 2] : 0.f;
+    g.w = (c.w >= 0.f && c.w <= 1.f) ? g_wsum[p] : 0.f;
+    reinterpret_cast<float4*>(g_c4)[p] = g;
+}
+
+// ------------------------------------------------------------------ antialiasing (dr.antialias, nerf/renderer.py:930-931; Laine et al. 2020 section 3.4)
+// For every horizontally / vertically adjacent pixel pair that shows two different triangles (or a triangle and the background), the nearer
+// pixel's triangle is searched for the SILHOUETTE edge (no neighbour across it, or a neighbour facing the other way on screen) that crosses the
+// segment between the two pixel centres.  alpha = position of the crossing along that segment (0 at the nearer pixel's centre): for
+// alpha >= 0.5 the front surface spills (alpha - 0.5) into the other pixel, below 0.5 it leaves (0.5 - alpha) of its own pixel to the other
+// colour.  The blend weights depend on the edge's screen position, which is what gives vertex positions a gradient at silhouettes.
+struct AaPair {
+    int front, other;        // pixel indices
+    int v0, v1;              // vertex ids of the crossing silhouette edge
+    float alpha, t;          // crossing position between the centres; parameter along the edge
+    float x0, y0, x1, y1;    // edge end points in pixel units
+    float dir;               // +1 / -1: direction from front to other along the pair's axis
+};
+
+__device__ __forceinline__ void to_pixels(const float4 c, int H, int W, float& sx, float& sy) {
+    sx = (c.x / c.w * 0.5f + 0.5f) * W;
+    sy = (c.y / c.w * 0.5f + 0.5f) * H;
+}
+
+__device__ __forceinline__ float screen_area(const float* __restrict__ clip, const int* __restrict__ faces, int f) {
+    const float4 a = reinterpret_cast<const float4*>(clip)[faces[3 * (size_t)f]], b = reinterpret_cast<const float4*>(clip)[faces[3 * (size_t)f + 1]],
+                 c = reinterpret_cast<const float4*>(clip)[faces[3 * (size_t)f + 2]];
+    const float ax = a.x / a.w, ay = a.y / a.w;
+    return (b.x / b.w - ax) * (c.y / c.w - ay) - (c.x / c.w - ax) * (b.y / b.w - ay);
+}
+
+__device__ __forceinline__ bool aa_pair(AaPair& o, int p, int q, bool horizontal, const float* __restrict__ rast, const float* __restrict__ clip,
+                                        const int* __restrict__ faces, const int* __restrict__ face_adj, int adj_faces, int H, int W) {
+    const float4 rp = reinterpret_cast<const float4*>(rast)[p], rq = reinterpret_cast<const float4*>(rast)[q];
+    if (rp.w == rq.w) return false;
+    const bool p_front = rq.w <= 0.f || (rp.w > 0.f && rp.z < rq.z);
+    o.front = p_front ? p : q;
+    o.other = p_front ? q : p;
+    o.dir = p_front ? 1.f : -1.f;
+    const int tri = (int)(p_front ? rp.w : rq.w) - 1;
+    const float fx = (o.front % W) + 0.5f, fy = (o.front / W) + 0.5f;
+    const float area = screen_area(clip, faces, tri);
+    float best = 2.f;
+    bool found = false;
+    for (int k = 0; k < 3; k++) {
+        const int adj = tri < adj_faces ? face_adj[3 * (size_t)tri + k] : -1;
+        if (adj >= 0) { const float a2 = screen_area(clip, faces, adj); if ((a2 > 0.f) == (area > 0.f)) continue; }      // interior edge: both sides face alike
+        const int i0 = faces[3 * (size_t)tri + k], i1 = faces[3 * (size_t)tri + (k + 1) % 3];
+        float x0, y0, x1, y1;
+        to_pixels(reinterpret_cast<const float4*>(clip)[i0], H, W, x0, y0);
+        to_pixels(reinterpret_cast<const float4*>(clip)[i1], H, W, x1, y1);
+        // horizontal pair: the edge must span the row's centre line; vertical pair: the column's
+        const float a0 = horizontal ? y0 - fy : x0 - fx, a1 = horizontal ? y1 - fy : x1 - fx;
+        if (!((a0 < 0.f) != (a1 < 0.f))) continue;
+        const float t = a0 / (a0 - a1);
+        const float c = horizontal ? x0 + t * (x1 - x0) : y0 + t * (y1 - y0);
+        const float alpha = (c - (horizontal ? fx : fy)) * o.dir;
+        if (alpha >= 0.f && alpha <= 1.f && alpha < best) { best = alpha; found = true; o.v0 = i0; o.v1 = i1; o.t = t; o.x0 = x0; o.y0 = y0; o.x1 = x1; o.y1 = y1; }
+    }
+    o.alpha = best;
+    return found;
+}
+
+__global__ void __launch_bounds__(256) k_antialias_fwd(const float* __restrict__ c4, const float* __restrict__ rast, const float* __restrict__ clip,
+                                                       const int* __restrict__ faces, const int* __restrict__ face_adj, int adj_faces, int H, int W,
+                                                       float* __restrict__ out /* pre-filled with c4 */) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= H * W) return;
+    const int ix = p % W, iy = p / W;
+    for (int axis = 0; axis < 2; axis++) {
+        if (axis == 0 ? ix + 1 >= W : iy + 1 >= H) continue;
+        const int q = axis == 0 ? p + 1 : p + W;
+        AaPair a;
+        if (!aa_pair(a, p, q, axis == 0, rast, clip, faces, face_adj, adj_faces, H, W)) continue;
+        const float4 cf = reinterpret_cast<const float4*>(c4)[a.front], co = reinterpret_cast<const float4*>(c4)[a.other];
+        const bool into_other = a.alpha >= 0.5f;
+        const float w = into_other ? a.alpha - 0.5f : 0.5f - a.alpha;
+        const int dst = into_other ? a.other : a.front;
+        const float s = into_other ? 1.f : -1.f;                 // other += w (front - other)   |   front += w (other - front)
+        atomicAdd(&out[4 * (size_t)dst], s * w * (cf.x - co.x)); atomicAdd(&out[4 * (size_t)dst + 1], s * w * (cf.y - co.y));
+        atomicAdd(&out[4 * (size_t)dst + 2], s * w * (cf.z - co.z)); atomicAdd(&out[4 * (size_t)dst + 3], s * w * (cf.w - co.w));
+    }
+}
+
+// g_out [P,4] -> g_c4 [P,4] (pre-filled with g_out: the identity part) and d_verts (through the crossing position of the silhouette edge)
+__global__ void __launch_bounds__(256) k_antialias_bwd(const float* __restrict__ g_out, const float* __restrict__ c4, const float* __restrict__ rast,
+                                                       const float* __restrict__ clip, const int* __restrict__ faces, const int* __restrict__ face_adj,
+                                                       int adj_faces, const float* __restrict__ mvp, int H, int W, float* __restrict__ g_c4,
+                                                       float* __restrict__ d_verts) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= H * W) return;
+    const int ix = p % W, iy = p / W;
+    for (int axis = 0; axis < 2; axis++) {
+        if (axis == 0 ? ix + 1 >= W : iy + 1 >= H) continue;
+        const int q = axis == 0 ? p + 1 : p + W;
+        AaPair a;
+        if (!aa_pair(a, p, q, axis == 0, rast, clip, faces, face_adj, adj_faces, H, W)) continue;
+        const float4 cf = reinterpret_cast<const float4*>(c4)[a.front], co = reinterpret_cast<const float4*>(c4)[a.other];
+        const bool into_other = a.alpha >= 0.5f;
+        const float w = into_other ? a.alpha - 0.5f : 0.5f - a.alpha;
+        const int dst = into_other ? a.other : a.front;
+        const float4 g = reinterpret_cast<const float4*>(g_out)[dst];
+        const float s = into_other ? 1.f : -1.f;
+        // colour gradients: out[dst] += s w (cf - co)
+        atomicAdd(&g_c4[4 * (size_t)a.front], s * w * g.x); atomicAdd(&g_c4[4 * (size_t)a.front + 1], s * w * g.y);
+        atomicAdd(&g_c4[4 * (size_t)a.front + 2], s * w * g.z); atomicAdd(&g_c4[4 * (size_t)a.front + 3], s * w * g.w);
+        atomicAdd(&g_c4[4 * (size_t)a.other], -s * w * g.x); atomicAdd(&g_c4[4 * (size_t)a.other + 1], -s * w * g.y);
+        atomicAdd(&g_c4[4 * (size_t)a.other + 2], -s * w * g.z); atomicAdd(&g_c4[4 * (size_t)a.other + 3], -s * w * g.w);
+        if (!d_verts) continue;
+        // position gradient: d out / d w = s (cf - co), d w / d alpha = +1 (into other) / -1, alpha = (crossing - centre) * dir
+        const float gw = s * (g.x * (cf.x - co.x) + g.y * (cf.y - co.y) + g.z * (cf.z - co.z) + g.w * (cf.w - co.w));
+        const float gc = gw * (into_other ? 1.f : -1.f) * a.dir;      // wrt the crossing coordinate (x for horizontal pairs, y for vertical)
+        // crossing = u0 + t (u1 - u0), t = a0 / (a0 - a1), a_i = v_i - centre with (u, v) = (x, y) for horizontal pairs and (y, x) for vertical
+        const float u0 = axis == 0 ? a.x0 : a.y0, u1 = axis == 0 ? a.x1 : a.y1, v0 = axis == 0 ? a.y0 : a.x0, v1 = axis == 0 ? a.y1 : a.x1;
+        const float fc = axis == 0 ? (a.front / W) + 0.5f : (a.front % W) + 0.5f;
+        const float a0 = v0 - fc, a1 = v1 - fc, den = a0 - a1;
+        const float gt = gc * (u1 - u0);
+        const float gu0 = gc * (1.f - a.t), gu1 = gc * a.t;
+        const float gv0 = gt * (-a1) / (den * den), gv1 = gt * a0 / (den * den);      // dt/da0 = -a1 / den^2, dt/da1 = a0 / den^2
+        const float gsx[2] = {axis == 0 ? gu0 : gv0, axis == 0 ? gu1 : gv1}, gsy[2] = {axis == 0 ? gv0 : gu0, axis == 0 ? gv1 : gu1};
+        const int vid[2] = {a.v0, a.v1};
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+            const float4 c = reinterpret_cast<const float4*>(clip)[vid[e]];
+            // sx = (cx / cw * .5 + .5) W, sy = (cy / cw * .5 + .5) H
+            const float dcx = gsx[e] * 0.5f * W / c.w, dcy = gsy[e] * 0.5f * H / c.w;
+            const float dcw = -(gsx[e] * 0.5f * W * c.x + gsy[e] * 0.5f * H * c.y) / (c.w * c.w);
+#pragma unroll
+            for (int d = 0; d < 3; d++) atomicAdd(&d_verts[3 * (size_t)vid[e] + d], mvp[d] * dcx + mvp[4 + d] * dcy + mvp[12 + d] * dcw);
+        }
+    }
+}
+
+// face_adj[f][k] = the face on the other side of edge (i_k, i_{k+1}) of face f, from the sorted half-edge list (-1: none)
+__global__ void k_face_adjacency(const long long* __restrict__ keys, const int* __restrict__ order, const int* __restrict__ counts, int fcap, int* __restrict__ face_adj) {
+    const int nh = 3 * min(counts[1], fcap);
+    for (int h = blockIdx.x * blockDim.x + threadIdx.x; h + 1 < nh; h += gridDim.x * blockDim.x) {
+        if ((keys[h] >> 1) != (keys[h + 1] >> 1)) continue;
+        if (h > 0 && (keys[h - 1] >> 1) == (keys[h] >> 1)) continue;          // only the first pair of a (non-manifold) run
+        const int ha = order[h], hb = order[h + 1];
+        face_adj[ha] = hb / 3;                                               // face_adj is [fcap, 3] = indexed by half-edge id
+        face_adj[hb] = ha / 3;
+    }
+}
+
 inline int grid_for(long long n, int threads) { return (int)max(1ll, min((n + threads - 1) / threads, (long long)sdf_num_sms() * 16)); }
 
 }  // namespace
@@ -243,5 +449,71 @@ SDF_API int sdf_mesh_rasterize_backward(const float* rast, const float* clip, co
     SDF_CHECK_ARG(rast && clip && faces && verts && vert_n && mvp && d_verts && d_vert_n && (d_xyz || d_nrm), "mesh_rasterize_backward: null pointer");
     k_gbuffer_bwd<<<(H * W + 255) / 256, 256, 0, (cudaStream_t)stream>>>(rast, clip, faces, verts, vert_n, mvp, H, W, d_xyz, d_nrm, d_verts, d_vert_n);
     SDF_CHECK_LAUNCH("mesh_rasterize_backward");
+    return SDF_OK;
+}
+
+// shading of the G-buffer (nerf/renderer.py:916-928): mode 0 albedo, 1 lambertian, 2 textureless, 3 normal; light: 3 floats on the device.
+// c4 [P,4] = (rgb, coverage) before antialiasing / clamping.
+SDF_API int sdf_mesh_shade_forward(const float* albedo, const float* nrm, const float* mask, const float* light, float ambient, int mode, int P, float* c4,
+                                   void* stream) {
+    SDF_CHECK_ARG(albedo && nrm && mask && light && c4 && mode >= 0 && mode <= 3, "mesh_shade_forward: bad arguments");
+    if (P > 0) k_mesh_shade_fwd<<<(P + 255) / 256, 256, 0, (cudaStream_t)stream>>>(albedo, nrm, mask, light, ambient, mode, P, c4);
+    SDF_CHECK_LAUNCH("mesh_shade_forward");
+    return SDF_OK;
+}
+
+SDF_API int sdf_mesh_shade_backward(const float* g_c4, const float* albedo, const float* nrm, const float* mask, const float* light, float ambient, int mode,
+                                    int P, float* g_albedo, float* g_nrm, void* stream) {
+    SDF_CHECK_ARG(g_c4 && albedo && nrm && mask && light && g_albedo && g_nrm && mode >= 0 && mode <= 3, "mesh_shade_backward: bad arguments");
+    if (P > 0) k_mesh_shade_bwd<<<(P + 255) / 256, 256, 0, (cudaStream_t)stream>>>(g_c4, albedo, nrm, mask, light, ambient, mode, P, g_albedo, g_nrm);
+    SDF_CHECK_LAUNCH("mesh_shade_backward");
+    return SDF_OK;
+}
+
+// clamp(c4, 0, 1) -> image_c [P,3], weights_sum [P] (the inputs of sdf_background_forward, which adds (1 - alpha) * background), and its backward
+SDF_API int sdf_mesh_c4_split(const float* c4, int P, float* image_c, float* weights_sum, void* stream) {
+    SDF_CHECK_ARG(c4 && image_c && weights_sum, "mesh_c4_split: null pointer");
+    if (P > 0) k_mesh_c4_split<<<(P + 255) / 256, 256, 0, (cudaStream_t)stream>>>(c4, P, image_c, weights_sum);
+    SDF_CHECK_LAUNCH("mesh_c4_split");
+    return SDF_OK;
+}
+
+SDF_API int sdf_mesh_c4_split_backward(const float* g_image_c, const float* g_weights_sum, const float* c4, int P, float* g_c4, void* stream) {
+    SDF_CHECK_ARG(g_image_c && g_weights_sum && c4 && g_c4, "mesh_c4_split_backward: null pointer");
+    if (P > 0) k_mesh_c4_split_bwd<<<(P + 255) / 256, 256, 0, (cudaStream_t)stream>>>(g_image_c, g_weights_sum, c4, P, g_c4);
+    SDF_CHECK_LAUNCH("mesh_c4_split_backward");
+    return SDF_OK;
+}
+
+// adjacency of the first `fcap` faces from the sorted half-edge keys and the sort permutation (sdf_mesh_halfedge_keys + a sort): face_adj [fcap,3]
+SDF_API int sdf_mesh_face_adjacency(const long long* sorted_keys, const int* order, const int* counts, int fcap, int* face_adj, void* stream) {
+    SDF_CHECK_ARG(sorted_keys && order && counts && face_adj && fcap > 0, "mesh_face_adjacency: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    SDF_CHECK_CUDA(cudaMemsetAsync(face_adj, 0xff, sizeof(int) * 3 * (size_t)fcap, st));
+    k_face_adjacency<<<grid_for(3ll * fcap / 4 + 1, 256), 256, 0, st>>>(sorted_keys, order, counts, fcap, face_adj);
+    SDF_CHECK_LAUNCH("mesh_face_adjacency");
+    return SDF_OK;
+}
+
+// dr.antialias on the 4-channel (rgb, coverage) image (nerf/renderer.py:930-931).  face_adj covers the first adj_faces faces (others: every edge
+// counts as a silhouette).
+SDF_API int sdf_mesh_antialias_forward(const float* c4, const float* rast, const float* clip, const int* faces, const int* face_adj, int adj_faces, int H, int W,
+                                       float* out, void* stream) {
+    SDF_CHECK_ARG(c4 && rast && clip && faces && face_adj && out && H > 0 && W > 0, "mesh_antialias_forward: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    SDF_CHECK_CUDA(cudaMemcpyAsync(out, c4, sizeof(float) * 4 * (size_t)H * W, cudaMemcpyDeviceToDevice, st));
+    k_antialias_fwd<<<(H * W + 255) / 256, 256, 0, st>>>(c4, rast, clip, faces, face_adj, adj_faces, H, W, out);
+    SDF_CHECK_LAUNCH("mesh_antialias_forward");
+    return SDF_OK;
+}
+
+// g_out [P,4] -> g_c4 [P,4] (written) and d_verts [vcap,3] (ACCUMULATED; may be NULL)
+SDF_API int sdf_mesh_antialias_backward(const float* g_out, const float* c4, const float* rast, const float* clip, const int* faces, const int* face_adj,
+                                        int adj_faces, const float* mvp, int H, int W, float* g_c4, float* d_verts, void* stream) {
+    SDF_CHECK_ARG(g_out && c4 && rast && clip && faces && face_adj && mvp && g_c4, "mesh_antialias_backward: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    SDF_CHECK_CUDA(cudaMemcpyAsync(g_c4, g_out, sizeof(float) * 4 * (size_t)H * W, cudaMemcpyDeviceToDevice, st));
+    k_antialias_bwd<<<(H * W + 255) / 256, 256, 0, st>>>(g_out, c4, rast, clip, faces, face_adj, adj_faces, mvp, H, W, g_c4, d_verts);
+    SDF_CHECK_LAUNCH("mesh_antialias_backward");
     return SDF_OK;
 }

@@ -21,7 +21,8 @@ class GradBucket:
     def __init__(self, params):
         self.params = [p for p in params if p.requires_grad]
         dev = self.params[0].device
-        self.flat = torch.zeros(sum(p.numel() for p in self.params), device=dev, dtype=torch.float32)
+        pad4 = lambda n: (n + 3) // 4 * 4            # every slice starts 16-byte aligned: the fused Adan kernels read float4
+        self.flat = torch.zeros(sum(pad4(p.numel()) for p in self.params), device=dev, dtype=torch.float32)
         self.views = []
         off = 0
         for p in self.params:
@@ -31,7 +32,7 @@ class GradBucket:
                 v.copy_(p.grad)
             p.grad = v
             self.views.append(v)
-            off += n
+            off += pad4(n)
 
     def rehome(self):
         for p, v in zip(self.params, self.views):

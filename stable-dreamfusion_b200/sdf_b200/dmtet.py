@@ -58,6 +58,25 @@ class Mesh:
     def __init__(self, lattice, verts):
         self.lattice, self.verts = lattice, verts
         self.faces, self.counts = lattice.faces, lattice.counts
+        self._topo = None
+
+    def topology(self):
+        """sorted half-edge list of the first lattice.reg_faces faces (one library radix sort per step, shared by the regularisers and the
+        antialiasing pass): dict(keys int64 [3R] sorted, face_of int32 [3R], face_adj int32 [R, 3])"""
+        if self._topo is None:
+            lat = self.lattice
+            dev = lat.faces.device
+            R = lat.reg_faces
+            keys = torch.empty(3 * R, device=dev, dtype=torch.int64)
+            face_of = torch.empty(3 * R, device=dev, dtype=torch.int32)
+            st = _lib.stream()
+            _lib.call('sdf_mesh_halfedge_keys', P(lat.faces), P(lat.counts), lat.vcap, R, P(keys), P(face_of), st)
+            keys, order = torch.sort(keys)
+            order = order.to(torch.int32)
+            face_adj = torch.empty(R, 3, device=dev, dtype=torch.int32)
+            _lib.call('sdf_mesh_face_adjacency', P(keys), P(order), P(lat.counts), R, P(face_adj), st)
+            self._topo = dict(keys=keys, face_of=torch.div(order, 3, rounding_mode='floor').to(torch.int32), face_adj=face_adj)
+        return self._topo
 
 
 class _Extract(Function):
@@ -129,11 +148,11 @@ class _Rasterize(Function):
         _lib.call('sdf_mesh_rasterize', P(clip), P(lat.faces), P(lat.counts), lat.fcap, P(v), P(vn), H, W, P(zbuf), P(rast), P(xyz), P(nrm), P(mask), st)
         ctx.lat, ctx.hw = lat, (H, W)
         ctx.save_for_backward(v, vn, m, clip, rast)
-        ctx.mark_non_differentiable(mask, rast)
-        return xyz, nrm, mask, rast
+        ctx.mark_non_differentiable(mask, rast, clip)
+        return xyz, nrm, mask, rast, clip
 
     @staticmethod
-    def backward(ctx, g_xyz, g_nrm, _gm, _gr):
+    def backward(ctx, g_xyz, g_nrm, _gm, _gr, _gc):
         lat = ctx.lat
         H, W = ctx.hw
         v, vn, m, clip, rast = ctx.saved_tensors
@@ -145,40 +164,44 @@ class _Rasterize(Function):
         return d_verts, d_vn, None, None, None, None
 
 
-def rasterize(mesh, vert_n, mvp, H, W):
-    """one view: mvp [4, 4] (device).  -> xyz [H*W, 3], unit normal [H*W, 3], coverage mask [H*W] in {0, 1}, rast [H, W, 4] = (u, v, z/w, id + 1)"""
-    return _Rasterize.apply(mesh.verts, vert_n, mvp, mesh.lattice, H, W)
+def rasterize(mesh, vert_n, mvp, H, W, want_clip=False):
+    """one view: mvp [4, 4] (device).  -> xyz [H*W, 3], unit normal [H*W, 3], coverage mask [H*W] in {0, 1}, rast [H, W, 4] = (u, v, z/w, id + 1)
+    (+ the clip-space vertices [vcap, 4] with want_clip)"""
+    out = _Rasterize.apply(mesh.verts, vert_n, mvp, mesh.lattice, H, W)
+    return out if want_clip else out[:4]
 
 
 class _MeshLosses(Function):
     @staticmethod
-    def forward(ctx, verts, face_n, lat):
+    def forward(ctx, verts, face_n, lat, topo):
         dev = verts.device
         v, fn = verts.detach().contiguous(), face_n.detach().contiguous()
-        keys = torch.empty(3 * lat.reg_faces, device=dev, dtype=torch.int64)
-        face_of = torch.empty(3 * lat.reg_faces, device=dev, dtype=torch.int32)
-        st = _lib.stream()
-        _lib.call('sdf_mesh_halfedge_keys', P(lat.faces), P(lat.counts), lat.vcap, lat.reg_faces, P(keys), P(face_of), st)
-        keys, order = torch.sort(keys)                              # library radix sort: the one non-native launch of the stage
-        face_of = (order // 3).to(torch.int32)
         work = torch.empty(3 * lat.vcap + 4, device=dev)
         losses = torch.empty(2, device=dev)
-        _lib.call('sdf_mesh_losses_forward', P(keys), P(face_of), P(lat.counts), lat.vcap, lat.reg_faces, P(fn), P(v), P(work), P(losses), st)
-        ctx.lat = lat
-        ctx.save_for_backward(keys, face_of, fn, work)
+        _lib.call('sdf_mesh_losses_forward', P(topo['keys']), P(topo['face_of']), P(lat.counts), lat.vcap, lat.reg_faces, P(fn), P(v), P(work), P(losses),
+                  _lib.stream())
+        ctx.lat, ctx.topo = lat, topo
+        ctx.save_for_backward(fn, work)
         return losses
 
     @staticmethod
     def backward(ctx, g):
-        lat = ctx.lat
-        keys, face_of, fn, work = ctx.saved_tensors
+        lat, topo = ctx.lat, ctx.topo
+        fn, work = ctx.saved_tensors
         d_verts = torch.zeros(lat.vcap, 3, device=fn.device)
         d_fn = torch.zeros_like(fn)
-        _lib.call('sdf_mesh_losses_backward', P(keys), P(face_of), P(lat.counts), lat.vcap, lat.reg_faces, P(fn), P(work), P(g.float().contiguous()), P(d_fn),
-                  P(d_verts), _lib.stream())
-        return d_verts, d_fn, None
+        _lib.call('sdf_mesh_losses_backward', P(topo['keys']), P(topo['face_of']), P(lat.counts), lat.vcap, lat.reg_faces, P(fn), P(work),
+                  P(g.float().contiguous()), P(d_fn), P(d_verts), _lib.stream())
+        return d_verts, d_fn, None, None
 
 
 def mesh_losses(mesh, face_n):
     """-> tensor [2] = (normal_consistency, laplacian_smooth_loss) of the current mesh"""
-    return _MeshLosses.apply(mesh.verts, face_n, mesh.lattice)
+    return _MeshLosses.apply(mesh.verts, face_n, mesh.lattice, mesh.topology())
+
+
+def antialias_context(mesh, rast, clip, mvp):
+    """what csrc/meshrast.cu's antialiasing pass needs besides the image: the rasteriser's outputs and the face adjacency"""
+    lat = mesh.lattice
+    return dict(rast=rast, clip=clip, faces=lat.faces, face_adj=mesh.topology()['face_adj'], adj_faces=lat.reg_faces, mvp=mvp.detach().float().contiguous(),
+                vcap=lat.vcap)

@@ -1,0 +1,149 @@
+"""DMTet fine-tuning model: the -O hash-grid network as the texture + a signed-distance lattice as the geometry (BASELINE config C5).
+
+Mirrors the dmtet branches of the reference's NeRFRenderer / NeRFNetwork: parameters `sdf` [N] and `deform` [N, 3] on the lattice
+(nerf/renderer.py:296-303), `init_tet` from the trained density field (:818-857), `run_dmtet` (:862-954) and the extra optimiser
+groups (nerf/network_grid.py:168-170).  The rendering path is csrc/dmtet.cu + csrc/meshrast.cu through sdf_b200/dmtet.py; the texture
+lookup is the fused field kernel in albedo mode; the background mix is the same fused kernel the volume path uses.
+
+Deviations from the reference, stated where a user would look for them:
+  * the lattice is generated (sdf_b200/tetgrid.py), not loaded from tets/*.npz — same family and size class, different vertex numbering;
+  * `dr.antialias` is restated in csrc/meshrast.cu (silhouette-edge blending); nvdiffrast itself is absent: parity unpinned for that half;
+  * the texture lookup does not propagate d(albedo)/d(position) back into the geometry (the reference's GridEncoder does when its input
+    requires grad); geometry gradients come from the shading normals, the barycentrics, the silhouettes and the two mesh regularisers.
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+from torch.autograd import Function
+
+from . import _lib, dmtet, tetgrid
+from .ngp import InstantNGP
+
+P = _lib.ptr
+SHADING_ID = {'albedo': 0, 'lambertian': 1, 'textureless': 2, 'normal': 3}
+
+
+class _ShadeComposite(Function):
+    """shade the G-buffer, (antialias,) clamp, add (1 - alpha) * background, emit the NCHW image the guidance consumes"""
+
+    @staticmethod
+    def forward(ctx, albedo, nrm, mask, light, rays_d, bg_color, bw1, bb1, bw2, bb2, verts, aa, cfg):
+        dev = albedo.device
+        Pn, H, W = albedo.shape[0], cfg['H'], cfg['W']
+        st = _lib.stream()
+        a, n = albedo.detach().float().contiguous(), nrm.detach().contiguous()
+        c4 = torch.empty(Pn, 4, device=dev)
+        _lib.call('sdf_mesh_shade_forward', P(a), P(n), P(mask), P(light), float(cfg['ambient']), SHADING_ID[cfg['shading']], Pn, P(c4), st)
+        c4_aa = c4
+        if aa is not None:
+            c4_aa = torch.empty_like(c4)
+            _lib.call('sdf_mesh_antialias_forward', P(c4), P(aa['rast']), P(aa['clip']), P(aa['faces']), P(aa['face_adj']), aa['adj_faces'], H, W, P(c4_aa), st)
+        image_c, wsum = torch.empty(Pn, 3, device=dev), torch.empty(Pn, device=dev)
+        _lib.call('sdf_mesh_c4_split', P(c4_aa), Pn, P(image_c), P(wsum), st)
+        use_net = bg_color is None
+        bgc = None if use_net else bg_color.detach().float().contiguous()
+        bgw = [t.detach() for t in (bw1, bb1, bw2, bb2)] if use_net else [None] * 4
+        pred = torch.empty(1, 3, H, W, device=dev)
+        bg = torch.empty(Pn, 3, device=dev)
+        rd = rays_d.detach().contiguous()
+        _lib.call('sdf_background_forward', P(rd), Pn, *[P(t) for t in bgw], P(bgc), int(cfg['half_round']), P(image_c), P(wsum), P(bg), None, P(pred), H * W, 3, st)
+        ctx.cfg, ctx.use_net, ctx.aa = cfg, use_net, aa
+        ctx.save_for_backward(a, n, mask, light, rd, bgc if bgc is not None else torch.empty(0), wsum, c4, c4_aa, bw1, bb1, bw2, bb2)
+        return pred, wsum
+
+    @staticmethod
+    def backward(ctx, g_pred, g_wsum_out):
+        a, n, mask, light, rd, bgc, wsum, c4, c4_aa, bw1, bb1, bw2, bb2 = ctx.saved_tensors
+        cfg, aa = ctx.cfg, ctx.aa
+        dev = a.device
+        Pn, H, W = a.shape[0], cfg['H'], cfg['W']
+        st = _lib.stream()
+        g_image_c, g_ws = torch.empty(Pn, 3, device=dev), torch.empty(Pn, device=dev)
+        gb = [torch.zeros_like(t, dtype=torch.float32) if ctx.use_net else None for t in (bw1, bb1, bw2, bb2)]
+        bgw = [t.detach() for t in (bw1, bb1, bw2, bb2)] if ctx.use_net else [None] * 4
+        _lib.call('sdf_background_backward', None, P(g_pred.contiguous()), H * W, 3, P(rd), Pn, *[P(t) for t in bgw], P(bgc) if not ctx.use_net else None,
+                  int(cfg['half_round']), P(wsum), P(g_image_c), P(g_ws), *[P(t) for t in gb], st)
+        if g_wsum_out is not None:
+            g_ws.add_(g_wsum_out.reshape(-1))
+        g_c4 = torch.empty(Pn, 4, device=dev)
+        _lib.call('sdf_mesh_c4_split_backward', P(g_image_c), P(g_ws), P(c4_aa), Pn, P(g_c4), st)
+        g_verts = None
+        if aa is not None:
+            g_pre = torch.empty_like(g_c4)
+            g_verts = torch.zeros(aa['vcap'], 3, device=dev) if ctx.needs_input_grad[10] else None
+            _lib.call('sdf_mesh_antialias_backward', P(g_c4), P(c4), P(aa['rast']), P(aa['clip']), P(aa['faces']), P(aa['face_adj']), aa['adj_faces'],
+                      P(aa['mvp']), H, W, P(g_pre), P(g_verts), st)
+            g_c4 = g_pre
+        g_alb, g_nrm = torch.empty(Pn, 3, device=dev), torch.empty(Pn, 3, device=dev)
+        _lib.call('sdf_mesh_shade_backward', P(g_c4), P(a), P(n), P(mask), P(light), float(cfg['ambient']), SHADING_ID[cfg['shading']], Pn, P(g_alb), P(g_nrm), st)
+        return (g_alb, g_nrm, None, None, None, None, *[g if ctx.use_net else None for g in gb], g_verts, None, None)
+
+
+class DMTetNGP(InstantNGP):
+    def __init__(self, opt):
+        super().__init__(opt)
+        self.dmtet = True
+        n = tetgrid.cells_for(opt.tet_grid_size)
+        N = (n + 1) ** 3 + n ** 3
+        self.sdf = nn.Parameter(torch.zeros(N))                          # nerf/renderer.py:296-299
+        self.deform = nn.Parameter(torch.zeros(N, 3))
+        self.register_buffer('tet_scale', torch.ones(3))
+        self.lattice = None
+
+    def build_lattice(self, device):
+        self.lattice = dmtet.TetLattice(self.opt.tet_grid_size, device)
+        assert self.lattice.N == self.sdf.shape[0]
+        return self.lattice
+
+    def get_params(self, lr):
+        groups = super().get_params(lr)
+        if not getattr(self.opt, 'lock_geo', False):                     # nerf/network_grid.py:168-170
+            groups += [{'params': [self.sdf], 'lr': lr}, {'params': [self.deform], 'lr': lr}]
+        return groups
+
+    @torch.no_grad()
+    def init_tet(self, density_thresh=None):
+        """scale the lattice to the trained object and seed the signed distances from its density (nerf/renderer.py:835-857)"""
+        lat = self.lattice
+        thr = min(self.mean_density, float(self.opt.density_thresh)) if density_thresh is None else float(density_thresh)
+        sigma = self.density(lat.pos)['sigma']
+        valid = lat.pos[sigma > thr]
+        scale = valid.abs().amax(dim=0) + 1e-1 if valid.shape[0] > 0 else torch.ones(3, device=lat.pos.device)
+        self.tet_scale.copy_(scale)
+        lat.pos.mul_(scale)
+        sigma = self.density(lat.pos)['sigma']
+        self.sdf.data += (sigma - thr).clamp(-1, 1)
+        return scale
+
+    def render_mesh(self, mvp, rays_d, campos, H, W, *, light_d=None, ambient_ratio=1.0, shading='albedo', bg_color=None, antialias=True,
+                    mesh_losses=True):
+        """one view (the DMTet stage trains with batch 1 per GPU).  mvp [4, 4], rays_d [H*W, 3], campos [3] on the device.
+        -> dict(pred_rgb [1, 3, H, W], weights_sum [H*W], normal_loss, lap_loss)  (nerf/renderer.py:862-954)"""
+        opt, lat = self.opt, self.lattice
+        dev = mvp.device
+        if light_d is None:
+            l = campos + torch.randn(3, device=dev)                       # nerf/renderer.py:868-870
+            light_d = l / torch.sqrt(torch.clamp((l * l).sum(), min=1e-20))
+        lock = bool(getattr(opt, 'lock_geo', False))
+        if lock and shading in ('textureless', 'normal'):               # nothing to optimise in those modes without geometry (:913-915)
+            shading = 'lambertian'
+        sdf, deform = (self.sdf.detach(), self.deform.detach()) if lock else (self.sdf, self.deform)
+        mesh = dmtet.extract_mesh(lat, sdf, deform)
+        face_n, vert_n = dmtet.mesh_normals(mesh)
+        xyz, nrm, mask, rast, clip = dmtet.rasterize(mesh, vert_n, mvp, H, W, want_clip=True)
+        albedo = self.density(xyz.detach())['albedo']                    # texture lookup (:905-912), all pixels; masked inside the shading kernel
+        aa = None
+        if antialias:
+            aa = dmtet.antialias_context(mesh, rast, clip, mvp)
+        bn = self.bg_net.net if (self.bg_net is not None and bg_color is None) else None
+        if bn is None and bg_color is None:
+            bg_color = torch.ones(3, device=dev)                         # bg_radius <= 0: white (:940-941)
+        cfg = dict(H=H, W=W, ambient=float(ambient_ratio), shading=shading, half_round=self.half_round)
+        bgp = (bn[0].weight, bn[0].bias, bn[1].weight, bn[1].bias) if bn is not None else (None,) * 4
+        # mesh.verts is an input so that the antialiasing pass's silhouette gradients reach the vertices
+        pred, wsum = _ShadeComposite.apply(albedo, nrm, mask, light_d.float().contiguous(), rays_d, bg_color, *bgp, mesh.verts if aa is not None else None, aa, cfg)
+        out = {'pred_rgb': pred, 'image': pred, 'weights_sum': wsum, 'depth': rast[..., 2]}
+        if mesh_losses and (opt.lambda_mesh_normal > 0 or opt.lambda_mesh_laplacian > 0):
+            losses = dmtet.mesh_losses(mesh, face_n)
+            out['normal_loss'], out['lap_loss'] = losses[0], losses[1]
+        return out

@@ -24,7 +24,19 @@ def default_opt(**over):
         lr=1e-3,
         # presets
         fp16=True, cuda_ray=True, dmtet=False, taichi_ray=False, progressive_level=False,
+        # DMTet stage (main.py:46-50, 98, 137-138)
+        tet_grid_size=128, lock_geo=False, dmtet_reso_scale=8, lambda_mesh_normal=0.5, lambda_mesh_laplacian=0.5,
     )
+    for k, v in over.items():
+        setattr(o, k, v)
+    return o
+
+
+def dmtet_opt(**over):
+    """options of a `--dmtet` run after main.py:253-274: render size x dmtet_reso_scale, no latent / albedo warm-up, t_range of Magic3D's
+    fine stage"""
+    o = default_opt(dmtet=True, latent_iter_ratio=0.0, albedo_iter_ratio=0.0, t_range=[0.02, 0.50], progressive_view=False)
+    o.h, o.w = int(o.h * o.dmtet_reso_scale), int(o.w * o.dmtet_reso_scale)
     for k, v in over.items():
         setattr(o, k, v)
     return o

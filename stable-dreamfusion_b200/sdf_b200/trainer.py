@@ -53,7 +53,13 @@ class SDSTrainer:
         self.image_embeddings = image_embeddings
         self.rank, self.world_size = rank, world_size
         torch.manual_seed(seed)                       # identical initial parameters on every rank
-        self.model = InstantNGP(opt).to(device)
+        self.dmtet = bool(getattr(opt, 'dmtet', False))
+        if self.dmtet:
+            from .dmtet_model import DMTetNGP
+            self.model = DMTetNGP(opt).to(device)
+            self.model.build_lattice(device)
+        else:
+            self.model = InstantNGP(opt).to(device)
         self.model.train()
         # main.py:368
         self.optimizer = Adan(self.model.get_params(5 * opt.lr), eps=1e-8, weight_decay=2e-5, max_grad_norm=5.0, foreach=False)
@@ -80,11 +86,11 @@ class SDSTrainer:
             self.embeddings = {'uncond': te(['']), 'default': te([prompt])}
             for d in ('front', 'side', 'back'):
                 self.embeddings[d] = te([f'{prompt}, {d} view'])
-        self.ray_parallel = world_size > 1 and (opt.h * opt.w) % world_size == 0
+        self.ray_parallel = world_size > 1 and (opt.h * opt.w) % world_size == 0 and not self.dmtet      # the mesh stage is view-parallel
         self.rng_shared = np.random.default_rng(seed * 1000 + 999)
         # pinned staging ring for the poses: the host may run several steps ahead of the GPU, so a slot is only rewritten after
         # the copy that read it has completed (event per slot)
-        n_pose = opt.batch_size * (world_size if self.ray_parallel else 1)
+        n_pose = opt.batch_size * (world_size if self.ray_parallel else 1) * (2 if self.dmtet else 1)          # dmtet: pose + mvp per view
         self.pin_ring = [torch.zeros(n_pose, 4, 4).pin_memory() for _ in range(4)]
         self.pin_events = [None] * len(self.pin_ring)
         self.comm_stream = torch.cuda.Stream(device=device) if (world_size > 1 and device.type == 'cuda') else None
@@ -181,6 +187,8 @@ class SDSTrainer:
     def train_step(self, views=None, shading=None, read_loss=False):
         opt, dev = self.opt, self.device
         self._mark('start')
+        if self.dmtet:
+            return self._train_step_dmtet(views, shading, read_loss)
         if self.global_step % opt.update_extra_interval == 0:
             self.model.update_extra_state()
             if self.world_size > 1:
@@ -259,6 +267,49 @@ class SDSTrainer:
         self._mark('Adan step')
         if read_loss:
             return float(loss.item())          # device -> host read of the step's result (nerf/utils.py:1072)
+        return loss
+
+    # ------------------------------------------------------------------ DMTet stage (BASELINE config C5)
+    def _train_step_dmtet(self, views, shading, read_loss):
+        """one fine-tuning step of the mesh stage (nerf/utils.py:439-723 with opt.dmtet, nerf/renderer.py:862-954): sample a view, extract
+        + rasterise + texture + shade the mesh at opt.h x opt.w, SDS through the same guidance engine, mesh regularisers, fused Adan over
+        (table, MLP, background net, sdf, deform).  One view per GPU; gradients are all-reduced like the volume stage's."""
+        opt, dev = self.opt, self.device
+        assert opt.batch_size == 1, 'the DMTet stage renders one view per step and GPU'
+        if self.global_step % opt.update_extra_interval == 0:
+            self.model.update_extra_state()                  # the reference keeps refreshing the grid while cuda_ray is set (nerf/utils.py:1029-1031)
+        self.global_step += 1
+        poses_np, azimuth, fov = self.sample_views() if views is None else views
+        H, W = opt.h, opt.w
+        focal = H / (2 * math.tan(math.radians(fov) / 2))
+        near, far = float(opt.min_near), 1000.0
+        proj = np.array([[2 * focal / W, 0, 0, 0], [0, -2 * focal / H, 0, 0], [0, 0, -(far + near) / (far - near), -(2 * far * near) / (far - near)],
+                         [0, 0, -1, 0]], dtype=np.float32)                       # nerf/provider.py:222-229
+        mvp_np = (proj @ np.linalg.inv(poses_np[0].astype(np.float64)).astype(np.float32))[None]
+        both = self._upload_poses(np.concatenate([poses_np[:1], mvp_np], 0).astype(np.float32))      # host -> device: 128 bytes
+        poses, mvp = both[:1], both[1]
+        mode, ambient, _, bg_color = self._schedule(shading if shading != 'latent' else 'albedo', False)
+        if shading is None and mode == 'normal':             # no latent warm-up in this stage (main.py:270-272); step 1 would draw it
+            mode, ambient = 'lambertian', 1.0
+        rays_o, rays_d = self._rays(poses, fov)
+        out = self.model.render_mesh(mvp, rays_d, poses[0, :3, 3], H, W, ambient_ratio=ambient, shading=mode, bg_color=bg_color,
+                                     antialias=getattr(opt, 'mesh_antialias', True))
+        pred_rgb = out['pred_rgb']
+        self.last_pred_rgb = pred_rgb
+        self._mark('mesh render (marching tets, normals, rasterise, texture, shade, antialias, background)')
+        loss = self.guidance.train_step(self.text_z(azimuth), pred_rgb, as_latent=False, guidance_scale=opt.guidance_scale, grad_scale=opt.lambda_guidance)
+        self._mark('guidance (VAE encode, UNet, SDS gradient, VAE data-gradient)')
+        if 'normal_loss' in out:                              # nerf/utils.py:712-717
+            loss = loss + opt.lambda_mesh_normal * out['normal_loss'] + opt.lambda_mesh_laplacian * out['lap_loss']
+        loss.backward()
+        self._mark('backward (shade, rasterise, normals, regularisers, marching tets, field backward)')
+        if self.world_size > 1:
+            self._allreduce_grads()
+            self._mark('all-reduce')
+        self.optimizer.step(zero_grad=True, ema=(self.global_step % self.steps_per_epoch == 0))
+        self._mark('Adan step')
+        if read_loss:
+            return float(loss.item())
         return loss
 
     def _allreduce_grads(self):

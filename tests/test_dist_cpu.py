@@ -26,7 +26,7 @@ def _worker(rank, world, port, out):
     late = torch.nn.Parameter(torch.randn(4))          # receives its first gradient at step 1, on rank 1 only (a bg_net that a
     params = [table] + list(model.parameters()) + [late]   # schedule draw switches on later, and not on every rank)
     bucket = GradBucket(params)
-    assert late.grad is not None and bucket.flat.numel() == sum(p.numel() for p in params)
+    assert late.grad is not None and bucket.flat.numel() == sum((p.numel() + 3) // 4 * 4 for p in params)       # slices are 16-byte aligned
     results = []
     for step in range(3):
         g = torch.Generator().manual_seed(100 * step + rank)          # each rank sees its own "view"

@@ -207,3 +207,102 @@ def test_rasterizer_against_the_restatement_and_autograd(device):
     ((xyz_t * gx[hit]).sum() + (n_t * gn[hit]).sum()).backward()
     assert rel_l2(got_n, nt.grad) < 1e-3
     assert rel_l2(got_v, vt.grad) < 5e-3
+
+
+def test_antialias_blends_silhouettes_and_matches_finite_differences(device):
+    """dr.antialias restated (csrc/meshrast.cu): interior pixels are untouched, silhouette pixels blend, the analytic vertex gradient of a scalar
+    functional of the antialiased image agrees with central finite differences of the same functional (the rasterised triangle ids held fixed)"""
+    from sdf_b200 import _lib
+    P = _lib.ptr
+    lat, sdf, raw = lattice_and_params("b", device)
+    mesh = dmtet.extract_mesh(lat, sdf, raw)
+    nv, nf = lat.mesh_counts()
+    H = W = 64
+    mvp = look_at_mvp(device)
+    fn, vn = dmtet.mesh_normals(mesh)
+    xyz, nrm, mask, rast, clip = dmtet.rasterize(mesh, vn, mvp, H, W, want_clip=True)
+    topo = mesh.topology()
+    adj = topo["face_adj"][:nf].cpu().numpy()
+    faces = mesh.faces[:nf].cpu().numpy()
+    assert (adj >= 0).mean() > 0.99                                   # closed surface: (almost) every edge has a neighbour
+    f0 = 7
+    for k in range(3):                                                # adjacency is symmetric and shares the edge
+        g = adj[f0, k]
+        e = {faces[f0, k], faces[f0, (k + 1) % 3]}
+        assert f0 in adj[g] and e <= set(faces[g])
+    gen = torch.Generator(device=device).manual_seed(11)
+    c4 = torch.cat([torch.rand(H * W, 3, device=device, generator=gen) * mask[:, None], mask[:, None]], 1).contiguous()
+    wgt = torch.randn(H * W, 4, device=device, generator=gen)
+    st = _lib.stream()
+
+    def run(clip_t):
+        out = torch.empty_like(c4)
+        _lib.call("sdf_mesh_antialias_forward", P(c4), P(rast), P(clip_t), P(lat.faces), P(topo["face_adj"]), lat.reg_faces, H, W, P(out), st)
+        return out
+
+    out = run(clip)
+    changed = (out - c4).abs().sum(1) > 0
+    tri = rast[..., 3].reshape(-1)
+    interior = torch.zeros(H * W, dtype=torch.bool, device=device)
+    t2 = tri.view(H, W)
+    same = (t2[1:-1, 1:-1] > 0) & (t2[1:-1, 1:-1] == t2[:-2, 1:-1]) & (t2[1:-1, 1:-1] == t2[2:, 1:-1]) & (t2[1:-1, 1:-1] == t2[1:-1, :-2]) & (t2[1:-1, 1:-1] == t2[1:-1, 2:])
+    interior.view(H, W)[1:-1, 1:-1] = same
+    assert not changed[interior].any()
+    assert changed.sum() > 20                                          # the silhouette ring
+    cov = out[:, 3]
+    assert ((cov > 1e-3) & (cov < 1 - 1e-3)).sum() > 20 and cov.min() >= -1e-6 and cov.max() <= 1 + 1e-6
+    # analytic gradient wrt the vertices
+    g_c4 = torch.empty_like(c4)
+    d_verts = torch.zeros(lat.vcap, 3, device=device)
+    _lib.call("sdf_mesh_antialias_backward", P(wgt), P(c4), P(rast), P(clip), P(lat.faces), P(topo["face_adj"]), lat.reg_faces, P(mvp), H, W, P(g_c4), P(d_verts), st)
+    # colour gradient: the map c4 -> out is linear for fixed geometry: <wgt, A c4> = <A^T wgt, c4>
+    c4b = torch.rand(H * W, 4, device=device, generator=gen)
+    outb = torch.empty_like(c4b)
+    _lib.call("sdf_mesh_antialias_forward", P(c4b), P(rast), P(clip), P(lat.faces), P(topo["face_adj"]), lat.reg_faces, H, W, P(outb), st)
+    g_c4b = torch.empty_like(c4b)
+    _lib.call("sdf_mesh_antialias_backward", P(wgt), P(c4b), P(rast), P(clip), P(lat.faces), P(topo["face_adj"]), lat.reg_faces, P(mvp), H, W, P(g_c4b), None, st)
+    assert abs(float((wgt * outb).sum()) - float((g_c4b * c4b).sum())) < 1e-3 * float((wgt * outb).abs().sum())
+    # position gradient along random directions vs central differences (clip recomputed from the moved vertices, winners fixed).  The functional
+    # is only piecewise smooth (a crossing that slides past a pixel centre drops its pair), so the step is 2e-5 scene units (~4e-4 pixels) and
+    # three of four directions must agree: an occasional flipped pair is tolerated, a wrong derivative is not
+    ok = 0
+    for trial in range(4):
+        dirn = torch.zeros(lat.vcap, 3, device=device)
+        dirn[:nv] = torch.randn(nv, 3, device=device, generator=gen)
+        analytic = float((d_verts.double() * dirn.double()).sum())
+        vals = []
+        for eps in (2e-5, -2e-5):
+            v2 = (mesh.verts.detach().double() + eps * dirn.double()).float().contiguous()
+            clip2 = torch.empty_like(clip)
+            _lib.call("sdf_mesh_clip_transform", P(v2), P(lat.counts), lat.vcap, P(mvp), P(clip2), st)
+            vals.append(float((wgt.double() * run(clip2).double()).sum()))
+        fd = (vals[0] - vals[1]) / 4e-5
+        print("antialias d/dverts: analytic", analytic, "finite difference", fd)
+        ok += abs(analytic - fd) < 0.1 * max(abs(fd), abs(analytic), 1e-3)
+    assert ok >= 3
+
+
+def test_dmtet_training_steps(device):
+    """the mesh stage end to end on a reduced SD configuration: init_tet from the density blob gives a closed mesh, every shading mode steps,
+    the loss is finite, sdf / deform / table / MLP / background net all receive gradients and move, the regularisers are finite"""
+    from sdf_b200.options import dmtet_opt
+    from sdf_b200.trainer import SDSTrainer
+    from test_gpu_trainer import SmallGuidance
+    opt = dmtet_opt(h=128, w=128, tet_grid_size=32)
+    guidance = SmallGuidance(device, render_hw=128)
+    tr = SDSTrainer(opt, device, guidance, seed=0)
+    tr.model.update_extra_state()
+    scale = tr.model.init_tet()
+    assert (scale > 0.1).all() and (scale < 1.2).all()
+    before = {n: p.detach().clone() for n, p in tr.model.named_parameters()}
+    losses = []
+    for sh in ["lambertian", "textureless", "albedo", "normal", "lambertian", None]:
+        losses.append(tr.train_step(shading=sh, read_loss=True))
+    nv, nf = tr.model.lattice.mesh_counts()
+    assert nv > 100 and nf > 200 and abs(nf - 2 * nv) < 0.1 * nf            # closed genus-0 surface: F = 2V - 4
+    assert all(l == l and abs(l) < 1e12 for l in losses), losses
+    cov = float((tr.last_pred_rgb != tr.last_pred_rgb[..., :1, :1]).any(1).float().mean())
+    assert 0.01 < cov < 0.9, cov                                           # the object covers part of the frame
+    for n, p in tr.model.named_parameters():
+        assert torch.isfinite(p).all(), n
+        assert (p.detach() - before[n]).abs().max().item() > 0, f"{n} did not move"
