@@ -35,7 +35,9 @@ METRIC = "SDS steps/sec (64x64 render, SD-1.5 UNet)"
 CONFIGS = {"C2": dict(hw=64, note="BASELINE.json configs[1]: -O backbone, 64x64 render, 1 view/step/GPU"),
            "C3": dict(hw=128, note="BASELINE.json configs[2]: -O backbone, 128x128 render, 1 view/step/GPU (4 views over 4 GPUs)"),
            "C4": dict(hw=64, zero123=True, note="BASELINE.json configs[3]: Zero-1-to-3-shaped UNet guidance (8-channel input, 1-token context, 32x32 "
-                                               "latents, VAE 256x256), 64x64 render, 1 view/step/GPU")}
+                                               "latents, VAE 256x256), 64x64 render, 1 view/step/GPU"),
+           "C5": dict(hw=512, dmtet=True, note="BASELINE.json configs[4]: DMTet fine-tuning stage (tet lattice of the tets/128 size class), 512x512 rasterised "
+                                               "render + SD-1.5 SDS, 1 view/step/GPU")}
 CYCLE = ["latent"] * 5 + (["lambertian"] * 4 + ["textureless"]) * 4        # 20 % / 64 % / 16 %
 
 
@@ -282,7 +284,16 @@ def run_ours(args):
 
     hw = CONFIGS[args.config]["hw"]
     opt = default_opt(h=hw, w=hw, batch_size=1)
-    if CONFIGS[args.config].get("zero123"):
+    is_dmtet = bool(CONFIGS[args.config].get("dmtet"))
+    if is_dmtet:
+        from sdf_b200.options import dmtet_opt
+        opt = dmtet_opt(batch_size=1)                                   # main.py:253-274: 64 x dmtet_reso_scale 8 = 512, no latent / albedo phases
+        assert opt.h == hw
+        guidance = StableDiffusion(dev, weights="random", n_views=1, render_hw=hw, seed=0, capture=True)
+        trainer = SDSTrainer(opt, dev, guidance, seed=0, rank=rank, world_size=world)
+        trainer.model.update_extra_state()                              # stands for the coarse stage's trained density: the initial blob
+        trainer.model.init_tet()                                        # main.py:317-324 (init_with a checkpoint -> init_tet)
+    elif CONFIGS[args.config].get("zero123"):
         from guidance.zero123_utils import Zero123
         opt.guidance_scale, opt.latent_iter_ratio = 5.0, 0.0            # main.py:196-219 defaults of an image-only run
         opt.zero123_grad_scale = "angle"
@@ -294,7 +305,7 @@ def run_ours(args):
     else:
         guidance = StableDiffusion(dev, weights="random", n_views=1, render_hw=hw, seed=0, capture=True)
         trainer = SDSTrainer(opt, dev, guidance, seed=0, rank=rank, world_size=world)
-    cycle = [c for c in CYCLE if c != "latent"] if CONFIGS[args.config].get("zero123") else CYCLE
+    cycle = [c for c in CYCLE if c != "latent"] if (CONFIGS[args.config].get("zero123") or is_dmtet) else CYCLE
     eng = guidance.engine
     launches = {"n": 0}
     orig_call = _lib.call
@@ -429,7 +440,7 @@ def run_ours(args):
     # --- secondary figure: inference render rate at 800x800 with the device-side loop (no host sync per iteration,
     #     on-device alive-ray compaction); the reference's only published number is "~10 FPS at 800x800" on a V100 (readme.md:28)
     eval_fps = None
-    if world == 1 and not args.no_eval:
+    if world == 1 and not args.no_eval and not is_dmtet:
         try:
             from sdf_b200 import synth as _synth
             m = trainer.model
@@ -454,7 +465,7 @@ def run_ours(args):
             trainer.model.train()
 
     mg_check = None
-    if world > 1:
+    if world > 1 and not is_dmtet:
         try:
             mg_check = ray_parallel_selfcheck(opt, dev, rank, world)
         except Exception as e:
@@ -492,12 +503,13 @@ def run_ours(args):
                 cpu = {"value": None, "unit": "steps/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e!r}"}
         # --- the north star's comparison: the reference's own -O loop on this same GPU (N = 1 only; skipped with --no-ref-cuda)
         refc, vs = None, None
-        if world == 1 and not args.no_ref_cuda and args.config != "C4":        # the reference's Zero123 needs ldm + a checkpoint: no same-GPU arm
+        if world == 1 and not args.no_ref_cuda and args.config not in ("C4", "C5"):        # the reference's Zero123 needs ldm + a checkpoint, its DMTet stage nvdiffrast: no same-GPU arm
             try:
                 torch.cuda.empty_cache()
                 refc = time_reference_cuda(hw, steps=max(args.steps, 25), warmup=max(args.warmup, 10))
             except Exception as e:
                 refc = {"value": None, "error": repr(e)[-400:]}
+        mesh_counts = trainer.model.lattice.mesh_counts() if is_dmtet else None
         value = world * args.steps / (ms_res * 1e-3)
         if refc and refc.get("value"):
             vs = value / refc["value"]
@@ -511,7 +523,11 @@ def run_ours(args):
                 "vs_baseline_kind": "value / steps-per-second of the reference's own -O CUDA-extension training loop measured on this same GPU in this run "
                                     "(`reference_cuda` below; BASELINE.md publishes no number, its 3.1 defines this arm A)",
                 "dtype": "f16", "data": "synthetic",
-                "config": {"workload": f"{args.config}: -O instant-NGP backbone, {hw}x{hw} render, 1 view/step/GPU, " +
+                "config": {"workload": (f"{args.config}: DMTet fine-tuning stage: marching tetrahedra on a {trainer.model.lattice.N}-vertex / {trainer.model.lattice.F}-tet lattice "
+                                        f"(mesh {mesh_counts[0]} vertices / {mesh_counts[1]} faces), {hw}x{hw} rasterised + antialiased render textured by the -O hash-grid "
+                                        "network, 1 view/step/GPU, SD-1.5-shaped UNet (B=2 CFG) + VAE encoder 512x512, shading mix 80% lambertian / 20% textureless, mesh "
+                                        "normal-consistency + Laplacian regularisers, Adan step over table + MLP + bg net + sdf + deform") if is_dmtet else
+                                       f"{args.config}: -O instant-NGP backbone, {hw}x{hw} render, 1 view/step/GPU, " +
                                        ("Zero-1-to-3-shaped UNet (8-ch input, 1-token context, 32x32 latents, B=2 CFG) + VAE encoder 256x256, " if CONFIGS[args.config].get("zero123")
                                         else "SD-1.5-shaped UNet (B=2 CFG) + VAE encoder 512x512, ") +
                                        ("shading mix 80% lambertian / 20% textureless (no latent phase with image guidance), " if CONFIGS[args.config].get("zero123")
@@ -519,7 +535,7 @@ def run_ours(args):
                            "rays_per_view": hw * hw, "samples_last_step": trainer.last_M, "l2": "per-step working set (UNet weights 1.7 GB + activations) exceeds the 126 MB L2",
                            "parallelism": f"dp{world}" + (" (one view per GPU for the UNet/VAE; every GPU renders 1/N of the rays of every view, pixels and pixel "
                                                          "gradients exchanged by all-to-all; one gradient all-reduce)" if world > 1 else "")},
-                "e2e": {"value": e2e_v, "unit": "steps/s", "h2d_bytes_per_step": 64 * (world if trainer.ray_parallel else 1), "d2h_bytes_per_step": 4,
+                "e2e": {"value": e2e_v, "unit": "steps/s", "h2d_bytes_per_step": (128 if is_dmtet else 64) * (world if trainer.ray_parallel else 1), "d2h_bytes_per_step": 4,
                         "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": int(round(launches_per_step * args.steps)),
                 "roofline": fld, "roofline_gemm": roof_gemm, "reference_cuda": refc, "cpu_baseline": cpu, "clocks": sampler.summary()}
@@ -542,7 +558,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-cuda"],
                     help="reference = the reference's CPU path (driver contract); reference-cuda = arm (A) of SURVEY.md §8d: the reference's own "
                          "unmodified Python + CUDA extensions + PyTorch fp16 UNet/VAE on this GPU (oracle/ref_harness.py)")
-    ap.add_argument("--config", default="C2", choices=sorted(CONFIGS), help="BASELINE.json config: C2 = 64x64 (the metric's), C3 = 128x128")
+    ap.add_argument("--config", default="C2", choices=sorted(CONFIGS), help="BASELINE.json config: C2 = 64x64 (the metric's), C3 = 128x128, C4 = Zero123-shaped guidance, C5 = DMTet stage at 512x512")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-eval", action="store_true", help="skip the 800x800 inference-render figure")
     ap.add_argument("--no-ref-cuda", action="store_true", help="skip the same-GPU reference arm (vs_baseline stays null)")
