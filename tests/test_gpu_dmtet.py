@@ -306,3 +306,47 @@ def test_dmtet_training_steps(device):
     for n, p in tr.model.named_parameters():
         assert torch.isfinite(p).all(), n
         assert (p.detach() - before[n]).abs().max().item() > 0, f"{n} did not move"
+
+
+@pytest.mark.parametrize("shading", ["textureless", "normal", "lambertian", "albedo"])
+def test_render_mesh_image_matches_the_composed_restatement(device, shading):
+    """DMTetNGP.render_mesh (antialiasing off, constant background) against the numpy composition marching_tets -> mesh_normals -> rasterize_ref
+    -> interpolate_ref -> shade_composite_ref on the same lattice, parameters, camera and light; the texture network's albedo is taken from the
+    product's own field kernel (it is pinned separately, tests/test_gpu_fused_field.py)"""
+    from sdf_b200.dmtet_model import DMTetNGP
+    from sdf_b200.options import dmtet_opt
+    H = W = 64
+    opt = dmtet_opt(h=H, w=W, tet_grid_size=32)
+    torch.manual_seed(0)
+    model = DMTetNGP(opt).to(device)
+    lat = model.build_lattice(device)
+    g = torch.Generator(device="cpu").manual_seed(4)
+    pos = lat.pos.cpu()
+    model.sdf.data.copy_((0.5 - (pos * torch.tensor([1.0, 1.2, 0.9])).norm(dim=-1) + 0.05 * torch.randn(lat.N, generator=g)).to(device))
+    model.deform.data.copy_((0.3 * torch.randn(lat.N, 3, generator=g)).to(device))
+    mvp = look_at_mvp(device)
+    light = torch.nn.functional.normalize(torch.tensor([0.4, 0.7, 0.6], device=device), dim=0)
+    bg = torch.tensor([0.2, 0.5, 0.8], device=device)
+    rays_d = torch.nn.functional.normalize(torch.randn(H * W, 3, device=device), dim=-1)
+    out = model.render_mesh(mvp, rays_d, torch.zeros(3, device=device), H, W, light_d=light, ambient_ratio=0.3, shading=shading, bg_color=bg,
+                            antialias=False, mesh_losses=False)
+    img = out["pred_rgb"][0].permute(1, 2, 0).reshape(-1, 3).detach().cpu().numpy()
+    # the restatement
+    p = (lat.pos + torch.tanh(model.deform.detach()) / opt.tet_grid_size).cpu().numpy()
+    v, f = O.marching_tets(p, model.sdf.detach().cpu().numpy(), lat.tets.cpu().numpy())
+    fn, vn = O.mesh_normals(v, f)
+    clip = (np.concatenate([v, np.ones((len(v), 1), np.float32)], 1) @ mvp.cpu().numpy().T).astype(np.float32)
+    r = O.rasterize_ref(clip, f, H, W)
+    xyz = O.interpolate_ref(v, r, f).reshape(-1, 3)
+    n = O.safe_normalize(O.interpolate_ref(vn.astype(np.float32), r, f).reshape(-1, 3))
+    mask = (r[..., 3].reshape(-1) > 0).astype(np.float32)
+    n = n * mask[:, None]
+    albedo = model.density(torch.from_numpy(xyz).to(device))["albedo"].detach().float().cpu().numpy()
+    ref = O.shade_composite_ref(albedo, n, mask, light.cpu().numpy(), 0.3, shading, bg.cpu().numpy())
+    diff = np.abs(img - ref).max(-1)
+    # pixels whose winning triangle differs between the two rasterisers (ties on shared edges) are excluded; there are few of them
+    tri_k = out["depth"]                                  # z/w of the product's winners
+    agree = np.abs(tri_k.reshape(-1).cpu().numpy() - r[..., 2].reshape(-1)) < 1e-4
+    assert agree.mean() > 0.99
+    assert diff[agree].max() < 5e-3, diff[agree].max()
+    assert 0.05 < mask.mean() < 0.9

@@ -13,9 +13,17 @@ from sdf_b200.trainer import SDSTrainer
 
 dev = torch.device("cuda:0")
 shading = sys.argv[1] if len(sys.argv) > 1 else "lambertian"
-guidance = StableDiffusion(dev, weights="random", n_views=1, render_hw=64, seed=0, capture=False)     # eager lists: every launch is visible
-tr = SDSTrainer(default_opt(h=64, w=64), dev, guidance, seed=0)
-for s in ["latent", shading, shading]:
+dmtet = len(sys.argv) > 2 and sys.argv[2] == "dmtet"              # python tools/profile_step.py lambertian dmtet  -> one C5 step
+if dmtet:
+    from sdf_b200.options import dmtet_opt
+    guidance = StableDiffusion(dev, weights="random", n_views=1, render_hw=512, seed=0, capture=False)
+    tr = SDSTrainer(dmtet_opt(), dev, guidance, seed=0)
+    tr.model.update_extra_state()
+    tr.model.init_tet()
+else:
+    guidance = StableDiffusion(dev, weights="random", n_views=1, render_hw=64, seed=0, capture=False)     # eager lists: every launch is visible
+    tr = SDSTrainer(default_opt(h=64, w=64), dev, guidance, seed=0)
+for s in [shading if dmtet else "latent", shading, shading]:
     tr.train_step(shading=s)
 torch.cuda.synchronize()
 torch.cuda.cudart().cudaProfilerStart()
