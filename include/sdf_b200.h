@@ -322,10 +322,23 @@ int sdf_mesh_c4_split_backward(const float* g_image_c, const float* g_weights_su
 /* dr.antialias (nerf/renderer.py:930-931) restated: silhouette-edge coverage blending of the (rgb, coverage) image over horizontally / vertically
  * adjacent pixel pairs; face_adj [adj_faces,3] from sdf_mesh_face_adjacency (sorted half-edge keys + the sort permutation). */
 int sdf_mesh_face_adjacency(const long long* sorted_keys, const int* order, const int* counts, int fcap, int* face_adj, void* stream);
-int sdf_mesh_antialias_forward(const float* c4, const float* rast, const float* clip, const int* faces, const int* face_adj, int adj_faces, int H, int W,
-                               float* out, void* stream);
-int sdf_mesh_antialias_backward(const float* g_out, const float* c4, const float* rast, const float* clip, const int* faces, const int* face_adj,
-                                int adj_faces, const float* mvp, int H, int W, float* g_c4, float* d_verts /* may be NULL */, void* stream);
+int sdf_mesh_antialias_forward(const float* color, int C /* <= 8 */, const float* rast, const float* clip, const int* faces, const int* face_adj, int adj_faces,
+                               int H, int W, float* out, void* stream);
+/* position gradient ACCUMULATED into d_verts [.,3] through mvp, or into d_clip [.,4] when mvp == NULL */
+int sdf_mesh_antialias_backward(const float* g_out, const float* color, int C, const float* rast, const float* clip, const int* faces, const int* face_adj,
+                                int adj_faces, const float* mvp /* may be NULL */, int H, int W, float* g_color, float* d_pos /* may be NULL */, void* stream);
+/* the unfused primitives with nvdiffrast's semantics (dr.rasterize / dr.interpolate, nerf/renderer.py:895-898), bound by the drop-in package
+ * stable-dreamfusion_b200/nvdiffrast/torch so that the reference's own run_dmtet runs unchanged */
+int sdf_mesh_rasterize_only(const float* clip, const int* faces, const int* counts, int fcap, int H, int W, void* zbuf, float* rast, void* stream);
+int sdf_mesh_rasterize_uv_backward(const float* g_rast, const float* rast, const float* clip, const int* faces, int H, int W, float* d_clip, void* stream);
+int sdf_mesh_interpolate_forward(const float* attr, int C, const float* rast, const int* faces, int P, float* out, void* stream);
+int sdf_mesh_interpolate_backward(const float* g_out, const float* attr, int C, const float* rast, const int* faces, int P, float* d_attr /* may be NULL */,
+                                  float* d_rast /* may be NULL */, void* stream);
+
+/* d(albedo) / d(position) of the DMTet stage's texture lookup (nerf/renderer.py:905-912 with nerf/network_grid.py:68-79 and the grad_inputs path of
+ * gridencoder/grid.py:77-100): MLP data-gradient back to the features, contracted with sdf_grid_encode_forward's dy_dx. */
+int sdf_field_albedo_input_grad(const void* feat, const void* dy_dx, const float* w1, const float* b1, const float* w2, const float* b2, const float* w3,
+                                const float* b3, const float* g_albedo, const float* mask, int P, int L, float bound, float* d_xyz, void* stream);
 
 #ifdef __cplusplus
 }

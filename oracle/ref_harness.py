@@ -21,6 +21,9 @@ Commands (JSON spec on argv[1]):
   steps  : the reference Trainer (nerf/utils.py) wired as main.py:363-410 wires it, train_one_epoch over n steps; per step the
            inputs the Trainer drew (pose, shading, ambient ratio, background) and pred_rgb, loss, d loss/d pred_rgb; final parameters.
   time   : `steps` without capture, timed with CUDA events after a warm-up (bench.py --impl reference-cuda).
+  dmtet  : (ops='dropin' only) the reference's NeRFNetwork with opt.dmtet: its own DMTet class, run_dmtet, normal_consistency and
+           laplacian_smooth_loss (nerf/renderer.py:94-254, 862-954) on the drop-in gridencoder AND the drop-in nvdiffrast package; image +
+           parameter gradients per case.  The lattice file it loads (tets/<size>_tets.npz) is written from sdf_b200/tetgrid.py.
 """
 import json
 import os
@@ -103,8 +106,11 @@ def install(ops):
     for d in ("refpy", "refpy_ops"):
         if not os.path.isdir(os.path.join(REFDIR, d)):
             raise RuntimeError(f"oracle/_ref/{d} missing: run `python oracle/build_ref.py` where /root/reference exists")
-    for name in ["mcubes", "trimesh", "nvdiffrast", "nvdiffrast.torch", "meshutils", "cubvh", "xatlas", "pymeshlab", "tensorboardX", "imageio",
-                 "torchmetrics", "matplotlib", "matplotlib.pyplot", "lpips", "dearpygui", "dearpygui.dearpygui"]:
+    stubs = ["mcubes", "trimesh", "meshutils", "cubvh", "xatlas", "pymeshlab", "tensorboardX", "imageio",
+             "torchmetrics", "matplotlib", "matplotlib.pyplot", "lpips", "dearpygui", "dearpygui.dearpygui"]
+    if ops == "reference":
+        stubs += ["nvdiffrast", "nvdiffrast.torch"]          # not vendored by the reference and not installed; the drop-in arm binds the repository's package
+    for name in stubs:
         sys.modules.setdefault(name, _Stub(name))
     sys.modules["torch_ema"] = _torch_ema_module()
     paths = [os.path.join(REFDIR, "refpy")]
@@ -479,6 +485,66 @@ def cmd_time(spec):
                "global_step_start": int(spec.get("global_step", 0))}, open(spec["out"], "w"))
 
 
+def cmd_dmtet(spec):
+    """spec: ops='dropin', out, state (npz: parameters incl. sdf / deform), tet_grid_size, cases: [{shading, H, pose:[16], fovy, ambient, bg:[3],
+    light:[3], g_seed}], lambda_n, lambda_l"""
+    import tempfile
+    import numpy as np
+    import torch
+    assert spec["ops"] == "dropin", "nvdiffrast exists here only as the drop-in package"
+    install("dropin")
+    from sdf_b200 import tetgrid
+    size = int(spec["tet_grid_size"])
+    verts, tets = tetgrid.make_tet_grid(tetgrid.cells_for(size))
+    work = tempfile.mkdtemp(prefix="sdf_dmtet_")
+    os.makedirs(os.path.join(work, "tets"))
+    np.savez(os.path.join(work, "tets", f"{size}_tets.npz"), vertices=(-verts / 2).astype(np.float32), indices=tets)     # nerf/renderer.py:293-294 flips it back
+    os.chdir(work)
+    from nerf.network_grid import NeRFNetwork
+    from nerf.utils import get_rays
+    if spec.get("no_antialias"):               # debugging aid: isolate the rasterise / interpolate half
+        import nvdiffrast.torch as _dr
+        _dr.antialias = lambda color, *a, **k: color
+    dev = torch.device("cuda:0")
+    opt = make_opt(dmtet=True, tet_grid_size=size, lock_geo=False, **spec.get("opt", {}))
+    torch.manual_seed(spec.get("seed", 0))
+    model = NeRFNetwork(opt).to(dev)
+    _load_state(model, spec["state"])
+    model.train()
+    out = {}
+    for ci, c in enumerate(spec["cases"]):
+        H = W = int(c["H"])
+        pose = torch.tensor(c["pose"], dtype=torch.float32, device=dev).view(1, 4, 4)
+        focal = H / (2 * np.tan(np.deg2rad(c["fovy"]) / 2))
+        rays = get_rays(pose, np.array([focal, focal, H / 2, W / 2]), H, W, -1)
+        near, far = float(opt.min_near), 1000.0
+        proj = torch.tensor([[2 * focal / W, 0, 0, 0], [0, -2 * focal / H, 0, 0], [0, 0, -(far + near) / (far - near), -(2 * far * near) / (far - near)],
+                             [0, 0, -1, 0]], dtype=torch.float32, device=dev).unsqueeze(0)                           # nerf/provider.py:222-229
+        mvp = proj @ torch.inverse(pose)
+        for p in model.parameters():
+            p.grad = None
+        bg = torch.tensor(c["bg"], dtype=torch.float32, device=dev)
+        light = torch.tensor(c["light"], dtype=torch.float32, device=dev).view(1, 1, 1, 3)
+        # autocast=False isolates the algorithm: under fp16 autocast the reference's clip-space bmm (nerf/renderer.py:893-894) rounds vertex positions
+        # to half precision, which moves a handful of silhouette pixels to the neighbouring triangle / the background
+        with torch.autocast("cuda", dtype=torch.float16, enabled=bool(spec.get("autocast", True))):
+            res = model.render(rays["rays_o"], rays["rays_d"], mvp, H, W, staged=False, bg_color=bg, light_d=light, ambient_ratio=float(c["ambient"]),
+                               shading=c["shading"])
+        img = res["image"]
+        g = torch.Generator(device="cpu").manual_seed(int(c.get("g_seed", 100 + ci)))
+        G = torch.randn(1, H, W, 3, generator=g).to(dev) * float(spec.get("g_scale", 1.0))
+        loss = (img.float() * G).sum() + float(spec.get("lambda_n", 0.0)) * res["normal_loss"] + float(spec.get("lambda_l", 0.0)) * res["lap_loss"]
+        loss.backward()
+        k = f"c{ci}."
+        out[k + "image"], out[k + "weights_sum"] = _np(img), _np(res["weights_sum"])
+        out[k + "normal_loss"], out[k + "lap_loss"] = _np(res["normal_loss"]), _np(res["lap_loss"])
+        for n, p in model.named_parameters():
+            if p.grad is not None:
+                out[k + "grad." + n] = _np(p.grad)
+    torch.cuda.synchronize()
+    np.savez(spec["out"], **out)
+
+
 def run_subprocess(spec, timeout=1800):
     """used by tests / bench: run one command in a fresh interpreter (module names are global)"""
     import subprocess
@@ -488,7 +554,7 @@ def run_subprocess(spec, timeout=1800):
     return p
 
 
-COMMANDS = {"render": cmd_render, "points": cmd_points, "steps": cmd_steps, "time": cmd_time}
+COMMANDS = {"render": cmd_render, "points": cmd_points, "steps": cmd_steps, "time": cmd_time, "dmtet": cmd_dmtet}
 
 if __name__ == "__main__":
     if HERE in sys.path:

@@ -336,7 +336,7 @@ __device__ __forceinline__ bool aa_pair(AaPair& o, int p, int q, bool horizontal
     return found;
 }
 
-__global__ void __launch_bounds__(256) k_antialias_fwd(const float* __restrict__ c4, const float* __restrict__ rast, const float* __restrict__ clip,
+__global__ void __launch_bounds__(256) k_antialias_fwd(const float* __restrict__ c4, int C, const float* __restrict__ rast, const float* __restrict__ clip,
                                                        const int* __restrict__ faces, const int* __restrict__ face_adj, int adj_faces, int H, int W,
                                                        float* __restrict__ out /* pre-filled with c4 */) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -347,21 +347,20 @@ __global__ void __launch_bounds__(256) k_antialias_fwd(const float* __restrict__
         const int q = axis == 0 ? p + 1 : p + W;
         AaPair a;
         if (!aa_pair(a, p, q, axis == 0, rast, clip, faces, face_adj, adj_faces, H, W)) continue;
-        const float4 cf = reinterpret_cast<const float4*>(c4)[a.front], co = reinterpret_cast<const float4*>(c4)[a.other];
         const bool into_other = a.alpha >= 0.5f;
         const float w = into_other ? a.alpha - 0.5f : 0.5f - a.alpha;
         const int dst = into_other ? a.other : a.front;
         const float s = into_other ? 1.f : -1.f;                 // other += w (front - other)   |   front += w (other - front)
-        atomicAdd(&out[4 * (size_t)dst], s * w * (cf.x - co.x)); atomicAdd(&out[4 * (size_t)dst + 1], s * w * (cf.y - co.y));
-        atomicAdd(&out[4 * (size_t)dst + 2], s * w * (cf.z - co.z)); atomicAdd(&out[4 * (size_t)dst + 3], s * w * (cf.w - co.w));
+        for (int c = 0; c < C; c++) atomicAdd(&out[(size_t)C * dst + c], s * w * (c4[(size_t)C * a.front + c] - c4[(size_t)C * a.other + c]));
     }
 }
 
-// g_out [P,4] -> g_c4 [P,4] (pre-filled with g_out: the identity part) and d_verts (through the crossing position of the silhouette edge)
-__global__ void __launch_bounds__(256) k_antialias_bwd(const float* __restrict__ g_out, const float* __restrict__ c4, const float* __restrict__ rast,
+// g_out [P,C] -> g_c4 [P,C] (pre-filled with g_out: the identity part) and the position gradient through the crossing position of the silhouette
+// edge: into d_verts [.,3] through mvp, or (mvp == NULL) into d_clip [.,4] directly
+__global__ void __launch_bounds__(256) k_antialias_bwd(const float* __restrict__ g_out, const float* __restrict__ c4, int C, const float* __restrict__ rast,
                                                        const float* __restrict__ clip, const int* __restrict__ faces, const int* __restrict__ face_adj,
                                                        int adj_faces, const float* __restrict__ mvp, int H, int W, float* __restrict__ g_c4,
-                                                       float* __restrict__ d_verts) {
+                                                       float* __restrict__ d_pos) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= H * W) return;
     const int ix = p % W, iy = p / W;
@@ -370,20 +369,21 @@ __global__ void __launch_bounds__(256) k_antialias_bwd(const float* __restrict__
         const int q = axis == 0 ? p + 1 : p + W;
         AaPair a;
         if (!aa_pair(a, p, q, axis == 0, rast, clip, faces, face_adj, adj_faces, H, W)) continue;
-        const float4 cf = reinterpret_cast<const float4*>(c4)[a.front], co = reinterpret_cast<const float4*>(c4)[a.other];
         const bool into_other = a.alpha >= 0.5f;
         const float w = into_other ? a.alpha - 0.5f : 0.5f - a.alpha;
         const int dst = into_other ? a.other : a.front;
-        const float4 g = reinterpret_cast<const float4*>(g_out)[dst];
         const float s = into_other ? 1.f : -1.f;
-        // colour gradients: out[dst] += s w (cf - co)
-        atomicAdd(&g_c4[4 * (size_t)a.front], s * w * g.x); atomicAdd(&g_c4[4 * (size_t)a.front + 1], s * w * g.y);
-        atomicAdd(&g_c4[4 * (size_t)a.front + 2], s * w * g.z); atomicAdd(&g_c4[4 * (size_t)a.front + 3], s * w * g.w);
-        atomicAdd(&g_c4[4 * (size_t)a.other], -s * w * g.x); atomicAdd(&g_c4[4 * (size_t)a.other + 1], -s * w * g.y);
-        atomicAdd(&g_c4[4 * (size_t)a.other + 2], -s * w * g.z); atomicAdd(&g_c4[4 * (size_t)a.other + 3], -s * w * g.w);
-        if (!d_verts) continue;
+        float gw = 0.f;
+        for (int c = 0; c < C; c++) {
+            const float g = g_out[(size_t)C * dst + c];
+            // colour gradients: out[dst] += s w (cf - co)
+            atomicAdd(&g_c4[(size_t)C * a.front + c], s * w * g);
+            atomicAdd(&g_c4[(size_t)C * a.other + c], -s * w * g);
+            gw += g * (c4[(size_t)C * a.front + c] - c4[(size_t)C * a.other + c]);
+        }
+        if (!d_pos) continue;
         // position gradient: d out / d w = s (cf - co), d w / d alpha = +1 (into other) / -1, alpha = (crossing - centre) * dir
-        const float gw = s * (g.x * (cf.x - co.x) + g.y * (cf.y - co.y) + g.z * (cf.z - co.z) + g.w * (cf.w - co.w));
+        gw *= s;
         const float gc = gw * (into_other ? 1.f : -1.f) * a.dir;      // wrt the crossing coordinate (x for horizontal pairs, y for vertical)
         // crossing = u0 + t (u1 - u0), t = a0 / (a0 - a1), a_i = v_i - centre with (u, v) = (x, y) for horizontal pairs and (y, x) for vertical
         const float u0 = axis == 0 ? a.x0 : a.y0, u1 = axis == 0 ? a.x1 : a.y1, v0 = axis == 0 ? a.y0 : a.x0, v1 = axis == 0 ? a.y1 : a.x1;
@@ -400,8 +400,12 @@ __global__ void __launch_bounds__(256) k_antialias_bwd(const float* __restrict__
             // sx = (cx / cw * .5 + .5) W, sy = (cy / cw * .5 + .5) H
             const float dcx = gsx[e] * 0.5f * W / c.w, dcy = gsy[e] * 0.5f * H / c.w;
             const float dcw = -(gsx[e] * 0.5f * W * c.x + gsy[e] * 0.5f * H * c.y) / (c.w * c.w);
+            if (mvp) {
 #pragma unroll
-            for (int d = 0; d < 3; d++) atomicAdd(&d_verts[3 * (size_t)vid[e] + d], mvp[d] * dcx + mvp[4 + d] * dcy + mvp[12 + d] * dcw);
+                for (int d = 0; d < 3; d++) atomicAdd(&d_pos[3 * (size_t)vid[e] + d], mvp[d] * dcx + mvp[4 + d] * dcy + mvp[12 + d] * dcw);
+            } else {
+                atomicAdd(&d_pos[4 * (size_t)vid[e]], dcx); atomicAdd(&d_pos[4 * (size_t)vid[e] + 1], dcy); atomicAdd(&d_pos[4 * (size_t)vid[e] + 3], dcw);
+            }
         }
     }
 }
@@ -416,6 +420,90 @@ __global__ void k_face_adjacency(const long long* __restrict__ keys, const int* 
         face_adj[ha] = hb / 3;                                               // face_adj is [fcap, 3] = indexed by half-edge id
         face_adj[hb] = ha / 3;
     }
+}
+
+// ------------------------------------------------------------------ the unfused primitives (nvdiffrast's API surface: rasterize / interpolate)
+__global__ void __launch_bounds__(256) k_resolve_rast(const unsigned long long* __restrict__ zbuf, const float* __restrict__ clip, const int* __restrict__ faces,
+                                                      int H, int W, float* __restrict__ rast) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= H * W) return;
+    const unsigned long long key = zbuf[p];
+    float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (key != kEmpty) {
+        const int f = (int)(key & 0xffffffffu);
+        TriSetup t;
+        tri_setup(t, reinterpret_cast<const float4*>(clip)[faces[3 * (size_t)f]], reinterpret_cast<const float4*>(clip)[faces[3 * (size_t)f + 1]],
+                  reinterpret_cast<const float4*>(clip)[faces[3 * (size_t)f + 2]]);
+        float u, v, zw;
+        tri_eval(t, (p % W + 0.5f) / W * 2.f - 1.f, (p / W + 0.5f) / H * 2.f - 1.f, u, v, zw);
+        r = make_float4(u, v, zw, (float)(f + 1));
+    }
+    reinterpret_cast<float4*>(rast)[p] = r;
+}
+
+// d(u, v) of every covered pixel -> d(clip x, y, w) of its triangle's vertices (z carries no gradient)
+__global__ void __launch_bounds__(256) k_raster_uv_bwd(const float* __restrict__ g_rast, const float* __restrict__ rast, const float* __restrict__ clip,
+                                                       const int* __restrict__ faces, int H, int W, float* __restrict__ d_clip) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= H * W) return;
+    const float4 r = reinterpret_cast<const float4*>(rast)[p];
+    if (r.w <= 0.f) return;
+    const float4 g = reinterpret_cast<const float4*>(g_rast)[p];
+    const float du = g.x, dv = g.y;
+    if (du == 0.f && dv == 0.f) return;
+    const int f = (int)r.w - 1;
+    const int idx[3] = {faces[3 * (size_t)f], faces[3 * (size_t)f + 1], faces[3 * (size_t)f + 2]};
+    const float4 c0 = reinterpret_cast<const float4*>(clip)[idx[0]], c1 = reinterpret_cast<const float4*>(clip)[idx[1]], c2 = reinterpret_cast<const float4*>(clip)[idx[2]];
+    const float p0[3] = {c0.x, c0.y, c0.w}, p1[3] = {c1.x, c1.y, c1.w}, p2[3] = {c2.x, c2.y, c2.w};
+    const float P[3] = {(p % W + 0.5f) / W * 2.f - 1.f, (p / W + 0.5f) / H * 2.f - 1.f, 1.f};
+    float t0[3], t1[3], t2[3];
+    cross3(t0, p1, p2); cross3(t1, p2, p0); cross3(t2, p0, p1);
+    const float s = (P[0] * t0[0] + P[1] * t0[1] + t0[2]) + (P[0] * t1[0] + P[1] * t1[1] + t1[2]) + (P[0] * t2[0] + P[1] * t2[1] + t2[2]);
+    const float is = 1.f / s, u = r.x, v = r.y;
+    const float db0 = (du * (1.f - u) - dv * v) * is, db1 = (-du * u + dv * (1.f - v)) * is, db2 = (-du * u - dv * v) * is;
+    float Pxp0[3], Pxp1[3], Pxp2[3];
+    cross3(Pxp0, P, p0); cross3(Pxp1, P, p1); cross3(Pxp2, P, p2);
+    const int comp[3] = {0, 1, 3};
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+        atomicAdd(&d_clip[4 * (size_t)idx[0] + comp[d]], db1 * Pxp2[d] - db2 * Pxp1[d]);
+        atomicAdd(&d_clip[4 * (size_t)idx[1] + comp[d]], -db0 * Pxp2[d] + db2 * Pxp0[d]);
+        atomicAdd(&d_clip[4 * (size_t)idx[2] + comp[d]], db0 * Pxp1[d] - db1 * Pxp0[d]);
+    }
+}
+
+// out[p, c] = u a0[c] + v a1[c] + (1 - u - v) a2[c]; zeros where no triangle
+__global__ void __launch_bounds__(256) k_interpolate_fwd(const float* __restrict__ attr, int C, const float* __restrict__ rast, const int* __restrict__ faces, int P,
+                                                         float* __restrict__ out) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    const float4 r = reinterpret_cast<const float4*>(rast)[p];
+    if (r.w <= 0.f) { for (int c = 0; c < C; c++) out[(size_t)C * p + c] = 0.f; return; }
+    const int f = (int)r.w - 1;
+    const int i0 = faces[3 * (size_t)f], i1 = faces[3 * (size_t)f + 1], i2 = faces[3 * (size_t)f + 2];
+    const float q = 1.f - r.x - r.y;
+    for (int c = 0; c < C; c++) out[(size_t)C * p + c] = r.x * attr[(size_t)C * i0 + c] + r.y * attr[(size_t)C * i1 + c] + q * attr[(size_t)C * i2 + c];
+}
+
+__global__ void __launch_bounds__(256) k_interpolate_bwd(const float* __restrict__ g_out, const float* __restrict__ attr, int C, const float* __restrict__ rast,
+                                                         const int* __restrict__ faces, int P, float* __restrict__ d_attr, float* __restrict__ d_rast) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    const float4 r = reinterpret_cast<const float4*>(rast)[p];
+    float du = 0.f, dv = 0.f;
+    if (r.w > 0.f) {
+        const int f = (int)r.w - 1;
+        const int i0 = faces[3 * (size_t)f], i1 = faces[3 * (size_t)f + 1], i2 = faces[3 * (size_t)f + 2];
+        const float q = 1.f - r.x - r.y;
+        for (int c = 0; c < C; c++) {
+            const float g = g_out[(size_t)C * p + c];
+            if (g == 0.f) continue;
+            const float a0 = attr[(size_t)C * i0 + c], a1 = attr[(size_t)C * i1 + c], a2 = attr[(size_t)C * i2 + c];
+            if (d_attr) { atomicAdd(&d_attr[(size_t)C * i0 + c], r.x * g); atomicAdd(&d_attr[(size_t)C * i1 + c], r.y * g); atomicAdd(&d_attr[(size_t)C * i2 + c], q * g); }
+            du += g * (a0 - a2); dv += g * (a1 - a2);
+        }
+    }
+    if (d_rast) reinterpret_cast<float4*>(d_rast)[p] = make_float4(du, dv, 0.f, 0.f);
 }
 
 inline int grid_for(long long n, int threads) { return (int)max(1ll, min((n + threads - 1) / threads, (long long)sdf_num_sms() * 16)); }
@@ -495,25 +583,62 @@ SDF_API int sdf_mesh_face_adjacency(const long long* sorted_keys, const int* ord
     return SDF_OK;
 }
 
-// dr.antialias on the 4-channel (rgb, coverage) image (nerf/renderer.py:930-931).  face_adj covers the first adj_faces faces (others: every edge
-// counts as a silhouette).
-SDF_API int sdf_mesh_antialias_forward(const float* c4, const float* rast, const float* clip, const int* faces, const int* face_adj, int adj_faces, int H, int W,
-                                       float* out, void* stream) {
-    SDF_CHECK_ARG(c4 && rast && clip && faces && face_adj && out && H > 0 && W > 0, "mesh_antialias_forward: bad arguments");
+// dr.antialias (nerf/renderer.py:930-931) on a C-channel image (C <= 8; the product passes the 4-channel (rgb, coverage) image).  face_adj covers the
+// first adj_faces faces (others: every edge counts as a silhouette).
+SDF_API int sdf_mesh_antialias_forward(const float* color, int C, const float* rast, const float* clip, const int* faces, const int* face_adj, int adj_faces, int H,
+                                       int W, float* out, void* stream) {
+    SDF_CHECK_ARG(color && rast && clip && faces && face_adj && out && H > 0 && W > 0 && C >= 1 && C <= 8, "mesh_antialias_forward: bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
-    SDF_CHECK_CUDA(cudaMemcpyAsync(out, c4, sizeof(float) * 4 * (size_t)H * W, cudaMemcpyDeviceToDevice, st));
-    k_antialias_fwd<<<(H * W + 255) / 256, 256, 0, st>>>(c4, rast, clip, faces, face_adj, adj_faces, H, W, out);
+    SDF_CHECK_CUDA(cudaMemcpyAsync(out, color, sizeof(float) * C * (size_t)H * W, cudaMemcpyDeviceToDevice, st));
+    k_antialias_fwd<<<(H * W + 255) / 256, 256, 0, st>>>(color, C, rast, clip, faces, face_adj, adj_faces, H, W, out);
     SDF_CHECK_LAUNCH("mesh_antialias_forward");
     return SDF_OK;
 }
 
-// g_out [P,4] -> g_c4 [P,4] (written) and d_verts [vcap,3] (ACCUMULATED; may be NULL)
-SDF_API int sdf_mesh_antialias_backward(const float* g_out, const float* c4, const float* rast, const float* clip, const int* faces, const int* face_adj,
-                                        int adj_faces, const float* mvp, int H, int W, float* g_c4, float* d_verts, void* stream) {
-    SDF_CHECK_ARG(g_out && c4 && rast && clip && faces && face_adj && mvp && g_c4, "mesh_antialias_backward: bad arguments");
+// g_out [P,C] -> g_color [P,C] (written) and the position gradient, ACCUMULATED: d_pos = d_verts [.,3] when mvp is given (chain through
+// clip = [v,1] @ mvp^T), d_clip [.,4] when mvp == NULL; d_pos may be NULL
+SDF_API int sdf_mesh_antialias_backward(const float* g_out, const float* color, int C, const float* rast, const float* clip, const int* faces, const int* face_adj,
+                                        int adj_faces, const float* mvp, int H, int W, float* g_color, float* d_pos, void* stream) {
+    SDF_CHECK_ARG(g_out && color && rast && clip && faces && face_adj && g_color && C >= 1 && C <= 8, "mesh_antialias_backward: bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
-    SDF_CHECK_CUDA(cudaMemcpyAsync(g_c4, g_out, sizeof(float) * 4 * (size_t)H * W, cudaMemcpyDeviceToDevice, st));
-    k_antialias_bwd<<<(H * W + 255) / 256, 256, 0, st>>>(g_out, c4, rast, clip, faces, face_adj, adj_faces, mvp, H, W, g_c4, d_verts);
+    SDF_CHECK_CUDA(cudaMemcpyAsync(g_color, g_out, sizeof(float) * C * (size_t)H * W, cudaMemcpyDeviceToDevice, st));
+    k_antialias_bwd<<<(H * W + 255) / 256, 256, 0, st>>>(g_out, color, C, rast, clip, faces, face_adj, adj_faces, mvp, H, W, g_color, d_pos);
     SDF_CHECK_LAUNCH("mesh_antialias_backward");
+    return SDF_OK;
+}
+
+// ---- the unfused primitives behind the nvdiffrast-shaped package (stable-dreamfusion_b200/nvdiffrast/torch): what the reference's own
+// run_dmtet binds (nerf/renderer.py:895-898).  counts[1] = number of faces (device).
+SDF_API int sdf_mesh_rasterize_only(const float* clip, const int* faces, const int* counts, int fcap, int H, int W, void* zbuf, float* rast, void* stream) {
+    SDF_CHECK_ARG(clip && faces && counts && zbuf && rast && H > 0 && W > 0, "mesh_rasterize_only: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    SDF_CHECK_CUDA(cudaMemsetAsync(zbuf, 0xff, sizeof(unsigned long long) * (size_t)H * W, st));
+    k_raster_tris<<<grid_for((long long)fcap * 32 / 8 + 1, 256), 256, 0, st>>>(clip, faces, counts, H, W, (unsigned long long*)zbuf);
+    k_resolve_rast<<<(H * W + 255) / 256, 256, 0, st>>>((const unsigned long long*)zbuf, clip, faces, H, W, rast);
+    SDF_CHECK_LAUNCH("mesh_rasterize_only");
+    return SDF_OK;
+}
+
+// g_rast [H,W,4] (only the u, v channels are read) -> d_clip [V,4], ACCUMULATED
+SDF_API int sdf_mesh_rasterize_uv_backward(const float* g_rast, const float* rast, const float* clip, const int* faces, int H, int W, float* d_clip, void* stream) {
+    SDF_CHECK_ARG(g_rast && rast && clip && faces && d_clip, "mesh_rasterize_uv_backward: null pointer");
+    k_raster_uv_bwd<<<(H * W + 255) / 256, 256, 0, (cudaStream_t)stream>>>(g_rast, rast, clip, faces, H, W, d_clip);
+    SDF_CHECK_LAUNCH("mesh_rasterize_uv_backward");
+    return SDF_OK;
+}
+
+// dr.interpolate: attr [V,C] -> out [P,C]; backward: d_attr [V,C] ACCUMULATED (may be NULL), d_rast [P,4] = (du, dv, 0, 0) written (may be NULL)
+SDF_API int sdf_mesh_interpolate_forward(const float* attr, int C, const float* rast, const int* faces, int P, float* out, void* stream) {
+    SDF_CHECK_ARG(attr && rast && faces && out && C >= 1, "mesh_interpolate_forward: bad arguments");
+    if (P > 0) k_interpolate_fwd<<<(P + 255) / 256, 256, 0, (cudaStream_t)stream>>>(attr, C, rast, faces, P, out);
+    SDF_CHECK_LAUNCH("mesh_interpolate_forward");
+    return SDF_OK;
+}
+
+SDF_API int sdf_mesh_interpolate_backward(const float* g_out, const float* attr, int C, const float* rast, const int* faces, int P, float* d_attr, float* d_rast,
+                                          void* stream) {
+    SDF_CHECK_ARG(g_out && attr && rast && faces && (d_attr || d_rast) && C >= 1, "mesh_interpolate_backward: bad arguments");
+    if (P > 0) k_interpolate_bwd<<<(P + 255) / 256, 256, 0, (cudaStream_t)stream>>>(g_out, attr, C, rast, faces, P, d_attr, d_rast);
+    SDF_CHECK_LAUNCH("mesh_interpolate_backward");
     return SDF_OK;
 }

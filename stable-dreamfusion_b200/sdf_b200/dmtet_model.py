@@ -8,8 +8,8 @@ lookup is the fused field kernel in albedo mode; the background mix is the same 
 Deviations from the reference, stated where a user would look for them:
   * the lattice is generated (sdf_b200/tetgrid.py), not loaded from tets/*.npz — same family and size class, different vertex numbering;
   * `dr.antialias` is restated in csrc/meshrast.cu (silhouette-edge blending); nvdiffrast itself is absent: parity unpinned for that half;
-  * the texture lookup does not propagate d(albedo)/d(position) back into the geometry (the reference's GridEncoder does when its input
-    requires grad); geometry gradients come from the shading normals, the barycentrics, the silhouettes and the two mesh regularisers.
+  * the texture network's parameter gradients come from the fused field kernels (fp16 table, fp16 MLP: the -O arithmetic), its position
+    gradient (which the reference obtains from GridEncoder's grad_inputs) from csrc/field_dx.cu on the side.
 """
 import numpy as np
 import torch
@@ -37,7 +37,7 @@ class _ShadeComposite(Function):
         c4_aa = c4
         if aa is not None:
             c4_aa = torch.empty_like(c4)
-            _lib.call('sdf_mesh_antialias_forward', P(c4), P(aa['rast']), P(aa['clip']), P(aa['faces']), P(aa['face_adj']), aa['adj_faces'], H, W, P(c4_aa), st)
+            _lib.call('sdf_mesh_antialias_forward', P(c4), 4, P(aa['rast']), P(aa['clip']), P(aa['faces']), P(aa['face_adj']), aa['adj_faces'], H, W, P(c4_aa), st)
         image_c, wsum = torch.empty(Pn, 3, device=dev), torch.empty(Pn, device=dev)
         _lib.call('sdf_mesh_c4_split', P(c4_aa), Pn, P(image_c), P(wsum), st)
         use_net = bg_color is None
@@ -71,12 +71,43 @@ class _ShadeComposite(Function):
         if aa is not None:
             g_pre = torch.empty_like(g_c4)
             g_verts = torch.zeros(aa['vcap'], 3, device=dev) if ctx.needs_input_grad[10] else None
-            _lib.call('sdf_mesh_antialias_backward', P(g_c4), P(c4), P(aa['rast']), P(aa['clip']), P(aa['faces']), P(aa['face_adj']), aa['adj_faces'],
+            _lib.call('sdf_mesh_antialias_backward', P(g_c4), P(c4), 4, P(aa['rast']), P(aa['clip']), P(aa['faces']), P(aa['face_adj']), aa['adj_faces'],
                       P(aa['mvp']), H, W, P(g_pre), P(g_verts), st)
             g_c4 = g_pre
         g_alb, g_nrm = torch.empty(Pn, 3, device=dev), torch.empty(Pn, 3, device=dev)
         _lib.call('sdf_mesh_shade_backward', P(g_c4), P(a), P(n), P(mask), P(light), float(cfg['ambient']), SHADING_ID[cfg['shading']], Pn, P(g_alb), P(g_nrm), st)
         return (g_alb, g_nrm, None, None, None, None, *[g if ctx.use_net else None for g in gb], g_verts, None, None)
+
+
+class _TexturePositionGrad(Function):
+    """identity on the albedo that adds the reference's d(albedo)/d(position) to the graph (nerf/renderer.py:905-912: the texture is looked up at
+    points that carry the mesh's autograd graph, and gridencoder/grid.py:77-100 returns grad_inputs).  Forward: the drop-in encoder kernel at the
+    pixel points with dy_dx; backward: csrc/field_dx.cu."""
+
+    @staticmethod
+    def forward(ctx, albedo, xyz, mask, table_half, offsets, w1, b1, w2, b2, w3, b3, cfg):
+        Pn = xyz.shape[0]
+        L = cfg['L']
+        u = ((xyz.detach() + cfg['bound']) / (2 * cfg['bound'])).float().contiguous()
+        alloc = torch.zeros if cfg['levels_active'] < L else torch.empty          # levels beyond max_level are not written by the encoder
+        feat = alloc(Pn, 2 * L, device=xyz.device, dtype=torch.half)
+        dy_dx = alloc(Pn, L * 6, device=xyz.device, dtype=torch.half)
+        _lib.call('sdf_grid_encode_forward', P(u), P(table_half), P(offsets), P(feat), Pn, 3, 2, L, cfg['levels_active'], float(cfg['S']), int(cfg['H']), P(dy_dx),
+                  0, 0, int(cfg['smoothstep']), 1, _lib.stream())
+        ctx.cfg = cfg
+        ctx.save_for_backward(feat, dy_dx, mask, w1.detach().float().contiguous(), b1.detach().float().contiguous(), w2.detach().float().contiguous(),
+                              b2.detach().float().contiguous(), w3.detach().float().contiguous(), b3.detach().float().contiguous())
+        return albedo.view_as(albedo)
+
+    @staticmethod
+    def backward(ctx, g_albedo):
+        feat, dy_dx, mask, w1, b1, w2, b2, w3, b3 = ctx.saved_tensors
+        Pn = feat.shape[0]
+        g = g_albedo.float().contiguous()
+        d_xyz = torch.empty(Pn, 3, device=feat.device)
+        _lib.call('sdf_field_albedo_input_grad', P(feat), P(dy_dx), P(w1), P(b1), P(w2), P(b2), P(w3), P(b3), P(g), P(mask), Pn, ctx.cfg['L'], float(ctx.cfg['bound']),
+                  P(d_xyz), _lib.stream())
+        return (g_albedo, d_xyz) + (None,) * 10
 
 
 class DMTetNGP(InstantNGP):
@@ -132,6 +163,11 @@ class DMTetNGP(InstantNGP):
         face_n, vert_n = dmtet.mesh_normals(mesh)
         xyz, nrm, mask, rast, clip = dmtet.rasterize(mesh, vert_n, mvp, H, W, want_clip=True)
         albedo = self.density(xyz.detach())['albedo']                    # texture lookup (:905-912), all pixels; masked inside the shading kernel
+        if not lock and shading in ('albedo', 'lambertian') and getattr(opt, 'texture_position_grad', True):
+            c, n = self.field_cfg(), self.sigma_net.net
+            cfg_t = dict(L=c['L'], levels_active=c['levels_active'], S=c['S'], H=c['H'], smoothstep=c['smoothstep'], bound=self.bound)
+            albedo = _TexturePositionGrad.apply(albedo, xyz, mask, self.table_half(), c['offsets'], n[0].weight, n[0].bias, n[1].weight, n[1].bias, n[2].weight,
+                                                n[2].bias, cfg_t)
         aa = None
         if antialias:
             aa = dmtet.antialias_context(mesh, rast, clip, mvp)

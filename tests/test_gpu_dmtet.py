@@ -237,7 +237,7 @@ def test_antialias_blends_silhouettes_and_matches_finite_differences(device):
 
     def run(clip_t):
         out = torch.empty_like(c4)
-        _lib.call("sdf_mesh_antialias_forward", P(c4), P(rast), P(clip_t), P(lat.faces), P(topo["face_adj"]), lat.reg_faces, H, W, P(out), st)
+        _lib.call("sdf_mesh_antialias_forward", P(c4), 4, P(rast), P(clip_t), P(lat.faces), P(topo["face_adj"]), lat.reg_faces, H, W, P(out), st)
         return out
 
     out = run(clip)
@@ -254,13 +254,13 @@ def test_antialias_blends_silhouettes_and_matches_finite_differences(device):
     # analytic gradient wrt the vertices
     g_c4 = torch.empty_like(c4)
     d_verts = torch.zeros(lat.vcap, 3, device=device)
-    _lib.call("sdf_mesh_antialias_backward", P(wgt), P(c4), P(rast), P(clip), P(lat.faces), P(topo["face_adj"]), lat.reg_faces, P(mvp), H, W, P(g_c4), P(d_verts), st)
+    _lib.call("sdf_mesh_antialias_backward", P(wgt), P(c4), 4, P(rast), P(clip), P(lat.faces), P(topo["face_adj"]), lat.reg_faces, P(mvp), H, W, P(g_c4), P(d_verts), st)
     # colour gradient: the map c4 -> out is linear for fixed geometry: <wgt, A c4> = <A^T wgt, c4>
     c4b = torch.rand(H * W, 4, device=device, generator=gen)
     outb = torch.empty_like(c4b)
-    _lib.call("sdf_mesh_antialias_forward", P(c4b), P(rast), P(clip), P(lat.faces), P(topo["face_adj"]), lat.reg_faces, H, W, P(outb), st)
+    _lib.call("sdf_mesh_antialias_forward", P(c4b), 4, P(rast), P(clip), P(lat.faces), P(topo["face_adj"]), lat.reg_faces, H, W, P(outb), st)
     g_c4b = torch.empty_like(c4b)
-    _lib.call("sdf_mesh_antialias_backward", P(wgt), P(c4b), P(rast), P(clip), P(lat.faces), P(topo["face_adj"]), lat.reg_faces, P(mvp), H, W, P(g_c4b), None, st)
+    _lib.call("sdf_mesh_antialias_backward", P(wgt), P(c4b), 4, P(rast), P(clip), P(lat.faces), P(topo["face_adj"]), lat.reg_faces, P(mvp), H, W, P(g_c4b), None, st)
     assert abs(float((wgt * outb).sum()) - float((g_c4b * c4b).sum())) < 1e-3 * float((wgt * outb).abs().sum())
     # position gradient along random directions vs central differences (clip recomputed from the moved vertices, winners fixed).  The functional
     # is only piecewise smooth (a crossing that slides past a pixel centre drops its pair), so the step is 2e-5 scene units (~4e-4 pixels) and
@@ -350,3 +350,86 @@ def test_render_mesh_image_matches_the_composed_restatement(device, shading):
     assert agree.mean() > 0.99
     assert diff[agree].max() < 5e-3, diff[agree].max()
     assert 0.05 < mask.mean() < 0.9
+
+
+HAVE_REFPY = os.path.isdir(os.path.join(ROOT, "oracle", "_ref", "refpy"))
+
+
+@pytest.mark.skipif(not HAVE_REFPY, reason="oracle/_ref/refpy (byte-compiled reference Python) not built")
+def test_reference_run_dmtet_on_the_dropin_packages_vs_render_mesh(device, tmp_path):
+    """The reference's OWN run_dmtet (its DMTet class, normals, shading, dr.rasterize / dr.interpolate / dr.antialias call sequence, mesh losses:
+    nerf/renderer.py:94-254, 862-954, unmodified, byte-compiled) executed on the drop-in gridencoder + the drop-in nvdiffrast package, against
+    DMTetNGP.render_mesh on the same lattice, parameters, camera, light and background.
+    Tolerances: image 2e-2; mesh losses 1e-4; sdf / deform gradients rel-L2 <= 3e-2 in the shading modes without texture (textureless, normal) and
+    <= 8e-2 with texture (fp16 table / MLP arithmetic on this side); hash-table gradient cosine >= 0.99 with texture — all against the reference run with
+    autocast off (under fp16 autocast its clip-space bmm rounds vertex positions to half precision and a few silhouette pixels change owner: that run is
+    bounded loosely and reported)."""
+    from oracle import ref_harness as RH
+    from sdf_b200 import synth
+    from sdf_b200.dmtet_model import DMTetNGP
+    from sdf_b200.options import dmtet_opt
+    H = W = 96
+    opt = dmtet_opt(h=H, w=W, tet_grid_size=32)
+    torch.manual_seed(0)
+    model = DMTetNGP(opt).to(device)
+    lat = model.build_lattice(device)
+    g = torch.Generator(device="cpu").manual_seed(4)
+    pos = lat.pos.cpu()
+    with torch.no_grad():
+        s0 = 0.5 - (pos * torch.tensor([1.0, 1.2, 0.9])).norm(dim=-1) + 0.04 * torch.randn(lat.N, generator=g)
+        # |sdf| >= 0.03: a lattice vertex with a near-zero value collapses the mesh vertices of all its edges into a fan of sliver triangles whose
+        # normal gradients (1 / area) cancel catastrophically in fp32 — both implementations are then noise-limited (measured: the 3 lattice
+        # vertices with |sdf| < 0.005 of the unclamped field carried the whole 3.4 % gradient difference; every other entry agreed to 1e-3)
+        s0 = torch.where(s0 >= 0, s0.clamp(min=0.03), s0.clamp(max=-0.03))
+        model.sdf.copy_(s0.to(device))
+        model.deform.copy_((0.3 * torch.randn(lat.N, 3, generator=g)).to(device))
+        model.encoder.embeddings.copy_(((torch.rand(model.encoder.embeddings.shape, generator=g) - 0.5) * 2.0).to(device))
+    state = str(tmp_path / "state.npz")
+    sd = {k: (v.detach().float().cpu().numpy() if v.dtype != torch.uint8 else v.cpu().numpy()) for k, v in model.state_dict().items()}
+    np.savez(state, mean_density=np.float32(0.0), **sd)
+    cases = [dict(shading=s, H=H, pose=synth.circle_pose(3.0, 75.0, 35.0).reshape(-1).tolist(), fovy=24.0, ambient=0.4, bg=[0.2, 0.6, 0.9],
+                  light=[0.37, 0.74, 0.56], g_seed=50 + i) for i, s in enumerate(["textureless", "normal", "lambertian", "albedo"])]
+    out = str(tmp_path / "ref.npz")
+    RH.run_subprocess(dict(cmd="dmtet", ops="dropin", out=out, state=state, tet_grid_size=32, cases=cases, lambda_n=0.7, lambda_l=1.3, autocast=False))
+    R = np.load(out)
+    out16 = str(tmp_path / "ref16.npz")          # the same under fp16 autocast (how the reference Trainer runs it): reported, loosely bounded
+    RH.run_subprocess(dict(cmd="dmtet", ops="dropin", out=out16, state=state, tet_grid_size=32, cases=cases, lambda_n=0.7, lambda_l=1.3, autocast=True))
+    R16 = np.load(out16)
+    model.train()
+    for ci, c in enumerate(cases):
+        pose = np.array(c["pose"], np.float32).reshape(4, 4)
+        ro, rd = synth.get_rays(pose, H, W, c["fovy"])
+        focal = H / (2 * np.tan(np.deg2rad(c["fovy"]) / 2))
+        near, far = float(opt.min_near), 1000.0
+        proj = np.array([[2 * focal / W, 0, 0, 0], [0, -2 * focal / H, 0, 0], [0, 0, -(far + near) / (far - near), -(2 * far * near) / (far - near)], [0, 0, -1, 0]],
+                        np.float32)
+        mvp = torch.from_numpy(proj @ np.linalg.inv(pose)).to(device)
+        for p in model.parameters():
+            p.grad = None
+        res = model.render_mesh(mvp, torch.from_numpy(rd).to(device), torch.from_numpy(pose[:3, 3].copy()).to(device), H, W,
+                                light_d=torch.tensor(c["light"], device=device), ambient_ratio=c["ambient"], shading=c["shading"],
+                                bg_color=torch.tensor(c["bg"], device=device), antialias=True, mesh_losses=True)
+        img = res["pred_rgb"][0].permute(1, 2, 0)
+        G = torch.randn(1, H, W, 3, generator=torch.Generator(device="cpu").manual_seed(c["g_seed"])).to(device)[0]
+        loss = (img * G).sum() + 0.7 * res["normal_loss"] + 1.3 * res["lap_loss"]
+        loss.backward()
+        k = f"c{ci}."
+        ref_img = R[k + "image"][0]
+        d_img = np.abs(img.detach().cpu().numpy() - ref_img)
+        assert abs(float(res["normal_loss"]) - float(R[k + "normal_loss"])) < 1e-4 and abs(float(res["lap_loss"]) - float(R[k + "lap_loss"])) < 1e-4
+        assert np.quantile(d_img, 0.999) < 2e-2 and d_img.mean() < 2e-3, (c["shading"], d_img.max(), d_img.mean())
+        gs, gd = torch.from_numpy(R[k + "grad.sdf"]).to(device), torch.from_numpy(R[k + "grad.deform"]).to(device)
+        rs, rd_ = rel_l2(model.sdf.grad, gs), rel_l2(model.deform.grad, gd)
+        d16 = np.abs(img.detach().cpu().numpy() - R16[k + "image"][0])
+        print(f"{c['shading']:12s} image max {d_img.max():.2e} mean {d_img.mean():.2e}   d sdf rel-L2 {rs:.3e}   d deform rel-L2 {rd_:.3e}   "
+              f"[vs the fp16-autocast run: image mean {d16.mean():.2e}, pixels off by > 0.05: {(d16.max(-1) > 0.05).mean():.4f}]")
+        assert d16.mean() < 5e-3 and (d16.max(-1) > 0.05).mean() < 0.02
+        # with texture the geometry gradient also carries d albedo / d position (csrc/field_dx.cu vs the reference's GridEncoder grad_inputs in fp32)
+        lim = 3e-2 if c["shading"] in ("textureless", "normal") else 8e-2
+        assert rs < lim and rd_ < lim, (c["shading"], rs, rd_)
+        if c["shading"] in ("lambertian", "albedo"):
+            gt = torch.from_numpy(R[k + "grad.encoder.embeddings"]).to(device)
+            mine = model.encoder.embeddings.grad
+            cos = float((mine * gt).sum() / (mine.norm() * gt.norm()))
+            print(f"             hash-table gradient cosine {cos:.5f}  rel-L2 {rel_l2(mine, gt):.3e}")
+            assert cos > 0.99
