@@ -116,3 +116,31 @@ def test_default_options_equal_the_reference_parser_output():
             assert list(a) == list(b), k
         else:
             assert a == b, (k, a, b)
+
+
+def test_dmtet_options_follow_main_py_overrides():
+    """main.py:253-274 for a `--dmtet` run: render size x dmtet_reso_scale, Magic3D's fine-stage t_range, no latent / albedo warm-up;
+    the mesh-regulariser weights and lattice size are the parser defaults (main.py:47,134-135) recorded in tests/golden/options_O.json"""
+    import json
+    from sdf_b200.options import dmtet_opt
+    o = dmtet_opt()
+    ref = json.load(open(os.path.join(ROOT, "tests", "golden", "options_O.json")))
+    ref = ref.get("opt", ref)
+    assert (o.h, o.w) == (int(64 * ref["dmtet_reso_scale"]), int(64 * ref["dmtet_reso_scale"])) == (512, 512)
+    assert o.t_range == [0.02, 0.50] and o.latent_iter_ratio == 0 and o.albedo_iter_ratio == 0 and o.dmtet
+    for k in ("tet_grid_size", "lambda_mesh_normal", "lambda_mesh_laplacian", "lock_geo", "dmtet_reso_scale"):
+        assert getattr(o, k) == ref[k], k
+
+
+def test_nvdiffrast_dropin_exposes_the_surface_run_dmtet_binds():
+    """nerf/renderer.py:12,309-312,895-931 use exactly these names of `nvdiffrast.torch` (no GPU work here: import + signatures)"""
+    import inspect
+    import nvdiffrast.torch as dr
+    assert dr.__file__.startswith(os.path.join(ROOT, "stable-dreamfusion_b200"))
+    for name in ("RasterizeCudaContext", "RasterizeGLContext", "rasterize", "interpolate", "antialias"):
+        assert hasattr(dr, name), name
+    assert list(inspect.signature(dr.rasterize).parameters)[:4] == ["glctx", "pos", "tri", "resolution"]
+    assert list(inspect.signature(dr.interpolate).parameters)[:3] == ["attr", "rast", "tri"]
+    assert list(inspect.signature(dr.antialias).parameters)[:4] == ["color", "rast", "pos", "tri"]
+    dr.RasterizeCudaContext()
+    dr.RasterizeGLContext()
