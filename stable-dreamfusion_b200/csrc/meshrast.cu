@@ -1,7 +1,7 @@
 // meshrast.cu — differentiable triangle rasterisation for the DMTet stage (BASELINE config C5), sm_100a.
 //
 // The reference calls nvdiffrast (requirements.txt:36, not vendored) for rasterize / interpolate / antialias (nerf/renderer.py:893-934).  This
-// file implements the same image formation with the published algorithm (Laine et al. 2020, sections 3.2-3.4) in five kernels:
+// file implements the same image formation with the published algorithm (Laine et al. 2020, sections 3.2-3.4):
 //   k_clip_transform   clip = [v, 1] @ mvp^T                                                    (nerf/renderer.py:893-894)
 //   k_raster_tris      one WARP per triangle: clip-space homogeneous edge functions over the triangle's pixel bounding box, perspective-correct
 //                      barycentrics, z/w depth test by a 64-bit atomicMin of (depth bits << 32 | triangle id)   — DMTet meshes are 1e5 triangles
@@ -10,7 +10,11 @@
 //                      [dr.interpolate x2], safe_normalize(normal), coverage mask                 (nerf/renderer.py:895-903)
 //   k_gbuffer_bwd      d(position), d(normal) -> d(vertex positions) through the attributes AND through the barycentrics (the clip-space
 //                      derivative of u, v: nvdiffrast's rasterize backward), d(vertex normals)
-//   k_antialias_*      silhouette-edge coverage blending of the colour image, forward and backward (section 3.4)
+//   k_mesh_shade_*, k_mesh_c4_split*   shading of the G-buffer (:916-928) and the clamp in front of the background mix (:930-947)
+//   k_antialias_*      silhouette-edge coverage blending of a C-channel image, forward and backward (section 3.4); k_face_adjacency builds the
+//                      neighbour table it needs from the sorted half-edge list
+//   k_resolve_rast, k_raster_uv_bwd, k_interpolate_*   the same primitives UNFUSED, with nvdiffrast's call granularity, behind the drop-in
+//                      package nvdiffrast/torch.py so that the reference's own run_dmtet runs unchanged
 // Conventions (nvdiffrast's): pixel (ix, iy) centre at ndc ((ix + .5) / W * 2 - 1, (iy + .5) / H * 2 - 1), row 0 = ndc y -1; u, v are the
 // barycentrics of vertices 0 and 1; triangle ids are stored + 1, 0 = background; triangles with a vertex at w <= 0 are dropped (the orbit
 // cameras of the DMTet stage keep the whole object in front of the near plane).  Parity is checked against oracle/dmtet_ref.py's restatement of the
