@@ -43,9 +43,9 @@ CYCLE = ["latent"] * 5 + (["lambertian"] * 4 + ["textureless"]) * 4        # 20 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the two field kernels, from the ncu --set full capture summarised in
 # profiles/ (the fp16 table is L2-resident: DRAM traffic is ~11 % of the 4.8 GB of algorithmic bytes, most of it the feature stash)
-FIELD_DRAM_TRAFFIC = {"fwd_dram_bytes": 212.0e6, "bwd_dram_bytes": 318.6e6, "at_samples": 432000,
-                      "source": "profiles/r02_kernels.md (ncu --set full, same 432 k-sample launches; 180 MB of the forward's writes and 193 MB of the "
-                                "backward's reads are the feature stash)"}
+FIELD_DRAM_TRAFFIC = {"fwd_dram_bytes": 211.5e6, "bwd_dram_bytes": 287.8e6, "at_samples": 432365,
+                      "source": "profiles/r02_kernels.md addendum (ncu --set full on the marched default-view sample set; 178 MB of the forward's writes and 194 MB "
+                                "of the backward's reads are the feature stash)"}
 
 
 def peaks():

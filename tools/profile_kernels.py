@@ -21,6 +21,17 @@ m.attach_half_mirror(opt)
 M = 432000
 g = torch.Generator(device=dev).manual_seed(1)
 xyz = ((torch.rand(M, 3, device=dev, generator=g) * 2 - 1) * 0.5).contiguous()
+if "marched" in sys.argv:
+    # the sample set bench.py's `roofline` uses: the default view marched through the model's occupancy grid (16 consecutive samples of a warp sit on
+    # one or two rays, which is what the coarse-level pre-summation of the backward exploits):  python tools/profile_kernels.py marched field-only
+    import raymarching as _rm
+    from sdf_b200 import synth as _sy
+    m.update_extra_state()
+    _ro, _rd = _sy.get_rays(_sy.circle_pose(3.2, 90.0, 0.0), 64, 64, 20.0)
+    _ro, _rd = torch.from_numpy(_ro).to(dev), torch.from_numpy(_rd).to(dev)
+    _n, _f = _rm.near_far_from_aabb(_ro, _rd, m.aabb_train, 0.2)
+    xyz = _rm.march_rays_train(_ro, _rd, m.bound, m.density_bitfield, m.cascade, m.grid_size, _n, _f, True, 0.0, 1024)[0].contiguous()
+    M = int(xyz.shape[0])
 l = torch.nn.functional.normalize(torch.randn(M, 3, device=dev, generator=g), dim=-1).contiguous()
 c = m.field_cfg()
 sn = m.sigma_net.net
@@ -66,12 +77,13 @@ def adan():
     opt.step(zero_grad=False)
 
 
-for fn in (field, attn, plan.run, adan):
+fns = (field,) if "field-only" in sys.argv else (field, attn, plan.run, adan)
+for fn in fns:
     fn(); fn()
 torch.cuda.synchronize()
 torch.cuda.cudart().cudaProfilerStart()
-for fn in (field, attn, plan.run, adan):
+for fn in fns:
     fn()
 torch.cuda.synchronize()
 torch.cuda.cudart().cudaProfilerStop()
-print("profiled: field fwd/bwd, attention, conv GEMM", (bn, pair, sk), ", Adan")
+print("profiled:", [f.__name__ if hasattr(f, "__name__") else "gemm" for f in fns], "M =", M, "conv GEMM config", (bn, pair, sk))
