@@ -107,71 +107,97 @@ __global__ void __launch_bounds__(64) k_background_bwd(const float* __restrict__
     if (net) load_bg_weights(s, w1, b1, w2, b2, hr);
     __syncthreads();
     const int tid = threadIdx.x;
-    const uint32_t n = blockIdx.x * blockDim.x + tid;
-    const bool in = n < N;
-    float g[3] = {0.f, 0.f, 0.f}, g_w_extra = 0.f;
-    if (in) {
-        if (g_pred) {
-            const uint32_t b = n / HW, pix = n - b * HW;
-            const float* gp = g_pred + (size_t)b * C * HW + pix;
-            g[0] = gp[0]; g[1] = gp[HW]; g[2] = gp[2 * (size_t)HW];
-            if (C > 3) g_w_extra = gp[3 * (size_t)HW];
+    // weight-gradient partial sums stay in registers across the block's chunks of 64 rays and are flushed once: at 512x512 (DMTet stage) a flush per
+    // chunk meant 4 096 blocks x 1 379 same-address global atomics
+    constexpr int kW1PerThread = (kBgHid * kBgIn + 63) / 64, kW2PerThread = (3 * kBgHid + 63) / 64;
+    float acc_w1[kW1PerThread], acc_w2[kW2PerThread], acc_b1 = 0.f, acc_b2 = 0.f;
+#pragma unroll
+    for (int q = 0; q < kW1PerThread; q++) acc_w1[q] = 0.f;
+#pragma unroll
+    for (int q = 0; q < kW2PerThread; q++) acc_w2[q] = 0.f;
+    for (uint32_t chunk = blockIdx.x; (size_t)chunk * 64 < N; chunk += gridDim.x) {
+        const uint32_t n = chunk * 64 + tid;
+        const bool in = n < N;
+        float g[3] = {0.f, 0.f, 0.f}, g_w_extra = 0.f;
+        if (in) {
+            if (g_pred) {
+                const uint32_t b = n / HW, pix = n - b * HW;
+                const float* gp = g_pred + (size_t)b * C * HW + pix;
+                g[0] = gp[0]; g[1] = gp[HW]; g[2] = gp[2 * (size_t)HW];
+                if (C > 3) g_w_extra = gp[3 * (size_t)HW];
+            }
+            if (g_image) { g[0] += g_image[(size_t)n * 3]; g[1] += g_image[(size_t)n * 3 + 1]; g[2] += g_image[(size_t)n * 3 + 2]; }
         }
-        if (g_image) { g[0] += g_image[(size_t)n * 3]; g[1] += g_image[(size_t)n * 3 + 1]; g[2] += g_image[(size_t)n * 3 + 2]; }
-    }
-    float bg[3] = {0.f, 0.f, 0.f}, hid[kBgHid], enc[kBgIn];
-    if (net) {
-        float d[3] = {0.f, 0.f, 0.f};
-        if (in) { d[0] = rays_d[(size_t)n * 3]; d[1] = rays_d[(size_t)n * 3 + 1]; d[2] = rays_d[(size_t)n * 3 + 2]; }
-        freq39(d, enc);
-        bg_mlp(s, enc, hid, bg, hr);
-    } else if (in) {
-        bg[0] = bg_const[0]; bg[1] = bg_const[1]; bg[2] = bg_const[2];
-    }
-    const float T = in ? 1.f - ws[n] : 0.f;
-    if (in) {
-        g_image_c[(size_t)n * 3] = g[0]; g_image_c[(size_t)n * 3 + 1] = g[1]; g_image_c[(size_t)n * 3 + 2] = g[2];
-        g_ws[n] = g_w_extra - (g[0] * bg[0] + g[1] * bg[1] + g[2] * bg[2]);
+        float bg[3] = {0.f, 0.f, 0.f}, hid[kBgHid], enc[kBgIn];
+        if (net) {
+            float d[3] = {0.f, 0.f, 0.f};
+            if (in) { d[0] = rays_d[(size_t)n * 3]; d[1] = rays_d[(size_t)n * 3 + 1]; d[2] = rays_d[(size_t)n * 3 + 2]; }
+            freq39(d, enc);
+            bg_mlp(s, enc, hid, bg, hr);
+        } else if (in) {
+            bg[0] = bg_const[0]; bg[1] = bg_const[1]; bg[2] = bg_const[2];
+        }
+        const float T = in ? 1.f - ws[n] : 0.f;
+        if (in) {
+            g_image_c[(size_t)n * 3] = g[0]; g_image_c[(size_t)n * 3 + 1] = g[1]; g_image_c[(size_t)n * 3 + 2] = g[2];
+            g_ws[n] = g_w_extra - (g[0] * bg[0] + g[1] * bg[1] + g[2] * bg[2]);
+        }
+        if (!net) continue;
+        // d bg -> pre-sigmoid -> hidden
+        float dz[3];
+#pragma unroll
+        for (int c = 0; c < 3; c++) dz[c] = in ? T * g[c] * bg[c] * (1.f - bg[c]) : 0.f;
+#pragma unroll
+        for (int j = 0; j < kBgHid; j++) {
+            const float dh = dz[0] * s.w2[j] + dz[1] * s.w2[kBgHid + j] + dz[2] * s.w2[2 * kBgHid + j];
+            s_dh[tid][j] = hid[j] > 0.f ? dh : 0.f;
+            s_hid[tid][j] = hid[j];
+        }
+#pragma unroll
+        for (int i = 0; i < kBgIn; i++) s_enc[tid][i] = rh(enc[i], hr);
+        s_do[tid][0] = dz[0]; s_do[tid][1] = dz[1]; s_do[tid][2] = dz[2];
+        __syncthreads();
+        // weight gradients of this chunk's 64 rays
+#pragma unroll
+        for (int q = 0; q < kW1PerThread; q++) {
+            const int e = tid + 64 * q;
+            if (e < kBgHid * kBgIn) {
+                const int j = e / kBgIn, i = e - j * kBgIn;
+                float a = 0.f;
+                for (int r = 0; r < 64; r++) a = fmaf(s_dh[r][j], s_enc[r][i], a);
+                acc_w1[q] += a;
+            }
+        }
+        if (tid < kBgHid) {
+            float a = 0.f;
+            for (int r = 0; r < 64; r++) a += s_dh[r][tid];
+            acc_b1 += a;
+        }
+#pragma unroll
+        for (int q = 0; q < kW2PerThread; q++) {
+            const int e = tid + 64 * q;
+            if (e < 3 * kBgHid) {
+                const int c = e / kBgHid, j = e - c * kBgHid;
+                float a = 0.f;
+                for (int r = 0; r < 64; r++) a = fmaf(s_do[r][c], s_hid[r][j], a);
+                acc_w2[q] += a;
+            }
+        }
+        if (tid >= 32 && tid < 35) {
+            const int c = tid - 32;
+            float a = 0.f;
+            for (int r = 0; r < 64; r++) a += s_do[r][c];
+            acc_b2 += a;
+        }
+        __syncthreads();                     // the staging arrays are rewritten by the next chunk
     }
     if (!net) return;
-    // d bg -> pre-sigmoid -> hidden
-    float dz[3];
 #pragma unroll
-    for (int c = 0; c < 3; c++) dz[c] = in ? T * g[c] * bg[c] * (1.f - bg[c]) : 0.f;
+    for (int q = 0; q < kW1PerThread; q++) { const int e = tid + 64 * q; if (e < kBgHid * kBgIn) atomicAdd(&gw1[e], acc_w1[q]); }
+    if (tid < kBgHid) atomicAdd(&gb1[tid], acc_b1);
 #pragma unroll
-    for (int j = 0; j < kBgHid; j++) {
-        const float dh = dz[0] * s.w2[j] + dz[1] * s.w2[kBgHid + j] + dz[2] * s.w2[2 * kBgHid + j];
-        s_dh[tid][j] = hid[j] > 0.f ? dh : 0.f;
-        s_hid[tid][j] = hid[j];
-    }
-#pragma unroll
-    for (int i = 0; i < kBgIn; i++) s_enc[tid][i] = rh(enc[i], hr);
-    s_do[tid][0] = dz[0]; s_do[tid][1] = dz[1]; s_do[tid][2] = dz[2];
-    __syncthreads();
-    // weight gradients of this block's 64 rays
-    for (int e = tid; e < kBgHid * kBgIn; e += 64) {
-        const int j = e / kBgIn, i = e - j * kBgIn;
-        float a = 0.f;
-        for (int r = 0; r < 64; r++) a = fmaf(s_dh[r][j], s_enc[r][i], a);
-        atomicAdd(&gw1[e], a);
-    }
-    if (tid < kBgHid) {
-        float a = 0.f;
-        for (int r = 0; r < 64; r++) a += s_dh[r][tid];
-        atomicAdd(&gb1[tid], a);
-    }
-    for (int e = tid; e < 3 * kBgHid; e += 64) {
-        const int c = e / kBgHid, j = e - c * kBgHid;
-        float a = 0.f;
-        for (int r = 0; r < 64; r++) a = fmaf(s_do[r][c], s_hid[r][j], a);
-        atomicAdd(&gw2[e], a);
-    }
-    if (tid >= 32 && tid < 35) {
-        const int c = tid - 32;
-        float a = 0.f;
-        for (int r = 0; r < 64; r++) a += s_do[r][c];
-        atomicAdd(&gb2[c], a);
-    }
+    for (int q = 0; q < kW2PerThread; q++) { const int e = tid + 64 * q; if (e < 3 * kBgHid) atomicAdd(&gw2[e], acc_w2[q]); }
+    if (tid >= 32 && tid < 35) atomicAdd(&gb2[tid - 32], acc_b2);
 }
 
 // ---------------------------------------------------------------- regularisers
@@ -361,7 +387,7 @@ SDF_API int sdf_background_backward(const float* g_image, const float* g_pred, u
     SDF_CHECK_ARG(!w1 || (b1 && w2 && b2 && rays_d && gw1 && gb1 && gw2 && gb2), "background_backward: bg_net needs all parameters and gradient buffers");
     SDF_CHECK_ARG(w1 || bg_const, "background_backward: either the bg_net parameters or a constant colour");
     SDF_CHECK_ARG(!g_pred || (HW > 0 && N % HW == 0 && (C == 3 || C == 4)), "background_backward: g_pred needs N = B * HW and C in {3, 4}");
-    k_background_bwd<<<cdiv(N, 64), 64, 0, (cudaStream_t)stream>>>(g_image, g_pred, HW, C, rays_d, N, w1, b1, w2, b2, bg_const, half_round, weights_sum,
+    k_background_bwd<<<min(cdiv(N, 64), (uint32_t)(6 * sdf_num_sms())), 64, 0, (cudaStream_t)stream>>>(g_image, g_pred, HW, C, rays_d, N, w1, b1, w2, b2, bg_const, half_round, weights_sum,
                                                                      g_image_c, g_weights_sum, gw1, gb1, gw2, gb2);
     SDF_CHECK_LAUNCH("background_backward");
     return SDF_OK;
