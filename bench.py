@@ -535,8 +535,10 @@ def run_ours(args):
                            "rays_per_view": hw * hw, "samples_last_step": trainer.last_M, "l2": "per-step working set (UNet weights 1.7 GB + activations) exceeds the 126 MB L2",
                            "parallelism": f"dp{world}" + (" (one view per GPU for the UNet/VAE; every GPU renders 1/N of the rays of every view, pixels and pixel "
                                                          "gradients exchanged by all-to-all; one gradient all-reduce)" if world > 1 else "")},
-                "e2e": {"value": e2e_v, "unit": "steps/s", "h2d_bytes_per_step": (128 if is_dmtet else 64) * (world if trainer.ray_parallel else 1), "d2h_bytes_per_step": 4,
-                        "ms_per_step": ms_e2e / args.steps},
+                "e2e": {"value": e2e_v, "unit": "steps/s", "h2d_bytes_per_step": (128 if is_dmtet else 64) * (world if trainer.ray_parallel else 1) + (12 * world if trainer.ray_parallel else 0),
+                        "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps,
+                        "how": "every step: pose (+ per-view light offset when ray-parallel) copied from pinned host memory, the step's loss copied to a pinned word on a "
+                               "side stream as soon as it exists (before the backward) and waited for by the host before the step returns"},
                 "gpu_launches": int(round(launches_per_step * args.steps)),
                 "roofline": fld, "roofline_gemm": roof_gemm, "reference_cuda": refc, "cpu_baseline": cpu, "clocks": sampler.summary()}
         if stages is not None:

@@ -42,6 +42,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "bra FA_WAIT;\n\t"
         "FA_DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+__device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+// wait with a sleep between polls: the producer / issuer warps share their scheduler with a softmax warp, and a hot try_wait loop
+// (measured: a third of all instructions the kernel issued) takes issue slots from it
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity, unsigned ns) {
+    while (!mbar_try(bar, parity)) __nanosleep(ns);
+}
 __device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3) {
     asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
                  ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
@@ -316,6 +327,250 @@ k_flash_attn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------------------------
+// Version 2 of the kernel (SDF_FLASH_TC_V=2): same tiles, same operand layouts, a shorter dependency chain per key tile.
+//   * a softmax thread pulls its whole 128-score row of S into registers with ONE TMEM wait (four x32 loads in flight) and releases
+//     the S columns at once (s_free), so the MMA warp computes S_{j+1} while the exponentials of tile j are still running;
+//   * O accumulates in TMEM across key tiles (accumulate flag of the P V product) instead of travelling TMEM -> registers every tile;
+//     the running maximum is only moved — and O rescaled in place, tcgen05.ld / multiply / tcgen05.st — when some row of the warp
+//     sees its maximum grow by more than 2^8 (P stays <= 256 in fp16; the row sum carries the same stale maximum, so O / l is exact);
+//   * K and V have separate two-stage rings: K_j is released by S_j (early), V_j by T_j.
+// Exponentials are fp32 MUFU.EX2 (sm_100a's MUFU.EX2.F16 is not packed: the f16x2 form costs two MUFU slots as well), packed once.
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t v[16]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+                 "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+                 ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+                   "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+constexpr float kRescaleLog2 = 8.f;
+
+template <int D16>
+__global__ void __launch_bounds__(kThreads, 2)
+k_flash_attn_tc2(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v,
+                 const FaArgs a) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    unsigned char* sQ = smem;                         // 16 KB
+    unsigned char* sK = smem + kTileBytes;            // 2 x 16 KB
+    unsigned char* sV = smem + 3 * kTileBytes;        // 2 x 16 KB
+    unsigned char* sP = smem + 5 * kTileBytes;        // 2 x 16 KB: keys 0..63 | keys 64..127
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 7 * kTileBytes);
+    uint64_t* q_full = bars;              // 1
+    uint64_t* k_full = bars + 1;          // 2
+    uint64_t* k_empty = bars + 3;         // 2
+    uint64_t* v_full = bars + 5;          // 2
+    uint64_t* v_empty = bars + 7;         // 2
+    uint64_t* s_full = bars + 9;          // S_j ready in TMEM
+    uint64_t* s_free = bars + 10;         // S_j is in the softmax threads' registers (128 arrivals)
+    uint64_t* p_full = bars + 11;         // P_j in smem, O rescaled if it had to be (128 arrivals)
+    uint64_t* t_full = bars + 12;         // O += P_j V_j retired: P and the V stage are free again
+    uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(bars + 13);
+    if (threadIdx.x == 0 && reinterpret_cast<unsigned char*>(bars) + 128 > smem_raw + (7 * kTileBytes + 128 + 896)) __trap();   // alignment slack exhausted
+
+    pdl_trigger();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q0 = blockIdx.x * kBM, bh = blockIdx.y, b = bh / a.heads, h = bh - b * a.heads;
+    const int n_tiles = (a.nkv + kBN - 1) / kBN;
+
+    if (warp == 4 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_q) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_k) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_v) : "memory");
+    }
+    if (warp == 5 && lane == 0) {
+        mbar_init(q_full, 1);
+        for (int i = 0; i < 2; i++) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1); }
+        mbar_init(s_full, 1); mbar_init(s_free, 128); mbar_init(p_full, 128); mbar_init(t_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_smem)), "r"(256));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_base_smem;
+    pdl_wait();
+
+    if (warp == 4) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            mbar_expect_tx(q_full, kTileBytes);
+            tma_load_4d(&map_q, q_full, sQ, 0, h, q0, b);
+            for (int j = 0; j < n_tiles; j++) {
+                const int st = j & 1;
+                const uint32_t ph = ((j >> 1) & 1) ^ 1;
+                mbar_wait_backoff(&k_empty[st], ph, 256);
+                mbar_expect_tx(&k_full[st], kTileBytes);
+                tma_load_4d(&map_k, &k_full[st], sK + st * kTileBytes, 0, h, j * kBN, b);
+                mbar_wait_backoff(&v_empty[st], ph, 256);
+                mbar_expect_tx(&v_full[st], kTileBytes);
+                tma_load_4d(&map_v, &v_full[st], sV + st * kTileBytes, 0, h, j * kBN, b);
+            }
+        }
+    } else if (warp == 5) {
+        // ===================== MMA issuer =====================
+        constexpr uint32_t idesc_s = (1u << 4) | ((uint32_t)(kBN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);                     // K-major A and B
+        constexpr uint32_t idesc_t = (1u << 4) | (1u << 16) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);         // B (= V) MN-major, N = 64
+        const uint64_t dq = make_desc_sw128(smem_u32(sQ));
+        mbar_wait(q_full, 0);
+        mbar_wait(&k_full[0], 0);
+        tc_fence_after();
+        if (lane == 0) {
+            const uint64_t dk = make_desc_sw128(smem_u32(sK));
+#pragma unroll
+            for (int k = 0; k < D16 / 16; k++) umma_f16(tmem_base, dq + (uint64_t)(k * 2), dk + (uint64_t)(k * 2), idesc_s, k > 0 ? 1u : 0u);
+            umma_commit(&k_empty[0]);
+            umma_commit(s_full);
+        }
+        __syncwarp();
+        for (int j = 0; j < n_tiles; j++) {
+            const int st = j & 1;
+            if (j + 1 < n_tiles) {
+                // S_{j+1}: as soon as K_{j+1} has landed and the softmax threads hold S_j in registers
+                const int sn = (j + 1) & 1;
+                mbar_wait_backoff(&k_full[sn], ((j + 1) >> 1) & 1, 32);
+                mbar_wait_backoff(s_free, j & 1, 32);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint64_t dk = make_desc_sw128(smem_u32(sK + sn * kTileBytes));
+#pragma unroll
+                    for (int k = 0; k < D16 / 16; k++) umma_f16(tmem_base, dq + (uint64_t)(k * 2), dk + (uint64_t)(k * 2), idesc_s, k > 0 ? 1u : 0u);
+                    umma_commit(&k_empty[sn]);
+                    umma_commit(s_full);
+                }
+                __syncwarp();
+            }
+            mbar_wait_backoff(&v_full[st], (j >> 1) & 1, 32);
+            mbar_wait_backoff(p_full, j & 1, 32);               // P_j written (generic -> async proxy fenced by the writers), O rescaled
+            tc_fence_after();
+            if (lane == 0) {
+                const uint64_t dv = make_desc_sw128(smem_u32(sV + st * kTileBytes));
+#pragma unroll
+                for (int k = 0; k < kBN / 16; k++) {
+                    const uint64_t dp = make_desc_sw128(smem_u32(sP + (k >> 2) * kTileBytes)) + (uint64_t)((k & 3) * 2);
+                    umma_f16(tmem_base + 128, dp, dv + (uint64_t)(k * 128), idesc_t, (j > 0 || k > 0) ? 1u : 0u);
+                }
+                umma_commit(&v_empty[st]);
+                umma_commit(t_full);
+            }
+            __syncwarp();
+        }
+    } else {
+        // ===================== softmax: thread r <-> query row r <-> TMEM lane r =====================
+        const int r = warp * 32 + lane;
+        const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16);
+        float m_used = -INFINITY, l = 0.f;
+        unsigned char* p_row = sP + r * 128;
+        const int sw = r & 7;
+        for (int j = 0; j < n_tiles; j++) {
+            mbar_wait(s_full, j & 1);
+            tc_fence_after();
+            uint32_t s[4][32];
+#pragma unroll
+            for (int c = 0; c < 4; c++) tmem_ld32(t_row + c * 32, s[c]);
+            tmem_ld_wait();
+            tc_fence_before();
+            mbar_arrive(s_free);                               // the S columns may be overwritten by S_{j+1}
+            const int key0 = j * kBN;
+            const bool ragged = key0 + kBN > a.nkv;
+            float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+            if (ragged) {
+#pragma unroll
+                for (int c = 0; c < 4; c++)
+#pragma unroll
+                    for (int i = 0; i < 32; i++) {
+                        if (key0 + c * 32 + i >= a.nkv) s[c][i] = __float_as_uint(-INFINITY);
+                    }
+            }
+#pragma unroll
+            for (int c = 0; c < 4; c++)
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) mx4[c] = fmaxf(mx4[c], fmaxf(__uint_as_float(s[c][i]), __uint_as_float(s[c][i + 1])));
+            const float m_new = fmaxf(fmaxf(m_used, fmaxf(mx4[0], mx4[1])), fmaxf(mx4[2], mx4[3]));
+            // T_{j-1} retired: O is complete up to tile j-1 and the P buffer may be rewritten
+            if (j > 0) { mbar_wait(t_full, (j - 1) & 1); tc_fence_after(); }
+            const bool need = (m_new - m_used) * a.scale_log2 > kRescaleLog2;        // first tile: m_used = -inf
+            if (__any_sync(0xffffffffu, need)) {
+                const float alpha = need ? ex2((m_used - m_new) * a.scale_log2) : 1.f;
+                if (need) m_used = m_new;
+                l *= alpha;
+                if (j > 0) {
+#pragma unroll
+                    for (int c0 = 0; c0 < D16; c0 += 16) {
+                        uint32_t v[16];
+                        tmem_ld16(t_row + 128 + c0, v);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 16; i++) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+                        tmem_st16(t_row + 128 + c0, v);
+                    }
+                    tmem_st_wait();
+                }
+            }
+            const float mb = m_used * a.scale_log2;
+            float rs = 0.f;
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                uint32_t pk[16];
+                __half2 acc2[4] = {__float2half2_rn(0.f), __float2half2_rn(0.f), __float2half2_rn(0.f), __float2half2_rn(0.f)};
+#pragma unroll
+                for (int i = 0; i < 16; i++) {
+                    const float p0 = ex2(fmaf(__uint_as_float(s[c][2 * i]), a.scale_log2, -mb));
+                    const float p1 = ex2(fmaf(__uint_as_float(s[c][2 * i + 1]), a.scale_log2, -mb));
+                    uint32_t p2;
+                    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(p2) : "f"(p1), "f"(p0));          // hi = p1, lo = p0
+                    pk[i] = p2;
+                    acc2[i & 3] = __hadd2(acc2[i & 3], *reinterpret_cast<const __half2*>(&p2));
+                }
+#pragma unroll
+                for (int q = 0; q < 4; q++) { const float2 f2 = __half22float2(acc2[q]); rs += f2.x + f2.y; }
+                // columns c*32 .. c*32+31 of row r: chunk (c >> 1), 16-byte units u = (c & 1) * 4 .. +3, physical unit = u ^ (r & 7)
+                unsigned char* base = p_row + (c >> 1) * kTileBytes;
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int unit = ((c & 1) * 4 + u) ^ sw;
+                    *reinterpret_cast<uint4*>(base + unit * 16) = make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+                }
+            }
+            l += rs;
+            // publish P (and the rescaled O) to the tensor core
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            tc_fence_before();
+            mbar_arrive(p_full);
+        }
+        mbar_wait(t_full, (n_tiles - 1) & 1);
+        tc_fence_after();
+        // ---- O / l -> fp16 -> global
+        const int qi = q0 + r;
+        const float inv = 1.f / l;
+        __half* op = a.o + ((size_t)b * a.n + qi) * a.ldo + h * a.d;
+#pragma unroll
+        for (int c0 = 0; c0 < D16; c0 += 16) {
+            uint32_t v[16];
+            tmem_ld16(t_row + 128 + c0, v);
+            tmem_ld_wait();
+            if (qi < a.n) {
+#pragma unroll
+                for (int i = 0; i < 16; i += 2) {
+                    if (c0 + i < a.d) *reinterpret_cast<__half2*>(op + c0 + i) = __floats2half2_rn(__uint_as_float(v[i]) * inv, __uint_as_float(v[i + 1]) * inv);
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256));
+    }
+}
+
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -344,14 +599,15 @@ int make_head_map(CUtensorMap* map, const void* base, int d, int heads, int toke
     return SDF_OK;
 }
 
-template <int D16>
+template <int D16, int V>
 int launch_tc(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const FaArgs& a, int B, cudaStream_t st) {
     constexpr int kSmem = 7 * kTileBytes + 128 + 896;       // tiles + barriers + alignment slack: two CTAs per SM
     static bool attr_set[64] = {false};
+    auto kern = (V == 2) ? k_flash_attn_tc2<D16> : k_flash_attn_tc<D16>;
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 64 && !attr_set[dev]) {
-        SDF_CHECK_CUDA(cudaFuncSetAttribute(k_flash_attn_tc<D16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+        SDF_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
         attr_set[dev] = true;
     }
     cudaLaunchConfig_t cfg = {};
@@ -360,7 +616,7 @@ int launch_tc(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& m
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = sdf_pdl_enabled() ? 1 : 0;
-    SDF_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k_flash_attn_tc<D16>, mq, mk, mv, a));
+    SDF_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, mq, mk, mv, a));
     return SDF_OK;
 }
 
@@ -379,11 +635,16 @@ int sdf_flash_attention_tc(const void* q, const void* k, const void* v, void* o,
     FaArgs a;
     a.o = (__half*)o; a.n = n; a.nkv = nkv; a.heads = heads; a.d = d; a.ldo = ldo; a.scale_log2 = scale * 1.4426950408889634f;
     const int d16 = (d + 15) / 16 * 16;
+    // SDF_FLASH_TC_V selects the kernel version (1: O in registers, S read twice; 2 (default): O in TMEM, S in registers, lazy rescale:
+    // 153 vs 181 us at B2 x 8 heads x 4096 x d40, tools/bench_attn.py)
+    static const int ver = [] { const char* e = getenv("SDF_FLASH_TC_V"); return (e && e[0] == '1') ? 1 : 2; }();
+#define TC(DD) rc = (ver == 2) ? launch_tc<DD, 2>(mq, mk, mv, a, B, st) : launch_tc<DD, 1>(mq, mk, mv, a, B, st)
     switch (d16) {
-        case 16: rc = launch_tc<16>(mq, mk, mv, a, B, st); break;
-        case 32: rc = launch_tc<32>(mq, mk, mv, a, B, st); break;
-        case 48: rc = launch_tc<48>(mq, mk, mv, a, B, st); break;
-        default: rc = launch_tc<64>(mq, mk, mv, a, B, st); break;
+        case 16: TC(16); break;
+        case 32: TC(32); break;
+        case 48: TC(48); break;
+        default: TC(64); break;
     }
+#undef TC
     return rc;
 }

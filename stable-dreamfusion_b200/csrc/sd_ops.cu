@@ -10,7 +10,6 @@
 //   nearest x2                   openaimodel.py:110-120, bilinear 64->512: guidance/sd_utils.py:93
 //   SDS gradient                 guidance/sd_utils.py:103-131,160-161
 #include "common.cuh"
-#include <cstdlib>
 
 namespace {
 
@@ -146,6 +145,7 @@ __global__ void __launch_bounds__(256) k_gn_apply(const __half* __restrict__ x, 
         }
     }
 }
+
 
 // GroupNorm(+SiLU) backward wrt x (weights frozen).  Pass 1: per (img, group) sums of dy_hat and dy_hat * xhat,
 // where dy_hat = dL/d(normalised*gamma+beta) (after undoing SiLU) * gamma.  Pass 2: dx.
@@ -843,7 +843,9 @@ SDF_API int sdf_groupnorm_apply(const void* x, int ldx, void* y, int ldy, int Ni
 // was measured 2-4x SLOWER than these two passes on B200: 60 us vs 14 us at 2x4096x320; the spin on a contended L2 line costs
 // more than re-reading 5 MB.  A thread-block-cluster variant (8 CTAs per (image, group slab), partial sums added through distributed shared
 // memory between two cluster barriers, one launch, no atomics) measured 17 us with 256-thread CTAs and 70 us with 1024-thread CTAs against
-// 12 us for these two passes: 128 CTAs expose too little memory parallelism for a 5 MB tensor.  Not kept either.)
+// 12 us for these two passes: 128 CTAs expose too little memory parallelism for a 5 MB tensor.  Not kept either.  A third one-launch
+// variant — ONE 1024-thread block per (image, group) holding its whole slab in shared memory, so that no statistics cross blocks at all —
+// made the UNet's launch list 0.26 ms SLOWER (6.04 vs 5.78 ms as a CUDA graph, tools/bench_lists.py): 64 blocks again.  Removed.)
 static int groupnorm_forward_impl(const void* x, int ldx, void* y, int ldy, int Nimg, int HW, int C, int G, const float* gamma, const float* beta,
                                   float eps, int silu_act, float* stats, void* stream, bool zero_stats) {
     SDF_CHECK_ARG(x && y && gamma && beta && stats, "groupnorm_forward: null pointer");

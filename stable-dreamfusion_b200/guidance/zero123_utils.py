@@ -87,7 +87,7 @@ class _Zero123Loss(torch.autograd.Function):
             scales = [1.0] * B
         else:
             scales = [min(a) / (180.0 / R) * float(grad_scale) for a in angles]
-        z.view_scale.copy_(torch.tensor(scales, dtype=torch.float32))          # pageable source: staged by the driver, no reuse hazard
+        z.view_scale.copy_(z.staging().upload(torch.tensor(scales, dtype=torch.float32)))       # pinned staging: no host sync
         # random draws in the reference's order: posterior sample (encode_imgs) -> t -> noise (zero123_utils.py:133-156)
         if not as_latent:
             eng.eps_post.copy_(torch.randn(B, 4, hw, hw, device=dev))
@@ -169,6 +169,7 @@ class Zero123(nn.Module):
         hw = self.engine.lat_hw
         self.eps_acc = torch.zeros(2 * n_views, hw, hw, 8, device=device)
         self._cond_key = None
+        self._t_ring = None
         self.num_train_timesteps = 1000
         self.min_step = int(self.num_train_timesteps * t_range[0])
         self.max_step = int(self.num_train_timesteps * t_range[1])
@@ -201,6 +202,12 @@ class Zero123(nn.Module):
             v.append(v_eng.moments[:1, :, :, :4].float().permute(0, 3, 1, 2).contiguous())
         return c, v
 
+    def staging(self):
+        """pinned ring for the per-step host scalars (camera deltas, per-view scales): a pageable `copy_` would synchronise the stream"""
+        if self._t_ring is None:
+            self._t_ring = _lib.PinnedRing(4 * self.nv, self.device, slots=16)
+        return self._t_ring
+
     def set_condition(self, embeddings, r, polar, azimuth, radius):
         """write reference image r's conditioning into the UNet inputs: context row = cc_projection([CLIP | T]) for every view, channels 4..7
         of the conditional half = c_concat (zero123_utils.py:161-172)"""
@@ -221,7 +228,7 @@ class Zero123(nn.Module):
             self.engine.unet.x_in[B:, :, :, 4:8].copy_(cc.permute(0, 2, 3, 1).expand(B, -1, -1, -1))
             self.engine.unet.x_in[:B, :, :, 4:8].zero_()
             self._cond_key = key
-        cin[:, self.cd:self.cd + 4].copy_(torch.tensor(T, dtype=torch.float32))
+        cin[:, self.cd:self.cd + 4].copy_(self.staging().upload(torch.tensor(T, dtype=torch.float32)))
         self.cc_run()
 
     # ------------------------------------------------------------------ SDS

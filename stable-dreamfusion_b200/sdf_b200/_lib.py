@@ -112,3 +112,31 @@ def require_cuda(*tensors):
     for t in tensors:
         if t is not None and not t.is_cuda:
             raise RuntimeError("sdf_b200: expected a CUDA tensor (there is no CPU path)")
+
+
+class PinnedRing:
+    """Small host -> device uploads that never block the host: a ring of pinned staging slots, each rewritten only after the copy
+    that read it has completed (event per slot).  A plain `cpu_tensor.to(device)` from pageable memory synchronises the stream —
+    one such call per step stops the host from running ahead of the GPU."""
+
+    def __init__(self, numel, device, slots=4, dtype=torch.float32):
+        self.device = device
+        self.slots = [torch.zeros(numel, dtype=dtype).pin_memory() for _ in range(slots)]
+        self.events = [None] * slots
+        self.next = 0
+
+    def upload(self, src):
+        """src: CPU tensor or numpy array with at most `numel` elements -> device tensor of the same shape"""
+        src = torch.as_tensor(src)
+        k, n = self.next, src.numel()
+        slot = self.slots[k]
+        if n > slot.numel():
+            raise ValueError(f"PinnedRing: {n} elements exceed the slot capacity {slot.numel()}")
+        self.next = (k + 1) % len(self.slots)
+        if self.events[k] is not None:
+            self.events[k].synchronize()
+        slot[:n].copy_(src.reshape(-1).to(slot.dtype))
+        out = slot[:n].to(self.device, non_blocking=True)
+        self.events[k] = torch.cuda.Event()
+        self.events[k].record()
+        return out.view(src.shape)

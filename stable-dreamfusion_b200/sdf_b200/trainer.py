@@ -91,9 +91,14 @@ class SDSTrainer:
         # pinned staging ring for the poses: the host may run several steps ahead of the GPU, so a slot is only rewritten after
         # the copy that read it has completed (event per slot)
         n_pose = opt.batch_size * (world_size if self.ray_parallel else 1) * (2 if self.dmtet else 1)          # dmtet: pose + mvp per view
-        self.pin_ring = [torch.zeros(n_pose, 4, 4).pin_memory() for _ in range(4)]
-        self.pin_events = [None] * len(self.pin_ring)
+        self.pin_ring = _lib.PinnedRing(n_pose * 16, device)
+        self.pin_small = _lib.PinnedRing(3 * max(n_pose, 1), device, slots=8)      # light offsets, background colours
         self.comm_stream = torch.cuda.Stream(device=device) if (world_size > 1 and device.type == 'cuda') else None
+        # loss read-back (nerf/utils.py:1072 reads loss.item() every step): the value exists before the backward starts, so it travels to a
+        # pinned word on a side stream while backward + optimiser run, and the host waits for that 4-byte copy only — not for the step
+        self.read_stream = torch.cuda.Stream(device=device)
+        self.loss_dev = torch.zeros(1, device=device)
+        self.loss_pin = torch.zeros(1).pin_memory()
         self.perturb = True              # march jitter (nerf/utils.py:537 perturb=True); the multi-GPU self-check turns it off
         self.stage_events = None         # set to [] to record (name, cuda event) marks of the next step (bench.py --breakdown)
 
@@ -138,15 +143,7 @@ class SDSTrainer:
         return torch.cat([e['uncond']] * len(azimuth) + cond, dim=0)
 
     def _upload_poses(self, poses_np):
-        slot = self.global_step % len(self.pin_ring)
-        if self.pin_events[slot] is not None:
-            self.pin_events[slot].synchronize()
-        n = poses_np.shape[0]
-        self.pin_ring[slot][:n].copy_(torch.from_numpy(poses_np))
-        poses = self.pin_ring[slot][:n].to(self.device, non_blocking=True)
-        self.pin_events[slot] = torch.cuda.Event()
-        self.pin_events[slot].record()
-        return poses
+        return self.pin_ring.upload(np.ascontiguousarray(poses_np, dtype=np.float32))
 
     def _rays(self, poses, fov, first=0, stride=1):
         H, W = self.opt.h, self.opt.w
@@ -178,9 +175,9 @@ class SDSTrainer:
         if use_net:
             bg = None
         elif ray_par:
-            bg = torch.from_numpy(self.rng_shared.random(3).astype(np.float32)).to(dev)
+            bg = self.pin_small.upload(self.rng_shared.random(3).astype(np.float32))
         else:
-            bg = torch.rand(3).to(dev)
+            bg = self.pin_small.upload(torch.rand(3))                 # the reference's draw (nerf/utils.py:533), staged through pinned memory
         return mode, ambient, False, bg
 
     # ------------------------------------------------------------------ one optimisation step
@@ -202,7 +199,7 @@ class SDSTrainer:
             # all W * B views of the step, identical on every rank; this rank owns views [rank * B, rank * B + B)
             poses_np, az_all, fov = self.sample_views(WS * Bv, self.rng_shared)
             azimuth = az_all[self.rank * Bv:(self.rank + 1) * Bv]
-            light_off = torch.from_numpy(self.rng_shared.standard_normal((WS * Bv, 3)).astype(np.float32)).to(dev)
+            light_off = self.pin_small.upload(self.rng_shared.standard_normal((WS * Bv, 3)).astype(np.float32))
         else:
             poses_np, azimuth, fov = self.sample_views() if views is None else views
         poses = self._upload_poses(poses_np)                      # host -> device: the step's only input
@@ -217,6 +214,22 @@ class SDSTrainer:
             rays_o, rays_d = self._rays(poses, fov)
             light = None
         return self.run_step(rays_o, rays_d, azimuth, mode, ambient, as_latent, bg_color, light_d=light, ray_par=ray_par, read_loss=read_loss)
+
+    def _loss_read_begin(self, loss):
+        """enqueue the device -> host copy of this step's loss behind the kernels that produced it; returns the event to wait on"""
+        self.loss_dev.copy_(loss.detach().reshape(1))
+        ready = torch.cuda.Event()
+        ready.record()
+        with torch.cuda.stream(self.read_stream):
+            self.read_stream.wait_event(ready)
+            self.loss_pin.copy_(self.loss_dev, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(self.read_stream)
+        return done
+
+    def _loss_read_end(self, done):
+        done.synchronize()
+        return float(self.loss_pin[0])
 
     def run_step(self, rays_o, rays_d, azimuth, mode, ambient, as_latent, bg_color, light_d=None, ray_par=False, read_loss=False):
         """render -> guidance -> backward -> optimiser for given rays and schedule draws (train_step draws them; parity tests replay
@@ -257,6 +270,7 @@ class SDSTrainer:
         loss = loss + out['reg']                                    # entropy + orientation (nerf/utils.py:690-704), lambdas folded in
         if opt.lambda_opacity > 0:
             loss = loss + opt.lambda_opacity * (out['weights_sum'] ** 2).mean()
+        pending = self._loss_read_begin(loss) if read_loss else None
         loss.backward()
         self._mark('backward (background, composite, field backward)')
         if self.world_size > 1:
@@ -266,7 +280,7 @@ class SDSTrainer:
         self.optimizer.step(zero_grad=True, ema=(self.global_step % self.steps_per_epoch == 0))
         self._mark('Adan step')
         if read_loss:
-            return float(loss.item())          # device -> host read of the step's result (nerf/utils.py:1072)
+            return self._loss_read_end(pending)          # device -> host read of the step's result (nerf/utils.py:1072)
         return loss
 
     # ------------------------------------------------------------------ DMTet stage (BASELINE config C5)
@@ -301,6 +315,7 @@ class SDSTrainer:
         self._mark('guidance (VAE encode, UNet, SDS gradient, VAE data-gradient)')
         if 'normal_loss' in out:                              # nerf/utils.py:712-717
             loss = loss + opt.lambda_mesh_normal * out['normal_loss'] + opt.lambda_mesh_laplacian * out['lap_loss']
+        pending = self._loss_read_begin(loss) if read_loss else None
         loss.backward()
         self._mark('backward (shade, rasterise, normals, regularisers, marching tets, field backward)')
         if self.world_size > 1:
@@ -309,7 +324,7 @@ class SDSTrainer:
         self.optimizer.step(zero_grad=True, ema=(self.global_step % self.steps_per_epoch == 0))
         self._mark('Adan step')
         if read_loss:
-            return float(loss.item())
+            return self._loss_read_end(pending)
         return loss
 
     def _allreduce_grads(self):

@@ -99,3 +99,25 @@ def test_flash_attention_tcgen05_path(device, n, d, heads):
     assert torch.isfinite(o.float()).all()
     err = (o.float() - ref).abs()
     assert (err <= 4e-3 + 4e-3 * ref.abs()).all(), (err.max().item(), ref.abs().max().item())
+
+
+@pytest.mark.parametrize("n,d,heads", [(2048, 40, 2), (1111, 64, 1)])
+def test_flash_attention_tcgen05_growing_scores(device, n, d, heads):
+    """keys whose magnitude grows 12x along the sequence: the running row maximum keeps moving by many powers of two from key tile to
+    key tile, which is the path that rescales the output accumulator (version 2 of the tcgen05 kernel keeps O in TMEM and only rescales it
+    when a row's maximum grows by more than 2^8; version 1 rescales every tile).  Same bar as the other attention tests."""
+    B = 2
+    C = heads * d
+    g = torch.Generator(device="cpu").manual_seed(7 * n + d)
+    qkv = torch.randn(B, n, 3 * C, generator=g) * 1.5
+    qkv[..., C:2 * C] *= torch.linspace(1.0, 12.0, n).view(1, n, 1)
+    qkv = qkv.to(device).half()
+    q, k, v = qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:]
+    o = torch.full((B, n, C), float("nan"), device=device, dtype=torch.float16)
+    _lib.call("sdf_flash_attention", q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), B, heads, n, n, d, 3 * C, 3 * C, C, d ** -0.5, _lib.stream())
+    torch.cuda.synchronize()
+    qf, kf, vf = (t.float().reshape(B, n, heads, d).permute(0, 2, 1, 3) for t in (q, k, v))
+    ref = (torch.softmax(qf @ kf.transpose(-1, -2) * d ** -0.5, -1) @ vf).permute(0, 2, 1, 3).reshape(B, n, C)
+    assert torch.isfinite(o.float()).all()
+    err = (o.float() - ref).abs()
+    assert (err <= 4e-3 + 4e-3 * ref.abs()).all(), (err.max().item(), ref.abs().max().item())
