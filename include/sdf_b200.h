@@ -178,6 +178,18 @@ int sdf_gemm_plan_create(const void* a, long long a_sx, long long a_sy, long lon
                          const float* bias, const void* temb, int temb_ld,
                          const void* residual, long long r_sx, long long r_sy, long long r_simg,
                          int act, float alpha, int splitk, float* workspace, int block_n, int cta_pair);
+/* the same for a STRIDED 3x3 convolution (taps = 9): H, W are the OUTPUT geometry, the input a is [Nimg, H*stride, W*stride, .] and
+ *   out[img,y,x,n] = ... sum a[img, y*stride + ky - pad_lo, x*stride + kx - pad_lo, c] * wt[n, (ky*3+kx)*Cin + c] ...
+ * read straight out of the input with an element-strided TMA box (no im2col buffer): the UNet's Downsample (stride 2, pad 1,
+ * ldm/modules/diffusionmodules/openaimodel.py:130-138) is (stride 2, pad_lo 1), the VAE encoder's (zero pad (0,1,0,1) then stride 2,
+ * model.py:67-79) is (stride 2, pad_lo 0).  stride in {1, 2}; stride = 1, pad_lo = 1 is sdf_gemm_plan_create. */
+int sdf_gemm_plan_create_strided(const void* a, long long a_sx, long long a_sy, long long a_simg, int a_c_valid,
+                                 const void* wt, long long w_ld, long long w_sy, long long w_simg, int w_k_valid, int n_rows_w,
+                                 int Nimg, int H, int W, int Cin, int taps, int N,
+                                 void* out, long long o_sx, long long o_sy, long long o_simg,
+                                 const float* bias, const void* temb, int temb_ld,
+                                 const void* residual, long long r_sx, long long r_sy, long long r_simg,
+                                 int act, float alpha, int splitk, float* workspace, int block_n, int cta_pair, int stride, int pad_lo);
 /* let the plan's epilogue accumulate the GroupNorm(32, C) statistics of a consumer of its output (two consumers per plan): stats fp32
  * [Nimg, 32, 2] zeroed by the caller; channel_offset = consumer channel of this product's column 0 (concatenated inputs).  Returns
  * SDF_ERR_UNSUPPORTED for split-K / ragged-N / GEGLU plans: the caller then keeps sdf_groupnorm_forward's own statistics pass. */

@@ -347,17 +347,20 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 
 constexpr float kRescaleLog2 = 8.f;
 
-template <int D16>
-__global__ void __launch_bounds__(kThreads, 2)
+template <int D16, int BN, int OCC>
+__global__ void __launch_bounds__(kThreads, OCC)
 k_flash_attn_tc2(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v,
                  const FaArgs a) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     unsigned char* sQ = smem;                         // 16 KB
-    unsigned char* sK = smem + kTileBytes;            // 2 x 16 KB
-    unsigned char* sV = smem + 3 * kTileBytes;        // 2 x 16 KB
-    unsigned char* sP = smem + 5 * kTileBytes;        // 2 x 16 KB: keys 0..63 | keys 64..127
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 7 * kTileBytes);
+    constexpr int kKV = BN * 128;                     // one K or V stage: BN keys x 64 fp16
+    constexpr int kPT = BN / 64;                      // P: one 16 KB swizzled tile per 64 keys
+    constexpr int kTiles = kTileBytes + 4 * kKV + kPT * kTileBytes;
+    unsigned char* sK = smem + kTileBytes;            // 2 stages
+    unsigned char* sV = sK + 2 * kKV;                 // 2 stages
+    unsigned char* sP = sV + 2 * kKV;                 // keys 0..63 | keys 64..127
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kTiles);
     uint64_t* q_full = bars;              // 1
     uint64_t* k_full = bars + 1;          // 2
     uint64_t* k_empty = bars + 3;         // 2
@@ -368,12 +371,12 @@ k_flash_attn_tc2(const __grid_constant__ CUtensorMap map_q, const __grid_constan
     uint64_t* p_full = bars + 11;         // P_j in smem, O rescaled if it had to be (128 arrivals)
     uint64_t* t_full = bars + 12;         // O += P_j V_j retired: P and the V stage are free again
     uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(bars + 13);
-    if (threadIdx.x == 0 && reinterpret_cast<unsigned char*>(bars) + 128 > smem_raw + (7 * kTileBytes + 128 + 896)) __trap();   // alignment slack exhausted
+    if (threadIdx.x == 0 && reinterpret_cast<unsigned char*>(bars) + 128 > smem_raw + (kTiles + 128 + 896)) __trap();   // alignment slack exhausted
 
     pdl_trigger();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q0 = blockIdx.x * kBM, bh = blockIdx.y, b = bh / a.heads, h = bh - b * a.heads;
-    const int n_tiles = (a.nkv + kBN - 1) / kBN;
+    const int n_tiles = (a.nkv + BN - 1) / BN;
 
     if (warp == 4 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_q) : "memory");
@@ -387,7 +390,7 @@ k_flash_attn_tc2(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_smem)), "r"(256));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_smem)), "r"(2 * BN));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     tc_fence_before();
@@ -405,16 +408,16 @@ k_flash_attn_tc2(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                 const int st = j & 1;
                 const uint32_t ph = ((j >> 1) & 1) ^ 1;
                 mbar_wait_backoff(&k_empty[st], ph, 256);
-                mbar_expect_tx(&k_full[st], kTileBytes);
-                tma_load_4d(&map_k, &k_full[st], sK + st * kTileBytes, 0, h, j * kBN, b);
+                mbar_expect_tx(&k_full[st], kKV);
+                tma_load_4d(&map_k, &k_full[st], sK + st * kKV, 0, h, j * BN, b);
                 mbar_wait_backoff(&v_empty[st], ph, 256);
-                mbar_expect_tx(&v_full[st], kTileBytes);
-                tma_load_4d(&map_v, &v_full[st], sV + st * kTileBytes, 0, h, j * kBN, b);
+                mbar_expect_tx(&v_full[st], kKV);
+                tma_load_4d(&map_v, &v_full[st], sV + st * kKV, 0, h, j * BN, b);
             }
         }
     } else if (warp == 5) {
         // ===================== MMA issuer =====================
-        constexpr uint32_t idesc_s = (1u << 4) | ((uint32_t)(kBN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);                     // K-major A and B
+        constexpr uint32_t idesc_s = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);                     // K-major A and B
         constexpr uint32_t idesc_t = (1u << 4) | (1u << 16) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);         // B (= V) MN-major, N = 64
         const uint64_t dq = make_desc_sw128(smem_u32(sQ));
         mbar_wait(q_full, 0);
@@ -437,7 +440,7 @@ k_flash_attn_tc2(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                 mbar_wait_backoff(s_free, j & 1, 32);
                 tc_fence_after();
                 if (lane == 0) {
-                    const uint64_t dk = make_desc_sw128(smem_u32(sK + sn * kTileBytes));
+                    const uint64_t dk = make_desc_sw128(smem_u32(sK + sn * kKV));
 #pragma unroll
                     for (int k = 0; k < D16 / 16; k++) umma_f16(tmem_base, dq + (uint64_t)(k * 2), dk + (uint64_t)(k * 2), idesc_s, k > 0 ? 1u : 0u);
                     umma_commit(&k_empty[sn]);
@@ -449,11 +452,11 @@ k_flash_attn_tc2(const __grid_constant__ CUtensorMap map_q, const __grid_constan
             mbar_wait_backoff(p_full, j & 1, 32);               // P_j written (generic -> async proxy fenced by the writers), O rescaled
             tc_fence_after();
             if (lane == 0) {
-                const uint64_t dv = make_desc_sw128(smem_u32(sV + st * kTileBytes));
+                const uint64_t dv = make_desc_sw128(smem_u32(sV + st * kKV));
 #pragma unroll
-                for (int k = 0; k < kBN / 16; k++) {
+                for (int k = 0; k < BN / 16; k++) {
                     const uint64_t dp = make_desc_sw128(smem_u32(sP + (k >> 2) * kTileBytes)) + (uint64_t)((k & 3) * 2);
-                    umma_f16(tmem_base + 128, dp, dv + (uint64_t)(k * 128), idesc_t, (j > 0 || k > 0) ? 1u : 0u);
+                    umma_f16(tmem_base + BN, dp, dv + (uint64_t)(k * 128), idesc_t, (j > 0 || k > 0) ? 1u : 0u);
                 }
                 umma_commit(&v_empty[st]);
                 umma_commit(t_full);
@@ -470,25 +473,25 @@ k_flash_attn_tc2(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         for (int j = 0; j < n_tiles; j++) {
             mbar_wait(s_full, j & 1);
             tc_fence_after();
-            uint32_t s[4][32];
+            uint32_t s[BN / 32][32];
 #pragma unroll
-            for (int c = 0; c < 4; c++) tmem_ld32(t_row + c * 32, s[c]);
+            for (int c = 0; c < BN / 32; c++) tmem_ld32(t_row + c * 32, s[c]);
             tmem_ld_wait();
             tc_fence_before();
             mbar_arrive(s_free);                               // the S columns may be overwritten by S_{j+1}
-            const int key0 = j * kBN;
-            const bool ragged = key0 + kBN > a.nkv;
+            const int key0 = j * BN;
+            const bool ragged = key0 + BN > a.nkv;
             float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
             if (ragged) {
 #pragma unroll
-                for (int c = 0; c < 4; c++)
+                for (int c = 0; c < BN / 32; c++)
 #pragma unroll
                     for (int i = 0; i < 32; i++) {
                         if (key0 + c * 32 + i >= a.nkv) s[c][i] = __float_as_uint(-INFINITY);
                     }
             }
 #pragma unroll
-            for (int c = 0; c < 4; c++)
+            for (int c = 0; c < BN / 32; c++)
 #pragma unroll
                 for (int i = 0; i < 32; i += 2) mx4[c] = fmaxf(mx4[c], fmaxf(__uint_as_float(s[c][i]), __uint_as_float(s[c][i + 1])));
             const float m_new = fmaxf(fmaxf(m_used, fmaxf(mx4[0], mx4[1])), fmaxf(mx4[2], mx4[3]));
@@ -503,11 +506,11 @@ k_flash_attn_tc2(const __grid_constant__ CUtensorMap map_q, const __grid_constan
 #pragma unroll
                     for (int c0 = 0; c0 < D16; c0 += 16) {
                         uint32_t v[16];
-                        tmem_ld16(t_row + 128 + c0, v);
+                        tmem_ld16(t_row + BN + c0, v);
                         tmem_ld_wait();
 #pragma unroll
                         for (int i = 0; i < 16; i++) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
-                        tmem_st16(t_row + 128 + c0, v);
+                        tmem_st16(t_row + BN + c0, v);
                     }
                     tmem_st_wait();
                 }
@@ -515,7 +518,7 @@ k_flash_attn_tc2(const __grid_constant__ CUtensorMap map_q, const __grid_constan
             const float mb = m_used * a.scale_log2;
             float rs = 0.f;
 #pragma unroll
-            for (int c = 0; c < 4; c++) {
+            for (int c = 0; c < BN / 32; c++) {
                 uint32_t pk[16];
                 __half2 acc2[4] = {__float2half2_rn(0.f), __float2half2_rn(0.f), __float2half2_rn(0.f), __float2half2_rn(0.f)};
 #pragma unroll
@@ -552,7 +555,7 @@ k_flash_attn_tc2(const __grid_constant__ CUtensorMap map_q, const __grid_constan
 #pragma unroll
         for (int c0 = 0; c0 < D16; c0 += 16) {
             uint32_t v[16];
-            tmem_ld16(t_row + 128 + c0, v);
+            tmem_ld16(t_row + BN + c0, v);
             tmem_ld_wait();
             if (qi < a.n) {
 #pragma unroll
@@ -567,9 +570,11 @@ k_flash_attn_tc2(const __grid_constant__ CUtensorMap map_q, const __grid_constan
     __syncthreads();
     if (warp == 0) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256));
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * BN));
     }
 }
+
+
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -585,13 +590,13 @@ PFN_encodeTiled get_encode_fa() {
     return fn;
 }
 
-// (d, heads, tokens, batch) view of a [B, tokens, ld] fp16 projection buffer; box = 64 x 1 x 128 x 1, zero fill out of bounds
-int make_head_map(CUtensorMap* map, const void* base, int d, int heads, int tokens, int B, int ld) {
+// (d, heads, tokens, batch) view of a [B, tokens, ld] fp16 projection buffer; box = 64 x 1 x box_rows x 1, zero fill out of bounds
+int make_head_map(CUtensorMap* map, const void* base, int d, int heads, int tokens, int B, int ld, int box_rows) {
     PFN_encodeTiled enc = get_encode_fa();
     if (!enc) { sdf_set_error("flash_attention(tc): cuTensorMapEncodeTiled unavailable"); return SDF_ERR_CUDA; }
     cuuint64_t dims[4] = {(cuuint64_t)d, (cuuint64_t)heads, (cuuint64_t)tokens, (cuuint64_t)B};
     cuuint64_t strides[3] = {(cuuint64_t)d * 2, (cuuint64_t)ld * 2, (cuuint64_t)tokens * ld * 2};
-    cuuint32_t box[4] = {64, 1, 128, 1};
+    cuuint32_t box[4] = {64, 1, (cuuint32_t)box_rows, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -599,11 +604,18 @@ int make_head_map(CUtensorMap* map, const void* base, int d, int heads, int toke
     return SDF_OK;
 }
 
+// V = 1: k_flash_attn_tc (O in registers, S read twice, 128-key tiles, 2 CTAs / SM)
+// V = 2: k_flash_attn_tc2<D16, 128, 2> (O in TMEM, S row in registers, lazy rescale)
+// V = 4: k_flash_attn_tc2<D16, 64, 3>: the same with 64-key tiles — 65 KB of shared memory, 128 TMEM columns and <= 112 registers per
+//        thread, so THREE CTAs (12 softmax warps) share an SM
+template <int V> struct TcCfg { static constexpr int BN = (V == 4) ? 64 : 128, OCC = (V == 4) ? 3 : 2; };
 template <int D16, int V>
 int launch_tc(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const FaArgs& a, int B, cudaStream_t st) {
-    constexpr int kSmem = 7 * kTileBytes + 128 + 896;       // tiles + barriers + alignment slack: two CTAs per SM
+    constexpr int BN = TcCfg<V>::BN;
+    constexpr int kSmem = kTileBytes + 4 * BN * 128 + (BN / 64) * kTileBytes + 128 + 896;       // tiles + barriers + alignment slack
     static bool attr_set[64] = {false};
-    auto kern = (V == 2) ? k_flash_attn_tc2<D16> : k_flash_attn_tc<D16>;
+    void (*kern)(CUtensorMap, CUtensorMap, CUtensorMap, FaArgs);
+    if (V == 1) kern = k_flash_attn_tc<D16>; else kern = k_flash_attn_tc2<D16, BN, TcCfg<V>::OCC>;
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 64 && !attr_set[dev]) {
@@ -627,18 +639,18 @@ int launch_tc(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& m
 int sdf_flash_attention_tc(const void* q, const void* k, const void* v, void* o, int B, int heads, int n, int nkv, int d, int ldq, int ldk, int ldo,
                            float scale, cudaStream_t st) {
     if (d > 64 || d % 8 != 0 || ldq % 8 != 0 || ldk % 8 != 0 || ldo % 2 != 0) return SDF_ERR_UNSUPPORTED;
+    // SDF_FLASH_TC_V selects the kernel version (see launch_tc); measured at B2 x 8 heads x 4096 x d40 with tools/bench_attn.py: 1: 181 us, 2: 149 us
+    static const int ver = [] { const char* e = getenv("SDF_FLASH_TC_V"); return (e && (e[0] == '1' || e[0] == '2' || e[0] == '4')) ? e[0] - '0' : 2; }();
+    const int kv_rows = ver == 4 ? 64 : 128;
     CUtensorMap mq, mk, mv;
     int rc;
-    if ((rc = make_head_map(&mq, q, d, heads, n, B, ldq))) return rc;
-    if ((rc = make_head_map(&mk, k, d, heads, nkv, B, ldk))) return rc;
-    if ((rc = make_head_map(&mv, v, d, heads, nkv, B, ldk))) return rc;
+    if ((rc = make_head_map(&mq, q, d, heads, n, B, ldq, 128))) return rc;
+    if ((rc = make_head_map(&mk, k, d, heads, nkv, B, ldk, kv_rows))) return rc;
+    if ((rc = make_head_map(&mv, v, d, heads, nkv, B, ldk, kv_rows))) return rc;
     FaArgs a;
     a.o = (__half*)o; a.n = n; a.nkv = nkv; a.heads = heads; a.d = d; a.ldo = ldo; a.scale_log2 = scale * 1.4426950408889634f;
     const int d16 = (d + 15) / 16 * 16;
-    // SDF_FLASH_TC_V selects the kernel version (1: O in registers, S read twice; 2 (default): O in TMEM, S in registers, lazy rescale:
-    // 153 vs 181 us at B2 x 8 heads x 4096 x d40, tools/bench_attn.py)
-    static const int ver = [] { const char* e = getenv("SDF_FLASH_TC_V"); return (e && e[0] == '1') ? 1 : 2; }();
-#define TC(DD) rc = (ver == 2) ? launch_tc<DD, 2>(mq, mk, mv, a, B, st) : launch_tc<DD, 1>(mq, mk, mv, a, B, st)
+#define TC(DD) rc = (ver == 4) ? launch_tc<DD, 4>(mq, mk, mv, a, B, st) : (ver == 2) ? launch_tc<DD, 2>(mq, mk, mv, a, B, st) : launch_tc<DD, 1>(mq, mk, mv, a, B, st)
     switch (d16) {
         case 16: TC(16); break;
         case 32: TC(32); break;

@@ -42,7 +42,8 @@ struct GemmArgs {
     int M, N, Cin, taps;             // Cin = K elements iterated per tap (multiple of 64; the TMA zero-fills past the real extent)
     int H, W, Nimg;                  // A-side geometry: x (pixels / tokens), y (rows / heads), img (images / batch)
     int tw, th, tn;                  // tile rectangle, tw*th*tn <= 128 rows
-    int pad;                         // 1 for 3x3 (tap offsets -1..1), 0 for 1x1
+    int pad;                         // 1 for 3x3 (tap offsets -pad_lo .. 2 - pad_lo), 0 for 1x1
+    int stride, pad_lo;              // strided 3x3: input pixel = output pixel * stride + tap - pad_lo (element-strided TMA box)
     int splitk;                      // >= 1
     int w_by, w_bimg;                // B operand indexed by the tile's y / img coordinate (batched products: attention)
     const float* bias;               // [N] fp32 or null
@@ -258,18 +259,19 @@ k_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtens
                 const uint32_t a_bytes = (uint32_t)(g.tw * g.th * g.tn * kBlockK * 2);
                 for (int kb = kb0; kb < kb1; kb++) {
                     const int tap = kb / kb_per_tap, cb = kb - tap * kb_per_tap;
-                    const int dy = g.pad ? tap / 3 - 1 : 0, dx = g.pad ? tap % 3 - 1 : 0;
+                    const int dy = g.pad ? tap / 3 - g.pad_lo : 0, dx = g.pad ? tap % 3 - g.pad_lo : 0;
+                    const int xa = x0 * g.stride + dx, ya = y0 * g.stride + dy;
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     unsigned char* sa = smem + stage * L::kStageBytes;
                     if (PAIR) {
                         // both CTAs' loads complete on the leader's barrier, which expects the bytes of the whole pair
                         if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * (a_bytes + (uint32_t)L::kBBytes));
                         const uint32_t bar = map_to_cta(smem_u32(&full_bar[stage]), 0);
-                        tma_load_4d_pair(&map_a, bar, sa, cb * kBlockK, x0 + dx, y0 + dy, i0);
+                        tma_load_4d_pair(&map_a, bar, sa, cb * kBlockK, xa, ya, i0);
                         tma_load_4d_pair(&map_b, bar, sa + L::kABytes, kb * kBlockK, n0, 0, 0);
                     } else {
                         mbar_expect_tx(&full_bar[stage], a_bytes + L::kBBytes);
-                        tma_load_4d(&map_a, &full_bar[stage], sa, cb * kBlockK, x0 + dx, y0 + dy, i0);
+                        tma_load_4d(&map_a, &full_bar[stage], sa, cb * kBlockK, xa, ya, i0);
                         tma_load_4d(&map_b, &full_bar[stage], sa + L::kABytes, kb * kBlockK, n0, g.w_by ? y0 : 0, g.w_bimg ? i0 : 0);
                     }
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -625,13 +627,15 @@ int launch_gemm(const GemmPlan& p, cudaStream_t st) {
 //   cta_pair : 1 -> 2-CTA clusters (tcgen05 cta_group::2, M = 256 per MMA, each CTA stages half of the weight tile);
 //              block_n in {128, 160, 256}; not for batched products.
 // Returns a handle >= 0 or a negative error code.
-SDF_API int sdf_gemm_plan_create(const void* a, long long a_sx, long long a_sy, long long a_simg, int a_c_valid,
+SDF_API int sdf_gemm_plan_create_strided(const void* a, long long a_sx, long long a_sy, long long a_simg, int a_c_valid,
                                  const void* wt, long long w_ld, long long w_sy, long long w_simg, int w_k_valid, int n_rows_w,
                                  int Nimg, int H, int W, int Cin, int taps, int N,
                                  void* out, long long o_sx, long long o_sy, long long o_simg,
                                  const float* bias, const void* temb, int temb_ld,
                                  const void* residual, long long r_sx, long long r_sy, long long r_simg,
-                                 int act, float alpha, int splitk, float* workspace, int block_n, int cta_pair) {
+                                 int act, float alpha, int splitk, float* workspace, int block_n, int cta_pair, int stride, int pad_lo) {
+    SDF_CHECK_ARG(stride == 1 || (stride == 2 && taps == 9), "gemm_plan: stride must be 1, or 2 for a 3x3 convolution");
+    SDF_CHECK_ARG(pad_lo == 0 || pad_lo == 1, "gemm_plan: pad_lo must be 0 or 1");
     SDF_CHECK_ARG(a && wt && out, "gemm_plan: null pointer");
     SDF_CHECK_ARG(Cin > 0 && Cin % kBlockK == 0, "gemm_plan: Cin must be a positive multiple of 64");
     SDF_CHECK_ARG(taps == 1 || taps == 9, "gemm_plan: taps must be 1 or 9");
@@ -662,6 +666,7 @@ SDF_API int sdf_gemm_plan_create(const void* a, long long a_sx, long long a_sy, 
         g.tn = std::max(1, std::min(Nimg, kBlockM / (g.tw * g.th)));
     }
     g.pad = taps == 9 ? 1 : 0;
+    g.stride = stride; g.pad_lo = pad_lo;
     {   // no split may own an empty K range: shrink splitk to ceil(kb / ceil(kb / splitk))
         const int kb_total = taps * (Cin / kBlockK);
         if (splitk > kb_total) splitk = kb_total;
@@ -679,11 +684,13 @@ SDF_API int sdf_gemm_plan_create(const void* a, long long a_sx, long long a_sy, 
 
     auto stride_or = [](long long s, long long fallback) { return (cuuint64_t)((s != 0 ? s : fallback) * 2); };
     {   // A: 4-D map (c, x, y, img), 128B swizzle, zero OOB fill
-        cuuint64_t dims[4] = {(cuuint64_t)a_c_valid, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)Nimg};
-        const long long fx = a_sx, fy = a_sy ? a_sy : a_sx * W, fi = a_simg ? a_simg : fy * H;
+        // strided convolution: the map covers the INPUT (stride x the output extent); a box that traverses tw * stride elements with
+        // element stride `stride` lands tw pixels — the same dense [tn][th][tw][64] smem tile as the unit-stride case
+        cuuint64_t dims[4] = {(cuuint64_t)a_c_valid, (cuuint64_t)W * stride, (cuuint64_t)H * stride, (cuuint64_t)Nimg};
+        const long long fx = a_sx, fy = a_sy ? a_sy : a_sx * W * stride, fi = a_simg ? a_simg : fy * H * stride;
         cuuint64_t strides[3] = {(cuuint64_t)fx * 2, (cuuint64_t)fy * 2, (cuuint64_t)fi * 2};
-        cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)g.tw, (cuuint32_t)g.th, (cuuint32_t)g.tn};
-        cuuint32_t estr[4] = {1, 1, 1, 1};
+        cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)(g.tw * stride), (cuuint32_t)(g.th * stride), (cuuint32_t)g.tn};
+        cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
         CUresult r = enc(&p->map_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(a), dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -708,6 +715,18 @@ SDF_API int sdf_gemm_plan_create(const void* a, long long a_sx, long long a_sy, 
     std::lock_guard<std::mutex> lk(g_plan_mu);
     g_plans.push_back(p);
     return (int)g_plans.size() - 1;
+}
+
+SDF_API int sdf_gemm_plan_create(const void* a, long long a_sx, long long a_sy, long long a_simg, int a_c_valid,
+                                 const void* wt, long long w_ld, long long w_sy, long long w_simg, int w_k_valid, int n_rows_w,
+                                 int Nimg, int H, int W, int Cin, int taps, int N,
+                                 void* out, long long o_sx, long long o_sy, long long o_simg,
+                                 const float* bias, const void* temb, int temb_ld,
+                                 const void* residual, long long r_sx, long long r_sy, long long r_simg,
+                                 int act, float alpha, int splitk, float* workspace, int block_n, int cta_pair) {
+    return sdf_gemm_plan_create_strided(a, a_sx, a_sy, a_simg, a_c_valid, wt, w_ld, w_sy, w_simg, w_k_valid, n_rows_w, Nimg, H, W, Cin, taps, N,
+                                        out, o_sx, o_sy, o_simg, bias, temb, temb_ld, residual, r_sx, r_sy, r_simg, act, alpha, splitk, workspace,
+                                        block_n, cta_pair, 1, 1);
 }
 
 // Ask a plan's epilogue to accumulate the GroupNorm statistics of a consumer of its output: stats fp32 [Nimg, 32, 2] (sum, sum of squares;

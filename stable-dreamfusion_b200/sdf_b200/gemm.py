@@ -77,19 +77,22 @@ class GemmPlan:
     """Keeps the operand tensors alive and owns the native plan handle."""
 
     def __init__(self, a, a_strides, a_c_valid, wt, w_strides, w_k_valid, n_rows_w, Nimg, H, W, Cin, taps, N, out, o_strides,
-                 bias=None, temb=None, temb_ld=0, residual=None, r_strides=(0, 0, 0), act=None, alpha=1.0, splitk=1, block_n=None, cta_pair=0):
+                 bias=None, temb=None, temb_ld=0, residual=None, r_strides=(0, 0, 0), act=None, alpha=1.0, splitk=1, block_n=None, cta_pair=0,
+                 stride=1, pad_lo=1):
+        """H, W: OUTPUT geometry.  stride = 2 (taps = 9 only): a is [Nimg, 2H, 2W, .] and is read through an element-strided TMA box
+        (input pixel = 2 * output pixel + tap - pad_lo): the UNet's Downsample is pad_lo = 1, the VAE encoder's (0,1,0,1)-padded one pad_lo = 0."""
         self.keep = (a, wt, out, bias, temb, residual)
         block_n = pick_block_n(N) if block_n is None else block_n
         self.workspace = torch.empty(Nimg * H * W, N, device=out.device, dtype=torch.float32) if splitk > 1 else None
         self.flops = 2.0 * Nimg * H * W * N * taps * Cin
         self.shape = dict(M=Nimg * H * W, N=N, K=taps * Cin, taps=taps, block_n=block_n, splitk=splitk, pair=int(cta_pair))
-        h = _lib.lib().cdll.sdf_gemm_plan_create(
+        h = _lib.lib().cdll.sdf_gemm_plan_create_strided(
             _lib.ptr(a), *[int(s) for s in a_strides], int(a_c_valid), _lib.ptr(wt), *[int(s) for s in w_strides], int(w_k_valid), int(n_rows_w),
             int(Nimg), int(H), int(W), int(Cin), int(taps), int(N), _lib.ptr(out), *[int(s) for s in o_strides],
             _lib.ptr(bias), _lib.ptr(temb), int(temb_ld), _lib.ptr(residual), *[int(s) for s in r_strides],
-            ACT[act], float(alpha), int(splitk), _lib.ptr(self.workspace), int(block_n), int(cta_pair))
+            ACT[act], float(alpha), int(splitk), _lib.ptr(self.workspace), int(block_n), int(cta_pair), int(stride), int(pad_lo))
         if h < 0:
-            raise RuntimeError(f"sdf_gemm_plan_create failed ({h}): {_lib.lib().last_error()}")
+            raise RuntimeError(f"sdf_gemm_plan_create_strided failed ({h}): {_lib.lib().last_error()}")
         self.handle = h
         self.gn_slots = 0
         tw = 128 if W >= 128 else W
@@ -117,18 +120,21 @@ class GemmPlan:
             pass
 
 
-def conv_plan(a, c_valid, wt, N, out, *, taps, bias=None, temb=None, residual=None, act=None, alpha=1.0, splitk=1, block_n=None, cta_pair=0):
-    """a: [Nimg, H, W, lda] fp16 (channels [0, c_valid) are read); wt packed by pack_conv_weight; out: [Nimg, H, W, ldo]."""
-    Nimg, H, W, lda = a.shape
+def conv_plan(a, c_valid, wt, N, out, *, taps, bias=None, temb=None, residual=None, act=None, alpha=1.0, splitk=1, block_n=None, cta_pair=0,
+              stride=1, pad_lo=1):
+    """a: [Nimg, H * stride, W * stride, lda] fp16 (channels [0, c_valid) are read); wt packed by pack_conv_weight; out: [Nimg, H, W, ldo]."""
+    Nimg, Hin, Win, lda = a.shape
+    H, W = Hin // stride, Win // stride
     ldo = out.shape[-1]
     cin_iter = wt.shape[1] // taps
     r_str = (0, 0, 0)
     if residual is not None:
         ldr = residual.shape[-1]
         r_str = (ldr, W * ldr, H * W * ldr)
-    return GemmPlan(a, (lda, W * lda, H * W * lda), c_valid, wt, (wt.shape[1], 0, 0), wt.shape[1], wt.shape[0], Nimg, H, W, cin_iter, taps, N,
+    return GemmPlan(a, (lda, Win * lda, Hin * Win * lda), c_valid, wt, (wt.shape[1], 0, 0), wt.shape[1], wt.shape[0], Nimg, H, W, cin_iter, taps, N,
                     out, (ldo, W * ldo, H * W * ldo), bias=bias, temb=temb, temb_ld=0 if temb is None else temb.shape[-1],
-                    residual=residual, r_strides=r_str, act=act, alpha=alpha, splitk=splitk, block_n=block_n, cta_pair=cta_pair)
+                    residual=residual, r_strides=r_str, act=act, alpha=alpha, splitk=splitk, block_n=block_n, cta_pair=cta_pair,
+                    stride=stride, pad_lo=pad_lo)
 
 
 def linear_plan(a, k_valid, wt, N, out, *, bias=None, residual=None, act=None, alpha=1.0, splitk=1, block_n=None, cta_pair=0):

@@ -37,6 +37,7 @@ FUSE_GN_STATS = os.environ.get('SDF_FUSE_GN_STATS', '0') != '0'
 # forward 210 us direct vs 92 us GEMM, data-gradient 248 us vs 123 us -> the tcgen05 path wins even at 3/64 useful k-columns; off by default.
 DIRECT_CONV_IN = os.environ.get('SDF_DIRECT_CONV_IN', '0') != '0'
 FUSE_GEGLU = os.environ.get('SDF_FUSE_GEGLU', '1') != '0'                 # A/B switch: GEGLU in the projection GEMM's epilogue      # A/B switch for the cta_group::2 GEMM variant
+STRIDED_TMA_CONV = os.environ.get('SDF_STRIDED_TMA_CONV', '1') != '0'    # A/B switch: stride-2 convolutions through an element-strided TMA box (0: im2col + 1-tap GEMM)
 
 
 def _r(x, m):
@@ -183,7 +184,7 @@ class Builder:
     # ---- dense
     def gemm(self, name, a, c_valid, wt, N, out, *, taps=1, bias=None, temb=None, temb_ld=0, residual=None, act=None, alpha=1.0,
              splitk=None, block_n=None, w_strides=None, w_k_valid=None, n_rows_w=None, geom=None, a_strides=None, o_strides=None,
-             r_strides=None, cin_iter=None):
+             r_strides=None, cin_iter=None, stride=1, pad_lo=1):
         """a / out / residual: View (or (ptr-holder, strides) through a_strides/o_strides with geom=(Nimg,H,W))."""
         Nimg, H, W = geom if geom is not None else (a.Nimg, a.H, a.W)
         a_str = a_strides if a_strides is not None else a.strides()
@@ -211,7 +212,7 @@ class Builder:
         plan = GemmPlan(wrap(a), a_str, c_valid, wrap(wt), w_str, (taps * cin_iter if w_k_valid is None else w_k_valid),
                         (wt.shape[0] if n_rows_w is None else n_rows_w), Nimg, H, W, cin_iter, taps, N, wrap(out), o_str, bias=bias,
                         temb=wrap(temb) if temb is not None else None, temb_ld=temb_ld, residual=wrap(residual) if residual is not None else None,
-                        r_strides=r_str, act=act, alpha=alpha, splitk=sk, block_n=bn, cta_pair=pair)
+                        r_strides=r_str, act=act, alpha=alpha, splitk=sk, block_n=bn, cta_pair=pair, stride=stride, pad_lo=pad_lo)
         self.flops += 2.0 * M * N * taps * c_valid
         self.add(name, plan.run)
         if isinstance(out, View):
@@ -667,10 +668,15 @@ class UNetEngine:
     def _down(self, p, x, out):
         b, B = self.b, self.B
         C = x.C
+        w4 = self.sd[p + '.op.weight'].to(self.dev)
+        if STRIDED_TMA_CONV:
+            # 3x3, stride 2, pad 1 (openaimodel.py:130-138) read straight out of x through an element-strided TMA box: no im2col buffer
+            b.gemm(p + '.op', x, C, pack_conv_weight(w4), C, out, taps=9, bias=self._f32(p + '.op.bias'), geom=(B, x.H // 2, x.W // 2),
+                   a_strides=x.strides(), stride=2, pad_lo=1)
+            return
         col = torch.empty(B, x.H // 2, x.W // 2, 9 * C, device=self.dev, dtype=torch.float16)
         b.im2col_s2(p + '.im2col', x, col, 1, 1)
-        w4 = self.sd[p + '.op.weight'].to(self.dev)                                  # [Cout, C, 3, 3] -> [Cout, tap*C + c]
-        w = _pack_linear(w4.permute(0, 2, 3, 1).reshape(w4.shape[0], 9 * C), self.dev)
+        w = _pack_linear(w4.permute(0, 2, 3, 1).reshape(w4.shape[0], 9 * C), self.dev)                # [Cout, C, 3, 3] -> [Cout, tap*C + c]
         b.gemm(p + '.op', View(col), 9 * C, w, C, out, bias=self._f32(p + '.op.bias'))
 
     def _up(self, p, x, out):
@@ -837,13 +843,18 @@ class VaeEncoderEngine:
         fb, bb, dev, B = self.fb, self.bb, self.dev, self.B
         C = x.C
         Ho = x.H // 2
-        col = torch.empty(B, Ho, Ho, 9 * C, device=dev, dtype=torch.float16)
-        fb.im2col_s2(p + '.im2col', x, col, 0, 0)                 # (0,1,0,1) zero pad: reads one row / column past the border
         w4 = self.sd[p + '.conv.weight'].to(dev)
         w2 = w4.permute(0, 2, 3, 1).reshape(C, 9 * C)              # [Cout, tap*C + c]
-        w = _pack_linear(w2, dev)
         out = View(fb.buf(B, Ho, Ho, C))
-        fb.gemm(p + '.conv', View(col), 9 * C, w, C, out, bias=self._f32(p + '.conv.bias'))
+        if STRIDED_TMA_CONV:
+            # (0,1,0,1) zero pad then stride 2 (model.py:67-79): input pixel = 2 * output pixel + tap, the TMA zero-fills the row / column
+            # past the border; no im2col buffer (302 MB at 512x512x128)
+            fb.gemm(p + '.conv', x, C, pack_conv_weight(w4), C, out, taps=9, bias=self._f32(p + '.conv.bias'), geom=(B, Ho, Ho),
+                    a_strides=x.strides(), stride=2, pad_lo=0)
+        else:
+            col = torch.empty(B, Ho, Ho, 9 * C, device=dev, dtype=torch.float16)
+            fb.im2col_s2(p + '.im2col', x, col, 0, 0)
+            fb.gemm(p + '.conv', View(col), 9 * C, _pack_linear(w2, dev), C, out, bias=self._f32(p + '.conv.bias'))
         wt = w2.t().contiguous()                                   # [9C, C] : d col = d out . W
 
         def backward(dout):

@@ -238,3 +238,26 @@ def test_epilogue_groupnorm_statistics(device, Cout, H, block_n, pair, coff, Cto
                   stats.data_ptr(), _lib.stream())
         ref = F.silu(F.group_norm(x.permute(0, 3, 1, 2), 32, gamma, beta, 1e-5)).permute(0, 2, 3, 1)
         assert (y.float() - ref).abs().max().item() < 2e-2 * max(1.0, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("Nimg,Hin,Cin,Cout,pad_lo,bn,pair", [(2, 64, 320, 320, 1, 160, 0), (2, 32, 640, 640, 1, 160, 0), (2, 16, 1280, 1280, 1, 128, 0),
+                                                       (1, 512, 128, 128, 0, 128, 0), (1, 256, 256, 256, 0, 256, 1), (1, 128, 512, 512, 0, 128, 0),
+                                                       (2, 20, 64, 96, 1, 128, 0)])
+def test_conv3x3_stride2_strided_tma(device, Nimg, Hin, Cin, Cout, pad_lo, bn, pair):
+    """3x3 stride-2 convolutions read through an element-strided TMA box (sdf_gemm_plan_create_strided): the UNet's Downsample
+    (pad 1 on every side, openaimodel.py:130-138) and the VAE encoder's ((0,1,0,1) zero pad then pad 0, model.py:67-79), against F.conv2d"""
+    a = rnd(Nimg, Hin, Hin, Cin, device=device, seed=1)
+    w = rnd(Cout, Cin, 3, 3, device=device, scale=1.0 / math.sqrt(9 * Cin), seed=2)
+    bias = rnd(Cout, device=device, seed=3).float()
+    Ho = Hin // 2
+    out = torch.full((Nimg, Ho, Ho, Cout), float("nan"), device=device, dtype=torch.float16)
+    plan = gemm.conv_plan(a.contiguous(), Cin, gemm.pack_conv_weight(w), Cout, out, taps=9, bias=bias, block_n=bn, cta_pair=pair, stride=2, pad_lo=pad_lo)
+    plan.run()
+    torch.cuda.synchronize()
+    x = a.float().permute(0, 3, 1, 2)
+    if pad_lo == 0:
+        x = F.pad(x, (0, 1, 0, 1))
+        ref = F.conv2d(x, w.float(), bias, stride=2, padding=0)
+    else:
+        ref = F.conv2d(x, w.float(), bias, stride=2, padding=1)
+    check(out, ref.permute(0, 2, 3, 1), 9 * Cin)

@@ -9,7 +9,7 @@ import torch
 from sdf_b200 import _lib
 
 if len(sys.argv) == 1:
-    for tc, ver in (("1", "1"), ("1", "2"), ("0", "1")):
+    for tc, ver in (("1", "2"), ("1", "4")):
         subprocess.run([sys.executable, os.path.abspath(__file__), tc], env=dict(os.environ, SDF_FLASH_TC=tc, SDF_FLASH_TC_V=ver), timeout=300)
     sys.exit(0)
 dev = torch.device("cuda:0")

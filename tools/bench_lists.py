@@ -1,6 +1,6 @@
 """A/B timing of the three SD launch lists as the bench replays them (CUDA graphs): UNet forward, VAE forward, VAE data-gradient.
 Every variant runs in its own process (the kernels read their switches once):
-    python tools/bench_lists.py                      # default switches vs SDF_GN_FUSED=0 vs SDF_FLASH_TC_V=1
+    python tools/bench_lists.py                      # default switches vs SDF_STRIDED_TMA_CONV=0 vs SDF_FLASH_TC_V=1
     python tools/bench_lists.py one                  # this process's environment only
 Median of 30 replays per list, CUDA events, 256 MB L2 flush between replays."""
 import os
@@ -9,7 +9,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "stable-dreamfusion_b200")]
 
-VARIANTS = [{}, {"SDF_GN_FUSED": "0"}, {"SDF_FLASH_TC_V": "1"}, {"SDF_GN_FUSED": "0", "SDF_FLASH_TC_V": "1"}]
+VARIANTS = [{}, {"SDF_STRIDED_TMA_CONV": "0"}, {"SDF_FLASH_TC_V": "1"}]
 if len(sys.argv) == 1:
     for v in VARIANTS:
         subprocess.run([sys.executable, os.path.abspath(__file__), "one"], env=dict(os.environ, **v, BENCH_LISTS_TAG=repr(v)), timeout=600)
