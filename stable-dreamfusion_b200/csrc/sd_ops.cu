@@ -10,6 +10,7 @@
 //   nearest x2                   openaimodel.py:110-120, bilinear 64->512: guidance/sd_utils.py:93
 //   SDS gradient                 guidance/sd_utils.py:103-131,160-161
 #include "common.cuh"
+#include <cstdlib>
 
 namespace {
 
@@ -820,17 +821,45 @@ __global__ void __launch_bounds__(256) k_conv3x3_cin_small_dgrad(const __half* _
 #define LAUNCH_1D(kernel, total, st, ...)                                                       \
     do { const long long t_ = (total); if (t_ > 0) sdf_launch_pdl(kernel, dim3((unsigned)((t_ + 255) / 256)), dim3(256), (size_t)0, st, __VA_ARGS__); } while (0)
 
+
+// Pixels per block of the slab decomposition the GroupNorm kernels share (a block = 256 threads walking `ppb` pixels of one image).
+// Small tensors: at least ~4 blocks per SM.  Large tensors (the VAE's 512x512 / 256x256 levels: 1 000+ blocks of a few microseconds
+// each): the grid is sized to a WHOLE number of waves of the kernel's resident blocks — 1 024 blocks on 444 slots run as three rounds
+// with the last one a third full, and every block pays its prologue (statistics -> per-channel constants) again; 863 blocks run as two.
+template <typename K>
+static int gn_slots(K kernel, size_t smem) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 256, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    return per_sm * sdf_num_sms();
+}
+static int gn_pixels_per_block(int HW, int Nimg, int C, int slots) {
+    const int vpp = C / 8;
+    const int ngroups = max(1, 256 / max(1, vpp));
+    int ppb = max(1, min(HW, (256 * 16 * 8) / C));
+    const int want_blocks = 4 * sdf_num_sms();
+    const int ppb_small = max(ngroups, (int)(((long long)HW * Nimg + want_blocks - 1) / want_blocks));
+    if (ppb_small < ppb) ppb = ppb_small;
+    // SDF_GN_WAVES: 0 = keep the fixed slab size, n = at most n whole waves (default 1: one full wave of long blocks; 1 / 2 / 3 measure the same within 0.5 %)
+    static const int max_waves = [] { const char* e = getenv("SDF_GN_WAVES"); return e ? atoi(e) : 1; }();
+    const long long blocks = (long long)((HW + ppb - 1) / ppb) * Nimg;
+    if (max_waves > 0 && blocks > slots) {
+        const long long waves = min((long long)max_waves, blocks / slots);     // >= 1: round DOWN to whole waves, blocks get longer
+        const long long per_img = max(1LL, waves * slots / Nimg);
+        int p = (int)((HW + per_img - 1) / per_img);
+        p = (p + ngroups - 1) / ngroups * ngroups;                     // whole pixel groups: every thread of a block walks the same count
+        ppb = max(ppb, min(HW, p));
+    }
+    return ppb;
+}
+
 // GroupNorm(+SiLU) whose statistics were accumulated by the producing GEMM's epilogue (sdf_gemm_plan_set_gn_stats): the apply pass only
 SDF_API int sdf_groupnorm_apply(const void* x, int ldx, void* y, int ldy, int Nimg, int HW, int C, int G, const float* gamma, const float* beta,
                                 float eps, int silu_act, const float* stats, void* stream) {
     SDF_CHECK_ARG(x && y && gamma && beta && stats, "groupnorm_apply: null pointer");
     SDF_CHECK_ARG(C % 8 == 0 && C % G == 0 && ldx % 8 == 0 && ldy % 8 == 0, "groupnorm_apply: C %% 8, C %% G, ld %% 8 must be 0");
     cudaStream_t st = (cudaStream_t)stream;
-    const int vpp = C / 8;
-    int ppb = max(1, min(HW, (256 * 16 * 8) / C));
-    const int want_blocks = 4 * sdf_num_sms();
-    const int ppb_small = max(max(1, 256 / max(1, vpp)), (int)(((long long)HW * Nimg + want_blocks - 1) / want_blocks));
-    if (ppb_small < ppb) ppb = ppb_small;
+    static const int slots_a[2] = {gn_slots(k_gn_apply<false>, 0), gn_slots(k_gn_apply<true>, 0)};
+    const int ppb = gn_pixels_per_block(HW, Nimg, C, slots_a[silu_act ? 1 : 0]);
     dim3 grid((HW + ppb - 1) / ppb, Nimg);
     if (silu_act) sdf_launch_pdl(k_gn_apply<true>, dim3(grid), dim3(256), (size_t)(0), st, (const __half*)x, ldx, (__half*)y, ldy, HW, C, G, ppb, stats, gamma, beta, eps);
     else sdf_launch_pdl(k_gn_apply<false>, dim3(grid), dim3(256), (size_t)(0), st, (const __half*)x, ldx, (__half*)y, ldy, HW, C, G, ppb, stats, gamma, beta, eps);
@@ -852,15 +881,13 @@ static int groupnorm_forward_impl(const void* x, int ldx, void* y, int ldy, int 
     SDF_CHECK_ARG(C % 8 == 0 && C % G == 0 && ldx % 8 == 0 && ldy % 8 == 0, "groupnorm_forward: C %% 8, C %% G, ld %% 8 must be 0");
     cudaStream_t st = (cudaStream_t)stream;
     if (zero_stats) SDF_CHECK_CUDA(cudaMemsetAsync(stats, 0, sizeof(float) * 2 * G * Nimg, st));
-    const int vpp = C / 8;
-    // two passes: ~16 vectors per thread for large tensors, at least ~4 blocks per SM for small ones
-    int ppb = max(1, min(HW, (256 * 16 * 8) / C));
-    const int want_blocks = 4 * sdf_num_sms();
-    const int ppb_small = max(max(1, 256 / max(1, vpp)), (int)(((long long)HW * Nimg + want_blocks - 1) / want_blocks));
-    if (ppb_small < ppb) ppb = ppb_small;
-    dim3 grid((HW + ppb - 1) / ppb, Nimg);
-    k_gn_stats<<<grid, 256, sizeof(float) * 2 * G, st>>>((const __half*)x, ldx, HW, C, G, ppb, stats);
+    // two passes: ~16 vectors per thread, at least ~4 blocks per SM for small tensors, whole waves for large ones (gn_pixels_per_block)
+    static const int slots_s = gn_slots(k_gn_stats, sizeof(float) * 2 * 32);
+    static const int slots_a[2] = {gn_slots(k_gn_apply<false>, 0), gn_slots(k_gn_apply<true>, 0)};
+    const int ppb_s = gn_pixels_per_block(HW, Nimg, C, slots_s), ppb = gn_pixels_per_block(HW, Nimg, C, slots_a[silu_act ? 1 : 0]);
+    k_gn_stats<<<dim3((HW + ppb_s - 1) / ppb_s, Nimg), 256, sizeof(float) * 2 * G, st>>>((const __half*)x, ldx, HW, C, G, ppb_s, stats);
     SDF_CHECK_LAUNCH("groupnorm(stats)");
+    dim3 grid((HW + ppb - 1) / ppb, Nimg);
     if (silu_act) sdf_launch_pdl(k_gn_apply<true>, dim3(grid), dim3(256), (size_t)(0), st, (const __half*)x, ldx, (__half*)y, ldy, HW, C, G, ppb, stats, gamma, beta, eps);
     else sdf_launch_pdl(k_gn_apply<false>, dim3(grid), dim3(256), (size_t)(0), st, (const __half*)x, ldx, (__half*)y, ldy, HW, C, G, ppb, stats, gamma, beta, eps);
     SDF_CHECK_LAUNCH("groupnorm(apply)");
@@ -885,16 +912,16 @@ SDF_API int sdf_groupnorm_backward(const void* x, int ldx, const void* dy, int l
     SDF_CHECK_ARG(C % 8 == 0 && C % G == 0, "groupnorm_backward: C %% 8 and C %% G must be 0");
     cudaStream_t st = (cudaStream_t)stream;
     SDF_CHECK_CUDA(cudaMemsetAsync(bstats, 0, sizeof(float) * 2 * G * Nimg, st));
-    int ppb = max(1, min(HW, (256 * 16 * 8) / C));
-    {
-        const int vpp = C / 8, want_blocks = 4 * sdf_num_sms();
-        const int ppb_small = max(max(1, 256 / max(1, vpp)), (int)(((long long)HW * Nimg + want_blocks - 1) / want_blocks));
-        if (ppb_small < ppb) ppb = ppb_small;
-    }
-    dim3 grid((HW + ppb - 1) / ppb, Nimg);
-    if (silu_act) k_gn_bwd_stats<true><<<grid, 256, sizeof(float) * 2 * G, st>>>((const __half*)x, ldx, (const __half*)dy, ldd, HW, C, G, ppb, stats, gamma, beta, eps, bstats);
-    else k_gn_bwd_stats<false><<<grid, 256, sizeof(float) * 2 * G, st>>>((const __half*)x, ldx, (const __half*)dy, ldd, HW, C, G, ppb, stats, gamma, beta, eps, bstats);
+    static const int slots_bs[2] = {gn_slots(k_gn_bwd_stats<false>, sizeof(float) * 2 * 32), gn_slots(k_gn_bwd_stats<true>, sizeof(float) * 2 * 32)};
+    static const int slots_ba[4] = {gn_slots(k_gn_bwd_apply<false, false>, 0), gn_slots(k_gn_bwd_apply<false, true>, 0),
+                                    gn_slots(k_gn_bwd_apply<true, false>, 0), gn_slots(k_gn_bwd_apply<true, true>, 0)};
+    const int ppb_s = gn_pixels_per_block(HW, Nimg, C, slots_bs[silu_act ? 1 : 0]);
+    const int ppb = gn_pixels_per_block(HW, Nimg, C, slots_ba[(silu_act ? 2 : 0) + (accumulate ? 1 : 0)]);
+    const dim3 grid_s((HW + ppb_s - 1) / ppb_s, Nimg);
+    if (silu_act) k_gn_bwd_stats<true><<<grid_s, 256, sizeof(float) * 2 * G, st>>>((const __half*)x, ldx, (const __half*)dy, ldd, HW, C, G, ppb_s, stats, gamma, beta, eps, bstats);
+    else k_gn_bwd_stats<false><<<grid_s, 256, sizeof(float) * 2 * G, st>>>((const __half*)x, ldx, (const __half*)dy, ldd, HW, C, G, ppb_s, stats, gamma, beta, eps, bstats);
     SDF_CHECK_LAUNCH("groupnorm_backward(stats)");
+    dim3 grid((HW + ppb - 1) / ppb, Nimg);
 #define GN_BWD_APPLY(A, B) sdf_launch_pdl(k_gn_bwd_apply<A, B>, dim3(grid), dim3(256), (size_t)(0), st, (const __half*)x, ldx, (const __half*)dy, ldd, (__half*)dx, ldo, HW, C, G, ppb, stats, bstats, gamma, beta, eps)
     if (silu_act) { if (accumulate) GN_BWD_APPLY(true, true); else GN_BWD_APPLY(true, false); }
     else { if (accumulate) GN_BWD_APPLY(false, true); else GN_BWD_APPLY(false, false); }

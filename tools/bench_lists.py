@@ -9,7 +9,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "stable-dreamfusion_b200")]
 
-VARIANTS = [{}, {"SDF_STRIDED_TMA_CONV": "0"}, {"SDF_FLASH_TC_V": "1"}]
+VARIANTS = [{}, {"SDF_GN_WAVES": "1"}, {"SDF_GN_WAVES": "3"}]
 if len(sys.argv) == 1:
     for v in VARIANTS:
         subprocess.run([sys.executable, os.path.abspath(__file__), "one"], env=dict(os.environ, **v, BENCH_LISTS_TAG=repr(v)), timeout=600)
