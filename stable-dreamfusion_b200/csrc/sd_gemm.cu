@@ -146,9 +146,27 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
     d |= (uint64_t)2 << 61;                          // SWIZZLE_128B
     return d;
 }
+// erf by Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7, far below the fp16 output's resolution): one MUFU.RCP, one MUFU.EX2 and
+// six FMAs instead of erff's branchy ~30-instruction sequence — the GEGLU projections (K = 320 / 640: five k-blocks per tile) are bound by
+// their epilogue, where the gate's GELU was two thirds of the instructions.  Compile with -DSDF_EXACT_ERF to restore erff.
+__device__ __forceinline__ float erf_as(float x) {
+    const float ax = fabsf(x);
+    float t;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, ax, 1.f)));
+    float p = fmaf(1.061405429f, t, -1.453152027f);
+    p = fmaf(p, t, 1.421413741f);
+    p = fmaf(p, t, -0.284496736f);
+    p = fmaf(p, t, 0.254829592f);
+    const float r = fmaf(-p * t, __expf(-ax * ax), 1.f);
+    return copysignf(r, x);
+}
 __device__ __forceinline__ float act_apply(float v, int act) {
     if (act == kActSilu) return v / (1.f + __expf(-v));
+#ifdef SDF_EXACT_ERF
     if (act == kActGelu) return 0.5f * v * (1.f + erff(v * 0.70710678118654752f));
+#else
+    if (act == kActGelu) return 0.5f * v * (1.f + erf_as(v * 0.70710678118654752f));
+#endif
     return v;
 }
 

@@ -10,7 +10,10 @@ Adan step, EMA once per epoch.  How it runs here:
   field backward scattering into the flat gradient bucket)  -> [NCCL all-reduce of the bucket]  -> fused Adan (+ fp16 table mirror,
   + EMA on epoch boundaries, + gradient zeroing)
 
-with no host synchronisation anywhere in the step (the loss is read only if the caller asks).
+with no host synchronisation anywhere in the step: the pose (and, ray-parallel, the per-view light offsets / background colour) go through a
+pinned staging ring (_lib.PinnedRing — a pageable `tensor.to(device)` would synchronise the stream), and when the caller asks for the loss
+(nerf/utils.py:1072 reads loss.item() every step) it is copied to a pinned word on a side stream as soon as it exists — before the backward —
+so the host waits for that 4-byte copy, not for the step, and already enqueues the next step while backward + optimiser run.
 
 Multi-GPU (new functionality, SURVEY.md §8e — the reference never initialises torch.distributed): one process per GPU.  Guidance is
 view-parallel (each rank owns its views' UNet/VAE work) but rendering is ray-parallel — every rank renders pixels rank::W of EVERY
