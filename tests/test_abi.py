@@ -58,6 +58,14 @@ def test_argument_errors_of_the_sd_kernels_without_a_gpu():
     assert plan(block_n=64, pair=1) == -1
     assert plan(block_n=256, pair=1, w_sy=64) == -1 and "cta_pair" in L.last_error()
     assert plan(act=3, N=104) == -1 and "GEGLU" in L.last_error()
+    # strided 3x3 convolution plans: stride in {1, 2} (2 only with taps = 9), pad_lo in {0, 1}
+    def splan(taps=9, stride=2, pad_lo=1):
+        return L.cdll.sdf_gemm_plan_create_strided(fake, LL(64), LL(64 * 16), LL(64 * 256), 64, fake, LL(9 * 64), LL(0), LL(0), 9 * 64, 128, 1, 8, 8, 64, taps, 128,
+                                                   fake, LL(128), LL(128 * 8), LL(128 * 64), None, None, 0, None, LL(0), LL(0), LL(0), 0, ctypes.c_float(1.0),
+                                                   1, None, 128, 0, stride, pad_lo)
+    assert splan(stride=3) == -1 and "stride" in L.last_error()
+    assert splan(taps=1, stride=2) == -1
+    assert splan(pad_lo=2) == -1 and "pad_lo" in L.last_error()
     assert plan(splitk=2) == -1 and "workspace" in L.last_error()
     # GroupNorm / LayerNorm shape contracts
     assert L.cdll.sdf_groupnorm_forward(fake, 12, fake, 12, 1, 4, 12, 4, fake, fake, ctypes.c_float(1e-5), 1, fake, None) == -1
