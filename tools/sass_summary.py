@@ -8,7 +8,7 @@ import subprocess
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "stable-dreamfusion_b200", "lib", "libsdf_b200.so")
 sass = subprocess.run(["cuobjdump", "-sass", LIB], capture_output=True, text=True).stdout
-COLS = [("UTCHMMA", r"\bUTCHMMA"), ("UTMALDG", r"\bUTMALDG"), ("LDTM", r"\bLDTM"), ("UTCBAR", r"\bUTCBAR"), ("SYNCS", r"\bSYNCS"),
+COLS = [("UTCHMMA", r"\bUTCHMMA"), ("UTMALDG", r"\bUTMALDG"), ("LDTM", r"\bLDTM"), ("STTM", r"\bSTTM"), ("UTCBAR", r"\bUTCBAR"), ("SYNCS", r"\bSYNCS"),
         ("HMMA", r"(?<![A-Z])HMMA"), ("LDSM", r"\bLDSM"), ("REDG", r"\bREDG|\bRED\."), ("ATOMS", r"\bATOMS"), ("MUFU.EX2", r"MUFU\.EX2")]
 cnt, cur = collections.OrderedDict(), None
 for line in sass.splitlines():
@@ -25,7 +25,7 @@ names = subprocess.run(["c++filt"], input="\n".join(cnt), capture_output=True, t
 want = ["k_gemm", "k_flash_attn", "k_field_forward<1, 2>", "k_field_backward<1, false, 16, true>", "k_march_train", "k_composite_train", "k_adan_step", "k_compact_alive",
         "k_background", "k_splitk", "k_gn_apply", "k_raster_tris", "k_gbuffer_bwd", "k_antialias", "k_mt_emit", "k_albedo_input_grad"]
 print("# SASS evidence, round 2 — `cuobjdump -sass stable-dreamfusion_b200/lib/libsdf_b200.so` (sm_100a): mnemonic counts per kernel\n")
-print("`UTCHMMA` = tcgen05.mma (kind::f16), `UTMALDG` = TMA tensor load, `LDTM` = tcgen05.ld (TMEM -> registers), `UTCBAR` = tcgen05.commit, `SYNCS` = mbarrier,")
+print("`UTCHMMA` = tcgen05.mma (kind::f16), `UTMALDG` = TMA tensor load, `LDTM` = tcgen05.ld (TMEM -> registers), `STTM` = tcgen05.st (registers -> TMEM), `UTCBAR` = tcgen05.commit, `SYNCS` = mbarrier,")
 print("`HMMA` = legacy mma.sync, `LDSM` = ldmatrix, `REDG` = global reductions, `ATOMS` = shared-memory atomics, `MUFU.EX2` = hardware exp2.\n")
 print("| kernel | " + " | ".join(n for n, _ in COLS) + " |")
 print("|---|" + "---:|" * len(COLS))
@@ -37,7 +37,7 @@ for fn, d in zip(cnt, names):
         continue
     seen.add(d)
     print(f"| `{d}` | " + " | ".join(str(cnt[fn][n]) for n, _ in COLS) + " |")
-print("\nReading: every `k_gemm<BLOCK_N, PAIR, STATS>` variant and `k_flash_attn_tc<D16>` issue tcgen05 MMAs fed by TMA with accumulators read back from TMEM")
+print("\nReading: every `k_gemm<BLOCK_N, PAIR, STATS>` variant and the attention kernels `k_flash_attn_tc2<D16, BN, OCC>` (default) / `k_flash_attn_tc<D16>` issue tcgen05 MMAs fed by TMA with accumulators read back from TMEM; version 2 also WRITES TMEM (`STTM`: the in-place rescale of the output accumulator)")
 print("(Blackwell-native).  `k_flash_attn<d>` (short sequences, 77-key cross-attention, d > 64) and the 32-64-64-4 MLP inside the fused field kernels use")
 print("`mma.sync` by design: those kernels are bound by scattered table lanes / MUFU, not by the MMA pipe (DESIGN.md §4).  The DMTet-stage kernels")
 print("(`k_mt_*`, `k_raster_tris`, `k_gbuffer_bwd`, `k_antialias_*`) are integer / scattered-fp32 streaming kernels with global reductions: no MMA by nature.")
