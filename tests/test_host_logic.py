@@ -144,3 +144,18 @@ def test_nvdiffrast_dropin_exposes_the_surface_run_dmtet_binds():
     assert list(inspect.signature(dr.antialias).parameters)[:4] == ["color", "rast", "pos", "tri"]
     dr.RasterizeCudaContext()
     dr.RasterizeGLContext()
+
+
+def test_bench_shading_cycle_is_the_reference_mix_in_every_window():
+    """bench.py's 25-step shading cycle: 20 % latent / 64 % lambertian / 16 % textureless (main.py:150-153 with the -O preset), interleaved so that
+    a timed window of any length — the driver chooses --steps — holds the mix to within one step and the resident and end-to-end windows match"""
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    c = bench.CYCLE
+    assert len(c) == 25 and c.count("latent") == 5 and c.count("lambertian") == 16 and c.count("textureless") == 4
+    ring = c + c + c
+    for start in range(25):
+        for K in (5, 10, 20, 25, 30, 40, 50):
+            w = ring[start:start + K]
+            assert abs(w.count("latent") - 0.2 * K) <= 1.0, (start, K)
+            assert abs(w.count("textureless") - 0.16 * K) <= 1.5, (start, K)
